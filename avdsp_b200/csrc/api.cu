@@ -1,0 +1,570 @@
+// api.cu -- the C ABI of the executor (include/avdsp_b200.h): instance management, state in HBM,
+// kernel selection, host<->device staging, and the reference's own entry points as a per-frame
+// compatibility path.  No CPU fallback exists: without a CUDA device every compute call fails.
+//
+// Reference behaviour mirrored here (citations: /root/reference/module_avdsp/):
+//   dspRuntimeInit / dspRuntimeReset   runtime/dsp_runtime.c:150-195 / :116-145
+//   dspFindCore / dspFindCoreBegin     runtime/dsp_runtime.c:42-77
+//   dspTpdfInit (PRNG seeding)         runtime/dsp_tpdf.h:85-99
+//   dsp_transfer (the batched caller)  linux/avdsp_plugin.c:71-163
+#include "../../include/avdsp_b200.h"
+#include "decoder.h"
+#include "kernels.h"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace avdsp;
+
+static thread_local std::string g_lastError;
+static int setErr(int code, const std::string& msg) { g_lastError = msg; return code; }
+static int cudaErr(cudaError_t e, const char* what) {
+    return setErr(AVDSP_B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cudaErr(e_, #call); } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// state initialisation == dspRuntimeReset for every stream
+__global__ void k_init_state(int* __restrict__ state, int W, int auxOff, int memOff, int nMem,
+                             const int* __restrict__ memInit, const int* __restrict__ seeds,
+                             int defaultDither, int nStreams) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nStreams) return;
+    int* st = state + (size_t)s * W;
+    const unsigned u = seeds ? (unsigned)seeds[s] : 0u;
+    int* aux = st + auxOff;
+    // dspTpdfInit, runtime/dsp_tpdf.h:93-97
+    aux[AUX_S0] = (int)(u | 1u);
+    aux[AUX_S1] = (int)__funnelshift_l(u | 8u, u | 8u, 7);
+    aux[AUX_S2] = (int)__funnelshift_l(u | 16u, u | 16u, 11);
+    aux[AUX_S3] = (int)__funnelshift_l(u | 24u, u | 24u, 17);
+    aux[AUX_TPDF_VALUE] = 0;
+    aux[AUX_TPDF_RANDOM] = (int)u;
+    aux[AUX_DITHER] = defaultDither;
+    aux[AUX_PAD] = 0;
+    for (int k = 0; k < 2 * nMem; k++) st[memOff + k] = memInit[k];
+}
+
+// integer-pipe microbenchmark: 8 independent mad.wide.s32 chains per thread
+__global__ void __launch_bounds__(256) k_int_peak(long long* out, int iters, int a0, int b0) {
+    long long acc[8];
+    int a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = k;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+    }
+    long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += acc[k];
+    if (s == 0x123456789abcdefll) out[0] = s;     // never true in practice; keeps the chains alive
+}
+
+struct avdsp_b200 {
+    int device = 0, numSMs = 148;
+    int nStreams = 0;
+    Lowered L;
+    std::vector<int32_t> seeds;
+    int* dState = nullptr;
+    int* dBig = nullptr; size_t bigWords = 0;
+    int* dMemInit = nullptr;
+    int* dSeeds = nullptr;
+    ChainLane* dLanes = nullptr;
+    ChainGeom geom{};
+    bool chainUsable = false;
+    int period = 0, kernelSel = AVDSP_B200_KERNEL_AUTO, lastKernel = 0;
+    long long launches = 0;
+    cudaStream_t stream = nullptr;          // for the synchronous calls
+    // host-memspace staging: a few slots of device buffers + copy streams
+    static constexpr int kSlots = 3;
+    cudaStream_t slotStream[kSlots] = {nullptr, nullptr, nullptr};
+    int* slotIn[kSlots] = {nullptr, nullptr, nullptr};
+    int* slotOut[kSlots] = {nullptr, nullptr, nullptr};
+    size_t slotInWords = 0, slotOutWords = 0;
+    std::string trace;
+};
+
+static int uploadPlanData(avdsp_b200* h) {
+    cudaSetDevice(h->device);
+    const Lowered& L = h->L;
+    // big pool (FIR taps, data tables)
+    if (h->dBig) { cudaFree(h->dBig); h->dBig = nullptr; }
+    h->bigWords = L.bigPool.size();
+    if (h->bigWords) {
+        CU(cudaMalloc(&h->dBig, h->bigWords * 4));
+        CU(cudaMemcpy(h->dBig, L.bigPool.data(), h->bigWords * 4, cudaMemcpyHostToDevice));
+    }
+    // chain geometry
+    h->chainUsable = false;
+    if (L.chainOk && chainKernelSupports(L.chain)) {
+        std::vector<ChainLane> lanes(1024);
+        if (planChainGeometry(L.chain, h->nStreams, h->numSMs, &h->geom, lanes.data())) {
+            if (!h->dLanes) CU(cudaMalloc(&h->dLanes, 1024 * sizeof(ChainLane)));
+            CU(cudaMemcpy(h->dLanes, lanes.data(), 1024 * sizeof(ChainLane), cudaMemcpyHostToDevice));
+            h->chainUsable = true;
+        }
+    }
+    char line[256];
+    h->trace = L.trace;
+    if (h->chainUsable)
+        snprintf(line, sizeof line, "chain kernel geometry: %d streams/CTA, %d sections/lane, %d lane threads, %d work threads, tile %d frames, depth %d, %zu B smem\n",
+                 h->geom.streamsPerCta, h->geom.secPerLane, h->geom.laneThreads, h->geom.workThreads, h->geom.tileFrames, h->geom.maxDepth, h->geom.smemBytes);
+    else
+        snprintf(line, sizeof line, "chain kernel not used: %s\n", L.chainOk ? "geometry does not fit" : L.chainWhyNot.c_str());
+    h->trace += line;
+    return 0;
+}
+
+static int initState(avdsp_b200* h) {
+    cudaSetDevice(h->device);
+    const PlanHeader& P = h->L.gen.h;
+    const size_t words = (size_t)h->nStreams * P.stateWords;
+    CU(cudaMemsetAsync(h->dState, 0, words * 4, h->stream));
+    std::vector<int32_t> memInit(2 * std::max(P.nMem, 1), 0);
+    for (int k = 0; k < P.nMem; k++) {   // initial MEM values come from the program bytes
+        memInit[2 * k] = h->L.words[h->L.memWord[k]];
+        memInit[2 * k + 1] = h->L.words[h->L.memWord[k] + 1];
+    }
+    if (h->dMemInit) { cudaFree(h->dMemInit); h->dMemInit = nullptr; }
+    CU(cudaMalloc(&h->dMemInit, memInit.size() * 4));
+    CU(cudaMemcpyAsync(h->dMemInit, memInit.data(), memInit.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    if (!h->seeds.empty()) {
+        if (!h->dSeeds) CU(cudaMalloc(&h->dSeeds, (size_t)h->nStreams * 4));
+        CU(cudaMemcpyAsync(h->dSeeds, h->seeds.data(), (size_t)h->nStreams * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    const int th = 128;
+    k_init_state<<<(h->nStreams + th - 1) / th, th, 0, h->stream>>>(h->dState, P.stateWords, P.auxOff, P.memOff, P.nMem, h->dMemInit,
+                                                                     h->seeds.empty() ? nullptr : h->dSeeds, P.defaultDither, h->nStreams);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static void freeAll(avdsp_b200* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->dState) cudaFree(h->dState);
+    if (h->dBig) cudaFree(h->dBig);
+    if (h->dMemInit) cudaFree(h->dMemInit);
+    if (h->dSeeds) cudaFree(h->dSeeds);
+    if (h->dLanes) cudaFree(h->dLanes);
+    for (int k = 0; k < avdsp_b200::kSlots; k++) {
+        if (h->slotIn[k]) cudaFree(h->slotIn[k]);
+        if (h->slotOut[k]) cudaFree(h->slotOut[k]);
+        if (h->slotStream[k]) cudaStreamDestroy(h->slotStream[k]);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" {
+
+const char* avdsp_b200_last_error(void) { return g_lastError.c_str(); }
+
+int avdsp_b200_create(avdsp_b200_t** out, const int32_t* prog, int progWords, int fs, int format,
+                      int nStreams, const int32_t* seeds, int defaultDither, int device) {
+    if (!out) return setErr(AVDSP_B200_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (nStreams < 1) return setErr(AVDSP_B200_ERR_ARG, "nStreams must be >= 1");
+    std::unique_ptr<avdsp_b200, void (*)(avdsp_b200*)> h(new avdsp_b200, freeAll);
+    std::string err;
+    const int rc = decodeProgram(prog, progWords, 0x7FFFFFFF, format, fs, defaultDither, &h->L, &err);
+    if (rc < 0) return setErr(rc, err);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return setErr(AVDSP_B200_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                               " (avdsp_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return setErr(AVDSP_B200_ERR_ARG, "device ordinal out of range");
+    h->device = device;
+    h->nStreams = nStreams;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    h->numSMs = prop.multiProcessorCount;
+    if (seeds) h->seeds.assign(seeds, seeds + nStreams);
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t words = (size_t)nStreams * h->L.gen.h.stateWords;
+    CU(cudaMalloc(&h->dState, std::max<size_t>(words, 1) * 4));
+    int r = uploadPlanData(h.get()); if (r < 0) return r;
+    r = initState(h.get()); if (r < 0) return r;
+    g_lastError.clear();
+    *out = h.release();
+    return rc;
+}
+
+void avdsp_b200_destroy(avdsp_b200_t* h) { freeAll(h); }
+
+int avdsp_b200_reset(avdsp_b200_t* h, int fs, const int32_t* seeds, int defaultDither) {
+    if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
+    if (fs != h->L.fs || defaultDither != h->L.defaultDither) {
+        Lowered nl;
+        std::string err;
+        const std::vector<int32_t> words = h->L.words;
+        const int rc = decodeProgram(words.data(), (int)words.size(), 0x7FFFFFFF, h->L.format, fs, defaultDither, &nl, &err);
+        if (rc < 0) return setErr(rc, err);
+        if (nl.gen.h.stateWords != h->L.gen.h.stateWords) return setErr(AVDSP_B200_ERR_ARG, "state layout changed on reset");
+        h->L = nl;
+        const int r = uploadPlanData(h); if (r < 0) return r;
+    }
+    if (seeds) h->seeds.assign(seeds, seeds + h->nStreams); else h->seeds.clear();
+    return initState(h);
+}
+
+int avdsp_b200_io_map(const avdsp_b200_t* h, int* nIn, int* inIdx, int* nOut, int* outIdx) {
+    if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
+    const PlanHeader& P = h->L.gen.h;
+    if (nIn) *nIn = P.nIn;
+    if (nOut) *nOut = P.nOut;
+    if (inIdx) for (int k = 0; k < P.nIn; k++) inIdx[k] = P.inIdx[k];
+    if (outIdx) for (int k = 0; k < P.nOut; k++) outIdx[k] = P.outIdx[k];
+    return 0;
+}
+
+int avdsp_b200_set_order(avdsp_b200_t* h, int period) {
+    if (!h || period < 0) return setErr(AVDSP_B200_ERR_ARG, "bad period");
+    h->period = period; return 0;
+}
+int avdsp_b200_set_kernel(avdsp_b200_t* h, int which) {
+    if (!h || which < 0 || which > 2) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
+    h->kernelSel = which; return 0;
+}
+int avdsp_b200_last_kernel(const avdsp_b200_t* h) { return h ? h->lastKernel : 0; }
+long long avdsp_b200_launch_count(const avdsp_b200_t* h) { return h ? h->launches : 0; }
+int avdsp_b200_state_words(const avdsp_b200_t* h) { return h ? h->L.gen.h.stateWords : 0; }
+int avdsp_b200_data_size(const avdsp_b200_t* h) { return h ? h->L.gen.h.dataSize : 0; }
+int avdsp_b200_aux_offset(const avdsp_b200_t* h) { return h ? h->L.gen.h.auxOff : 0; }
+int avdsp_b200_mem_offset(const avdsp_b200_t* h) { return h ? h->L.gen.h.memOff : 0; }
+int avdsp_b200_num_mem(const avdsp_b200_t* h) { return h ? h->L.gen.h.nMem : 0; }
+int avdsp_b200_mem_word(const avdsp_b200_t* h, int k) { return (h && k >= 0 && k < (int)h->L.memWord.size()) ? h->L.memWord[k] : -1; }
+int avdsp_b200_num_streams(const avdsp_b200_t* h) { return h ? h->nStreams : 0; }
+int avdsp_b200_num_cores(const avdsp_b200_t* h) { return h ? h->L.gen.h.nCores : 0; }
+const char* avdsp_b200_trace(const avdsp_b200_t* h) { return h ? h->trace.c_str() : ""; }
+
+} // extern "C"
+
+// One launch over streams [first, first+n) with device buffers.  coreSel/plan override serve the
+// dspRuntime_<fmt> compatibility path.
+static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int layout, int first, int n,
+                       cudaStream_t stream, int coreSel = -1, const GenericPlan* planOverride = nullptr) {
+    if (nFrames == 0 || n == 0) return 0;
+    const GenericPlan& G = planOverride ? *planOverride : h->L.gen;
+    const PlanHeader& P = G.h;
+    const int nIn = P.nIn, nOut = P.nOut;
+    long long inSS, outSS; int inFS, inCS, outFS, outCS;
+    if (layout == AVDSP_B200_INTERLEAVED) {
+        inSS = (long long)nFrames * nIn; inFS = nIn; inCS = 1;
+        outSS = (long long)nFrames * nOut; outFS = nOut; outCS = 1;
+    } else if (layout == AVDSP_B200_PLANAR) {
+        inSS = (long long)nFrames * nIn; inFS = 1; inCS = nFrames;
+        outSS = (long long)nFrames * nOut; outFS = 1; outCS = nFrames;
+    } else return setErr(AVDSP_B200_ERR_ARG, "unknown layout");
+    int* st = h->dState + (size_t)first * P.stateWords;
+    const bool wantChain = h->kernelSel != AVDSP_B200_KERNEL_GENERIC && h->chainUsable && h->period == 0 && coreSel < 0 && !planOverride;
+    if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN && !wantChain)
+        return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel requested but this program/order does not map to it: " + h->L.chainWhyNot);
+    cudaError_t e;
+    if (wantChain) {
+        ChainArgs A{};
+        A.in = in; A.out = out; A.state = st; A.lanes = h->dLanes;
+        A.nStreams = n; A.nFrames = nFrames;
+        A.inStreamStride = inSS; A.outStreamStride = outSS;
+        A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
+        e = launchChain(h->L.chain, h->geom, A, stream);
+        h->lastKernel = AVDSP_B200_KERNEL_CHAIN;
+    } else {
+        GenericArgs A{};
+        A.in = in; A.out = out; A.state = st; A.bigPool = h->dBig;
+        A.nStreams = n; A.nFrames = nFrames;
+        A.inStreamStride = inSS; A.outStreamStride = outSS;
+        A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
+        A.coreSel = coreSel; A.period = coreSel >= 0 ? 0 : h->period;
+        for (int c = 0; c < P.nCores && c < kMaxCores; c++) { A.coreInMask[c] = h->L.cores[c].usedIn; A.coreOutMask[c] = h->L.cores[c].usedOut; }
+        e = launchGeneric(G, A, stream);
+        h->lastKernel = AVDSP_B200_KERNEL_GENERIC;
+    }
+    if (e != cudaSuccess) return cudaErr(e, "kernel launch");
+    h->launches++;
+    return 0;
+}
+
+static int ensureSlots(avdsp_b200* h, size_t inWords, size_t outWords) {
+    for (int k = 0; k < avdsp_b200::kSlots; k++)
+        if (!h->slotStream[k]) CU(cudaStreamCreateWithFlags(&h->slotStream[k], cudaStreamNonBlocking));
+    if (inWords > h->slotInWords) {
+        for (int k = 0; k < avdsp_b200::kSlots; k++) { if (h->slotIn[k]) cudaFree(h->slotIn[k]); h->slotIn[k] = nullptr; }
+        for (int k = 0; k < avdsp_b200::kSlots; k++) CU(cudaMalloc(&h->slotIn[k], inWords * 4));
+        h->slotInWords = inWords;
+    }
+    if (outWords > h->slotOutWords) {
+        for (int k = 0; k < avdsp_b200::kSlots; k++) { if (h->slotOut[k]) cudaFree(h->slotOut[k]); h->slotOut[k] = nullptr; }
+        for (int k = 0; k < avdsp_b200::kSlots; k++) CU(cudaMalloc(&h->slotOut[k], outWords * 4));
+        h->slotOutWords = outWords;
+    }
+    return 0;
+}
+
+extern "C" {
+
+int avdsp_b200_process_range(avdsp_b200_t* h, const void* in, void* out, int nFrames, int layout,
+                             int firstStream, int nStreams, void* cudaStream) {
+    if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
+    if (nFrames < 0 || firstStream < 0 || nStreams < 0 || firstStream + nStreams > h->nStreams) return setErr(AVDSP_B200_ERR_ARG, "bad frame/stream range");
+    if ((!in && h->L.gen.h.nIn) || (!out && h->L.gen.h.nOut)) return setErr(AVDSP_B200_ERR_ARG, "NULL buffer");
+    CU(cudaSetDevice(h->device));
+    return launchRange(h, (const int*)in, (int*)out, nFrames, layout, firstStream, nStreams, (cudaStream_t)cudaStream);
+}
+
+int avdsp_b200_process_async(avdsp_b200_t* h, const void* in, void* out, int nFrames, int layout, void* cudaStream) {
+    if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
+    return avdsp_b200_process_range(h, in, out, nFrames, layout, 0, h->nStreams, cudaStream);
+}
+
+int avdsp_b200_process(avdsp_b200_t* h, const void* in, void* out, int nFrames, int layout, int memspace) {
+    if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
+    if (nFrames < 0) return setErr(AVDSP_B200_ERR_ARG, "negative frame count");
+    if (nFrames == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    if (memspace == AVDSP_B200_DEVICE) {
+        const int r = avdsp_b200_process_range(h, in, out, nFrames, layout, 0, h->nStreams, h->stream);
+        if (r < 0) return r;
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (memspace != AVDSP_B200_HOST) return setErr(AVDSP_B200_ERR_ARG, "unknown memspace");
+    // Host buffers: streams are independent and both layouts are stream-major, so the batch is cut into
+    // groups of streams that flow through kSlots staging buffers: copy-in, kernel and copy-out of
+    // successive groups overlap on separate CUDA streams (PCIe both directions + SMs busy at once).
+    const PlanHeader& P = h->L.gen.h;
+    if ((!in && P.nIn) || (!out && P.nOut)) return setErr(AVDSP_B200_ERR_ARG, "NULL buffer");
+    const size_t inPer = (size_t)nFrames * P.nIn, outPer = (size_t)nFrames * P.nOut;   // words per stream
+    const size_t perStream = std::max<size_t>(inPer + outPer, 1);
+    size_t grp = std::max<size_t>(1, ((size_t)64 << 20) / perStream);                 // ~256 MB per group
+    grp = std::min<size_t>(grp, (size_t)h->nStreams);
+    if ((size_t)h->nStreams > grp && grp >= 64) grp = grp / 32 * 32;
+    const int r0 = ensureSlots(h, std::max<size_t>(grp * inPer, 1), std::max<size_t>(grp * outPer, 1));
+    if (r0 < 0) return r0;
+    const int32_t* hin = (const int32_t*)in; int32_t* hout = (int32_t*)out;
+    int slot = 0;
+    for (size_t s0 = 0; s0 < (size_t)h->nStreams; s0 += grp, slot = (slot + 1) % avdsp_b200::kSlots) {
+        const size_t n = std::min(grp, (size_t)h->nStreams - s0);
+        cudaStream_t cs = h->slotStream[slot];
+        if (inPer) CU(cudaMemcpyAsync(h->slotIn[slot], hin + s0 * inPer, n * inPer * 4, cudaMemcpyHostToDevice, cs));
+        const int r = launchRange(h, h->slotIn[slot], h->slotOut[slot], nFrames, layout, (int)s0, (int)n, cs);
+        if (r < 0) return r;
+        if (outPer) CU(cudaMemcpyAsync(hout + s0 * outPer, h->slotOut[slot], n * outPer * 4, cudaMemcpyDeviceToHost, cs));
+    }
+    for (int k = 0; k < avdsp_b200::kSlots; k++) CU(cudaStreamSynchronize(h->slotStream[k]));
+    return 0;
+}
+
+int avdsp_b200_reload_params(avdsp_b200_t* h, const int32_t* prog, int progWords) {
+    if (!h || !prog) return setErr(AVDSP_B200_ERR_ARG, "NULL argument");
+    std::string err;
+    const int rc = relowerProgram(prog, progWords, &h->L, &err);
+    if (rc < 0) return setErr(rc, err);
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    const int r = uploadPlanData(h);
+    return r < 0 ? r : rc;
+}
+
+int avdsp_b200_get_state(avdsp_b200_t* h, int stream, int32_t* words) {
+    if (!h || !words || stream < 0 || stream >= h->nStreams) return setErr(AVDSP_B200_ERR_ARG, "bad stream index");
+    CU(cudaSetDevice(h->device));
+    const int W = h->L.gen.h.stateWords;
+    CU(cudaMemcpy(words, h->dState + (size_t)stream * W, (size_t)W * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int avdsp_b200_set_state(avdsp_b200_t* h, int stream, const int32_t* words) {
+    if (!h || !words || stream < 0 || stream >= h->nStreams) return setErr(AVDSP_B200_ERR_ARG, "bad stream index");
+    CU(cudaSetDevice(h->device));
+    const int W = h->L.gen.h.stateWords;
+    CU(cudaMemcpy(h->dState + (size_t)stream * W, words, (size_t)W * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+double avdsp_b200_measure_int_peak(int device, int iters) {
+    if (cudaSetDevice(device) != cudaSuccess) { setErr(AVDSP_B200_ERR_CUDA, "no CUDA device"); return 0.0; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0.0;
+    long long* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return 0.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    k_int_peak<<<blocks, threads>>>(d, iters / 8 + 1, 3, 5);          // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(a);
+        k_int_peak<<<blocks, threads>>>(d, iters, 3 + rep, 5);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) { best = 0.0; break; }
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        const double rate = (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
+        best = std::max(best, rate);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    return best;
+}
+
+} // extern "C"
+
+// =============================================================================================
+// Reference entry points (per-frame compatibility path).  One live program per process, exactly
+// like the reference (dspHeaderPtr and the fs/TPDF globals are file-scope there).
+// =============================================================================================
+namespace {
+struct Compat {
+    int32_t* code = nullptr;
+    int maxSize = 0, total = 0, dataSize = 0;
+    int fs = 0, seed = 0, dither = 0, format = 0;
+    bool haveReset = false;
+    avdsp_b200* h = nullptr;
+    GenericPlan plan;                 // the program's plan with an identity 32-slot io map
+    int* dIo = nullptr;               // 32 in + 32 out words on the device
+    std::vector<int32_t> stateHost;
+} g_compat;
+
+int compatFormatGuess(const int32_t* code) { return ((uint32_t)code[H_FORMAT] & 0xFFFF) ? FMT_INT64 : FMT_FLOAT; }
+
+int compatBuild(int format) {
+    Compat& C = g_compat;
+    if (C.h) { avdsp_b200_destroy(C.h); C.h = nullptr; }
+    if (C.dIo) { cudaFree(C.dIo); C.dIo = nullptr; }
+    const int32_t seed = C.seed;
+    const int rc = avdsp_b200_create(&C.h, C.code, C.total, C.fs, format, 1, &seed, C.dither, 0);
+    if (rc < 0) return rc;
+    C.format = format;
+    C.plan = C.h->L.gen;
+    C.plan.h.nIn = C.plan.h.nOut = kIoSlots;
+    for (int k = 0; k < kIoSlots; k++) C.plan.h.inIdx[k] = C.plan.h.outIdx[k] = (uint8_t)k;
+    CU(cudaMalloc(&C.dIo, 2 * kIoSlots * 4));
+    C.stateHost.assign(C.plan.h.stateWords, 0);
+    return rc;
+}
+
+int compatRun(int format, int32_t* corePtr, int* rundata, void* io) {
+    Compat& C = g_compat;
+    if (!C.code || !C.haveReset) return setErr(AVDSP_B200_ERR_ARG, "dspRuntime called before dspRuntimeInit/dspRuntimeReset");
+    if (!C.h || C.format != format) { const int rc = compatBuild(format); if (rc < 0) return rc; }
+    avdsp_b200* h = C.h;
+    // live parameter patching: the reference re-reads the program every frame
+    if (memcmp(C.code, h->L.words.data(), (size_t)C.total * 4) != 0) {
+        const int rc = avdsp_b200_reload_params(h, C.code, C.total);
+        if (rc < 0) return rc;
+        const GenericPlan keep = C.plan;
+        C.plan = h->L.gen;
+        C.plan.h.nIn = keep.h.nIn; C.plan.h.nOut = keep.h.nOut;
+        memcpy(C.plan.h.inIdx, keep.h.inIdx, sizeof keep.h.inIdx); memcpy(C.plan.h.outIdx, keep.h.outIdx, sizeof keep.h.outIdx);
+    }
+    const long word = corePtr - C.code;
+    int core = -1;
+    for (size_t c = 0; c < h->L.cores.size(); c++)
+        if (h->L.cores[c].coreWord == word || h->L.cores[c].beginWord == word) { core = (int)c; break; }
+    if (core < 0) return setErr(AVDSP_B200_ERR_ARG, "core pointer does not designate a DSP_CORE of the loaded program");
+    const PlanHeader& P = C.plan.h;
+    CU(cudaSetDevice(h->device));
+    // the caller owns the data area and the MEM words: device copy follows the caller's buffer
+    if (rundata && P.dataSize) CU(cudaMemcpyAsync(h->dState, rundata, (size_t)P.dataSize * 4, cudaMemcpyHostToDevice, h->stream));
+    if (P.nMem) {
+        for (int k = 0; k < P.nMem; k++) { C.stateHost[2 * k] = C.code[h->L.memWord[k]]; C.stateHost[2 * k + 1] = C.code[h->L.memWord[k] + 1]; }
+        CU(cudaMemcpyAsync(h->dState + P.memOff, C.stateHost.data(), (size_t)P.nMem * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(cudaMemcpyAsync(C.dIo, io, kIoSlots * 4, cudaMemcpyHostToDevice, h->stream));
+    const int r = launchRange(h, C.dIo, C.dIo + kIoSlots, 1, AVDSP_B200_INTERLEAVED, 0, 1, h->stream, core, &C.plan);
+    if (r < 0) return r;
+    CU(cudaMemcpyAsync(io, C.dIo + kIoSlots, kIoSlots * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (rundata && P.dataSize) CU(cudaMemcpyAsync(rundata, h->dState, (size_t)P.dataSize * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (P.nMem) CU(cudaMemcpyAsync(C.stateHost.data(), h->dState + P.memOff, (size_t)P.nMem * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < P.nMem; k++) {       // STORE_MEM lands in the caller's code area (runtime/dsp_runtime.c:760-766)
+        const int w = h->L.memWord[k];
+        C.code[w] = C.stateHost[2 * k]; C.code[w + 1] = C.stateHost[2 * k + 1];
+        h->L.words[w] = C.code[w]; h->L.words[w + 1] = C.code[w + 1];
+    }
+    return 0;
+}
+} // namespace
+
+extern "C" {
+
+int dspRuntimeReset(const int fs, int random, int defaultDither) {
+    Compat& C = g_compat;
+    if (!C.code) return setErr(-1, "dspRuntimeReset before dspRuntimeInit");
+    const int fi = freqToIndex(fs);
+    if (fi >= kNumFreq) return setErr(-1, "sampling frequency not supported");
+    if (fi < C.code[H_FREQMIN] || fi > C.code[H_FREQMAX]) return setErr(-2, "sampling freq not compatible with encoded dsp program");
+    C.fs = fs; C.seed = random; C.dither = defaultDither; C.haveReset = true;
+    // the reference clears the data area that follows the code (runtime/dsp_runtime.c:137-141)
+    memset(C.code + C.total, 0, (size_t)C.dataSize * 4);
+    if (C.h) { avdsp_b200_destroy(C.h); C.h = nullptr; }       // rebuilt lazily for the format of the first dspRuntime_<fmt> call
+    return 0;
+}
+
+int dspRuntimeInit(int32_t* codePtr, int maxSize, const int fs, int random, int defaultDither) {
+    Compat& C = g_compat;
+    if (!codePtr || wordOpcode(codePtr[0]) != OP_HEADER) return setErr(-1, "no dsp header in this program");
+    const int total = codePtr[H_TOTAL], dsz = codePtr[H_DATASIZE];
+    if (total < H_WORDS || dsz < 0 || (long long)total + dsz > (long long)maxSize) return setErr(-6, "program+data is over the allowed size");
+    // validation only (no device work yet): lower for the first frequency the program covers
+    Lowered tmp; std::string err;
+    const int fmin = codePtr[H_FREQMIN];
+    const int vfs = (fmin >= 0 && fmin < kNumFreq) ? kFreqTable[fmin] : 0;
+    const int rc = decodeProgram(codePtr, total, maxSize, compatFormatGuess(codePtr), vfs, defaultDither, &tmp, &err);
+    if (rc < 0) return setErr(rc, err);
+    if (C.h) { avdsp_b200_destroy(C.h); C.h = nullptr; }
+    C.code = codePtr; C.maxSize = maxSize; C.total = total; C.dataSize = dsz; C.haveReset = false;
+    if (fs) { const int r = dspRuntimeReset(fs, random, defaultDither); if (r) return r; }
+    return total;
+}
+
+int32_t* dspFindCore(int32_t* codePtr, const int numCore) {
+    if (!codePtr) return nullptr;
+    const int w = findCoreWord(codePtr, numCore);
+    return w < 0 ? nullptr : codePtr + w;
+}
+int32_t* dspFindCoreBegin(int32_t* corePtr) {
+    if (!corePtr) return nullptr;
+    return corePtr + findCoreBeginWord(corePtr, 0);
+}
+
+int dspRuntime_2(int32_t* c, int* d, void* io) { return compatRun(FMT_INT64, c, d, io); }
+int dspRuntime_3(int32_t* c, int* d, void* io) { return compatRun(FMT_FLOAT, c, d, io); }
+int dspRuntime_4(int32_t* c, int* d, void* io) { return compatRun(FMT_DOUBLE, c, d, io); }
+int dspRuntime_5(int32_t* c, int* d, void* io) { return compatRun(FMT_FLOAT_FLOAT, c, d, io); }
+int dspRuntime_6(int32_t* c, int* d, void* io) { return compatRun(FMT_DOUBLE_FLOAT, c, d, io); }
+
+// DSP_QNM family (runtime/dsp_header.h:276-285): x -> fixed point with m mantissa bits in a b-bit
+// container, saturating at the container limits, truncating toward zero.
+static long long qmb(double x, int m, int b) {
+    if (m >= b || b > 64 || m < 1) return 0;                       // the macro divides by zero here
+    const double lim = (double)(1ULL << (b - m - 1));
+    if (x >= lim) return b >= 64 ? 9223372036854775807LL : (long long)((1ULL << (b - 1)) - 1);
+    if (-x > lim) return b >= 64 ? (-9223372036854775807LL - 1LL) : (long long)(1ULL << (b - 1));   // positive magnitude, as the macro yields
+    if (b >= 33) return (long long)(x * (double)(1LL << m));
+    return (long long)(int)(x * (double)(1L << m));
+}
+long long dspQNM(double x, int n, int m) { return qmb(x, m, n + m); }
+long long dspQM64(double x, int m) { return qmb(x, m, 64); }
+int dspQM32(double x, int m) { return (int)qmb(x, m, 32); }
+
+const char* dspOpcodeText[AVDSP_B200_MAX_OPCODE] = {
+    "DSP_END_OF_CODE", "\nDSP_HEADER", "DSP_NOP", "\nDSP_CORE", "\nDSP_PARAM", "\nDSP_PARAM_NUM", "DSP_SERIAL",
+    "DSP_TPDF_CALC", "DSP_TPDF", "DSP_WHITE", "DSP_CLRXY", "DSP_SWAPXY", "DSP_COPYXY", "DSP_COPYYX",
+    "DSP_ADDXY", "DSP_ADDYX", "DSP_SUBXY", "DSP_SUBYX", "DSP_MULXY", "DSP_DIVXY", "DSP_DIVYX", "DSP_AVGXY", "DSP_AVGYX",
+    "DSP_NEGX", "DSP_NEGY", "DSP_SQRTX", "DSP_SHIFT", "DSP_VALUE", "DSP_VALUE_INT", "DSP_MUL_VALUE", "DSP_MUL_VALUE_INT",
+    "DSP_DIV_VALUE", "DSP_DIV_VALUE_INT", "DSP_AND_VALUE_INT",
+    "DSP_LOAD", "DSP_LOAD_GAIN", "DSP_LOAD_MUX", "DSP_STORE", "DSP_LOAD_STORE", "DSP_LOAD_MEM", "DSP_STORE_MEM",
+    "DSP_GAIN", "DSP_SAT0DB", "DSP_SAT0DB_TPDF", "DSP_SAT0DB_GAIN", "DSP_SAT0DB_TPDF_GAIN",
+    "DSP_DELAY_1", "DSP_DELAY", "DSP_DELAY_DP", "DSP_DATA_TABLE", "DSP_BIQUADS", "DSP_FIR",
+    "DSP_RMS", "DSP_DCBLOCK", "DSP_DITHER", "DSP_DITHER_NS2", "DSP_DISTRIB", "DSP_DIRAC", "DSP_SQUAREWAVE", "DSP_CLIP",
+    "DSP_LOAD_MEM_DATA", "DSP_SINE",
+};
+
+} // extern "C"

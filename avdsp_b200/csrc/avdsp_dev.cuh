@@ -1,0 +1,188 @@
+// avdsp_dev.cuh -- device-side arithmetic primitives of the AVDSP executor (sm_100a).
+//
+// These define the numerics the kernels must reproduce.  Fixed point (DSP_FORMAT 2) is bit-exact
+// by construction: int32 x int32 -> int64 products, wrapping 64-bit adds, arithmetic shifts
+// (reference: runtime/dsp_fpmath.h, runtime/dsp_biquadSTD.h:25-77).  The float formats follow the
+// reference's hand-rolled IEEE helpers (runtime/dsp_ieee754.h) -- truncating multiply, truncating
+// int->float, exponent-field shifts -- restated with integer ops so results do not depend on FMA
+// contraction or rounding-mode flags.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "plan.h"
+
+namespace avdsp {
+
+// ---------------------------------------------------------------- fixed point ----------------
+__device__ __forceinline__ long long mul32(int a, int b) { return (long long)a * (long long)b; }          // mul.wide.s32
+__device__ __forceinline__ long long mac32(long long acc, int a, int b) { return acc + (long long)a * (long long)b; } // mad.wide.s32 (IMAD.WIDE)
+
+// dspSaturate64_031 (dsp_fpmath.h:84-98): clamp s4.59 to [-1,1) and return s.31 in the low word
+__device__ __forceinline__ long long sat64_031(long long a) {
+    const long long lim = 1ll << (kMant + 31);
+    if (a >= lim) return 0x7FFFFFFFll;
+    if (a < -lim) return (long long)0xFFFFFFFF80000000ull;
+    return a >> kMant;
+}
+
+// checkbiquadsat (dsp_biquadSTD.h:25-32): test on the high word only; the negative side clamps one
+// high-word step early (hi <= 1-2^27).
+__device__ __forceinline__ long long biquadSat(long long acc) {
+    const int hi = (int)(acc >> 32);
+    const int satpos = 1 << (kMantBQ - 1);
+    // in range  <=>  -satpos+2 <= hi <= satpos-1  <=>  (unsigned)(hi + satpos - 2) <= 2*satpos - 3
+    if (__builtin_expect((unsigned)(hi + (satpos - 2)) > (unsigned)(2 * satpos - 3), 0)) {
+        acc = (hi >= satpos) ? (((long long)satpos << 32) - 1) : -((long long)satpos << 32);
+    }
+    return acc;
+}
+
+// one DF1 biquad section with error feedback (dsp_calc_biquads_int, dsp_biquadSTD.h:34-77).
+// state: acc (64-bit, "mantissa reintegration"), x1, x2, y1, y2.  coef: b0 b1 b2 (a1-1) a2 in Q4.28.
+struct BqStateI { long long acc; int x1, x2, y1, y2; };
+__device__ __forceinline__ int biquadStepI(BqStateI& s, int x, int b0, int b1, int b2, int a1, int a2) {
+    long long acc = s.acc;
+    acc = mac32(acc, x, b0);
+    acc = mac32(acc, s.x1, b1);
+    acc = mac32(acc, s.x2, b2);
+    acc = mac32(acc, s.y1, a1);
+    acc = mac32(acc, s.y2, a2);
+    acc = biquadSat(acc);
+    s.acc = acc;
+    const int y = (int)(acc >> kMantBQ);
+    s.x2 = s.x1; s.x1 = x; s.y2 = s.y1; s.y1 = y;
+    return y;
+}
+
+// ---------------------------------------------------------------- dither PRNG ------------------
+// xoshiro128+ (dsp_tpdf.h:35-49) and the TPDF value (dsp_tpdf.h:103-130)
+struct Prng { unsigned s0, s1, s2, s3; };
+__device__ __forceinline__ unsigned prngNext(Prng& g) {
+    const unsigned r = g.s0 + g.s3, t = g.s1 << 9;
+    g.s2 ^= g.s0; g.s3 ^= g.s1; g.s1 ^= g.s2; g.s0 ^= g.s3; g.s2 ^= t;
+    g.s3 = __funnelshift_l(g.s3, g.s3, 11);
+    return r;
+}
+__device__ __forceinline__ int tpdfDraw(Prng& g, int& white) {
+    const int r1 = (int)prngNext(g), r2 = (int)prngNext(g);
+    white = r2;
+    return (r1 >> 1) + (r2 >> 1);
+}
+// dspTpdfPrepare (dsp_tpdf.h:55-80)
+__host__ __device__ __forceinline__ int ditherMask(int dither)  { return (int)(0xFFFFFFFFu << ((32 - dither) & 31)); }
+__host__ __device__ __forceinline__ int ditherShift(int dither) { return kMant - dither + 1; }
+__device__ __forceinline__ long long tpdfScaledI(int v, int shift) {       // dspTpdfApply :141-145
+    const long long t = v;
+    return shift >= 0 ? (long long)((unsigned long long)t << (shift & 63)) : (t >> ((-shift) & 63));
+}
+
+// ---------------------------------------------------------------- IEEE helpers -----------------
+// dspMulFloatFloat (dsp_ieee754.h:336-375): 24x24 mantissa product, TRUNCATED, inputs/outputs
+// flushed to +0 when the (pre-normalisation) exponent underflows.  Exact integer restatement.
+__device__ __forceinline__ float mulFF(float a, float b) {
+    const unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
+    const int ea = (ua >> 23) & 255, eb = (ub >> 23) & 255;
+    if (ea == 0 || eb == 0) return 0.0f;
+    int e = ea + eb - 127;
+    if (e < 1) return 0.0f;
+    if ((ua ^ ub) & 0x80000000u) e |= 256;
+    const unsigned long long p = (unsigned long long)((ua & 0x7FFFFFu) | 0x800000u) * ((ub & 0x7FFFFFu) | 0x800000u);
+    unsigned hi = (unsigned)(p >> 22);
+    if (hi & (1u << 25)) { e++; hi >>= 2; } else hi >>= 1;
+    return __uint_as_float((hi & 0x7FFFFFu) | ((unsigned)e << 23));
+}
+// Fast form of the same product for hot loops: mul.rz.ftz.f32 agrees with mulFF whenever
+// ea+eb-127 >= 1 (normal result, no overflow); callers handle the vanishing range themselves.
+__device__ __forceinline__ float mulFF_fast(float a, float b) {
+    float r; asm("mul.rz.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
+}
+// dspMulFloatDouble (:377-410): exact float x float product as a double (zero/denormal inputs -> +0)
+__device__ __forceinline__ double mulFD(float a, float b) {
+    const unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
+    if (((ua >> 23) & 255) == 0 || ((ub >> 23) & 255) == 0) return 0.0;
+    return __dmul_rn((double)a, (double)b);       // 48-bit product: exact in binary64
+}
+// dspIntToFloatScaled (:204-250): truncating conversion, at most 7 right shifts (INT_MIN quirk kept)
+__device__ __forceinline__ float i2fScaled(int x, int shift) {
+    if (x == 0) return 0.0f;
+    int e = 0;
+    unsigned acc = (unsigned)x;
+    if (x < 0) { acc = 0u - acc; e = 256; }
+    const int p = 31 - __clz(acc);
+    if (p > 23) { int r = p - 23; if (r > 7) r = 7; acc >>= r; e += r; }
+    else        { acc <<= (23 - p); e -= (23 - p); }
+    e += 127 + 23 - shift;
+    return __uint_as_float((acc & 0x7FFFFFu) | ((unsigned)e << 23));
+}
+// dspIntToDoubleScaled (:252-295): exact
+__device__ __forceinline__ double i2dScaled(int x, int shift) {
+    if (x == 0) return 0.0;
+    int e = 0;
+    unsigned acc = (unsigned)x;
+    if (x < 0) { acc = 0u - acc; e = 2048; }
+    const int p = 31 - __clz(acc);
+    acc <<= (31 - p); e -= (31 - p);
+    e += 1054 - shift;
+    const unsigned long long m = ((unsigned long long)acc << 21) & ((1ull << 52) - 1);
+    return __longlong_as_double((long long)(m | ((unsigned long long)(long long)e << 52)));
+}
+// dsps31Float0DB (:60-83) / dsps31Double0DB (:85-107); shift counts wrap like the x86 build of the
+// reference (that is what the oracle pins).
+__device__ __forceinline__ int f2s31(float f) {
+    const unsigned u = __float_as_uint(f);
+    const int e = (u >> 23) & 255;
+    if (e == 0) return 0;
+    unsigned m = ((u & 0x7FFFFFu) | 0x800000u) << 8;
+    const int n = 127 - e;
+    if (n > 0) m >>= (n & 31); else m = 0x7FFFFFFFu;
+    if (u & 0x80000000u) m = 0u - m;
+    return (int)m;
+}
+__device__ __forceinline__ int d2s31(double d) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    const int e = (int)((u >> 52) & 2047);
+    if (e == 0) return 0;
+    long long m = (long long)((u & ((1ull << 52) - 1)) | (1ull << 52));
+    const int n = 1044 - e;
+    if (n > 21) m >>= (n & 63); else m = 0x7FFFFFFF;
+    if ((long long)u < 0) m = -m;
+    return (int)m;
+}
+__device__ __forceinline__ float satF(float f) {                  // dspSaturateFloat0db :170-184
+    const int e = ((int)__float_as_uint(f)) >> 23;
+    if (e >= 127) return 1.0f;
+    if (e < 0 && e >= -129) return -1.0f;
+    return f;
+}
+__device__ __forceinline__ double satD(double d) {                // dspSaturateDouble0db :187-199
+    const int e = (int)(__double_as_longlong(d) >> 52);
+    if (e >= 1023) return 1.0;
+    if (e < 0 && e >= -1025) return -1.0;
+    return d;
+}
+__device__ __forceinline__ float  shiftF(float f, int s)  { return __uint_as_float(__float_as_uint(f) + ((unsigned)s << 23)); }
+__device__ __forceinline__ double shiftD(double d, int s) { return __longlong_as_double(__double_as_longlong(d) + (long long)((unsigned long long)(long long)s << 52)); }
+__device__ __forceinline__ float truncF(float f, int bit) {       // dspTruncateFloat0DB :112-138
+    int i = (int)__float_as_uint(f);
+    const int e = (i >> 23) & 255;
+    if (e == 0) return 0.0f;
+    const int n = 151 - bit - e;
+    if (n > 0) {
+        if (n >= 24) i = (i >= 0) ? 0 : (int)((unsigned)(256 + 128 - bit) << 23);
+        else { const int mask = (int)(0xFFFFFFFFu << n); if (i < 0) i += ~mask; i &= mask; }
+    }
+    return __uint_as_float((unsigned)i);
+}
+__device__ __forceinline__ double truncD(double d, int bit) {     // dspTruncateDouble0DB :141-167
+    long long i = __double_as_longlong(d);
+    const int e = (int)((i >> 52) & 2047);
+    if (e == 0) return 0.0;
+    const int n = 1076 - bit - e;
+    if (n > 0) {
+        if (n >= 53) i = (i >= 0) ? 0 : (long long)((unsigned long long)(unsigned)((2048 + 1024 - bit) << 20) << 32);
+        else { const long long mask = (long long)(~0ull << n); if (i < 0) i += ~mask; i &= mask; }
+    }
+    return __longlong_as_double(i);
+}
+
+} // namespace avdsp

@@ -1,0 +1,458 @@
+// decoder.cpp -- validate + lower an AVDSP program.  See decoder.h / plan.h.
+//
+// Reference behaviour being restated (citations: /root/reference/module_avdsp/):
+//   validation      runtime/dsp_runtime.c:150-195 (dspRuntimeInit), :116-145 (dspRuntimeReset),
+//                   runtime/dsp_header.h:234-251 (dspCalcSumCore)
+//   core discovery  runtime/dsp_runtime.c:42-77  (dspFindCore, dspFindCoreBegin)
+//   operand decode  runtime/dsp_runtime.c:302-1314, one `case` per opcode
+//   PARAM layouts   encoder/dsp_encoder.c (biquads :1225-1290, mux :798-813, delay :1088-1160)
+#include "decoder.h"
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+namespace avdsp {
+
+namespace {
+
+struct Fail { int code; std::string msg; };
+
+struct Ctx {
+    Lowered* L;
+    const int32_t* w;       // program words
+    int total;
+    uint32_t delayFactor;
+    int nMemSlots = 0;
+    std::map<int, int> memSlotOfWord;
+
+    [[noreturn]] void fail(int code, const char* fmt, int a = 0, int b = 0) {
+        char buf[256]; snprintf(buf, sizeof buf, fmt, a, b);
+        throw Fail{code, buf};
+    }
+    int32_t code(int idx, int atOp) {
+        if (idx < 0 || idx >= total) fail(ERR_MALFORMED, "opcode at word %d points outside the program (%d)", atOp, idx);
+        return w[idx];
+    }
+    void checkData(int off, int n, int atOp) {
+        if (off < 0 || n < 0 || off + n > L->dataSize) fail(ERR_MALFORMED, "opcode at word %d: data offset %d outside the data area", atOp, off);
+    }
+    void checkIo(int io, int atOp) {
+        if (io < 0 || io >= kIoSlots) fail(ERR_MALFORMED, "opcode at word %d: io index %d out of range", atOp, io);
+    }
+    int pool(int32_t v) {
+        GenericPlan& g = L->gen;
+        if (g.h.nPool >= kMaxPool) fail(ERR_PLAN_SIZE, "plan pool full (%d words)", kMaxPool);
+        g.pool[g.h.nPool] = v;
+        return g.h.nPool++;
+    }
+    void emit(int op, int n, int32_t a, int32_t b, int32_t c) {
+        GenericPlan& g = L->gen;
+        if (g.h.nOps >= kMaxOps) fail(ERR_PLAN_SIZE, "plan has more than %d micro-ops", kMaxOps);
+        MicroOp& m = g.ops[g.h.nOps++];
+        m.op = (uint16_t)op; m.n = (uint16_t)n; m.a = a; m.b = b; m.c = c;
+    }
+    int memSlot(int wordIdx, int atOp) {
+        if (wordIdx < 0 || wordIdx + 1 >= total) fail(ERR_MALFORMED, "opcode at word %d: MEM location %d outside the program", atOp, wordIdx);
+        auto it = memSlotOfWord.find(wordIdx);
+        if (it != memSlotOfWord.end()) return it->second;
+        int s = nMemSlots++;
+        memSlotOfWord[wordIdx] = s;
+        L->memWord.push_back(wordIdx);
+        return s;
+    }
+};
+
+int aluWords(int aluClass) { return aluClass == ALU_F32 ? 1 : 2; }
+
+// Lower the opcodes of one core: [begin, next DSP_CORE / END_OF_CODE)
+void lowerCore(Ctx& cx, int begin) {
+    Lowered* L = cx.L;
+    const int32_t* w = cx.w;
+    const int aw = aluWords(L->gen.h.aluClass);
+    int p = begin;
+    for (;;) {
+        if (p < 0 || p >= cx.total) cx.fail(ERR_MALFORMED, "opcode walk left the program at word %d", p);
+        const int op = wordOpcode(w[p]), skip = wordSkip(w[p]);
+        if (skip == 0 || op == OP_CORE) return;            // dsp_runtime.c:321-331
+        if (p + skip > cx.total) cx.fail(ERR_MALFORMED, "opcode at word %d overruns the program", p);
+        auto arg = [&](int k) -> int32_t {
+            if (k + 1 >= skip && !(op == OP_DELAY || op == OP_DELAY_DP)) cx.fail(ERR_MALFORMED, "opcode at word %d: missing argument %d", p, k);
+            return cx.code(p + 1 + k, p);
+        };
+        switch (op) {
+        case OP_HEADER: case OP_NOP: case OP_PARAM: case OP_PARAM_NUM: case OP_SERIAL:
+            break;                                          // skipped at run time (:333,852-868)
+        case OP_SWAPXY: case OP_COPYXY: case OP_COPYYX: case OP_CLRXY:
+        case OP_ADDXY: case OP_ADDYX: case OP_SUBXY: case OP_SUBYX: case OP_MULXY:
+        case OP_DIVXY: case OP_DIVYX: case OP_AVGXY: case OP_AVGYX: case OP_NEGX: case OP_NEGY:
+        case OP_SQRTX: case OP_SAT0DB: case OP_SAT0DB_TPDF: case OP_WHITE:
+            cx.emit(op, 0, 0, 0, 0); break;
+        case OP_SHIFT: case OP_MUL_VALUE: case OP_MUL_VALUE_INT: case OP_DIV_VALUE:
+        case OP_DIV_VALUE_INT: case OP_AND_VALUE_INT: case OP_CLIP:
+            cx.emit(op, 0, arg(0), 0, 0); break;            // immediate below the opcode
+        case OP_GAIN: case OP_SAT0DB_GAIN: case OP_SAT0DB_TPDF_GAIN: case OP_VALUE: case OP_VALUE_INT:
+            cx.emit(op, 0, cx.code(p + arg(0), p), 0, 0); break;   // relative pointer -> immediate
+        case OP_TPDF_CALC: case OP_TPDF: {
+            int d = arg(0); if (d == 0) d = L->defaultDither;      // dsp_tpdf.h:56
+            cx.checkData(arg(1), aw, p);
+            cx.emit(op, 0, d, arg(1), 0); break; }
+        case OP_LOAD: case OP_STORE:
+            cx.checkIo(arg(0), p); cx.emit(op, 0, arg(0), 0, 0); break;
+        case OP_LOAD_GAIN:
+            cx.checkIo(arg(0), p); cx.emit(op, 0, arg(0), cx.code(p + arg(1), p), 0); break;
+        case OP_LOAD_MUX: {
+            int t = p + arg(0);
+            int n = (int16_t)(cx.code(t, p) & 0xFFFF);
+            if (n < 0) n = 0;
+            int first = L->gen.h.nPool;
+            for (int k = 0; k < n; k++) {
+                int io = cx.code(t + 1 + 2 * k, p); cx.checkIo(io, p);
+                cx.pool(io); cx.pool(cx.code(t + 2 + 2 * k, p));
+            }
+            cx.checkData(arg(1), aw, p);
+            cx.emit(op, n, first, arg(1), 0); break; }
+        case OP_LOAD_STORE: {
+            int n = (skip - 1) / 2, first = L->gen.h.nPool;
+            for (int k = 0; k < n; k++) {
+                int i = arg(2 * k), o = arg(2 * k + 1); cx.checkIo(i, p); cx.checkIo(o, p);
+                cx.pool(i); cx.pool(o);
+            }
+            cx.emit(op, n, first, 0, 0); break; }
+        case OP_LOAD_MEM: case OP_STORE_MEM:
+            cx.emit(op, 0, cx.memSlot(p + arg(0), p), 0, 0); break;   // slot index, turned into an offset later
+        case OP_LOAD_MEM_DATA:
+            cx.checkData(arg(0), aw, p); cx.emit(op, 0, arg(0), 0, 0); break;
+        case OP_DELAY_1:
+            cx.checkData(arg(0), aw, p); cx.emit(op, 0, arg(0), 0, 0); break;
+        case OP_DELAY: case OP_DELAY_DP: {                  // :769-824
+            uint32_t maxSize = (uint32_t)arg(0);
+            int off = arg(1), rel = arg(2);
+            uint32_t n;
+            if (rel == 0) n = (uint32_t)(((uint64_t)maxSize * cx.delayFactor) >> 32);
+            else {
+                uint32_t us = (uint32_t)cx.code(p + rel, p) & 0xFFFFu;
+                n = (uint32_t)(((uint64_t)us * cx.delayFactor) >> 32);
+                if (n > maxSize) n = maxSize;
+            }
+            if (n == 0) break;                              // "sanity check ... delay=0 to bypass it"
+            cx.checkData(off, 1 + (int)n * (op == OP_DELAY_DP ? aw : 1), p);
+            cx.emit(op, 0, off, (int32_t)n, 0); break; }
+        case OP_BIQUADS: {                                  // :827-849
+            int off = arg(0), h = p + arg(1);
+            int num = (int16_t)(cx.code(h, p) & 0xFFFF);
+            if (cx.code(h + 1, p) == 0 || num <= 0) break;  // bypass flag: X untouched
+            cx.checkData(off, 6 * num, p);
+            int stride = 2 + 6 * L->nFreq, c0 = h + 5 + 6 * L->fsRel;
+            int first = L->gen.h.nPool;
+            for (int s = 0; s < num; s++)
+                for (int k = 0; k < 5; k++) cx.pool(cx.code(c0 + s * stride + k, p));
+            cx.emit(op, num, off, first, 0); break; }
+        case OP_FIR: {                                      // :928-969
+            int rel = arg(L->fsRel);
+            if (rel == 0) break;
+            int off = arg(L->nFreq);
+            int t = p + rel;
+            int lw = cx.code(t, p), delay = lw >> 16;
+            if (delay) {
+                if (delay < 0) cx.fail(ERR_MALFORMED, "opcode at word %d: negative FIR delay", p);
+                cx.checkData(off, 1 + delay, p);
+                cx.emit(OP_FIR, 0, off, delay, 0);          // n==0: plain ring delay of `delay` samples
+            } else if (lw > 0) {
+                cx.checkData(off, lw, p);
+                cx.code(t + lw, p);                          // bounds
+                FirDesc fd; fd.tapsOff = (int)L->bigPool.size(); fd.length = lw; fd.stateOff = off;
+                for (int k = 0; k < lw; k++) L->bigPool.push_back(w[t + 1 + k]);
+                L->firs.push_back(fd);
+                cx.emit(OP_FIR, 1, off, fd.tapsOff, lw);    // n==1: convolution, b=taps offset, c=length
+            }
+            break; }
+        case OP_DATA_TABLE: {                               // :900-923
+            int size = arg(2), idxOff = arg(3), t = p + arg(4);
+            if (size <= 0) cx.fail(ERR_MALFORMED, "opcode at word %d: empty data table", p);
+            cx.code(t + size - 1, p);
+            cx.checkData(idxOff, 1, p);
+            int first = L->gen.h.nPool;
+            cx.pool(arg(0)); cx.pool(arg(1)); cx.pool(size); cx.pool(idxOff); cx.pool((int)L->bigPool.size());
+            for (int k = 0; k < size; k++) L->bigPool.push_back(w[t + k]);
+            cx.emit(op, 0, first, 0, 0); break; }
+        case OP_DCBLOCK:
+            cx.checkData(arg(0), aw + 2, p); cx.emit(op, 0, arg(0), arg(1 + L->fsRel), 0); break;
+        case OP_DITHER:
+            cx.checkData(arg(0), 3 * aw, p); cx.emit(op, 0, arg(0), 0, 0); break;
+        case OP_DITHER_NS2: {
+            cx.checkData(arg(0), 3, p);
+            int t = p + arg(1) + 3 * L->fsRel, first = L->gen.h.nPool;
+            for (int k = 0; k < 3; k++) cx.pool(cx.code(t + k, p));
+            cx.emit(op, 0, arg(0), first, 0); break; }
+        case OP_RMS: {
+            int off = arg(0), delay = arg(1);
+            if (delay < 0) cx.fail(ERR_MALFORMED, "opcode at word %d: negative RMS delay", p);
+            cx.checkData(off, 5 + 2 * aw + delay * aw, p);
+            int first = L->gen.h.nPool;
+            cx.pool(arg(2 + 2 * L->fsRel)); cx.pool(arg(3 + 2 * L->fsRel));
+            cx.emit(op, 0, off, delay, first); break; }
+        case OP_DISTRIB:
+            cx.checkIo(arg(0), p);
+            if (arg(1) < 2) cx.fail(ERR_MALFORMED, "opcode at word %d: DISTRIB size < 2", p);
+            cx.checkData(arg(2), 1 + arg(1), p);
+            cx.emit(op, 0, arg(0), arg(1), arg(2)); break;
+        case OP_DIRAC: case OP_SQUAREWAVE:
+            cx.checkData(arg(0), 1, p); cx.emit(op, 0, arg(0), arg(1), arg(2 + L->fsRel)); break;
+        case OP_SINE:   // WIP in the reference and does not compile there
+            cx.fail(ERR_UNSUPPORTED, "DSP_SINE at word %d is not executable in the reference either", p);
+        default:
+            cx.fail(ERR_OPCODE_NEW, "unknown opcode %d at word %d", op, p);
+        }
+        p += skip;
+    }
+}
+
+// ---- chain recognition ------------------------------------------------------------------------
+struct ChainFail { std::string why; };
+
+int chainPool(ChainPlan& c, int32_t v) {
+    if (c.h.nPool >= kMaxChainPool) throw ChainFail{"chain pool full"};
+    c.pool[c.h.nPool] = v; return c.h.nPool++;
+}
+
+void buildChainPlan(Lowered* L) {
+    const GenericPlan& g = L->gen;
+    ChainPlan& c = L->chain;
+    memset(&c, 0, sizeof c);
+    c.h.format = g.h.format; c.h.aluClass = g.h.aluClass; c.h.sampleInt = g.h.sampleInt;
+    c.h.nIn = g.h.nIn; c.h.nOut = g.h.nOut;
+    c.h.dataSize = g.h.dataSize; c.h.stateWords = g.h.stateWords; c.h.auxOff = g.h.auxOff;
+    c.h.storeDither = g.h.defaultDither;
+    for (int k = 0; k < kIoSlots; k++) c.h.chainOfOut[k] = -1;
+    if (!g.h.sampleInt) throw ChainFail{"float-sample formats 5/6 run on the generic executor"};
+
+    int inChOfSlot[kIoSlots], outChOfSlot[kIoSlots];
+    for (int k = 0; k < kIoSlots; k++) inChOfSlot[k] = outChOfSlot[k] = -1;
+    for (int k = 0; k < g.h.nIn; k++)  inChOfSlot[g.h.inIdx[k]] = k;
+    for (int k = 0; k < g.h.nOut; k++) outChOfSlot[g.h.outIdx[k]] = k;
+    // every io slot written anywhere in the program
+    uint32_t written = 0;
+    for (int i = 0; i < g.h.nOps; i++) {
+        const MicroOp& m = g.ops[i];
+        if (m.op == OP_STORE || m.op == OP_DISTRIB) written |= 1u << m.a;
+        if (m.op == OP_LOAD_STORE) for (int k = 0; k < m.n; k++) written |= 1u << g.pool[m.a + 2 * k + 1];
+    }
+    auto inputCh = [&](int slot) -> int {
+        if ((written >> slot) & 1u) throw ChainFail{"an input slot is also written by the program (io hand-off between paths)"};
+        if (inChOfSlot[slot] < 0) return -1;    // never fed by the host: reads 0
+        return inChOfSlot[slot];
+    };
+
+    for (int core = 0; core < g.h.nCores; core++) {
+        int i = g.h.coreStart[core], e = g.h.coreStart[core + 1];
+        if (i < e && g.ops[i].op == OP_TPDF_CALC) {
+            if (core != 0 || c.h.nChains != 0 || c.h.hasTpdfCalc) throw ChainFail{"TPDF_CALC not at the very start of core 1"};
+            c.h.hasTpdfCalc = 1; c.h.tpdfDither = g.ops[i].a; c.h.tpdfDataOff = g.ops[i].b;
+            c.h.storeDither = g.ops[i].a;
+            i++;
+        }
+        while (i < e) {
+            if (c.h.nChains >= kMaxChains) throw ChainFail{"more than kMaxChains signal paths"};
+            ChainDesc& d = c.chains[c.h.nChains];
+            memset(&d, 0, sizeof d);
+            d.muxStateOff = -1; d.delayOff = -1;
+            const MicroOp& s = g.ops[i];
+            if (s.op == OP_LOAD)           { d.srcKind = SRC_LOAD;      d.srcCh = (int16_t)inputCh(s.a); }
+            else if (s.op == OP_LOAD_GAIN) { d.srcKind = SRC_LOAD_GAIN; d.srcCh = (int16_t)inputCh(s.a); d.srcArg = s.b; }
+            else if (s.op == OP_LOAD_MUX) {
+                d.srcKind = SRC_LOAD_MUX; d.srcCh = (int16_t)s.n; d.muxStateOff = s.b;
+                d.srcArg = c.h.nPool;
+                for (int k = 0; k < s.n; k++) { chainPool(c, inputCh(g.pool[s.a + 2 * k])); chainPool(c, g.pool[s.a + 2 * k + 1]); }
+            } else throw ChainFail{"a signal path does not start with LOAD / LOAD_GAIN / LOAD_MUX"};
+            i++;
+            d.coefOff = c.h.nPool;
+            std::vector<int> secOff;
+            std::vector<int32_t> coefs;
+            while (i < e && g.ops[i].op == OP_BIQUADS) {
+                for (int k = 0; k < g.ops[i].n; k++) {
+                    secOff.push_back(g.ops[i].a + 6 * k);
+                    for (int q = 0; q < 5; q++) coefs.push_back(g.pool[g.ops[i].b + 5 * k + q]);
+                }
+                i++;
+            }
+            for (int32_t v : coefs) chainPool(c, v);
+            d.secStateOff = c.h.nPool;
+            for (int v : secOff) chainPool(c, v);
+            d.nsec = (int16_t)secOff.size();
+            if (i < e && g.ops[i].op == OP_GAIN) { d.hasGain = 1; d.gainBits = g.ops[i].a; i++; }
+            if (i >= e) throw ChainFail{"a signal path ends without saturation/store"};
+            switch (g.ops[i].op) {
+            case OP_SAT0DB:           d.satKind = SAT_PLAIN; break;
+            case OP_SAT0DB_TPDF:      d.satKind = SAT_TPDF; break;
+            case OP_SAT0DB_GAIN:      d.satKind = SAT_GAIN; d.satGainBits = g.ops[i].a; break;
+            case OP_SAT0DB_TPDF_GAIN: d.satKind = SAT_TPDF_GAIN; d.satGainBits = g.ops[i].a; break;
+            default: throw ChainFail{"a signal path has an opcode the chain kernel does not fuse"};
+            }
+            i++;
+            if (i < e && g.ops[i].op == OP_DELAY) { d.delayOff = g.ops[i].a; d.delayN = g.ops[i].b; i++; }
+            if (i >= e || g.ops[i].op != OP_STORE) throw ChainFail{"a signal path does not end with STORE"};
+            while (i < e && g.ops[i].op == OP_STORE) {
+                if (d.nStores >= kMaxChainStores) throw ChainFail{"too many STOREs on one path"};
+                int ch = outChOfSlot[g.ops[i].a];
+                if (ch < 0) throw ChainFail{"STORE to a slot outside the declared outputs"};
+                if (c.h.chainOfOut[ch] >= 0) throw ChainFail{"two paths store to the same output"};
+                c.h.chainOfOut[ch] = c.h.nChains;
+                d.storeCh[d.nStores++] = (uint8_t)ch;
+                i++;
+            }
+            if (d.nsec > c.h.maxSec) c.h.maxSec = d.nsec;
+            c.h.totalSec += d.nsec;
+            c.h.nChains++;
+        }
+    }
+    if (c.h.nChains == 0) throw ChainFail{"no signal path"};
+    c.h.tpdfShift = kMant - c.h.storeDither + 1;
+}
+
+void lowerAll(Lowered* L) {
+    Ctx cx; cx.L = L; cx.w = L->words.data(); cx.total = L->totalLength;
+    cx.delayFactor = (uint32_t)(4294.967296 * (double)L->fs);      // dsp_runtime.c:81-90
+    GenericPlan& g = L->gen;
+    const std::vector<int> keepMem = L->memWord;                   // keep slot numbering stable on re-lowering
+    L->memWord.clear();
+    for (size_t k = 0; k < keepMem.size(); k++) cx.memSlot(keepMem[k], 0);
+    g.h.nOps = 0; g.h.nPool = 0;
+    L->bigPool.clear(); L->firs.clear();
+
+    g.h.nCores = (int)L->cores.size();
+    uint32_t usedIn = 0, usedOut = 0;
+    for (int c = 0; c < g.h.nCores; c++) {
+        g.h.coreStart[c] = g.h.nOps;
+        lowerCore(cx, L->cores[c].beginWord);
+        usedIn |= L->cores[c].usedIn; usedOut |= L->cores[c].usedOut;
+    }
+    g.h.coreStart[g.h.nCores] = g.h.nOps;
+    g.h.nIn = g.h.nOut = 0;
+    for (int k = 0; k < kIoSlots; k++) {
+        if ((usedIn >> k) & 1u)  g.h.inIdx[g.h.nIn++] = (uint8_t)k;
+        if ((usedOut >> k) & 1u) g.h.outIdx[g.h.nOut++] = (uint8_t)k;
+    }
+    // state block layout
+    g.h.dataSize = L->dataSize;
+    g.h.auxOff = (L->dataSize + 1) & ~1;
+    g.h.memOff = g.h.auxOff + kAuxWords;
+    g.h.nMem = cx.nMemSlots;
+    g.h.stateWords = (g.h.memOff + 2 * g.h.nMem + 3) & ~3;
+    for (int i = 0; i < g.h.nOps; i++)
+        if (g.ops[i].op == OP_LOAD_MEM || g.ops[i].op == OP_STORE_MEM) g.ops[i].a = g.h.memOff + 2 * g.ops[i].a;
+
+    try { buildChainPlan(L); L->chainOk = true; L->chainWhyNot.clear(); }
+    catch (const ChainFail& f) { L->chainOk = false; L->chainWhyNot = f.why; }
+
+    // lowering trace (the B200 counterpart of the reference's DSP_PRINTF>=2 opcode trace)
+    char line[160];
+    L->trace.clear();
+    for (int c = 0; c < g.h.nCores; c++) {
+        snprintf(line, sizeof line, "core %d: ops [%d,%d)\n", c + 1, g.h.coreStart[c], g.h.coreStart[c + 1]); L->trace += line;
+        for (int i = g.h.coreStart[c]; i < g.h.coreStart[c + 1]; i++) {
+            const MicroOp& m = g.ops[i];
+            snprintf(line, sizeof line, "  %3d op=%2d n=%d a=%d b=%d c=%d\n", i, m.op, m.n, m.a, m.b, m.c); L->trace += line;
+        }
+    }
+    snprintf(line, sizeof line, "state: data=%d aux@%d mem@%d x%d words/stream=%d; chain kernel: %s%s\n",
+             g.h.dataSize, g.h.auxOff, g.h.memOff, g.h.nMem, g.h.stateWords, L->chainOk ? "yes" : "no: ", L->chainWhyNot.c_str());
+    L->trace += line;
+}
+
+} // namespace
+
+int findCoreWord(const int32_t* prog, int numCore) {
+    if (wordOpcode(prog[0]) != OP_HEADER) return -1;
+    int p = 0, num = 0;
+    for (;;) {
+        int sk = wordSkip(prog[p]);
+        if (sk == 0) return num == 0 ? 0 : -1;      // no DSP_CORE at all: the program itself (:50-52)
+        if (wordOpcode(prog[p]) == OP_CORE && ++num == numCore) return p;
+        p += sk;
+    }
+}
+
+int findCoreBeginWord(const int32_t* prog, int p) {
+    if (p < 0 || wordOpcode(prog[p]) != OP_CORE) return p;
+    for (;;) {
+        int op = wordOpcode(prog[p]), sk = wordSkip(prog[p]);
+        if (sk == 0) return p;
+        if (op == OP_CORE || op == OP_NOP || op == OP_PARAM || op == OP_PARAM_NUM) p += sk; else return p;
+    }
+}
+
+int decodeProgram(const int32_t* prog, int progWords, int maxWords, int format, int fs,
+                  int defaultDither, Lowered* L, std::string* err) {
+    auto bad = [&](int code, const char* msg) { if (err) *err = msg; return code; };
+    if (format < FMT_INT64 || format > FMT_DOUBLE_FLOAT) return bad(ERR_FORMAT, "DSP_FORMAT must be 2..6");
+    if (!prog || progWords < H_WORDS || wordOpcode(prog[0]) != OP_HEADER) return bad(ERR_NO_HEADER, "no dsp header in this program");
+    const int total = prog[H_TOTAL], dsz = prog[H_DATASIZE];
+    if (total < H_WORDS || dsz < 0 || total > progWords) return bad(ERR_TOO_LARGE, "header totalLength exceeds the words provided");
+    if ((int64_t)total + dsz > (int64_t)maxWords) return bad(ERR_TOO_LARGE, "program+data is over the allowed size");
+    // dspCalcSumCore
+    uint32_t sum = 0; int ncores = 0, p = 0;
+    for (;;) {
+        if (p >= total) return bad(ERR_CHECKSUM, "opcode chain runs past totalLength");
+        int sk = wordSkip(prog[p]);
+        if (sk == 0) { if (ncores == 0) ncores = 1; break; }
+        if (wordOpcode(prog[p]) == OP_CORE) ncores++;
+        sum += (uint32_t)prog[p];
+        p += sk;
+    }
+    if (ncores < 1) return bad(ERR_NO_CORE, "no cores defined in the program");
+    if (sum != (uint32_t)prog[H_CHECKSUM]) return bad(ERR_CHECKSUM, "checksum problem with the program");
+    const int maxOpcode = (int)((uint32_t)prog[H_FORMAT] >> 16), enc = (int)((uint32_t)prog[H_FORMAT] & 0xFFFF);
+    if (maxOpcode >= OP_MAX_OPCODE) return bad(ERR_OPCODE_NEW, "program uses opcodes newer than this runtime");
+    // The reference converts encodings in place (dspChangeFormat) but that path is unreliable
+    // (SURVEY.md App. C #6); we require programs encoded for the format they run in.
+    if (format == FMT_INT64 ? enc != kMant : enc != 0) return bad(ERR_FORMAT, "program is not encoded for the requested DSP_FORMAT");
+    const int fi = freqToIndex(fs);
+    if (fi >= kNumFreq) return bad(ERR_NO_HEADER, "sampling frequency not supported");
+    const int fmin = prog[H_FREQMIN], fmax = prog[H_FREQMAX];
+    if (fi < fmin || fi > fmax) return bad(ERR_FS_RANGE, "sampling freq not compatible with encoded dsp program");
+
+    *L = Lowered{};
+    L->format = format; L->fs = fs; L->fsIndex = fi; L->fsRel = fi - fmin; L->nFreq = fmax - fmin + 1;
+    L->totalLength = total; L->dataSize = dsz; L->defaultDither = defaultDither;
+    L->words.assign(prog, prog + total);
+    L->gen.h.format = format;
+    L->gen.h.aluClass = (format == FMT_INT64) ? ALU_INT64 : (format == FMT_FLOAT || format == FMT_FLOAT_FLOAT) ? ALU_F32 : ALU_F64;
+    L->gen.h.sampleInt = (format <= FMT_DOUBLE) ? 1 : 0;
+    L->gen.h.defaultDither = defaultDither;
+    for (int k = 1; k <= kMaxCores + 1; k++) {
+        int cw = findCoreWord(prog, k);
+        if (cw < 0) break;
+        if (k > kMaxCores) return bad(ERR_PLAN_SIZE, "more DSP_CORE sections than the executor supports");
+        CoreInfo ci;
+        ci.coreWord = cw;
+        if (wordOpcode(prog[cw]) == OP_CORE) { ci.beginWord = findCoreBeginWord(prog, cw); ci.usedIn = (uint32_t)prog[cw + 1]; ci.usedOut = (uint32_t)prog[cw + 2]; }
+        else { ci.beginWord = 0; ci.usedIn = (uint32_t)prog[H_USEDIN]; ci.usedOut = (uint32_t)prog[H_USEDOUT]; }
+        L->cores.push_back(ci);
+        if (wordOpcode(prog[cw]) != OP_CORE) break;     // program without DSP_CORE: exactly one core (not 8x, App. C #8)
+    }
+    try { lowerAll(L); }
+    catch (const Fail& f) { if (err) *err = f.msg; return f.code; }
+    return total;
+}
+
+int relowerProgram(const int32_t* prog, int progWords, Lowered* L, std::string* err) {
+    if (progWords < L->totalLength) { if (err) *err = "fewer words than the loaded program"; return ERR_ARG; }
+    // structure (opcode words) must be unchanged: only parameter words may differ
+    int p = 0;
+    for (;;) {
+        if (prog[p] != L->words[p]) { if (err) *err = "opcode structure changed; create a new instance instead"; return ERR_ARG; }
+        int sk = wordSkip(prog[p]);
+        if (sk == 0) break;
+        p += sk;
+    }
+    std::vector<int32_t> keep = L->words;
+    GenericPlan keepGen = L->gen;
+    L->words.assign(prog, prog + L->totalLength);
+    const int oldState = L->gen.h.stateWords;
+    try { lowerAll(L); }
+    catch (const Fail& f) { L->words = keep; L->gen = keepGen; if (err) *err = f.msg; return f.code; }
+    if (L->gen.h.stateWords != oldState) { L->words = keep; lowerAll(L); if (err) *err = "state layout changed"; return ERR_ARG; }
+    return L->totalLength;
+}
+
+} // namespace avdsp

@@ -1,0 +1,50 @@
+// decoder.h -- host-side front half of the executor: validate an AVDSP program exactly like
+// dspRuntimeInit/dspRuntimeReset (runtime/dsp_runtime.c:116-195) and lower its opcode stream
+// (runtime/dsp_runtime.c:302-1314 is the semantics being lowered) into plans (plan.h).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "plan.h"
+
+namespace avdsp {
+
+struct CoreInfo {
+    int coreWord;      // index of the DSP_CORE word (or 0 when the program has none)
+    int beginWord;     // first executable opcode (dspFindCoreBegin)
+    uint32_t usedIn, usedOut;
+};
+
+struct Lowered {
+    // identity
+    int format = 0, fs = 0, fsIndex = 0, fsRel = 0, nFreq = 0;
+    int totalLength = 0, dataSize = 0, defaultDither = 0;
+    std::vector<int32_t> words;          // private copy of the program (totalLength words)
+    std::vector<CoreInfo> cores;
+    // plans
+    GenericPlan gen{};
+    bool chainOk = false;
+    std::string chainWhyNot;
+    ChainPlan chain{};
+    std::vector<int32_t> bigPool;        // FIR taps / data tables (device: HBM)
+    std::vector<FirDesc> firs;
+    // MEM words (LOAD_MEM / STORE_MEM targets inside the code area)
+    std::vector<int> memWord;            // code word index of each slot
+    // human readable trace of the lowering (replaces the reference's DSP_PRINTF=2 opcode trace)
+    std::string trace;
+};
+
+// returns totalLength (>0) or a negative Err.  `maxWords` is the caller's buffer size in words as
+// passed to dspRuntimeInit (size check -6); pass a huge value to skip.
+int decodeProgram(const int32_t* prog, int progWords, int maxWords, int format, int fs,
+                  int defaultDither, Lowered* out, std::string* err);
+
+// Re-read only the parameter words of an already decoded program (host edited gains / delays /
+// biquad coefficients in place; dump-file workflow, encoder/dsp_encoder.c:476-503).
+int relowerProgram(const int32_t* prog, int progWords, Lowered* inout, std::string* err);
+
+// reference helpers kept at the boundary (runtime/dsp_runtime.c:42-77)
+int findCoreWord(const int32_t* prog, int numCore /*1-based*/);   // -1 when absent
+int findCoreBeginWord(const int32_t* prog, int coreWord);
+
+} // namespace avdsp

@@ -1,0 +1,55 @@
+// kernels.h -- launch interfaces of the CUDA kernels (host side of kernel_*.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "plan.h"
+
+namespace avdsp {
+
+constexpr int kGenericThreads = 128;
+
+// PCM addressing is fully strided (in words) so interleaved [stream][frame][ch] and planar
+// [stream][ch][frame] layouts share the kernels.
+struct GenericArgs {
+    const int* in;  int* out;
+    int* state;                 // [nStreams][stateWords]
+    const int* bigPool;         // FIR taps / data tables in HBM
+    int nStreams, nFrames;
+    long long inStreamStride, outStreamStride;
+    int inFrameStride, inChStride, outFrameStride, outChStride;
+    int coreSel;                // -1: all cores; k: only core k (0-based)  -- dspRuntime_<fmt> compat path
+    int period;                 // 0: canonical order; >0: ALSA plugin order with this period
+    unsigned coreInMask[kMaxCores], coreOutMask[kMaxCores];
+};
+cudaError_t launchGeneric(const GenericPlan& plan, const GenericArgs& args, cudaStream_t stream);
+
+// ---- systolic chain kernel -------------------------------------------------------------------
+// Lane table entry: which biquad section(s) a thread of the CTA owns.
+struct ChainLane {
+    int slot;        // streamLocal * nChains + chain, or -1 for an idle lane
+    int depth;       // pipeline depth of this lane inside its chain (0 = head)
+    int flags;       // bit0 head, bit1 tail
+    int firstSec;    // index of the lane's first section inside the chain
+};
+struct ChainGeom {
+    int streamsPerCta;     // NS
+    int secPerLane;        // K
+    int laneThreads;       // threads that own sections (multiple of 32, may be 0)
+    int workThreads;       // threads taking part in the element-wise phases (>= laneThreads, multiple of 32)
+    int tileFrames;        // F
+    int maxDepth;          // pipeline depth in lanes
+    size_t smemBytes;
+};
+struct ChainArgs {
+    const int* in;  int* out;
+    int* state;
+    const ChainLane* lanes;     // [laneThreads]
+    int nStreams, nFrames;
+    long long inStreamStride, outStreamStride;
+    int inFrameStride, inChStride, outFrameStride, outChStride;
+};
+// choose CTA geometry for a plan and a stream count; fills the lane table (host memory)
+bool planChainGeometry(const ChainPlan& plan, int nStreams, int numSMs, ChainGeom* geom, ChainLane* lanesOut /*[1024]*/);
+cudaError_t launchChain(const ChainPlan& plan, const ChainGeom& geom, const ChainArgs& args, cudaStream_t stream);
+bool chainKernelSupports(const ChainPlan& plan);
+
+} // namespace avdsp

@@ -1,0 +1,128 @@
+// plan.h -- the lowered form of one AVDSP program: what the host decoder (decoder.cpp) produces
+// and what the CUDA kernels consume.  Plans are passed to kernels BY VALUE as __grid_constant__
+// parameters, i.e. they live in the constant bank for the duration of a launch: every micro-op
+// fetch, gain, coefficient and delay length is a warp-uniform constant-cache read, and no
+// process-global __constant__ symbol is needed (several programs can be live at once, unlike the
+// reference whose tables are file-scope globals, runtime/dsp_runtime.c:36-38,103-110).
+//
+// Per-stream mutable state lives in HBM as one block of `stateWords` int32 per stream ("AoS"):
+//   [0, dataSize)            the reference's data area, SAME word offsets (dsp_runtime.c:137-141)
+//   [auxOff, auxOff+8)       what the reference keeps in globals: xoshiro s[4], tpdfValue,
+//                            tpdfRandom, current global dither, pad            (dsp_tpdf.h:11-33)
+//   [memOff, memOff+2*nMem)  the 64-bit PARAM words targeted by LOAD_MEM/STORE_MEM, which the
+//                            reference mutates inside the code area (dsp_runtime.c:750-766)
+#pragma once
+#include <cstdint>
+#include "wire.h"
+
+namespace avdsp {
+
+// ---------------------------------------------------------------- error codes (C-ABI) ---------
+// The first six are the reference's own (dsp_runtime.c:116-195).
+enum Err : int {
+    ERR_NO_HEADER   = -1,   // also: unknown sampling frequency (dspRuntimeReset)
+    ERR_FS_RANGE    = -2,
+    ERR_NO_CORE     = -3,
+    ERR_CHECKSUM    = -4,
+    ERR_OPCODE_NEW  = -5,
+    ERR_TOO_LARGE   = -6,
+    ERR_FORMAT      = -7,   // ours: unsupported DSP_FORMAT or program encoded for another format
+    ERR_UNSUPPORTED = -8,   // ours: opcode / program shape the executor rejects (e.g. DSP_SINE)
+    ERR_ARG         = -9,
+    ERR_CUDA        = -10,
+    ERR_MALFORMED   = -11,  // ours: pointer/offset walks outside the program or data area
+    ERR_PLAN_SIZE   = -12,  // ours: lowered plan exceeds the kernel-parameter budget
+};
+
+enum AluClass : int { ALU_INT64 = 0, ALU_F32 = 1, ALU_F64 = 2 };
+
+constexpr int kMaxCores   = 16;
+constexpr int kMaxOps     = 320;
+constexpr int kMaxPool    = 2304;
+constexpr int kAuxWords   = 8;
+enum { AUX_S0 = 0, AUX_S1, AUX_S2, AUX_S3, AUX_TPDF_VALUE, AUX_TPDF_RANDOM, AUX_DITHER, AUX_PAD };
+
+// One lowered opcode.  `op` keeps the reference opcode number; operands are fully resolved:
+// relative code pointers became immediates / pool offsets, the fs column is picked, delay times are
+// samples, bypassed biquads and zero-length delays are dropped.
+struct MicroOp {
+    uint16_t op;
+    uint16_t n;        // count (mux pairs, biquad sections, load_store pairs)
+    int32_t  a, b, c;
+};
+
+struct PlanHeader {
+    int32_t format;            // DSP_FORMAT 2..6
+    int32_t aluClass;          // AluClass
+    int32_t sampleInt;         // 1: io[] holds int32 s.31, 0: float (formats 5/6)
+    int32_t nCores;
+    int32_t coreStart[kMaxCores + 1];   // ops[coreStart[c] .. coreStart[c+1])
+    int32_t nIn, nOut;
+    uint8_t inIdx[kIoSlots];   // io slot of input channel k   (ascending slot order)
+    uint8_t outIdx[kIoSlots];  // io slot of output channel k
+    int32_t defaultDither;
+    int32_t dataSize;          // words of the reference data area
+    int32_t stateWords;        // per-stream block size (multiple of 4)
+    int32_t auxOff, memOff, nMem;
+    int32_t nOps, nPool;
+};
+
+struct GenericPlan {
+    PlanHeader h;
+    MicroOp    ops[kMaxOps];
+    int32_t    pool[kMaxPool];
+};
+
+// ---------------------------------------------------------------- chain plan ------------------
+// A "chain" is one independent signal path   source -> [biquad cascade] -> [gain] -> saturate
+// (+dither,+gain) -> [delay] -> store(s).   Programs made only of such chains (C2, C3, C5 and most
+// crossovers) run on the systolic chain kernel instead of the generic interpreter.
+constexpr int kMaxChains     = 48;
+constexpr int kMaxChainPool  = 2560;
+constexpr int kMaxChainStores = 4;
+
+enum ChainSrc : int { SRC_LOAD = 0, SRC_LOAD_GAIN = 1, SRC_LOAD_MUX = 2 };
+enum ChainSat : int { SAT_PLAIN = 0, SAT_TPDF = 1, SAT_GAIN = 2, SAT_TPDF_GAIN = 3 };
+
+struct ChainDesc {
+    uint8_t  srcKind, satKind, hasGain, nStores;
+    uint8_t  storeCh[kMaxChainStores];   // OUTPUT CHANNEL numbers (not io slots)
+    int16_t  nsec;            // total biquad sections (concatenated consecutive BIQUADS ops)
+    int16_t  srcCh;           // SRC_LOAD/LOAD_GAIN: INPUT CHANNEL number;  LOAD_MUX: pair count
+    int32_t  srcArg;          // LOAD_GAIN: gain bits;  LOAD_MUX: pool offset of (inputChannel, gain) pairs
+    int32_t  muxStateOff;     // LOAD_MUX: data offset of the stored 64-bit result, else -1
+    int32_t  coefOff;         // pool offset of 5*nsec coefficients (b0 b1 b2 a1-1 a2 per section)
+    int32_t  secStateOff;     // pool offset of nsec data-area offsets (6 words each, dsp_biquadSTD.h:45)
+    int32_t  gainBits;        // optional GAIN between cascade and saturation
+    int32_t  satGainBits;     // SAT0DB_GAIN / SAT0DB_TPDF_GAIN
+    int32_t  delayOff, delayN;// ring in the data area ([index][n samples]); delayN==0: none
+};
+
+struct ChainHeader {
+    int32_t format, aluClass, sampleInt;
+    int32_t nChains, nIn, nOut;
+    int32_t hasTpdfCalc, tpdfDither, tpdfDataOff;   // DSP_TPDF_CALC at the start of core 1
+    int32_t storeDither;                            // dither whose mask applies to every STORE
+    int32_t tpdfShift;                              // 28 - dither + 1 (dsp_tpdf.h:63)
+    int32_t dataSize, stateWords, auxOff;
+    int32_t maxSec;                                 // longest cascade
+    int32_t totalSec;                               // sum of nsec
+    int32_t nPool;
+    int32_t chainOfOut[kIoSlots];                   // output channel -> chain (or -1: channel never written => 0)
+};
+
+struct ChainPlan {
+    ChainHeader h;
+    ChainDesc   chains[kMaxChains];
+    int32_t     pool[kMaxChainPool];
+};
+
+// ---------------------------------------------------------------- FIR plan -------------------
+// DSP_FIR taps live in HBM ("big pool"); one entry per FIR micro-op.
+struct FirDesc {
+    int32_t tapsOff;     // word offset into the big pool
+    int32_t length;      // taps
+    int32_t stateOff;    // data-area offset of the delay line (length words)
+};
+
+} // namespace avdsp

@@ -1,0 +1,153 @@
+"""Host-side mirror of the reference's runtime interface for the batched path.
+
+`Executor` plays the role of dspRuntimeInit + dspRuntimeReset + the per-period loop of dsp_transfer
+(/root/reference/module_avdsp/linux/avdsp_plugin.c:71-163) for `n_streams` independent instances of one
+program; all work happens in libavdsp_b200.so (hand-written CUDA, sm_100a).  Return codes of the
+reference (-1..-6) surface as `AvdspError.code`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+INTERLEAVED, PLANAR = 0, 1
+HOST, DEVICE = 0, 1
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CHAIN = 0, 1, 2
+KERNEL_NAMES = {0: "none", 1: "generic", 2: "chain"}
+
+
+class AvdspError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"avdsp_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _check(rc: int) -> int:
+    if rc < 0:
+        raise AvdspError(rc, _lib.last_error())
+    return rc
+
+
+class Executor:
+    """n_streams independent instances of one encoded DSP program on one GPU."""
+
+    def __init__(self, words, fs: int, fmt: int = 2, n_streams: int = 1, seeds=None, dither: int = 31, device: int = 0):
+        L = _lib.lib()
+        self._L = L
+        self.words = np.ascontiguousarray(words, dtype=np.int32)
+        self.fs, self.fmt, self.n_streams, self.device = fs, fmt, n_streams, device
+        self._h = C.c_void_p()
+        sp = None
+        if seeds is not None:
+            self._seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+            assert self._seeds.shape == (n_streams,)
+            sp = self._seeds.ctypes.data
+        self.total_length = _check(L.avdsp_b200_create(C.byref(self._h), self.words.ctypes.data, len(self.words), fs, fmt,
+                                                       n_streams, sp, dither, device))
+        n_in, n_out = C.c_int(), C.c_int()
+        a, b = (C.c_int * 32)(), (C.c_int * 32)()
+        L.avdsp_b200_io_map(self._h, C.byref(n_in), a, C.byref(n_out), b)
+        self.in_idx, self.out_idx = list(a[: n_in.value]), list(b[: n_out.value])
+        self.n_in, self.n_out = n_in.value, n_out.value
+        self.state_words = L.avdsp_b200_state_words(self._h)
+        self.data_size = L.avdsp_b200_data_size(self._h)
+        self.aux_offset = L.avdsp_b200_aux_offset(self._h)
+        self.mem_offset = L.avdsp_b200_mem_offset(self._h)
+        self.num_mem = L.avdsp_b200_num_mem(self._h)
+        self.mem_words = [L.avdsp_b200_mem_word(self._h, k) for k in range(self.num_mem)]
+        self.num_cores = L.avdsp_b200_num_cores(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.avdsp_b200_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # -- control -----------------------------------------------------------------------------------
+    def reset(self, fs=None, seeds=None, dither: int = 31):
+        sp = None
+        if seeds is not None:
+            self._seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+            sp = self._seeds.ctypes.data
+        _check(self._L.avdsp_b200_reset(self._h, self.fs if fs is None else fs, sp, dither))
+        if fs is not None:
+            self.fs = fs
+
+    def set_order(self, period: int = 0):
+        _check(self._L.avdsp_b200_set_order(self._h, period))
+
+    def set_kernel(self, which: int):
+        _check(self._L.avdsp_b200_set_kernel(self._h, which))
+
+    def reload_params(self, words):
+        w = np.ascontiguousarray(words, dtype=np.int32)
+        _check(self._L.avdsp_b200_reload_params(self._h, w.ctypes.data, len(w)))
+        self.words = w
+
+    @property
+    def last_kernel(self) -> str:
+        return KERNEL_NAMES[self._L.avdsp_b200_last_kernel(self._h)]
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.avdsp_b200_launch_count(self._h))
+
+    @property
+    def trace(self) -> str:
+        return self._L.avdsp_b200_trace(self._h).decode()
+
+    # -- state --------------------------------------------------------------------------------------
+    def get_state(self, stream: int) -> np.ndarray:
+        w = np.zeros(self.state_words, dtype=np.int32)
+        _check(self._L.avdsp_b200_get_state(self._h, stream, w.ctypes.data))
+        return w
+
+    def set_state(self, stream: int, words):
+        w = np.ascontiguousarray(words, dtype=np.int32)
+        assert w.shape == (self.state_words,)
+        _check(self._L.avdsp_b200_set_state(self._h, stream, w.ctypes.data))
+
+    # -- processing ---------------------------------------------------------------------------------
+    def _shapes(self, n_frames, layout):
+        if layout == INTERLEAVED:
+            return (self.n_streams, n_frames, self.n_in), (self.n_streams, n_frames, self.n_out)
+        return (self.n_streams, self.n_in, n_frames), (self.n_streams, self.n_out, n_frames)
+
+    def process(self, x, layout: int = INTERLEAVED, out=None):
+        """x: int32 PCM (float32 bit patterns for formats 5/6), [S, T, nIn] interleaved or [S, nIn, T]
+        planar.  numpy array -> host path (copies inside the call); torch CUDA tensor -> device path.
+        Returns the outputs in the same layout and memory space."""
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, dtype=np.int32)
+            n_frames = x.shape[1] if layout == INTERLEAVED else x.shape[2]
+            si, so = self._shapes(n_frames, layout)
+            assert x.shape == si, (x.shape, si)
+            y = np.empty(so, dtype=np.int32) if out is None else out
+            _check(self._L.avdsp_b200_process(self._h, x.ctypes.data, y.ctypes.data, n_frames, layout, HOST))
+            return y
+        import torch
+        assert x.is_cuda and x.dtype == torch.int32 and x.is_contiguous()
+        n_frames = x.shape[1] if layout == INTERLEAVED else x.shape[2]
+        si, so = self._shapes(n_frames, layout)
+        assert tuple(x.shape) == si, (tuple(x.shape), si)
+        y = torch.empty(so, dtype=torch.int32, device=x.device) if out is None else out
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _check(self._L.avdsp_b200_process_async(self._h, x.data_ptr(), y.data_ptr(), n_frames, layout, stream))
+        return y
+
+    def process_pinned(self, x_host, y_host, layout: int = INTERLEAVED):
+        """Host path on caller-owned (ideally pinned) buffers given as torch CPU tensors or numpy arrays."""
+        n_frames = x_host.shape[1] if layout == INTERLEAVED else x_host.shape[2]
+        xp = x_host.data_ptr() if hasattr(x_host, "data_ptr") else x_host.ctypes.data
+        yp = y_host.data_ptr() if hasattr(y_host, "data_ptr") else y_host.ctypes.data
+        _check(self._L.avdsp_b200_process(self._h, xp, yp, n_frames, layout, HOST))
+        return y_host
+
+
+def measure_int_peak(device: int = 0, iters: int = 4096) -> float:
+    """mad.wide.s32 per second the whole device sustains (denominator of the INT-pipe roofline)."""
+    return float(_lib.lib().avdsp_b200_measure_int_peak(device, iters))

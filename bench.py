@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement (BASELINE.json `metric`): channel-samples/s of the batched AVDSP
+executor on B200, with the roofline of the dominant kernel and the reference runtime timed on the host
+cores in the same run.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c5|c3]
+                  [--streams S] [--frames T]
+
+Workload at N=1 (config.workload): BASELINE.json configs[1] -- "DAC8PRO-style 8-ch 3-way crossover,
+fixed-point int64 format, 192 kHz, 4096 independent streams batched on 1xB200" = program
+tests/golden/programs/c2_testrpi_xover_f2_192k.bin (reference dspprogs/testrpi.c -crossover, encoded by the
+unchanged reference encoder), 4096 streams x 48000 frames (0.25 s of audio) per step.
+A "step" = one pass of the hot path over that batch: every stream advances by T frames.  For N>1 every
+rank owns 4096 streams of its own (weak scaling, no data-path collective).
+
+One JSON line on stdout (rank 0).  `value` = whole-job channel-samples/s with PCM resident in HBM;
+`e2e` = the same through the C-ABI host call (avdsp_b200_process, HOST memspace) on pinned host buffers,
+host<->device copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (program, DSP_FORMAT, fs, default streams, default frames, MACs/frame, description)
+    "c2": ("c2_testrpi_xover_f2_192k", 2, 192000, 4096, 48000, 240,
+           "C2 DAC8PRO-style 8-ch 3-way crossover (testrpi -crossover), int64 fixed point, 192 kHz"),
+    "c5": ("c5_mixer8x8_f2_192k", 2, 192000, 4096, 48000, 72,
+           "C5 8x8 matrix mixer + per-channel delays + gain/TPDF dither, int64 fixed point, 192 kHz"),
+    "c3": ("c3_peq16_f2_48k", 2, 48000, 65536, 4096, 160,
+           "C3 16-section parametric EQ per channel x2 (fixed-point encoding), 48 kHz"),
+}
+
+
+def prog_file(name):
+    return os.path.join(ROOT, "tests", "golden", "programs", name + ".bin")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU while the timed region runs (nvidia-smi, 200 ms)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_rate(prog, fmt, fs, frames, workers, streams_per_worker=1):
+    """Time the reference's own CPU implementation on the host cores (oracle/_ref, compiled from
+    /root/reference by oracle/Makefile); falls back to the C restatement (oracle/liboracle_avdsp.so)."""
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    exe, lib = os.path.join(refdir, "refbench"), os.path.join(refdir, f"libavdspruntime{fmt}.so")
+    if os.path.exists(exe) and os.path.exists(lib):
+        out = subprocess.run([exe, lib, prog_file(prog), str(fmt), str(fs), str(workers), str(streams_per_worker), str(frames)],
+                             capture_output=True, text=True, timeout=900)
+        if out.returncode == 0:
+            r = json.loads(out.stdout.strip().splitlines()[-1])
+            r.update(kind="reference", cores=workers)
+            return r
+    # "port": the oracle restatement, one core
+    import numpy as np
+    from oracle import pyoracle
+    from avdsp_b200 import program, synth
+    w = program.load(prog_file(prog))
+    o = pyoracle.Oracle(w, fmt, fs, seed=0)
+    x = synth.pcm("noise", 1, frames, len(o.ins), fs)[0]
+    t0 = time.perf_counter()
+    o.process(x)
+    dt = time.perf_counter() - t0
+    return {"frames": frames, "seconds": dt, "frames_per_s": frames / dt, "n_in": len(o.ins), "n_out": len(o.outs),
+            "kind": "port", "cores": 1, "workers": 1}
+
+
+def run_reference(args, wl):
+    prog, fmt, fs, S, T, macs, desc = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample of the workload per step: one stream per host core, `fr` frames each (~1-2 s per step)
+    fr = min(T, 400000) if args.frames is None else args.frames
+    for _ in range(args.warmup):
+        cpu_reference_rate(prog, fmt, fs, max(1000, fr // 20), cores)
+    tot_frames, tot_s, kind, n_out = 0.0, 0.0, "reference", 8
+    for _ in range(args.steps):
+        r = cpu_reference_rate(prog, fmt, fs, fr, cores)
+        tot_frames += r["frames"]; tot_s += r["seconds"]; kind = r["kind"]; n_out = r["n_out"]; used = r["cores"]
+    val = tot_frames * n_out / tot_s / 1e6
+    sample = f"{used} streams x {fr} frames per step (one stream per host thread), stream-major, canonical core order"
+    line = {"impl": "reference", "metric": "channel-samples/sec", "value": val, "unit": "Msps", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64" if fmt == 2 else "f32",
+            "data": "synthetic",
+            "config": {"workload": desc, "program": prog, "streams": S, "frames_per_step": T, "fs": fs},
+            "cpu_baseline": {"value": val, "unit": "Msps", "cores": used, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--streams", type=int, default=None)
+    ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import numpy as np
+    import torch
+    import avdsp_b200
+    from avdsp_b200 import synth
+
+    prog, fmt, fs, S, T, macs, desc = wl
+    S = args.streams or S
+    T = args.frames or T
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (avdsp_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    words = avdsp_b200.load_bin(prog_file(prog))
+    first = rank * S                                   # weak scaling: rank r owns streams [r*S, (r+1)*S)
+    seeds = np.arange(first, first + S, dtype=np.int32)
+    ex = avdsp_b200.Executor(words, fs, fmt, S, seeds=seeds, dither=31, device=local)
+    n_in, n_out = ex.n_in, ex.n_out
+    x = synth.pcm_torch("noise", S, T, n_in, dev, first_stream=first)       # synthetic PCM, resident in HBM
+    y = torch.empty((S, T, n_out), dtype=torch.int32, device=dev)
+
+    # ---- device-resident timing: K steps bracketed by barrier+sync, CUDA events on the launch stream
+    for _ in range(args.warmup):
+        ex.process(x, out=y)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = ex.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for a, b in evs:
+        a.record()
+        ex.process(x, out=y)
+        b.record()
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = ex.launch_count - l0
+    kernel_ms = sum(a.elapsed_time(b) for a, b in evs) / max(launches, 1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    frames_job = float(S) * T * world * args.steps
+    value = frames_job * n_out / (total_ms * 1e-3) / 1e6
+
+    # ---- end to end through the host-facing C-ABI call: pinned host PCM in, pinned host PCM out
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty((S, T, n_in), dtype=torch.int32).pin_memory()
+        yh = torch.empty((S, T, n_out), dtype=torch.int32).pin_memory()
+        xh.copy_(x)
+        torch.cuda.synchronize()
+        for _ in range(2):
+            ex.process_pinned(xh, yh)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ex.process_pinned(xh, yh)          # synchronous: returns when the outputs are in host memory
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": frames_job * n_out / float(dt.item()) / 1e6, "unit": "Msps",
+               "h2d_bytes_per_step": S * T * n_in * 4, "d2h_bytes_per_step": S * T * n_out * 4,
+               "ms_per_step": 1e3 * float(dt.item()) / args.steps,
+               "checksum": int(yh[0, :64].to(torch.int64).sum().item())}
+        del xh, yh
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    alg_bytes = float(S) * T * (n_in + n_out) * 4               # read every input once + write every output once
+    hbm = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+           "traffic": None, "peak_source": peak_src, "kernel": f"k_{ex.last_kernel}", "kernel_ms": kernel_ms,
+           "algorithmic_bytes_per_launch": alg_bytes}
+    hbm["frac"] = hbm["achieved"] / hbm["peak"]
+    int_peak = avdsp_b200.measure_int_peak(local, 4096)
+    alg_macs = float(S) * T * macs
+    roof_int = {"bound": "int_pipe", "achieved": alg_macs / (kernel_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
+                "unit": "T mad.wide.s32/s", "peak_source": "measured live (avdsp_b200_measure_int_peak)",
+                "algorithmic_macs_per_launch": alg_macs}
+    roof_int["frac"] = roof_int["achieved"] / roof_int["peak"] if int_peak else None
+
+    cpu = None
+    if not args.no_cpu:
+        cores = os.cpu_count() or 1
+        fr = 400000
+        r = cpu_reference_rate(prog, fmt, fs, fr, cores)
+        cpu = {"value": r["frames_per_s"] * r["n_out"] / 1e6, "unit": "Msps", "cores": r["cores"], "kind": r["kind"],
+               "sample": f"{r['workers']} streams x {fr} frames of the same program and PCM recipe, one stream per host thread, "
+                         f"{r['seconds']:.2f} s"}
+
+    line = {"metric": "channel-samples/sec", "value": value, "unit": "Msps", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64" if fmt == 2 else "f32", "data": "synthetic",
+            "config": {"workload": desc, "program": prog, "streams_per_gpu": S, "frames_per_step": T, "fs": fs,
+                       "n_in": n_in, "n_out": n_out, "layout": "interleaved [stream][frame][channel] int32",
+                       "l2": f"inputs+outputs {alg_bytes / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)",
+                       "kernel": ex.last_kernel, "frames_per_s": frames_job / (total_ms * 1e-3)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": hbm, "roofline_int": roof_int, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+/*
+ * avdsp_b200.h -- C ABI of the B200-native batched executor for AVDSP encoded DSP programs.
+ *
+ * This is the drop-in boundary of the hot path.  Plain pointers and sizes only; no torch/C++
+ * types.  Two groups of entry points:
+ *
+ *  (1) the reference runtime's own entry points, same names, arguments and return codes, so a host
+ *      written against /root/reference/module_avdsp/runtime/dsp_runtime.h:160-164 links unchanged
+ *      (per-frame compatibility path: every call is a 1-stream, 1-frame launch -- correct but slow);
+ *  (2) the batched variant the ALSA host (module_avdsp/linux/avdsp_plugin.c:71-163, dsp_transfer)
+ *      calls once per period for all frames -- and for any number of independent streams.
+ *
+ * All numerics are the reference's: DSP_FORMAT 2 (int64 accumulator) is bit-exact; formats 3..6
+ * reproduce the reference's hand-rolled IEEE helpers (runtime/dsp_ieee754.h) bit for bit in the
+ * generic executor and within the tolerance stated in DESIGN.md in the fused kernels.
+ *
+ * There is no CPU fallback: every compute entry point returns AVDSP_B200_ERR_CUDA when no CUDA
+ * device is usable.
+ */
+#ifndef AVDSP_B200_H_
+#define AVDSP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Reference entry points.  opcode_t is a 32-bit word (runtime/dsp_header.h:197-209) and
+ *     dspSample_t is a 32-bit word (int for formats 2..4, float for 5/6; runtime/dsp_runtime.h:51-127),
+ *     so both are spelled int32_t / void here.
+ * ------------------------------------------------------------------------------------------ */
+
+/* replaces dspRuntimeInit, runtime/dsp_runtime.c:150-195.
+ * returns totalLength (>0) or -1 no header, -3 no core, -4 checksum, -5 opcode too recent,
+ * -6 program+data larger than maxSize, and dspRuntimeReset's -1/-2 when fs != 0.
+ * The executor keeps `codePtr` (one live program per process, like the reference's dspHeaderPtr
+ * global, :36,156) and mirrors the data area / MEM words back into the caller's buffer after
+ * every dspRuntime_<fmt> call, since reference hosts own and inspect that buffer. */
+int  dspRuntimeInit(int32_t *codePtr, int maxSize, const int fs, int random, int defaultDither);
+/* replaces dspRuntimeReset, runtime/dsp_runtime.c:116-145.  0 | -1 unknown fs | -2 fs outside header range */
+int  dspRuntimeReset(const int fs, int random, int defaultDither);
+/* replaces dspFindCore, runtime/dsp_runtime.c:42-59 (numCore is 1-based; 0 when absent) */
+int32_t *dspFindCore(int32_t *codePtr, const int numCore);
+/* replaces dspFindCoreBegin, runtime/dsp_runtime.c:62-77 */
+int32_t *dspFindCoreBegin(int32_t *corePtr);
+/* replace dspRuntime_<DSP_FORMAT>, runtime/dsp_runtime.c:302-1314 (name mangling runtime/dsp_runtime.h:41-127,164):
+ * run ONE core for ONE frame.  io = the 32-slot sample array.  Always returns 0 like the reference
+ * (negative only when no program is loaded or CUDA failed). */
+int  dspRuntime_2(int32_t *corePtr, int *rundataPtr, void *io);
+int  dspRuntime_3(int32_t *corePtr, int *rundataPtr, void *io);
+int  dspRuntime_4(int32_t *corePtr, int *rundataPtr, void *io);
+int  dspRuntime_5(int32_t *corePtr, int *rundataPtr, void *io);
+int  dspRuntime_6(int32_t *corePtr, int *rundataPtr, void *io);
+/* replace dspQNM / dspQM64 / dspQM32, runtime/dsp_header.c:76-86 (macros runtime/dsp_header.h:276-285) */
+long long dspQNM(double x, int n, int m);
+long long dspQM64(double x, int m);
+int       dspQM32(double x, int m);
+/* replaces dspOpcodeText, runtime/dsp_header.c:10-73 */
+#define AVDSP_B200_MAX_OPCODE 62
+extern const char *dspOpcodeText[AVDSP_B200_MAX_OPCODE];
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Batched executor.  Replaces the per-period loop nest of dsp_transfer
+ *     (module_avdsp/linux/avdsp_plugin.c:95-142): "for core: for frame: gather io, dspRuntime, scatter".
+ * ------------------------------------------------------------------------------------------ */
+typedef struct avdsp_b200 avdsp_b200_t;
+
+/* error codes: the first six are the reference's (runtime/dsp_runtime.c:116-195) */
+enum {
+    AVDSP_B200_ERR_NO_HEADER   = -1,   /* also: unknown sampling frequency */
+    AVDSP_B200_ERR_FS_RANGE    = -2,
+    AVDSP_B200_ERR_NO_CORE     = -3,
+    AVDSP_B200_ERR_CHECKSUM    = -4,
+    AVDSP_B200_ERR_OPCODE_NEW  = -5,
+    AVDSP_B200_ERR_TOO_LARGE   = -6,
+    AVDSP_B200_ERR_FORMAT      = -7,   /* unsupported DSP_FORMAT / program encoded for another format */
+    AVDSP_B200_ERR_UNSUPPORTED = -8,   /* opcode the executor rejects (DSP_SINE: does not compile in the reference) */
+    AVDSP_B200_ERR_ARG         = -9,
+    AVDSP_B200_ERR_CUDA        = -10,
+    AVDSP_B200_ERR_MALFORMED   = -11,  /* a pointer/offset in the program leaves the program or its data area */
+    AVDSP_B200_ERR_PLAN_SIZE   = -12   /* lowered plan exceeds the kernel-parameter budget */
+};
+
+/* PCM layouts.  A "frame" is one sample for every channel (one dspRuntime call per core in the reference). */
+enum { AVDSP_B200_INTERLEAVED = 0,     /* [stream][frame][channel]  (what ALSA hands to dsp_transfer) */
+       AVDSP_B200_PLANAR      = 1 };   /* [stream][channel][frame] */
+enum { AVDSP_B200_HOST = 0, AVDSP_B200_DEVICE = 1 };
+/* kernel selection (diagnostics and tests; AUTO is the product behaviour) */
+enum { AVDSP_B200_KERNEL_AUTO = 0, AVDSP_B200_KERNEL_GENERIC = 1, AVDSP_B200_KERNEL_CHAIN = 2 };
+
+/* Load + validate + lower a program (dspRuntimeInit + dspRuntimeReset for nStreams independent
+ * instances).  prog: progWords little-endian 32-bit words exactly as written by dspcreate (.bin).
+ * format: DSP_FORMAT 2..6.  seeds: per-stream dither PRNG seed (`random` of dspRuntimeInit), NULL => 0
+ * for every stream (what the ALSA plugin passes, avdsp_plugin.c:178).  device: CUDA ordinal.
+ * returns totalLength (>0) or a negative error code. */
+int  avdsp_b200_create(avdsp_b200_t **out, const int32_t *prog, int progWords, int fs, int format,
+                       int nStreams, const int32_t *seeds, int defaultDither, int device);
+void avdsp_b200_destroy(avdsp_b200_t *);
+/* dspRuntimeReset for every stream: zero the data area, re-seed the PRNG, MEM words back to the
+ * program's initial values.  fs may change (must stay inside the program's range). */
+int  avdsp_b200_reset(avdsp_b200_t *, int fs, const int32_t *seeds, int defaultDither);
+
+/* I/O map = union of the DSP_CORE used-input / used-output bitmaps in ascending io-slot order
+ * (what avdsp_plugin.c:326-356 derives).  Arrays need room for 32 ints; any pointer may be NULL. */
+int  avdsp_b200_io_map(const avdsp_b200_t *, int *nIn, int *inIdx, int *nOut, int *outIdx);
+
+/* Process nFrames frames of every stream.  in: nStreams*nFrames*nIn 32-bit samples, out:
+ * nStreams*nFrames*nOut, both in `layout`; memspace says where the two buffers live.  Canonical
+ * order (frame-major, cores ascending, one io[] per frame) unless avdsp_b200_set_order chose the
+ * plugin's.  Any split of a frame range into successive calls gives identical output. Synchronous. */
+int  avdsp_b200_process(avdsp_b200_t *, const void *in, void *out, int nFrames, int layout, int memspace);
+/* Same with device buffers, enqueued on the caller's CUDA stream (cudaStream_t as void*), no sync. */
+int  avdsp_b200_process_async(avdsp_b200_t *, const void *in, void *out, int nFrames, int layout, void *cudaStream);
+/* Process a sub-range of the streams: [firstStream, firstStream+nStreams) (buffers hold only those). */
+int  avdsp_b200_process_range(avdsp_b200_t *, const void *in, void *out, int nFrames, int layout,
+                              int firstStream, int nStreams, void *cudaStream);
+
+/* period == 0: canonical order.  period > 0: the ALSA plugin's core-major loop nest with this period
+ * (avdsp_plugin.c:95-98), fresh io[] per (core, frame). */
+int  avdsp_b200_set_order(avdsp_b200_t *, int period);
+int  avdsp_b200_set_kernel(avdsp_b200_t *, int which);
+/* which kernel the last process call used (AVDSP_B200_KERNEL_*) and how many kernels were launched so far */
+int  avdsp_b200_last_kernel(const avdsp_b200_t *);
+long long avdsp_b200_launch_count(const avdsp_b200_t *);
+
+/* The host edited PARAM words (gains, delay times, biquad coefficients, bypass flags) of the loaded
+ * program -- the dump-file workflow, encoder/dsp_encoder.c:476-503.  Opcode structure must be unchanged. */
+int  avdsp_b200_reload_params(avdsp_b200_t *, const int32_t *prog, int progWords);
+
+/* Per-stream state block, int32 words:  [0,dataSize) = the reference data area, same word offsets
+ * (runtime/dsp_runtime.c:137-141);  then 8 aux words (xoshiro s0..s3, tpdfValue, tpdfRandom, current
+ * global dither, pad -- the reference's process globals, runtime/dsp_tpdf.h:11-33);  then the 64-bit
+ * LOAD_MEM/STORE_MEM words the reference keeps inside the code area (runtime/dsp_runtime.c:750-766). */
+int  avdsp_b200_state_words(const avdsp_b200_t *);
+int  avdsp_b200_data_size(const avdsp_b200_t *);
+int  avdsp_b200_aux_offset(const avdsp_b200_t *);
+int  avdsp_b200_mem_offset(const avdsp_b200_t *);
+int  avdsp_b200_num_mem(const avdsp_b200_t *);
+int  avdsp_b200_mem_word(const avdsp_b200_t *, int k);       /* code word index of MEM slot k */
+int  avdsp_b200_get_state(avdsp_b200_t *, int stream, int32_t *words);
+int  avdsp_b200_set_state(avdsp_b200_t *, int stream, const int32_t *words);
+
+int  avdsp_b200_num_streams(const avdsp_b200_t *);
+int  avdsp_b200_num_cores(const avdsp_b200_t *);
+/* human-readable lowering trace (the counterpart of the reference's DSP_PRINTF>=2 opcode trace) */
+const char *avdsp_b200_trace(const avdsp_b200_t *);
+/* message of the last failure in this thread ("" when none) */
+const char *avdsp_b200_last_error(void);
+
+/* Integer-pipe microbenchmark used for the INT roofline: runs `iters` dependent-free mad.wide.s32
+ * per thread on the whole device and returns the achieved rate in mad.wide/s (0 on failure). */
+double avdsp_b200_measure_int_peak(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVDSP_B200_H_ */

