@@ -271,7 +271,7 @@ class Asm:
         self.op("STORE"); self.word(io); self._out(io)
 
     def load_gain(self, io, g):
-        self.op("LOAD_GAIN"); self.word(io); self.word(2); self.num(g); self._in(io)
+        self.op("LOAD_GAIN"); self.word(io); self.word(3); self.num(g); self._in(io)
 
     def _ptr_op(self, name, addr, value=None):
         at = self.op(name)

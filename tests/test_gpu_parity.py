@@ -145,25 +145,38 @@ def test_planar_layout_and_device_path(oracle_lib):
         assert np.array_equal(yd.cpu().numpy(), ys)
 
 
+def _plugin_program():
+    """ALSA convention (in io[8+k], out io[k]); core 2 dithers with the TPDF value core 1 computes, so the
+    plugin's core-major order (core 2 sees the LAST value of the period) differs from the canonical order."""
+    from oracle import wire
+    a = wire.Asm(fmt=2, fmin=48000, fmax=48000)
+    a.core(); a.tpdf_calc(20); a.load_gain(8, 0.5); a.sat0db_tpdf(); a.store(0)
+    a.core(); a.load_gain(9, 0.25); a.sat0db_tpdf(); a.store(1); a.load(8); a.store(2)
+    return a.end()
+
+
 def test_plugin_order_mode(oracle_lib):
     """core-major loop nest of linux/avdsp_plugin.c:95-142 with a given period."""
-    w = load_program("ref_dacdiy1")
     fs, S, T, period = 48000, 3, 500, 128
-    ex = Executor(w, fs, 2, S, seeds=[0, 1, 2], dither=24)
-    x = synth.pcm("noise", S, T, ex.n_in, fs)
-    ex.set_order(period)
-    y = ex.process(x)
-    assert ex.last_kernel == "generic"
-    for s in range(S):
-        o = oracle_lib.Oracle(w, 2, fs, seed=s, dither=24)
-        # plugin convention: inputs are io[8+k], outputs io[k]
-        nin = max(ex.in_idx) - 8 + 1
-        nout = max(ex.out_idx) + 1
-        xin = np.zeros((T, nin), np.int32)
-        for k, slot in enumerate(ex.in_idx):
-            xin[:, slot - 8] = x[s, :, k]
-        yo = o.process_plugin_order(xin, period, nin, nout)
-        assert np.array_equal(y[s], yo[:, ex.out_idx]), s
+    for w in (_plugin_program(), load_program("c2_testrpi_xover_f2_192k")):
+        if w is not None and int(w[8]) == 9:
+            fs = 192000
+        ex = Executor(w, fs, 2, S, seeds=[0, 1, 2], dither=24)
+        x = synth.pcm("noise", S, T, ex.n_in, fs)
+        canon = Executor(w, fs, 2, S, seeds=[0, 1, 2], dither=24).process(x)
+        ex.set_order(period)
+        y = ex.process(x)
+        assert ex.last_kernel == "generic"
+        nin, nout = max(ex.in_idx) - 8 + 1, max(ex.out_idx) + 1
+        for s in range(S):
+            o = oracle_lib.Oracle(w, 2, fs, seed=s, dither=24)
+            xin = np.zeros((T, nin), np.int32)
+            for k, slot in enumerate(ex.in_idx):
+                xin[:, slot - 8] = x[s, :, k]
+            yo = o.process_plugin_order(xin, period, nin, nout)
+            assert np.array_equal(y[s], yo[:, ex.out_idx]), s
+        if int(w[8]) != 9:
+            assert not np.array_equal(y, canon), "the test program must distinguish the two orders"
 
 
 def test_reference_entry_points_per_frame(oracle_lib):
