@@ -49,21 +49,22 @@ __global__ void k_init_state(int* __restrict__ state, int W, int auxOff, int mem
     for (int k = 0; k < 2 * nMem; k++) st[memOff + k] = memInit[k];
 }
 
-// integer-pipe microbenchmark: 8 independent mad.wide.s32 chains per thread
+// integer-pipe microbenchmark: 8 independent chains of DATA-DEPENDENT mad.wide.s32 per thread (the
+// multiplicand is the running accumulator's low word, so nothing can be hoisted or strength-reduced)
 __global__ void __launch_bounds__(256) k_int_peak(long long* out, int iters, int a0, int b0) {
     long long acc[8];
-    int a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+    const int b = b0 + (int)blockIdx.x;
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = k;
+    for (int k = 0; k < 8; k++) acc[k] = a0 + k + (int)threadIdx.x;
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int k = 0; k < 8; k++)
-            asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+            asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((int)acc[k]), "r"(b));
     }
     long long s = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) s += acc[k];
-    if (s == 0x123456789abcdefll) out[0] = s;     // never true in practice; keeps the chains alive
+    for (int k = 0; k < 8; k++) s ^= acc[k];
+    if (s == 0x123456789abcdefll) out[0] = s;     // practically never true; keeps the chains alive
 }
 
 struct avdsp_b200 {
@@ -77,7 +78,10 @@ struct avdsp_b200 {
     int* dSeeds = nullptr;
     ChainLane* dLanes = nullptr;
     ChainGeom geom{};
-    bool chainUsable = false;
+    bool chainUsable = false;       // kernel_chain.cu  (v1: tile-synchronous)
+    ChainLane* dLanes2 = nullptr;
+    Chain2Geom geom2{};
+    bool chain2Usable = false;      // kernel_chain2.cu (v2: warp-specialised, the default)
     int period = 0, kernelSel = AVDSP_B200_KERNEL_AUTO, lastKernel = 0;
     long long launches = 0;
     cudaStream_t stream = nullptr;          // for the synchronous calls
@@ -110,8 +114,22 @@ static int uploadPlanData(avdsp_b200* h) {
             h->chainUsable = true;
         }
     }
-    char line[256];
+    h->chain2Usable = false;
+    if (L.chainOk && chain2Supports(L.chain)) {
+        std::vector<ChainLane> lanes(1024);
+        if (planChain2Geometry(L.chain, h->nStreams, h->numSMs, &h->geom2, lanes.data())) {
+            if (!h->dLanes2) CU(cudaMalloc(&h->dLanes2, 1024 * sizeof(ChainLane)));
+            CU(cudaMemcpy(h->dLanes2, lanes.data(), 1024 * sizeof(ChainLane), cudaMemcpyHostToDevice));
+            h->chain2Usable = true;
+        }
+    }
+    char line[320];
     h->trace = L.trace;
+    if (h->chain2Usable) {
+        snprintf(line, sizeof line, "chain kernel v2 geometry: %d streams/CTA, %d sections/lane, tile %d frames, gmax %d, %d section threads + %d helper threads, %d sources, %zu B smem\n",
+                 h->geom2.streamsPerCta, h->geom2.secPerLane, h->geom2.tileFrames, h->geom2.gmax, h->geom2.secThreads, h->geom2.helpThreads, L.chain.h.nSrc, h->geom2.smemBytes);
+        h->trace += line;
+    }
     if (h->chainUsable)
         snprintf(line, sizeof line, "chain kernel geometry: %d streams/CTA, %d sections/lane, %d lane threads, %d work threads, tile %d frames, depth %d, %zu B smem\n",
                  h->geom.streamsPerCta, h->geom.secPerLane, h->geom.laneThreads, h->geom.workThreads, h->geom.tileFrames, h->geom.maxDepth, h->geom.smemBytes);
@@ -154,6 +172,7 @@ static void freeAll(avdsp_b200* h) {
     if (h->dMemInit) cudaFree(h->dMemInit);
     if (h->dSeeds) cudaFree(h->dSeeds);
     if (h->dLanes) cudaFree(h->dLanes);
+    if (h->dLanes2) cudaFree(h->dLanes2);
     for (int k = 0; k < avdsp_b200::kSlots; k++) {
         if (h->slotIn[k]) cudaFree(h->slotIn[k]);
         if (h->slotOut[k]) cudaFree(h->slotOut[k]);
@@ -232,7 +251,7 @@ int avdsp_b200_set_order(avdsp_b200_t* h, int period) {
     h->period = period; return 0;
 }
 int avdsp_b200_set_kernel(avdsp_b200_t* h, int which) {
-    if (!h || which < 0 || which > 2) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
+    if (!h || which < 0 || which > 3) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
     h->kernelSel = which; return 0;
 }
 int avdsp_b200_last_kernel(const avdsp_b200_t* h) { return h ? h->lastKernel : 0; }
@@ -266,18 +285,32 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         outSS = (long long)nFrames * nOut; outFS = 1; outCS = nFrames;
     } else return setErr(AVDSP_B200_ERR_ARG, "unknown layout");
     int* st = h->dState + (size_t)first * P.stateWords;
-    const bool wantChain = h->kernelSel != AVDSP_B200_KERNEL_GENERIC && h->chainUsable && h->period == 0 && coreSel < 0 && !planOverride;
-    if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN && !wantChain)
+    const bool chainOrder = h->period == 0 && coreSel < 0 && !planOverride;
+    int use = AVDSP_B200_KERNEL_GENERIC;
+    if (chainOrder && h->kernelSel != AVDSP_B200_KERNEL_GENERIC) {
+        if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1) { if (h->chainUsable) use = AVDSP_B200_KERNEL_CHAIN_V1; }
+        else if (h->chain2Usable) use = AVDSP_B200_KERNEL_CHAIN;
+        else if (h->chainUsable) use = AVDSP_B200_KERNEL_CHAIN_V1;
+    }
+    if ((h->kernelSel == AVDSP_B200_KERNEL_CHAIN || h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1) && use == AVDSP_B200_KERNEL_GENERIC)
         return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel requested but this program/order does not map to it: " + h->L.chainWhyNot);
     cudaError_t e;
-    if (wantChain) {
+    if (use == AVDSP_B200_KERNEL_CHAIN) {
+        Chain2Args A{};
+        A.in = in; A.out = out; A.state = st; A.lanes = h->dLanes2;
+        A.nStreams = n; A.nFrames = nFrames;
+        A.inStreamStride = inSS; A.outStreamStride = outSS;
+        A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
+        e = launchChain2(h->L.chain, h->geom2, A, stream);
+        h->lastKernel = AVDSP_B200_KERNEL_CHAIN;
+    } else if (use == AVDSP_B200_KERNEL_CHAIN_V1) {
         ChainArgs A{};
         A.in = in; A.out = out; A.state = st; A.lanes = h->dLanes;
         A.nStreams = n; A.nFrames = nFrames;
         A.inStreamStride = inSS; A.outStreamStride = outSS;
         A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
         e = launchChain(h->L.chain, h->geom, A, stream);
-        h->lastKernel = AVDSP_B200_KERNEL_CHAIN;
+        h->lastKernel = AVDSP_B200_KERNEL_CHAIN_V1;
     } else {
         GenericArgs A{};
         A.in = in; A.out = out; A.state = st; A.bigPool = h->dBig;

@@ -14,8 +14,15 @@
 namespace avdsp {
 
 // ---------------------------------------------------------------- fixed point ----------------
-__device__ __forceinline__ long long mul32(int a, int b) { return (long long)a * (long long)b; }          // mul.wide.s32
-__device__ __forceinline__ long long mac32(long long acc, int a, int b) { return acc + (long long)a * (long long)b; } // mad.wide.s32 (IMAD.WIDE)
+// Spelled in PTX on purpose: written as (long long)a * b, NVVM hoists the sign extension of a loop-invariant
+// coefficient out of the loop and ptxas then emits a 64x64 multiply (IMAD.WIDE.U32 + 2 IMAD + SHF + IADD, 5
+// instructions) instead of one signed IMAD.WIDE.
+__device__ __forceinline__ long long mul32(int a, int b) {
+    long long r; asm("mul.wide.s32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ long long mac32(long long acc, int a, int b) {
+    long long r; asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(acc)); return r;
+}
 
 // dspSaturate64_031 (dsp_fpmath.h:84-98): clamp s4.59 to [-1,1) and return s.31 in the low word
 __device__ __forceinline__ long long sat64_031(long long a) {

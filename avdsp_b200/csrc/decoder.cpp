@@ -307,6 +307,22 @@ void buildChainPlan(Lowered* L) {
     }
     if (c.h.nChains == 0) throw ChainFail{"no signal path"};
     c.h.tpdfShift = kMant - c.h.storeDither + 1;
+    // deduplicate the sources of chains that have sections: crossovers feed several cascades from the same
+    // LOAD_GAIN (same input, same gain), so their x values are computed and staged once per frame
+    c.h.nSrc = 0;
+    for (int i = 0; i < c.h.nChains; i++) {
+        ChainDesc& d = c.chains[i];
+        d.srcId = -1;
+        if (d.nsec == 0) continue;
+        if (d.srcKind != SRC_LOAD_MUX)
+            for (int k = 0; k < c.h.nSrc && d.srcId < 0; k++) {
+                const ChainDesc& o = c.chains[c.h.srcChain[k]];
+                if (o.srcKind == d.srcKind && o.srcCh == d.srcCh && (d.srcKind == SRC_LOAD || o.srcArg == d.srcArg)) d.srcId = k;
+            }
+        if (d.srcId < 0) { d.srcId = c.h.nSrc; c.h.srcChain[c.h.nSrc++] = i; }
+    }
+    c.h.nUnwritten = 0;
+    for (int k = 0; k < c.h.nOut; k++) if (c.h.chainOfOut[k] < 0) c.h.nUnwritten++;
 }
 
 void lowerAll(Lowered* L) {

@@ -1,0 +1,506 @@
+// kernel_chain2.cu -- warp-specialised systolic executor for programs made of independent signal paths
+//     source (LOAD / LOAD_GAIN / LOAD_MUX) -> biquad cascade -> [GAIN] -> SAT0DB[_TPDF][_GAIN] -> [DELAY] -> STORE
+// (crossovers, EQs, matrix mixers: configs C2, C3, C5).  Fixed point (DSP_FORMAT 2), bit-exact.
+//
+// Why it looks like this (B200: 148 SMs, fma pipe = 64 mad.wide.s32 / clk / SM measured, 1 issue / clk / SMSP):
+//   * The biquad recurrence is sequential in time, so time stays a loop.  Parallelism = streams x paths x
+//     sections.  A *section lane* owns K consecutive sections of one cascade: state (64-bit accumulator,
+//     x1 x2 y1 y2; reference layout runtime/dsp_biquadSTD.h:45) and the 5 Q4.28 coefficients stay in
+//     registers for the whole launch.  The cascade is skewed in time ("systolic"): at step t the section
+//     with index g inside its cascade works on frame t-g, so all sections of a step are independent
+//     (ILP inside a lane, one __shfl_up between lanes) -- exact, because section g of frame n only needs
+//     section g-1 of the same frame (dsp_calc_biquads_int, runtime/dsp_biquadSTD.h:37-74).
+//   * Per section-step the budget is 5 IMAD.WIDE + ~2.5 instructions of saturation test (one branch per
+//     lane-step, taken only when some section saturates) + 1 funnel shift.  Nothing else is allowed into
+//     that loop: tiles are fully unrolled, shared-memory offsets are immediates, rings are indexed by STEP
+//     (identical position for every lane; the per-cascade skew is absorbed by the helpers), and there is
+//     no barrier inside a tile.
+//   * Everything else is element-wise over (stream, frame) and is done by *helper warps* of the same CTA,
+//     one tile ahead (sources -> x ring, each distinct source once) and one tile behind (accumulator ring ->
+//     gain / saturate / dither / delay / mask -> coalesced stores).  Helper warp 0 also advances the
+//     per-stream dither PRNG (xoshiro128+, strictly serial per stream: one lane per stream).  Roles meet
+//     only at tile boundaries through named barriers (bar.arrive / bar.sync): section warps never wait on HBM.
+//   * One CTA per SM owns NS = ceil(nStreams / #SM) streams for the whole launch; state never leaves the
+//     SM between tiles.  4096 streams -> 147 CTAs x 28 streams, single wave.
+//
+// Ring bookkeeping (F = tile length, g_c = cascade length - 1 = frame lag of cascade c's tail, gmax <= F):
+//   x ring    [stream][source][2F]  by step: head lanes read position t for frame t
+//   acc ring  [slot][2F]            by step: tail of cascade c writes at step t the accumulator of frame t-g_c
+//   post ring [slot][R]             by step: saturated s.31 value of the same frame; R >= F+gmax+longest delay (power
+//                                   of two): it doubles as the delay line, so steady state never touches HBM state
+//   tpdf ring [stream][4F]          by frame (helper warp 0 may run one tile ahead of the others)
+//   sink window i = frames [iF-gmax, (i+1)F-gmax): every cascade has finished them when tile i is done.
+#include "avdsp_dev.cuh"
+#include "kernels.h"
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+namespace avdsp {
+
+constexpr int kBarFull = 1;       // +parity : x tile ready            (helpers arrive, sections wait)
+constexpr int kBarDone = 3;       // +parity : section tile finished   (sections arrive, helpers wait)
+constexpr int kBarHelp = 5;       // helpers only
+
+__device__ __forceinline__ void barSync(int id, int n)   { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void barArrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+
+template <int K>
+struct Lane2 {
+    long long acc[K];
+    int x1[K], x2[K], y1[K], y2[K];
+    int b0[K], b1[K], b2[K], a1[K], a2[K];
+};
+
+constexpr unsigned kSatBias  = (1u << (kMantBQ - 1)) - 2u;       // in range  <=>  (unsigned)(hi + bias) <= limit
+constexpr unsigned kSatLimit = (1u << kMantBQ) - 3u;             // (checkbiquadsat, runtime/dsp_biquadSTD.h:25-32)
+
+// one lane-step, all K sections valid
+template <int K>
+__device__ __forceinline__ void laneStep(Lane2<K>& L, int xin) {
+    int in[K];
+    in[0] = xin;
+#pragma unroll
+    for (int j = 1; j < K; j++) in[j] = L.y1[j - 1];          // skew: section j takes what j-1 produced one step ago
+    long long a[K];
+    unsigned worst = 0;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        long long acc = L.acc[j];
+        acc = mac32(acc, L.x1[j], L.b1[j]);
+        acc = mac32(acc, L.x2[j], L.b2[j]);
+        acc = mac32(acc, L.y1[j], L.a1[j]);
+        acc = mac32(acc, L.y2[j], L.a2[j]);
+        acc = mac32(acc, in[j], L.b0[j]);
+        a[j] = acc;
+        worst = max(worst, (unsigned)((int)(acc >> 32)) + kSatBias);
+    }
+    // warp-uniform branch (vote): no divergence bookkeeping around the per-step shuffle
+    if (__any_sync(0xffffffffu, worst > kSatLimit)) {
+#pragma unroll
+        for (int j = 0; j < K; j++) a[j] = biquadSat(a[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        L.acc[j] = a[j];
+        L.x2[j] = L.x1[j]; L.x1[j] = in[j];
+        L.y2[j] = L.y1[j]; L.y1[j] = (int)(a[j] >> kMantBQ);
+    }
+}
+
+// lane-step at the edges of the launch: section j commits only when its frame t-g0-j lies in [0,T)
+template <int K>
+__device__ __forceinline__ void laneStepPred(Lane2<K>& L, int xin, int t, int g0, int T) {
+    int in[K];
+    in[0] = xin;
+#pragma unroll
+    for (int j = 1; j < K; j++) in[j] = L.y1[j - 1];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        if ((unsigned)(t - g0 - j) < (unsigned)T) {
+            long long acc = L.acc[j];
+            acc = mac32(acc, L.x1[j], L.b1[j]);
+            acc = mac32(acc, L.x2[j], L.b2[j]);
+            acc = mac32(acc, L.y1[j], L.a1[j]);
+            acc = mac32(acc, L.y2[j], L.a2[j]);
+            acc = mac32(acc, in[j], L.b0[j]);
+            acc = biquadSat(acc);
+            L.acc[j] = acc;
+            L.x2[j] = L.x1[j]; L.x1[j] = in[j];
+            L.y2[j] = L.y1[j]; L.y1[j] = (int)(acc >> kMantBQ);
+        }
+    }
+}
+
+// source value of a chain for one frame: LOAD / LOAD_GAIN / LOAD_MUX (dsp_runtime.c:565-607, 871-897)
+__device__ __forceinline__ long long chainSource(const ChainPlan& P, const ChainDesc& d, const int* __restrict__ in, int inChStride) {
+    if (d.srcKind == SRC_LOAD_MUX) {
+        long long X = 0;
+        for (int k = 0; k < d.srcCh; k++) {
+            const int ch = P.pool[d.srcArg + 2 * k], gain = P.pool[d.srcArg + 2 * k + 1];
+            X = mac32(X, ch >= 0 ? __ldg(in + (size_t)ch * inChStride) : 0, gain);
+        }
+        return X;
+    }
+    const int smp = d.srcCh >= 0 ? __ldg(in + (size_t)d.srcCh * inChStride) : 0;
+    return (d.srcKind == SRC_LOAD_GAIN) ? mul32(smp, d.srcArg) : (long long)smp;
+}
+
+template <int K, int F>
+__global__ void __launch_bounds__(1024, 1)
+k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Geom G) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NS = G.streamsPerCta, C = P.h.nChains, slots = NS * C, W = P.h.stateWords, T = A.nFrames;
+    const int nSrc = P.h.nSrc;
+    long long* acc_s = reinterpret_cast<long long*>(smem_raw);             // [slots][accPitch]
+    int* x_s    = reinterpret_cast<int*>(acc_s + (size_t)slots * G.accPitch);  // [NS*nSrc][xPitch]
+    int* post_s = x_s + (size_t)NS * nSrc * G.xPitch;                      // [slots][postPitch]
+    int* tpdf_s = post_s + (size_t)slots * G.postPitch;                    // [NS][tpdfPitch]
+    int* ridx_s = tpdf_s + (size_t)NS * G.tpdfPitch;                       // [slots] effective delay-ring index at launch start
+    int* stale_s = ridx_s + slots;                                         // [slots] stale ring index (>= n) or -1
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int s0 = blockIdx.x * NS, nsHere = min(NS, A.nStreams - s0);
+    const int nAll = G.secThreads + G.helpThreads;
+    const int gmax = G.gmax;
+    const int nTiles = (T + gmax + F - 1) / F;
+
+    if (tid < G.secThreads) {
+        // =========================================================================== section warps
+        Lane2<K> L;
+        const ChainLane e = A.lanes[tid];
+        const bool live = e.slot >= 0 && e.slot / C < nsHere;
+        const bool head = (e.flags & 1) != 0, tail = (e.flags & 2) != 0;
+        const int g0 = e.firstSec;                       // frame lag of this lane's first section
+        const int slot = e.slot < 0 ? 0 : e.slot;
+        int* stLane = nullptr;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            L.acc[k] = 0; L.x1[k] = L.x2[k] = L.y1[k] = L.y2[k] = 0;
+            L.b0[k] = L.b1[k] = L.b2[k] = L.a1[k] = L.a2[k] = 0;
+        }
+        const ChainDesc& d = P.chains[slot % C];
+        if (live) {
+            stLane = A.state + (size_t)(s0 + slot / C) * W;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int sec = g0 + k;
+                const int* cf = P.pool + d.coefOff + 5 * sec;
+                L.b0[k] = cf[0]; L.b1[k] = cf[1]; L.b2[k] = cf[2]; L.a1[k] = cf[3]; L.a2[k] = cf[4];
+                const int* q = stLane + P.pool[d.secStateOff + sec];
+                L.acc[k] = (long long)(((unsigned long long)(unsigned)q[1] << 32) | (unsigned)q[0]);
+                L.x1[k] = q[2]; L.x2[k] = q[3]; L.y1[k] = q[4]; L.y2[k] = q[5];
+            }
+        }
+        const int* xrow = x_s + (size_t)((slot / C) * nSrc + max(d.srcId, 0)) * G.xPitch;
+        long long* arow = acc_s + (size_t)slot * G.accPitch;
+
+        for (int i = 0; i < nTiles; i++) {
+            barSync(kBarFull + (i & 1), nAll);
+            const int* xs = xrow + (i & 1) * F;
+            long long* as = arow + (i & 1) * F;
+            const int t0 = i * F;
+            if (t0 >= gmax && t0 + F <= T) {
+#pragma unroll
+                for (int j = 0; j < F; j++) {
+                    int x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
+                    if (head) x = xs[j];
+                    laneStep<K>(L, x);
+                    if (tail) as[j] = L.acc[K - 1];
+                }
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < F; j++) {
+                    int x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
+                    if (head) x = xs[j];
+                    laneStepPred<K>(L, x, t0 + j, g0, T);
+                    if (tail) as[j] = L.acc[K - 1];
+                }
+            }
+            barArrive(kBarDone + (i & 1), nAll);
+        }
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                int* q = stLane + P.pool[d.secStateOff + g0 + k];
+                q[0] = (int)L.acc[k]; q[1] = (int)(L.acc[k] >> 32);
+                q[2] = L.x1[k]; q[3] = L.x2[k]; q[4] = L.y1[k]; q[5] = L.y2[k];
+            }
+        }
+        return;
+    }
+
+    // =============================================================================== helper warps
+    const int ht = tid - G.secThreads, hw = ht >> 5, nHW = G.helpThreads >> 5;
+    const int storeMask = ditherMask(P.h.storeDither);
+    const bool hasCalc = P.h.hasTpdfCalc != 0;
+    // warp 0 doubles as the dither PRNG: lane = stream
+    Prng g = {0, 0, 0, 0}; int tpdfValue = 0, tpdfRandom = 0, dith = 0; bool drew = false;
+    int* auxp = nullptr;
+    if (hw == 0 && lane < nsHere) {
+        auxp = A.state + (size_t)(s0 + lane) * W + P.h.auxOff;
+        g.s0 = auxp[AUX_S0]; g.s1 = auxp[AUX_S1]; g.s2 = auxp[AUX_S2]; g.s3 = auxp[AUX_S3];
+        tpdfValue = auxp[AUX_TPDF_VALUE]; tpdfRandom = auxp[AUX_TPDF_RANDOM]; dith = auxp[AUX_DITHER];
+    }
+    // Stream ownership: every helper warp but the PRNG warp owns the streams sl = ow, ow+nOwn, ... for the
+    // whole launch (their post rings and delay state are warp-private: only __syncwarp inside the sink).
+    const bool prngOnly = hasCalc && nHW > 1 && hw == 0;
+    const int ow = (hasCalc && nHW > 1) ? hw - 1 : hw;
+    const int nOwn = (hasCalc && nHW > 1) ? nHW - 1 : nHW;
+    const int R = G.postRing, RM = R - 1;
+    const bool vecOut = A.outChStride == 1 && (P.h.nOut & 3) == 0 && (A.outFrameStride & 3) == 0 &&
+                        (A.outStreamStride & 3) == 0 && ((size_t)A.out & 15) == 0;
+
+    // ---- delay lines.  Reference semantics (dsp_runtime.c:769-794): ring of n samples, frame f swaps with
+    // position (idx0+f) mod n, so the output of frame f is the post value of frame f-n.  Here the post ring
+    // (R >= F + gmax + n steps of history) IS the delay line: the prologue preloads the n samples the
+    // reference ring holds as "virtual frames" -n..-1, the epilogue writes the last n back in ring layout.
+    // A stale index idx0 >= n (delay shortened by reload_params) is used once by the reference and then
+    // wraps to 0: frame 0 swaps with ring[idx0], frames >= 1 behave like idx0 = n-1.
+    if (!prngOnly)
+        for (int sl = ow; sl < nsHere; sl += nOwn) {
+            int* st = A.state + (size_t)(s0 + sl) * W;
+            for (int c = 0; c < C; c++) {
+                const ChainDesc& d = P.chains[c];
+                const int n = d.delayN;
+                if (n <= 0) continue;
+                const int gc = d.nsec > 0 ? d.nsec - 1 : 0;
+                const int* ring = st + d.delayOff + 1;
+                const int idx0 = st[d.delayOff];
+                const bool stale = idx0 >= n || idx0 < 0;
+                int* prow = post_s + (size_t)(sl * C + c) * G.postPitch;
+                for (int k = lane; k < n; k += 32) {          // virtual frame j = k - n feeds output frame k
+                    int v;
+                    if (!stale) v = ring[(idx0 + k) % n];
+                    else v = (k == 0) ? ring[idx0] : ring[k - 1];
+                    prow[(k - n + gc) & RM] = v;
+                }
+                if (stale && lane == 0) prow[gc & RM] = ring[n - 1];     // takes the place of post(0), see above
+                if (lane == 0) { ridx_s[sl * C + c] = stale ? n - 1 : idx0; stale_s[sl * C + c] = stale ? idx0 : -1; }
+            }
+        }
+    __syncwarp();
+
+    // ---- source stage of tile `it`: frames [it*F, it*F+F) -> x ring (one value per distinct source), dither values
+    auto sourceTile = [&](int it) {
+        const int f0 = it * F;
+        if (f0 >= T) return;
+        if (hw == 0 && lane < nsHere) {
+            int* row = tpdf_s + lane * G.tpdfPitch + (it & 3) * F;
+            const int n = min(F, T - f0);
+            if (hasCalc) {
+                for (int j = 0; j < n; j++) {
+                    if (dith == P.h.tpdfDither) { tpdfValue = tpdfDraw(g, tpdfRandom); drew = true; }
+                    else dith = P.h.tpdfDither;      // table switch on the first frame after a reset: no draw (dsp_runtime.c:539-544)
+                    row[j] = tpdfValue;
+                }
+            } else {
+                for (int j = 0; j < n; j++) row[j] = tpdfValue;
+            }
+        }
+        if (nSrc == 0 || prngOnly) return;
+        for (int u = lane; u < F; u += 32) {
+            const int f = f0 + u;
+            if (f >= T) continue;
+            for (int sl = ow; sl < nsHere; sl += nOwn) {
+                const int* in = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)f * A.inFrameStride;
+                for (int k = 0; k < nSrc; k++) {
+                    const ChainDesc& d = P.chains[P.h.srcChain[k]];
+                    const long long X = chainSource(P, d, in, A.inChStride);
+                    x_s[(size_t)(sl * nSrc + k) * G.xPitch + (it & 1) * F + u] = (int)(X >> kMantBQ);
+                }
+            }
+        }
+    };
+
+    // ---- sink stage of window `iw`
+    auto sinkWindow = [&](int iw) {
+        if (prngOnly) return;
+        for (int sl = ow; sl < nsHere; sl += nOwn) {
+            int* st = A.state + (size_t)(s0 + sl) * W;
+            // A: step iw*F+u of every chain: accumulator (or inline source) -> [gain] -> saturate (+dither,+gain) -> post ring
+            for (int u = lane; u < F; u += 32) {
+                const int t = iw * F + u;
+                for (int c = 0; c < C; c++) {
+                    const ChainDesc& d = P.chains[c];
+                    const int gc = d.nsec > 0 ? d.nsec - 1 : 0;
+                    const int f = t - gc;
+                    if (f < 0 || f >= T) continue;
+                    long long X;
+                    if (d.nsec > 0) X = acc_s[(size_t)(sl * C + c) * G.accPitch + (iw & 1) * F + u];
+                    else {
+                        X = chainSource(P, d, A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)f * A.inFrameStride, A.inChStride);
+                        if (d.srcKind == SRC_LOAD_MUX && f == T - 1) { st[d.muxStateOff] = (int)X; st[d.muxStateOff + 1] = (int)(X >> 32); }
+                    }
+                    if (d.hasGain) X = X * (long long)d.gainBits;
+                    if (d.satKind >= SAT_GAIN) { X >>= kMant; X = X * (long long)d.satGainBits; }
+                    if (d.satKind & 1) X += tpdfScaledI(tpdf_s[sl * G.tpdfPitch + (f & (4 * F - 1))], P.h.tpdfShift);
+                    const int v = (int)sat64_031(X);
+                    if (f == 0 && d.delayN > 0 && stale_s[sl * C + c] >= 0) st[d.delayOff + 1 + stale_s[sl * C + c]] = v;
+                    else post_s[(size_t)(sl * C + c) * G.postPitch + (t & RM)] = v;
+                }
+            }
+            __syncwarp();
+            // B: frames [iw*F-gmax, +F): delayed read from the post ring + mask + store (16-byte stores when the layout allows)
+            for (int u = lane; u < F; u += 32) {
+                const int f = iw * F - gmax + u;
+                if (f < 0 || f >= T) continue;
+                int* out = A.out + (size_t)(s0 + sl) * A.outStreamStride + (size_t)f * A.outFrameStride;
+                for (int ch0 = 0; ch0 < P.h.nOut; ch0 += 4) {
+                    int val[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int ch = ch0 + q;
+                        const int c = ch < P.h.nOut ? P.h.chainOfOut[ch] : -1;
+                        int v = 0;          // outputs no path writes read as 0 (io[] is zeroed at the start of every frame)
+                        if (c >= 0) {
+                            const ChainDesc& d = P.chains[c];
+                            const int gc = d.nsec > 0 ? d.nsec - 1 : 0;
+                            v = post_s[(size_t)(sl * C + c) * G.postPitch + ((f - d.delayN + gc) & RM)] & storeMask;
+                        }
+                        val[q] = v;
+                    }
+                    if (vecOut) *reinterpret_cast<int4*>(out + ch0) = make_int4(val[0], val[1], val[2], val[3]);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) if (ch0 + q < P.h.nOut) out[(size_t)(ch0 + q) * A.outChStride] = val[q];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    };
+
+    sourceTile(0);
+    barArrive(kBarFull + 0, nAll);
+    for (int i = 0; i < nTiles; i++) {
+        if (i + 1 < nTiles) { sourceTile(i + 1); barArrive(kBarFull + ((i + 1) & 1), nAll); }
+        barSync(kBarDone + (i & 1), nAll);
+        sinkWindow(i);
+    }
+
+    if (auxp) {
+        auxp[AUX_S0] = g.s0; auxp[AUX_S1] = g.s1; auxp[AUX_S2] = g.s2; auxp[AUX_S3] = g.s3;
+        auxp[AUX_TPDF_VALUE] = tpdfValue; auxp[AUX_TPDF_RANDOM] = tpdfRandom; auxp[AUX_DITHER] = dith;
+        if (drew) {   // TPDF_CALC leaves its last value (as an ALU word) in the data area (dsp_runtime.c:541-543)
+            int* q = A.state + (size_t)(s0 + lane) * W + P.h.tpdfDataOff;
+            q[0] = tpdfValue; q[1] = tpdfValue >> 31;
+        }
+    }
+    if (prngOnly || T <= 0) return;
+    __syncwarp();
+    for (int sl = ow; sl < nsHere; sl += nOwn) {
+        int* st = A.state + (size_t)(s0 + sl) * W;
+        for (int c = 0; c < C; c++) {
+            const ChainDesc& d = P.chains[c];
+            // last LOAD_MUX value of chains with sections stays in the data area (dsp_runtime.c:893-896)
+            if (d.srcKind == SRC_LOAD_MUX && d.nsec > 0 && lane == 0) {
+                const long long X = chainSource(P, d, A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(T - 1) * A.inFrameStride, A.inChStride);
+                st[d.muxStateOff] = (int)X; st[d.muxStateOff + 1] = (int)(X >> 32);
+            }
+            // delay line back to the reference's ring layout: frame j sits at position (idx0+j) mod n
+            const int n = d.delayN;
+            if (n <= 0) continue;
+            const int gc = d.nsec > 0 ? d.nsec - 1 : 0;
+            const int idx0 = ridx_s[sl * C + c];
+            const int* prow = post_s + (size_t)(sl * C + c) * G.postPitch;
+            int* ring = st + d.delayOff + 1;
+            for (int k = lane; k < n; k += 32) {
+                const int j = T - n + k;                                     // frames T-n .. T-1 (virtual ones included)
+                ring[(int)(((long long)idx0 + j + n) % n)] = prow[(j + gc) & RM];
+            }
+            if (lane == 0) st[d.delayOff] = (int)(((long long)idx0 + T) % n);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int envInt2(const char* name, int dflt) { const char* v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
+
+// pack the section lanes of NS streams into warps (first-fit decreasing): a cascade never straddles a warp
+static int packLanes2(const ChainPlan& p, int NS, int K, ChainLane* out, int* gmax) {
+    struct Item { int slot, lanes; };
+    std::vector<Item> items;
+    const int C = p.h.nChains;
+    int gm = 0;
+    for (int s = 0; s < NS; s++)
+        for (int c = 0; c < C; c++) {
+            const int n = p.chains[c].nsec / K;
+            if (n > 0) items.push_back({s * C + c, n});
+            if (p.chains[c].nsec > 0) gm = std::max(gm, p.chains[c].nsec - 1);
+        }
+    if (gmax) *gmax = gm;
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.lanes > b.lanes; });
+    std::vector<int> fill;
+    std::vector<std::vector<Item>> warps;
+    for (const Item& it : items) {
+        if (it.lanes > 32) return -1;
+        size_t w = 0;
+        for (; w < fill.size(); w++) if (fill[w] + it.lanes <= 32) break;
+        if (w == fill.size()) { fill.push_back(0); warps.emplace_back(); }
+        fill[w] += it.lanes; warps[w].push_back(it);
+    }
+    const int threads = (int)fill.size() * 32;
+    if (threads > 1024) return -1;
+    if (out) {
+        for (int i = 0; i < threads; i++) { out[i].slot = -1; out[i].depth = 0; out[i].flags = 0; out[i].firstSec = 0; }
+        for (size_t w = 0; w < warps.size(); w++) {
+            int l = (int)w * 32;
+            for (const Item& it : warps[w])
+                for (int dpt = 0; dpt < it.lanes; dpt++, l++) {
+                    out[l].slot = it.slot; out[l].depth = dpt; out[l].firstSec = dpt * K;
+                    out[l].flags = (dpt == 0 ? 1 : 0) | (dpt == it.lanes - 1 ? 2 : 0);
+                }
+        }
+    }
+    return threads;
+}
+
+bool chain2Supports(const ChainPlan& plan) {
+    return plan.h.aluClass == ALU_INT64 && plan.h.nChains > 0 && plan.h.nOut > 0;
+}
+
+bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2Geom* geom, ChainLane* lanesOut) {
+    const int C = plan.h.nChains;
+    // sections per lane: the largest K in {4,2,1} (default 2) that divides every cascade (override: AVDSP_B200_K)
+    int K = envInt2("AVDSP_B200_K", 2);
+    if (K != 1 && K != 2 && K != 4) K = 2;
+    for (int c = 0; c < C; c++) while (plan.chains[c].nsec % K) K >>= 1;
+    int NS0 = envInt2("AVDSP_B200_NS", 0);
+    if (NS0 <= 0) NS0 = (nStreams + numSMs - 1) / numSMs;
+    NS0 = std::max(1, std::min(NS0, 32));
+    const int forceF = envInt2("AVDSP_B200_F", 0);
+    for (int NS = NS0; NS >= 1; NS--) {
+        for (int F : {32, 16}) {
+            if (forceF && F != forceF) continue;
+            int gm = 0;
+            const int lt = packLanes2(plan, NS, K, nullptr, &gm);
+            if (lt < 0) break;
+            if (gm > F) continue;                                    // sink window i must lie inside tiles i-1, i
+            int help = envInt2("AVDSP_B200_HW", 0);
+            if (help <= 0) help = lt > 0 ? std::max(2, (lt / 32 + 2) / 3) : std::min(24, std::max(4, NS));
+            help = std::max(1, std::min(help, 32 - lt / 32));
+            const int slots = NS * C;
+            Chain2Geom g{};
+            g.streamsPerCta = NS; g.secPerLane = K; g.tileFrames = F; g.gmax = gm;
+            g.secThreads = lt; g.helpThreads = help * 32;
+            int maxDelay = 0;
+            for (int c = 0; c < C; c++) maxDelay = std::max(maxDelay, plan.chains[c].delayN);
+            int R = 2 * F;
+            while (R < F + gm + maxDelay) R <<= 1;
+            g.postRing = R;
+            g.xPitch = 2 * F + 1; g.accPitch = 2 * F + 1; g.postPitch = R + 1; g.tpdfPitch = 4 * F + 1;
+            g.smemBytes = (size_t)slots * g.accPitch * 8 +
+                          ((size_t)NS * plan.h.nSrc * g.xPitch + (size_t)slots * g.postPitch + (size_t)NS * g.tpdfPitch + 2 * slots) * 4 + 16;
+            if (g.secThreads + g.helpThreads <= 1024 && g.smemBytes <= 226 * 1024) {
+                *geom = g;
+                if (lanesOut) packLanes2(plan, NS, K, lanesOut, nullptr);
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+cudaError_t launchChain2(const ChainPlan& plan, const Chain2Geom& geom, const Chain2Args& args, cudaStream_t stream) {
+    const int blocks = (args.nStreams + geom.streamsPerCta - 1) / geom.streamsPerCta;
+    const int threads = geom.secThreads + geom.helpThreads;
+    cudaError_t e = cudaSuccess;
+#define LAUNCH2(KK, FF) do { \
+    e = cudaFuncSetAttribute(k_chain2<KK, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geom.smemBytes); \
+    if (e != cudaSuccess) return e; \
+    k_chain2<KK, FF><<<blocks, threads, geom.smemBytes, stream>>>(plan, args, geom); } while (0)
+    const int key = geom.secPerLane * 100 + geom.tileFrames;
+    switch (key) {
+    case 432: LAUNCH2(4, 32); break;
+    case 416: LAUNCH2(4, 16); break;
+    case 232: LAUNCH2(2, 32); break;
+    case 216: LAUNCH2(2, 16); break;
+    case 132: LAUNCH2(1, 32); break;
+    default:  LAUNCH2(1, 16); break;
+    }
+#undef LAUNCH2
+    return cudaGetLastError();
+}
+
+} // namespace avdsp

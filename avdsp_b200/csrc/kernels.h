@@ -52,4 +52,28 @@ bool planChainGeometry(const ChainPlan& plan, int nStreams, int numSMs, ChainGeo
 cudaError_t launchChain(const ChainPlan& plan, const ChainGeom& geom, const ChainArgs& args, cudaStream_t stream);
 bool chainKernelSupports(const ChainPlan& plan);
 
+// ---- warp-specialised systolic chain kernel (kernel_chain2.cu) -----------------------------------
+struct Chain2Geom {
+    int streamsPerCta;     // NS
+    int secPerLane;        // K
+    int tileFrames;        // F: steps between barriers (32 or 16)
+    int gmax;              // largest frame offset of a cascade tail (longest cascade - 1)
+    int secThreads;        // threads that own sections (multiple of 32, may be 0)
+    int helpThreads;       // source / sink / dither threads (multiple of 32, >= 32)
+    int postRing;          // R: post ring length in steps (power of two >= F + gmax + longest delay)
+    int xPitch, accPitch, postPitch, tpdfPitch;   // shared-memory row pitches (elements)
+    size_t smemBytes;
+};
+struct Chain2Args {
+    const int* in;  int* out;
+    int* state;
+    const ChainLane* lanes;     // [secThreads]
+    int nStreams, nFrames;
+    long long inStreamStride, outStreamStride;
+    int inFrameStride, inChStride, outFrameStride, outChStride;
+};
+bool chain2Supports(const ChainPlan& plan);
+bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2Geom* geom, ChainLane* lanesOut /*[1024]*/);
+cudaError_t launchChain2(const ChainPlan& plan, const Chain2Geom& geom, const Chain2Args& args, cudaStream_t stream);
+
 } // namespace avdsp

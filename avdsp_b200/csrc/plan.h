@@ -87,6 +87,7 @@ enum ChainSat : int { SAT_PLAIN = 0, SAT_TPDF = 1, SAT_GAIN = 2, SAT_TPDF_GAIN =
 struct ChainDesc {
     uint8_t  srcKind, satKind, hasGain, nStores;
     uint8_t  storeCh[kMaxChainStores];   // OUTPUT CHANNEL numbers (not io slots)
+    int32_t  srcId;           // chains with sections: index of the (deduplicated) source feeding the head, else -1
     int16_t  nsec;            // total biquad sections (concatenated consecutive BIQUADS ops)
     int16_t  srcCh;           // SRC_LOAD/LOAD_GAIN: INPUT CHANNEL number;  LOAD_MUX: pair count
     int32_t  srcArg;          // LOAD_GAIN: gain bits;  LOAD_MUX: pool offset of (inputChannel, gain) pairs
@@ -108,6 +109,9 @@ struct ChainHeader {
     int32_t maxSec;                                 // longest cascade
     int32_t totalSec;                               // sum of nsec
     int32_t nPool;
+    int32_t nSrc;                                   // distinct sources among chains that have sections
+    int32_t srcChain[kMaxChains];                   // a chain that carries source k's description
+    int32_t nUnwritten;                             // output channels no path stores to (they read 0)
     int32_t chainOfOut[kIoSlots];                   // output channel -> chain (or -1: channel never written => 0)
 };
 

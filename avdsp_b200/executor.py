@@ -15,8 +15,8 @@ from . import _lib
 
 INTERLEAVED, PLANAR = 0, 1
 HOST, DEVICE = 0, 1
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CHAIN = 0, 1, 2
-KERNEL_NAMES = {0: "none", 1: "generic", 2: "chain"}
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CHAIN, KERNEL_CHAIN_V1 = 0, 1, 2, 3
+KERNEL_NAMES = {0: "none", 1: "generic", 2: "chain", 3: "chain_v1"}
 
 
 class AvdspError(RuntimeError):
