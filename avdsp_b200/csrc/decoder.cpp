@@ -323,6 +323,15 @@ void buildChainPlan(Lowered* L) {
     }
     c.h.nUnwritten = 0;
     for (int k = 0; k < c.h.nOut; k++) if (c.h.chainOfOut[k] < 0) c.h.nUnwritten++;
+    // "direct" chains: cascade -> SAT0DB.  The cascade output is already clamped to [-2^59, 2^59) by the
+    // per-section saturation, so dspSaturate64_031 reduces to acc>>28 == the tail section's y1.
+    c.h.nAcc = c.h.nProc = 0;
+    for (int i = 0; i < c.h.nChains; i++) {
+        ChainDesc& d = c.chains[i];
+        const bool direct = d.nsec > 0 && !d.hasGain && d.satKind == SAT_PLAIN;
+        d.accRow = (d.nsec > 0 && !direct) ? c.h.nAcc++ : -1;
+        if (!direct) c.h.procChain[c.h.nProc++] = i;
+    }
 }
 
 void lowerAll(Lowered* L) {

@@ -25,8 +25,10 @@
 //
 // Ring bookkeeping (F = tile length, g_c = cascade length - 1 = frame lag of cascade c's tail, gmax <= F):
 //   x ring    [stream][source][2F]  by step: head lanes read position t for frame t
-//   acc ring  [slot][2F]            by step: tail of cascade c writes at step t the accumulator of frame t-g_c
-//   post ring [slot][R]             by step: saturated s.31 value of the same frame; R >= F+gmax+longest delay (power
+//   acc ring  [stream][row][2F]     by step: tail of cascade c writes at step t the accumulator of frame t-g_c
+//                                   (only cascades followed by gain / dither; a cascade -> SAT0DB tail writes its y1
+//                                   straight into the post ring)
+//   post ring [slot][R]             by step: saturated s.31 value of the same frame; R >= 2F+gmax+longest delay (power
 //                                   of two): it doubles as the delay line, so steady state never touches HBM state
 //   tpdf ring [stream][4F]          by frame (helper warp 0 may run one tile ahead of the others)
 //   sink window i = frames [iF-gmax, (i+1)F-gmax): every cascade has finished them when tile i is done.
@@ -132,12 +134,14 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NS = G.streamsPerCta, C = P.h.nChains, slots = NS * C, W = P.h.stateWords, T = A.nFrames;
     const int nSrc = P.h.nSrc;
-    long long* acc_s = reinterpret_cast<long long*>(smem_raw);             // [slots][accPitch]
-    int* x_s    = reinterpret_cast<int*>(acc_s + (size_t)slots * G.accPitch);  // [NS*nSrc][xPitch]
+    const int nAcc = P.h.nAcc;
+    long long* acc_s = reinterpret_cast<long long*>(smem_raw);             // [NS*nAcc][accPitch]
+    int* x_s    = reinterpret_cast<int*>(acc_s + (size_t)NS * nAcc * G.accPitch);  // [NS*nSrc][xPitch]
     int* post_s = x_s + (size_t)NS * nSrc * G.xPitch;                      // [slots][postPitch]
     int* tpdf_s = post_s + (size_t)slots * G.postPitch;                    // [NS][tpdfPitch]
     int* ridx_s = tpdf_s + (size_t)NS * G.tpdfPitch;                       // [slots] effective delay-ring index at launch start
     int* stale_s = ridx_s + slots;                                         // [slots] stale ring index (>= n) or -1
+    int* sfix_s = stale_s + slots;                                         // [slots] stale case: ring[n-1], restored over post(0)
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int s0 = blockIdx.x * NS, nsHere = min(NS, A.nStreams - s0);
@@ -173,20 +177,25 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
             }
         }
         const int* xrow = x_s + (size_t)((slot / C) * nSrc + max(d.srcId, 0)) * G.xPitch;
-        long long* arow = acc_s + (size_t)slot * G.accPitch;
+        long long* arow = acc_s + (size_t)((slot / C) * nAcc + max(d.accRow, 0)) * G.accPitch;
+        int* prow = post_s + (size_t)slot * G.postPitch;
+        const bool tail64 = tail && d.accRow >= 0;       // the sink needs the full accumulator (gain / dither ahead of the saturation)
+        const int RM = G.postRing - 1;
 
         for (int i = 0; i < nTiles; i++) {
             barSync(kBarFull + (i & 1), nAll);
             const int* xs = xrow + (i & 1) * F;
             long long* as = arow + (i & 1) * F;
             const int t0 = i * F;
+            int* ps = prow + (t0 & RM);
             if (t0 >= gmax && t0 + F <= T) {
 #pragma unroll
                 for (int j = 0; j < F; j++) {
                     int x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
                     if (head) x = xs[j];
                     laneStep<K>(L, x);
-                    if (tail) as[j] = L.acc[K - 1];
+                    if (tail) ps[j] = L.y1[K - 1];
+                    if (tail64) as[j] = L.acc[K - 1];
                 }
             } else {
 #pragma unroll 1
@@ -194,7 +203,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
                     int x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
                     if (head) x = xs[j];
                     laneStepPred<K>(L, x, t0 + j, g0, T);
-                    if (tail) as[j] = L.acc[K - 1];
+                    if (tail && (unsigned)(t0 + j - g0 - (K - 1)) < (unsigned)T) ps[j] = L.y1[K - 1];
+                    if (tail64) as[j] = L.acc[K - 1];
                 }
             }
             barArrive(kBarDone + (i & 1), nAll);
@@ -255,8 +265,10 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
                     else v = (k == 0) ? ring[idx0] : ring[k - 1];
                     prow[(k - n + gc) & RM] = v;
                 }
-                if (stale && lane == 0) prow[gc & RM] = ring[n - 1];     // takes the place of post(0), see above
-                if (lane == 0) { ridx_s[sl * C + c] = stale ? n - 1 : idx0; stale_s[sl * C + c] = stale ? idx0 : -1; }
+                if (lane == 0) {
+                    ridx_s[sl * C + c] = stale ? n - 1 : idx0; stale_s[sl * C + c] = stale ? idx0 : -1;
+                    if (stale) { sfix_s[sl * C + c] = ring[n - 1]; prow[gc & RM] = ring[n - 1]; }   // takes the place of post(0), see above
+                }
             }
         }
     __syncwarp();
@@ -298,16 +310,18 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
         if (prngOnly) return;
         for (int sl = ow; sl < nsHere; sl += nOwn) {
             int* st = A.state + (size_t)(s0 + sl) * W;
-            // A: step iw*F+u of every chain: accumulator (or inline source) -> [gain] -> saturate (+dither,+gain) -> post ring
+            // A: step iw*F+u of every chain that needs post-processing: accumulator (or inline source) -> [gain] ->
+            //    saturate (+dither,+gain) -> post ring.  Direct chains were written by their tail lanes already.
             for (int u = lane; u < F; u += 32) {
                 const int t = iw * F + u;
-                for (int c = 0; c < C; c++) {
+                for (int k = 0; k < P.h.nProc; k++) {
+                    const int c = P.h.procChain[k];
                     const ChainDesc& d = P.chains[c];
                     const int gc = d.nsec > 0 ? d.nsec - 1 : 0;
                     const int f = t - gc;
                     if (f < 0 || f >= T) continue;
                     long long X;
-                    if (d.nsec > 0) X = acc_s[(size_t)(sl * C + c) * G.accPitch + (iw & 1) * F + u];
+                    if (d.nsec > 0) X = acc_s[(size_t)(sl * nAcc + d.accRow) * G.accPitch + (iw & 1) * F + u];
                     else {
                         X = chainSource(P, d, A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)f * A.inFrameStride, A.inChStride);
                         if (d.srcKind == SRC_LOAD_MUX && f == T - 1) { st[d.muxStateOff] = (int)X; st[d.muxStateOff + 1] = (int)(X >> 32); }
@@ -320,6 +334,17 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
                     else post_s[(size_t)(sl * C + c) * G.postPitch + (t & RM)] = v;
                 }
             }
+            // stale delay index on a direct chain (rare): its tail lane stored post(0) where the preloaded
+            // ring[n-1] has to stay; move it to where the reference puts it (ring[idx0])
+            if (iw * F <= gmax && lane == 0)
+                for (int c = 0; c < C; c++) {
+                    const ChainDesc& d = P.chains[c];
+                    if (d.nsec > 0 && d.accRow < 0 && d.delayN > 0 && stale_s[sl * C + c] >= 0 && (d.nsec - 1) / F == iw) {
+                        int* pr = post_s + (size_t)(sl * C + c) * G.postPitch + ((d.nsec - 1) & RM);
+                        st[d.delayOff + 1 + stale_s[sl * C + c]] = *pr;
+                        *pr = sfix_s[sl * C + c];
+                    }
+                }
             __syncwarp();
             // B: frames [iw*F-gmax, +F): delayed read from the post ring + mask + store (16-byte stores when the layout allows)
             for (int u = lane; u < F; u += 32) {
@@ -458,7 +483,7 @@ bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2G
             if (lt < 0) break;
             if (gm > F) continue;                                    // sink window i must lie inside tiles i-1, i
             int help = envInt2("AVDSP_B200_HW", 0);
-            if (help <= 0) help = lt > 0 ? std::max(2, (lt / 32 + 2) / 3) : std::min(24, std::max(4, NS));
+            if (help <= 0) help = lt > 0 ? std::max(2, std::min(32 - lt / 32, (NS + 1) / 2 + 1)) : std::min(24, std::max(4, NS));
             help = std::max(1, std::min(help, 32 - lt / 32));
             const int slots = NS * C;
             Chain2Geom g{};
@@ -467,11 +492,11 @@ bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2G
             int maxDelay = 0;
             for (int c = 0; c < C; c++) maxDelay = std::max(maxDelay, plan.chains[c].delayN);
             int R = 2 * F;
-            while (R < F + gm + maxDelay) R <<= 1;
+            while (R < 2 * F + gm + maxDelay) R <<= 1;      // tails write tile i while the sink still reads window i-1
             g.postRing = R;
             g.xPitch = 2 * F + 1; g.accPitch = 2 * F + 1; g.postPitch = R + 1; g.tpdfPitch = 4 * F + 1;
-            g.smemBytes = (size_t)slots * g.accPitch * 8 +
-                          ((size_t)NS * plan.h.nSrc * g.xPitch + (size_t)slots * g.postPitch + (size_t)NS * g.tpdfPitch + 2 * slots) * 4 + 16;
+            g.smemBytes = (size_t)NS * plan.h.nAcc * g.accPitch * 8 +
+                          ((size_t)NS * plan.h.nSrc * g.xPitch + (size_t)slots * g.postPitch + (size_t)NS * g.tpdfPitch + 3 * slots) * 4 + 16;
             if (g.secThreads + g.helpThreads <= 1024 && g.smemBytes <= 226 * 1024) {
                 *geom = g;
                 if (lanesOut) packLanes2(plan, NS, K, lanesOut, nullptr);

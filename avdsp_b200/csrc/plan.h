@@ -88,6 +88,8 @@ struct ChainDesc {
     uint8_t  srcKind, satKind, hasGain, nStores;
     uint8_t  storeCh[kMaxChainStores];   // OUTPUT CHANNEL numbers (not io slots)
     int32_t  srcId;           // chains with sections: index of the (deduplicated) source feeding the head, else -1
+    int32_t  accRow;          // chains whose sink needs the full 64-bit accumulator: row in the acc ring, else -1.
+                              // accRow < 0 && nsec > 0: "direct" chain (cascade -> SAT0DB): the tail's y1 IS the s.31 output
     int16_t  nsec;            // total biquad sections (concatenated consecutive BIQUADS ops)
     int16_t  srcCh;           // SRC_LOAD/LOAD_GAIN: INPUT CHANNEL number;  LOAD_MUX: pair count
     int32_t  srcArg;          // LOAD_GAIN: gain bits;  LOAD_MUX: pool offset of (inputChannel, gain) pairs
@@ -112,6 +114,9 @@ struct ChainHeader {
     int32_t nSrc;                                   // distinct sources among chains that have sections
     int32_t srcChain[kMaxChains];                   // a chain that carries source k's description
     int32_t nUnwritten;                             // output channels no path stores to (they read 0)
+    int32_t nAcc;                                   // acc-ring rows per stream
+    int32_t nProc;                                  // chains the sink has to post-process (everything but direct chains)
+    int32_t procChain[kMaxChains];
     int32_t chainOfOut[kIoSlots];                   // output channel -> chain (or -1: channel never written => 0)
 };
 
