@@ -14,15 +14,23 @@
 namespace avdsp {
 
 // ---------------------------------------------------------------- fixed point ----------------
-// Spelled in PTX on purpose: written as (long long)a * b, NVVM hoists the sign extension of a loop-invariant
-// coefficient out of the loop and ptxas then emits a 64x64 multiply (IMAD.WIDE.U32 + 2 IMAD + SHF + IADD, 5
-// instructions) instead of one signed IMAD.WIDE.
-__device__ __forceinline__ long long mul32(int a, int b) {
-    long long r; asm("mul.wide.s32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r;
-}
-__device__ __forceinline__ long long mac32(long long acc, int a, int b) {
-    long long r; asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(acc)); return r;
-}
+// 32x32 -> 64 signed multiply(-accumulate).  How this is spelled decides the SASS (sm_100a, CUDA 12.9):
+//   * plain (long long)a * b : NVVM hoists the sign extension of a loop-invariant coefficient out of the loop and
+//     the multiply becomes a 64x64 one (IMAD.WIDE.U32 + 2 IMAD + SHF + IADD: 5 instructions per MAC);
+//   * inline PTX mad.wide.s32 : ptxas splits chains of them into IMAD.WIDE(.., RZ) products plus 3-input
+//     IADD3/IADD3.X carry trees (11 instructions for acc + 5 products);
+//   * (long long)a * b on operands passed through an empty volatile asm ("opaque"): NVVM emits
+//     mul.wide.s32 + add.s64 and ptxas fuses each pair into ONE accumulating IMAD.WIDE (5 instructions).
+// IMAD.WIDE issues at 1/4 rate (measured: 31.6 / clk / SM, tools/microbench_int.cu), so the accumulating form
+// is both the fewest issue slots and the fewest fma-pipe cycles.
+__device__ __forceinline__ int opaque(int v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ long long mul32(int a, int b) { return (long long)opaque(a) * (long long)opaque(b); }
+__device__ __forceinline__ long long mac32(long long acc, int a, int b) { return acc + (long long)opaque(a) * (long long)opaque(b); }
+// low / high word of a 64-bit value without the trunc/shift patterns NVVM likes to re-widen
+__device__ __forceinline__ int lo32(long long v) { int l, h; asm("mov.b64 {%0,%1}, %2;" : "=r"(l), "=r"(h) : "l"(v)); (void)h; return l; }
+__device__ __forceinline__ int hi32(long long v) { int l, h; asm("mov.b64 {%0,%1}, %2;" : "=r"(l), "=r"(h) : "l"(v)); (void)l; return h; }
+// (int)(acc >> 28): one funnel shift
+__device__ __forceinline__ int q59ToS31(long long acc) { return (int)__funnelshift_r((unsigned)lo32(acc), (unsigned)hi32(acc), kMantBQ); }
 
 // dspSaturate64_031 (dsp_fpmath.h:84-98): clamp s4.59 to [-1,1) and return s.31 in the low word
 __device__ __forceinline__ long long sat64_031(long long a) {

@@ -47,6 +47,30 @@ constexpr int kBarHelp = 5;       // helpers only
 __device__ __forceinline__ void barSync(int id, int n)   { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void barArrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
+// ---- TMA (1-D bulk copy global -> shared, completion on an mbarrier): how input PCM tiles reach the SM
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tmaLoad1D(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned bar, unsigned parity) {
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <int K>
 struct Lane2 {
     long long acc[K];
@@ -75,7 +99,7 @@ __device__ __forceinline__ void laneStep(Lane2<K>& L, int xin) {
         acc = mac32(acc, L.y2[j], L.a2[j]);
         acc = mac32(acc, in[j], L.b0[j]);
         a[j] = acc;
-        worst = max(worst, (unsigned)((int)(acc >> 32)) + kSatBias);
+        worst = max(worst, (unsigned)hi32(acc) + kSatBias);
     }
     // warp-uniform branch (vote): no divergence bookkeeping around the per-step shuffle
     if (__any_sync(0xffffffffu, worst > kSatLimit)) {
@@ -86,7 +110,7 @@ __device__ __forceinline__ void laneStep(Lane2<K>& L, int xin) {
     for (int j = 0; j < K; j++) {
         L.acc[j] = a[j];
         L.x2[j] = L.x1[j]; L.x1[j] = in[j];
-        L.y2[j] = L.y1[j]; L.y1[j] = (int)(a[j] >> kMantBQ);
+        L.y2[j] = L.y1[j]; L.y1[j] = q59ToS31(a[j]);
     }
 }
 
@@ -109,22 +133,23 @@ __device__ __forceinline__ void laneStepPred(Lane2<K>& L, int xin, int t, int g0
             acc = biquadSat(acc);
             L.acc[j] = acc;
             L.x2[j] = L.x1[j]; L.x1[j] = in[j];
-            L.y2[j] = L.y1[j]; L.y1[j] = (int)(acc >> kMantBQ);
+            L.y2[j] = L.y1[j]; L.y1[j] = q59ToS31(acc);
         }
     }
 }
 
-// source value of a chain for one frame: LOAD / LOAD_GAIN / LOAD_MUX (dsp_runtime.c:565-607, 871-897)
-__device__ __forceinline__ long long chainSource(const ChainPlan& P, const ChainDesc& d, const int* __restrict__ in, int inChStride) {
+// source value of a chain for one frame: LOAD / LOAD_GAIN / LOAD_MUX (dsp_runtime.c:565-607, 871-897).
+// `in` points at channel 0 of the frame (global memory or the TMA-staged tile), chStride in words.
+__device__ __forceinline__ long long chainSource(const ChainPlan& P, const ChainDesc& d, const int* __restrict__ in, int chStride) {
     if (d.srcKind == SRC_LOAD_MUX) {
         long long X = 0;
         for (int k = 0; k < d.srcCh; k++) {
             const int ch = P.pool[d.srcArg + 2 * k], gain = P.pool[d.srcArg + 2 * k + 1];
-            X = mac32(X, ch >= 0 ? __ldg(in + (size_t)ch * inChStride) : 0, gain);
+            X = mac32(X, ch >= 0 ? in[(size_t)ch * chStride] : 0, gain);
         }
         return X;
     }
-    const int smp = d.srcCh >= 0 ? __ldg(in + (size_t)d.srcCh * inChStride) : 0;
+    const int smp = d.srcCh >= 0 ? in[(size_t)d.srcCh * chStride] : 0;
     return (d.srcKind == SRC_LOAD_GAIN) ? mul32(smp, d.srcArg) : (long long)smp;
 }
 
@@ -142,6 +167,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
     int* ridx_s = tpdf_s + (size_t)NS * G.tpdfPitch;                       // [slots] effective delay-ring index at launch start
     int* stale_s = ridx_s + slots;                                         // [slots] stale ring index (>= n) or -1
     int* sfix_s = stale_s + slots;                                         // [slots] stale case: ring[n-1], restored over post(0)
+    unsigned long long* mbar_s = reinterpret_cast<unsigned long long*>(smem_raw + G.mbarOff);   // [helper warps][2]
+    int* raw_s = reinterpret_cast<int*>(smem_raw + G.rawOff);              // [NS][2][F*nIn] input PCM tiles (TMA destination)
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int s0 = blockIdx.x * NS, nsHere = min(NS, A.nStreams - s0);
@@ -273,6 +300,39 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
         }
     __syncwarp();
 
+    // ---- input PCM tiles by TMA: lane 0 of every owner warp issues, two tiles ahead, one bulk copy per owned
+    // stream (interleaved: F*nIn contiguous words) or per (stream, channel) (planar: F contiguous words) into
+    // raw_s; completion is counted in bytes on the warp's mbarrier of that parity.  Tiles that cannot go through
+    // TMA (partial last tile, misaligned caller buffers) are read with plain loads instead.
+    const int nIn = P.h.nIn;
+    const int rowWords = F * nIn;
+    const bool interleavedIn = A.inChStride == 1 && A.inFrameStride == nIn;
+    const bool planarIn = A.inFrameStride == 1;
+    const bool tmaOk = G.rawOff != 0 && nSrc > 0 && nIn > 0 && ((size_t)A.in & 15) == 0 && (A.inStreamStride & 3) == 0 &&
+                       ((interleavedIn && (rowWords & 3) == 0) || (planarIn && !interleavedIn && (A.inChStride & 3) == 0 && (F & 3) == 0));
+    const int rawFS = interleavedIn ? nIn : 1, rawCS = interleavedIn ? 1 : F;     // strides inside a staged tile
+    const unsigned mbar0 = smemAddr(mbar_s + 2 * hw);
+    if (tmaOk && !prngOnly && lane == 0) { mbarInit(mbar0, 1); mbarInit(mbar0 + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncwarp();
+    auto tileUsesTma = [&](int it) { return tmaOk && (it + 1) * F <= T; };
+    auto issueTile = [&](int it) {
+        if (prngOnly || !tileUsesTma(it)) return;
+        __syncwarp();                                    // every lane is done reading the buffer being refilled
+        if (lane == 0) {
+            fenceProxyAsync();
+            int cnt = 0;
+            for (int sl = ow; sl < nsHere; sl += nOwn) cnt++;
+            const unsigned bar = mbar0 + 8 * (it & 1);
+            mbarExpectTx(bar, (unsigned)(cnt * rowWords * 4));
+            for (int sl = ow; sl < nsHere; sl += nOwn) {
+                const int* src = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(it * F) * A.inFrameStride;
+                const unsigned dst = smemAddr(raw_s + (size_t)(sl * 2 + (it & 1)) * rowWords);
+                if (interleavedIn) tmaLoad1D(dst, src, (unsigned)(rowWords * 4), bar);
+                else for (int ch = 0; ch < nIn; ch++) tmaLoad1D(dst + ch * F * 4, src + (size_t)ch * A.inChStride, (unsigned)(F * 4), bar);
+            }
+        }
+    };
+
     // ---- source stage of tile `it`: frames [it*F, it*F+F) -> x ring (one value per distinct source), dither values
     auto sourceTile = [&](int it) {
         const int f0 = it * F;
@@ -291,18 +351,23 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
             }
         }
         if (nSrc == 0 || prngOnly) return;
+        const bool staged = tileUsesTma(it);
+        if (staged) mbarWait(mbar0 + 8 * (it & 1), (unsigned)((it >> 1) & 1));
         for (int u = lane; u < F; u += 32) {
             const int f = f0 + u;
             if (f >= T) continue;
             for (int sl = ow; sl < nsHere; sl += nOwn) {
-                const int* in = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)f * A.inFrameStride;
+                const int* in = staged ? raw_s + (size_t)(sl * 2 + (it & 1)) * rowWords + u * rawFS
+                                       : A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)f * A.inFrameStride;
+                const int cs = staged ? rawCS : A.inChStride;
                 for (int k = 0; k < nSrc; k++) {
                     const ChainDesc& d = P.chains[P.h.srcChain[k]];
-                    const long long X = chainSource(P, d, in, A.inChStride);
+                    const long long X = chainSource(P, d, in, cs);
                     x_s[(size_t)(sl * nSrc + k) * G.xPitch + (it & 1) * F + u] = (int)(X >> kMantBQ);
                 }
             }
         }
+        issueTile(it + 2);                               // refill this parity's buffer two tiles ahead
     };
 
     // ---- sink stage of window `iw`
@@ -376,6 +441,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
         }
     };
 
+    issueTile(0);
+    issueTile(1);
     sourceTile(0);
     barArrive(kBarFull + 0, nAll);
     for (int i = 0; i < nTiles; i++) {
@@ -495,8 +562,14 @@ bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2G
             while (R < 2 * F + gm + maxDelay) R <<= 1;      // tails write tile i while the sink still reads window i-1
             g.postRing = R;
             g.xPitch = 2 * F + 1; g.accPitch = 2 * F + 1; g.postPitch = R + 1; g.tpdfPitch = 4 * F + 1;
-            g.smemBytes = (size_t)NS * plan.h.nAcc * g.accPitch * 8 +
-                          ((size_t)NS * plan.h.nSrc * g.xPitch + (size_t)slots * g.postPitch + (size_t)NS * g.tpdfPitch + 3 * slots) * 4 + 16;
+            size_t bytes = (size_t)NS * plan.h.nAcc * g.accPitch * 8 +
+                           ((size_t)NS * plan.h.nSrc * g.xPitch + (size_t)slots * g.postPitch + (size_t)NS * g.tpdfPitch + 3 * slots) * 4;
+            bytes = (bytes + 15) & ~(size_t)15;
+            g.mbarOff = (int)bytes; bytes += (size_t)help * 2 * 8;
+            bytes = (bytes + 127) & ~(size_t)127;
+            g.rawOff = plan.h.nSrc > 0 ? (int)bytes : 0;          // input tiles staged by TMA (only cascades read them)
+            if (plan.h.nSrc > 0) bytes += (size_t)NS * 2 * F * plan.h.nIn * 4;
+            g.smemBytes = bytes + 16;
             if (g.secThreads + g.helpThreads <= 1024 && g.smemBytes <= 226 * 1024) {
                 *geom = g;
                 if (lanesOut) packLanes2(plan, NS, K, lanesOut, nullptr);

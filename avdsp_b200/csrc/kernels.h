@@ -62,6 +62,7 @@ struct Chain2Geom {
     int helpThreads;       // source / sink / dither threads (multiple of 32, >= 32)
     int postRing;          // R: post ring length in steps (power of two >= F + gmax + longest delay)
     int xPitch, accPitch, postPitch, tpdfPitch;   // shared-memory row pitches (elements)
+    int mbarOff, rawOff;   // byte offsets of the helper warps' mbarriers / the TMA-staged input tiles (0: none)
     size_t smemBytes;
 };
 struct Chain2Args {
