@@ -322,7 +322,13 @@ void buildChainPlan(Lowered* L) {
         if (d.srcId < 0) { d.srcId = c.h.nSrc; c.h.srcChain[c.h.nSrc++] = i; }
     }
     c.h.nUnwritten = 0;
-    for (int k = 0; k < c.h.nOut; k++) if (c.h.chainOfOut[k] < 0) c.h.nUnwritten++;
+    for (int k = 0; k < kIoSlots; k++) {
+        c.h.outOff[k] = 0;
+        if (k < c.h.nOut) {
+            if (c.h.chainOfOut[k] < 0) c.h.nUnwritten++;
+            else { const ChainDesc& d = c.chains[c.h.chainOfOut[k]]; c.h.outOff[k] = (d.nsec > 0 ? d.nsec - 1 : 0) - d.delayN; }
+        }
+    }
     // "direct" chains: cascade -> SAT0DB.  The cascade output is already clamped to [-2^59, 2^59) by the
     // per-section saturation, so dspSaturate64_031 reduces to acc>>28 == the tail section's y1.
     c.h.nAcc = c.h.nProc = 0;
@@ -331,6 +337,20 @@ void buildChainPlan(Lowered* L) {
         const bool direct = d.nsec > 0 && !d.hasGain && d.satKind == SAT_PLAIN;
         d.accRow = (d.nsec > 0 && !direct) ? c.h.nAcc++ : -1;
         if (!direct) c.h.procChain[c.h.nProc++] = i;
+    }
+    for (int k = 0; k < kFastTab; k++) {
+        c.h.pChain[k] = c.h.pLag[k] = c.h.pFlags[k] = c.h.pGain[k] = c.h.pSatGain[k] = c.h.pDelayN[k] = 0; c.h.pAccRow[k] = -1;
+        c.h.sKind[k] = c.h.sArg[k] = 0; c.h.sCh[k] = -1;
+        if (k < c.h.nProc) {
+            const ChainDesc& d = c.chains[c.h.procChain[k]];
+            c.h.pChain[k] = c.h.procChain[k]; c.h.pLag[k] = d.nsec > 0 ? d.nsec - 1 : 0; c.h.pAccRow[k] = d.accRow;
+            c.h.pFlags[k] = (d.nsec > 0 ? PF_SECTIONS : 0) | (d.hasGain ? PF_GAIN : 0) | ((d.satKind & 1) ? PF_SAT_TPDF : 0) | (d.satKind >= SAT_GAIN ? PF_SAT_GAIN : 0);
+            c.h.pGain[k] = d.gainBits; c.h.pSatGain[k] = d.satGainBits; c.h.pDelayN[k] = d.delayN;
+        }
+        if (k < c.h.nSrc) {
+            const ChainDesc& d = c.chains[c.h.srcChain[k]];
+            c.h.sKind[k] = d.srcKind; c.h.sCh[k] = d.srcCh; c.h.sArg[k] = d.srcArg;
+        }
     }
 }
 

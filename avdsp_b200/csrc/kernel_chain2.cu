@@ -1,8 +1,9 @@
 // kernel_chain2.cu -- warp-specialised systolic executor for programs made of independent signal paths
 //     source (LOAD / LOAD_GAIN / LOAD_MUX) -> biquad cascade -> [GAIN] -> SAT0DB[_TPDF][_GAIN] -> [DELAY] -> STORE
-// (crossovers, EQs, matrix mixers: configs C2, C3, C5).  Fixed point (DSP_FORMAT 2), bit-exact.
+// (crossovers, EQs: configs C2, C3).  Fixed point (DSP_FORMAT 2), bit-exact.
 //
-// Why it looks like this (B200: 148 SMs, fma pipe = 64 mad.wide.s32 / clk / SM measured, 1 issue / clk / SMSP):
+// Why it looks like this (B200: 148 SMs; the signed 32x32+64 IMAD.WIDE issues at 1/4 rate = 31.6 / clk / SM
+// measured, everything else at 1 instruction / clk / SMSP):
 //   * The biquad recurrence is sequential in time, so time stays a loop.  Parallelism = streams x paths x
 //     sections.  A *section lane* owns K consecutive sections of one cascade: state (64-bit accumulator,
 //     x1 x2 y1 y2; reference layout runtime/dsp_biquadSTD.h:45) and the 5 Q4.28 coefficients stay in
@@ -10,16 +11,17 @@
 //     with index g inside its cascade works on frame t-g, so all sections of a step are independent
 //     (ILP inside a lane, one __shfl_up between lanes) -- exact, because section g of frame n only needs
 //     section g-1 of the same frame (dsp_calc_biquads_int, runtime/dsp_biquadSTD.h:37-74).
-//   * Per section-step the budget is 5 IMAD.WIDE + ~2.5 instructions of saturation test (one branch per
-//     lane-step, taken only when some section saturates) + 1 funnel shift.  Nothing else is allowed into
-//     that loop: tiles are fully unrolled, shared-memory offsets are immediates, rings are indexed by STEP
-//     (identical position for every lane; the per-cascade skew is absorbed by the helpers), and there is
-//     no barrier inside a tile.
+//   * A section costs 5 accumulating IMAD.WIDE = 20 fma-pipe cycles per warp; the lane-step around K=2 of them
+//     is 26 issue slots (SASS checked), so the section warps are fma-pipe bound and leave ~1/3 of the issue
+//     slots to the rest.  Nothing else is allowed into that loop: tiles are fully unrolled, shared-memory
+//     offsets are immediates, rings are indexed by STEP (identical position for every lane; the per-cascade
+//     skew is absorbed by the helpers), the saturation test is one vote + branch per lane-step.
 //   * Everything else is element-wise over (stream, frame) and is done by *helper warps* of the same CTA,
-//     one tile ahead (sources -> x ring, each distinct source once) and one tile behind (accumulator ring ->
-//     gain / saturate / dither / delay / mask -> coalesced stores).  Helper warp 0 also advances the
-//     per-stream dither PRNG (xoshiro128+, strictly serial per stream: one lane per stream).  Roles meet
-//     only at tile boundaries through named barriers (bar.arrive / bar.sync): section warps never wait on HBM.
+//     one tile ahead (TMA-staged PCM -> sources -> x ring) and one tile behind (accumulator ring -> gain /
+//     saturate / dither -> post ring; post ring -> delay -> mask -> 16-byte stores).  Helper warp 0 advances the
+//     per-stream dither PRNG (xoshiro128+, strictly serial per stream: one lane per stream).  Helper code keeps
+//     off the fma pipe: addresses are sums of host-precomputed byte offsets (constant-bank operands).
+//     Roles meet only at tile boundaries through named barriers (bar.arrive / bar.sync).
 //   * One CTA per SM owns NS = ceil(nStreams / #SM) streams for the whole launch; state never leaves the
 //     SM between tiles.  4096 streams -> 147 CTAs x 28 streams, single wave.
 //
@@ -42,13 +44,21 @@ namespace avdsp {
 
 constexpr int kBarFull = 1;       // +parity : x tile ready            (helpers arrive, sections wait)
 constexpr int kBarDone = 3;       // +parity : section tile finished   (sections arrive, helpers wait)
-constexpr int kBarHelp = 5;       // helpers only
+#ifndef AVDSP_UNR
+#define AVDSP_UNR 8
+#endif
+constexpr int UNR = AVDSP_UNR;    // section steps unrolled per loop iteration (must divide the tile length)
 
 __device__ __forceinline__ void barSync(int id, int n)   { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void barArrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
-// ---- TMA (1-D bulk copy global -> shared, completion on an mbarrier): how input PCM tiles reach the SM
+// ---- shared memory by 32-bit address (no generic-pointer arithmetic in the hot paths)
 __device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lds32(unsigned a) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ long long lds64(unsigned a) { long long v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(unsigned a, int v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
+// ---- TMA (1-D bulk copy global -> shared, completion on an mbarrier): how input PCM tiles reach the SM
 __device__ __forceinline__ void mbarInit(unsigned bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
@@ -81,15 +91,17 @@ struct Lane2 {
 constexpr unsigned kSatBias  = (1u << (kMantBQ - 1)) - 2u;       // in range  <=>  (unsigned)(hi + bias) <= limit
 constexpr unsigned kSatLimit = (1u << kMantBQ) - 3u;             // (checkbiquadsat, runtime/dsp_biquadSTD.h:25-32)
 
-// one lane-step, all K sections valid
+// one lane-step, all K sections valid, OPTIMISTIC: no saturation handling, only a sticky record of the largest
+// biased high word seen (checkbiquadsat, runtime/dsp_biquadSTD.h:25-32, fires iff that record exceeds kSatLimit).
+// The caller tests the record once per tile and, in the rare case it fired, replays the tile from a checkpoint
+// with laneStepExact.  (A vote + branch per step costs ~25 % of the loop: branches and VOTE are not free next to
+// a quarter-rate IMAD.WIDE stream, tools/microbench_mix.cu.)
 template <int K>
-__device__ __forceinline__ void laneStep(Lane2<K>& L, int xin) {
+__device__ __forceinline__ void laneStepFast(Lane2<K>& L, int xin, unsigned& worst) {
     int in[K];
     in[0] = xin;
 #pragma unroll
     for (int j = 1; j < K; j++) in[j] = L.y1[j - 1];          // skew: section j takes what j-1 produced one step ago
-    long long a[K];
-    unsigned worst = 0;
 #pragma unroll
     for (int j = 0; j < K; j++) {
         long long acc = L.acc[j];
@@ -98,19 +110,31 @@ __device__ __forceinline__ void laneStep(Lane2<K>& L, int xin) {
         acc = mac32(acc, L.y1[j], L.a1[j]);
         acc = mac32(acc, L.y2[j], L.a2[j]);
         acc = mac32(acc, in[j], L.b0[j]);
-        a[j] = acc;
         worst = max(worst, (unsigned)hi32(acc) + kSatBias);
+        L.acc[j] = acc;
+        L.x2[j] = L.x1[j]; L.x1[j] = in[j];
+        L.y2[j] = L.y1[j]; L.y1[j] = q59ToS31(acc);
     }
-    // warp-uniform branch (vote): no divergence bookkeeping around the per-step shuffle
-    if (__any_sync(0xffffffffu, worst > kSatLimit)) {
+}
+// the same lane-step with the reference's saturation applied to every section
+template <int K>
+__device__ __forceinline__ void laneStepExact(Lane2<K>& L, int xin) {
+    int in[K];
+    in[0] = xin;
 #pragma unroll
-        for (int j = 0; j < K; j++) a[j] = biquadSat(a[j]);
-    }
+    for (int j = 1; j < K; j++) in[j] = L.y1[j - 1];
 #pragma unroll
     for (int j = 0; j < K; j++) {
-        L.acc[j] = a[j];
+        long long acc = L.acc[j];
+        acc = mac32(acc, L.x1[j], L.b1[j]);
+        acc = mac32(acc, L.x2[j], L.b2[j]);
+        acc = mac32(acc, L.y1[j], L.a1[j]);
+        acc = mac32(acc, L.y2[j], L.a2[j]);
+        acc = mac32(acc, in[j], L.b0[j]);
+        acc = biquadSat(acc);
+        L.acc[j] = acc;
         L.x2[j] = L.x1[j]; L.x1[j] = in[j];
-        L.y2[j] = L.y1[j]; L.y1[j] = q59ToS31(a[j]);
+        L.y2[j] = L.y1[j]; L.y1[j] = q59ToS31(acc);
     }
 }
 
@@ -138,8 +162,7 @@ __device__ __forceinline__ void laneStepPred(Lane2<K>& L, int xin, int t, int g0
     }
 }
 
-// source value of a chain for one frame: LOAD / LOAD_GAIN / LOAD_MUX (dsp_runtime.c:565-607, 871-897).
-// `in` points at channel 0 of the frame (global memory or the TMA-staged tile), chStride in words.
+// source value of a chain for one frame from GLOBAL memory: LOAD / LOAD_GAIN / LOAD_MUX (dsp_runtime.c:565-607, 871-897)
 __device__ __forceinline__ long long chainSource(const ChainPlan& P, const ChainDesc& d, const int* __restrict__ in, int chStride) {
     if (d.srcKind == SRC_LOAD_MUX) {
         long long X = 0;
@@ -152,32 +175,37 @@ __device__ __forceinline__ long long chainSource(const ChainPlan& P, const Chain
     const int smp = d.srcCh >= 0 ? in[(size_t)d.srcCh * chStride] : 0;
     return (d.srcKind == SRC_LOAD_GAIN) ? mul32(smp, d.srcArg) : (long long)smp;
 }
+// LOAD_MUX from a TMA-staged tile (shared address of channel 0 of the frame, channel stride in bytes)
+__device__ __forceinline__ long long muxFromShared(const ChainPlan& P, const ChainDesc& d, unsigned a, unsigned chBytes) {
+    long long X = 0;
+    for (int k = 0; k < d.srcCh; k++) {
+        const int ch = P.pool[d.srcArg + 2 * k], gain = P.pool[d.srcArg + 2 * k + 1];
+        X = mac32(X, ch >= 0 ? lds32(a + ch * chBytes) : 0, gain);
+    }
+    return X;
+}
 
 template <int K, int F>
 __global__ void __launch_bounds__(1024, 1)
-k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Geom G) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NS = G.streamsPerCta, C = P.h.nChains, slots = NS * C, W = P.h.stateWords, T = A.nFrames;
+k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_constant__ Chain2Geom G) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int NS = G.streamsPerCta, C = P.h.nChains, W = P.h.stateWords, T = A.nFrames;
     const int nSrc = P.h.nSrc;
-    const int nAcc = P.h.nAcc;
-    long long* acc_s = reinterpret_cast<long long*>(smem_raw);             // [NS*nAcc][accPitch]
-    int* x_s    = reinterpret_cast<int*>(acc_s + (size_t)NS * nAcc * G.accPitch);  // [NS*nSrc][xPitch]
-    int* post_s = x_s + (size_t)NS * nSrc * G.xPitch;                      // [slots][postPitch]
-    int* tpdf_s = post_s + (size_t)slots * G.postPitch;                    // [NS][tpdfPitch]
-    int* ridx_s = tpdf_s + (size_t)NS * G.tpdfPitch;                       // [slots] effective delay-ring index at launch start
-    int* stale_s = ridx_s + slots;                                         // [slots] stale ring index (>= n) or -1
-    int* sfix_s = stale_s + slots;                                         // [slots] stale case: ring[n-1], restored over post(0)
-    unsigned long long* mbar_s = reinterpret_cast<unsigned long long*>(smem_raw + G.mbarOff);   // [helper warps][2]
-    int* raw_s = reinterpret_cast<int*>(smem_raw + G.rawOff);              // [NS][2][F*nIn] input PCM tiles (TMA destination)
-
-    const int tid = threadIdx.x, lane = tid & 31;
+    // helper warps take the LOW warp ids when G.helpersFirst (scheduler arbitration experiment)
+    const int tid = G.helpersFirst ? (threadIdx.x < G.helpThreads ? threadIdx.x + G.secThreads : threadIdx.x - G.helpThreads) : threadIdx.x;
+    const int lane = tid & 31;
     const int s0 = blockIdx.x * NS, nsHere = min(NS, A.nStreams - s0);
     const int nAll = G.secThreads + G.helpThreads;
     const int gmax = G.gmax;
     const int nTiles = (T + gmax + F - 1) / F;
+    const int RM = G.postRing - 1;
+    constexpr int XP = 2 * F + 1, AP = 2 * F + 1, TP = 4 * F + 1;        // row pitches (elements) of x / acc / tpdf rings
 
     if (tid < G.secThreads) {
         // =========================================================================== section warps
+        long long* acc_s = reinterpret_cast<long long*>(smem_raw);
+        int* x_s = reinterpret_cast<int*>(smem_raw + G.xOff);
+        int* post_s = reinterpret_cast<int*>(smem_raw + G.postOff);
         Lane2<K> L;
         const ChainLane e = A.lanes[tid];
         const bool live = e.slot >= 0 && e.slot / C < nsHere;
@@ -203,11 +231,12 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
                 L.x1[k] = q[2]; L.x2[k] = q[3]; L.y1[k] = q[4]; L.y2[k] = q[5];
             }
         }
-        const int* xrow = x_s + (size_t)((slot / C) * nSrc + max(d.srcId, 0)) * G.xPitch;
-        long long* arow = acc_s + (size_t)((slot / C) * nAcc + max(d.accRow, 0)) * G.accPitch;
+        const int* xrow = x_s + (size_t)((slot / C) * nSrc + max(d.srcId, 0)) * XP;
+        long long* arow = acc_s + (size_t)((slot / C) * P.h.nAcc + max(d.accRow, 0)) * AP;
         int* prow = post_s + (size_t)slot * G.postPitch;
         const bool tail64 = tail && d.accRow >= 0;       // the sink needs the full accumulator (gain / dither ahead of the saturation)
-        const int RM = G.postRing - 1;
+        int* ck = reinterpret_cast<int*>(smem_raw + G.ckOff) + tid;       // [6K words][secThreads]: tile-start checkpoint of this lane
+        const int CKP = G.secThreads;
 
         for (int i = 0; i < nTiles; i++) {
             barSync(kBarFull + (i & 1), nAll);
@@ -216,13 +245,43 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
             const int t0 = i * F;
             int* ps = prow + (t0 & RM);
             if (t0 >= gmax && t0 + F <= T) {
+                // checkpoint (shared memory: the LSU pipe is idle in this loop), optimistic tile, one test, rare replay
 #pragma unroll
-                for (int j = 0; j < F; j++) {
-                    int x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
-                    if (head) x = xs[j];
-                    laneStep<K>(L, x);
-                    if (tail) ps[j] = L.y1[K - 1];
-                    if (tail64) as[j] = L.acc[K - 1];
+                for (int k = 0; k < K; k++) {
+                    ck[(6 * k + 0) * CKP] = lo32(L.acc[k]); ck[(6 * k + 1) * CKP] = hi32(L.acc[k]);
+                    ck[(6 * k + 2) * CKP] = L.x1[k]; ck[(6 * k + 3) * CKP] = L.x2[k];
+                    ck[(6 * k + 4) * CKP] = L.y1[k]; ck[(6 * k + 5) * CKP] = L.y2[k];
+                }
+                unsigned worst = 0;
+                // unrolled in groups of UNR steps (immediate offsets inside a group): the section loop stays a few KB of code
+#pragma unroll 1
+                for (int j0 = 0; j0 < F; j0 += UNR) {
+#pragma unroll
+                    for (int jj = 0; jj < UNR; jj++) {
+                        const int j = j0 + jj;
+                        int x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
+                        if (head) x = xs[j];
+                        laneStepFast<K>(L, x, worst);
+                        if (tail) ps[j] = L.y1[K - 1];
+                        if (tail64) as[j] = L.acc[K - 1];
+                    }
+                }
+                if (__any_sync(0xffffffffu, worst > kSatLimit)) {
+                    // some section of this warp saturated somewhere in the tile: replay it exactly
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        L.acc[k] = (long long)(((unsigned long long)(unsigned)ck[(6 * k + 1) * CKP] << 32) | (unsigned)ck[(6 * k + 0) * CKP]);
+                        L.x1[k] = ck[(6 * k + 2) * CKP]; L.x2[k] = ck[(6 * k + 3) * CKP];
+                        L.y1[k] = ck[(6 * k + 4) * CKP]; L.y2[k] = ck[(6 * k + 5) * CKP];
+                    }
+#pragma unroll 1
+                    for (int j = 0; j < F; j++) {
+                        int x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
+                        if (head) x = xs[j];
+                        laneStepExact<K>(L, x);
+                        if (tail) ps[j] = L.y1[K - 1];
+                        if (tail64) as[j] = L.acc[K - 1];
+                    }
                 }
             } else {
 #pragma unroll 1
@@ -251,6 +310,12 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
     const int ht = tid - G.secThreads, hw = ht >> 5, nHW = G.helpThreads >> 5;
     const int storeMask = ditherMask(P.h.storeDither);
     const bool hasCalc = P.h.hasTpdfCalc != 0;
+    const unsigned sb = smemAddr(smem_raw);
+    int* post_s = reinterpret_cast<int*>(smem_raw + G.postOff);
+    int* tpdf_s = reinterpret_cast<int*>(smem_raw + G.tpdfOff);
+    int* ridx_s = reinterpret_cast<int*>(smem_raw + G.ridxOff);            // [slots] effective delay-ring index at launch start
+    int* stale_s = ridx_s + NS * C;                                        // [slots] stale ring index (>= n) or -1
+    int* sfix_s = stale_s + NS * C;                                        // [slots] stale case: ring[n-1], restored over post(0)
     // warp 0 doubles as the dither PRNG: lane = stream
     Prng g = {0, 0, 0, 0}; int tpdfValue = 0, tpdfRandom = 0, dith = 0; bool drew = false;
     int* auxp = nullptr;
@@ -264,16 +329,16 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
     const bool prngOnly = hasCalc && nHW > 1 && hw == 0;
     const int ow = (hasCalc && nHW > 1) ? hw - 1 : hw;
     const int nOwn = (hasCalc && nHW > 1) ? nHW - 1 : nHW;
-    const int R = G.postRing, RM = R - 1;
     const bool vecOut = A.outChStride == 1 && (P.h.nOut & 3) == 0 && (A.outFrameStride & 3) == 0 &&
                         (A.outStreamStride & 3) == 0 && ((size_t)A.out & 15) == 0;
 
     // ---- delay lines.  Reference semantics (dsp_runtime.c:769-794): ring of n samples, frame f swaps with
     // position (idx0+f) mod n, so the output of frame f is the post value of frame f-n.  Here the post ring
-    // (R >= F + gmax + n steps of history) IS the delay line: the prologue preloads the n samples the
+    // (R >= 2F + gmax + n steps of history) IS the delay line: the prologue preloads the n samples the
     // reference ring holds as "virtual frames" -n..-1, the epilogue writes the last n back in ring layout.
     // A stale index idx0 >= n (delay shortened by reload_params) is used once by the reference and then
     // wraps to 0: frame 0 swaps with ring[idx0], frames >= 1 behave like idx0 = n-1.
+    bool anyStale = false;
     if (!prngOnly)
         for (int sl = ow; sl < nsHere; sl += nOwn) {
             int* st = A.state + (size_t)(s0 + sl) * W;
@@ -285,6 +350,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
                 const int* ring = st + d.delayOff + 1;
                 const int idx0 = st[d.delayOff];
                 const bool stale = idx0 >= n || idx0 < 0;
+                anyStale |= stale;
                 int* prow = post_s + (size_t)(sl * C + c) * G.postPitch;
                 for (int k = lane; k < n; k += 32) {          // virtual frame j = k - n feeds output frame k
                     int v;
@@ -302,16 +368,16 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
 
     // ---- input PCM tiles by TMA: lane 0 of every owner warp issues, two tiles ahead, one bulk copy per owned
     // stream (interleaved: F*nIn contiguous words) or per (stream, channel) (planar: F contiguous words) into
-    // raw_s; completion is counted in bytes on the warp's mbarrier of that parity.  Tiles that cannot go through
-    // TMA (partial last tile, misaligned caller buffers) are read with plain loads instead.
+    // the raw tiles; completion is counted in bytes on the warp's mbarrier of that parity.  Tiles that cannot go
+    // through TMA (partial last tile, misaligned caller buffers) are read with plain loads instead.
     const int nIn = P.h.nIn;
-    const int rowWords = F * nIn;
+    const int rowBytes = F * nIn * 4;
     const bool interleavedIn = A.inChStride == 1 && A.inFrameStride == nIn;
     const bool planarIn = A.inFrameStride == 1;
     const bool tmaOk = G.rawOff != 0 && nSrc > 0 && nIn > 0 && ((size_t)A.in & 15) == 0 && (A.inStreamStride & 3) == 0 &&
-                       ((interleavedIn && (rowWords & 3) == 0) || (planarIn && !interleavedIn && (A.inChStride & 3) == 0 && (F & 3) == 0));
-    const int rawFS = interleavedIn ? nIn : 1, rawCS = interleavedIn ? 1 : F;     // strides inside a staged tile
-    const unsigned mbar0 = smemAddr(mbar_s + 2 * hw);
+                       ((interleavedIn && (rowBytes & 15) == 0) || (planarIn && !interleavedIn && (A.inChStride & 3) == 0 && (F & 3) == 0));
+    const unsigned rawFB = interleavedIn ? nIn * 4 : 4, rawCB = interleavedIn ? 4 : F * 4;   // frame / channel stride (bytes) in a staged tile
+    const unsigned mbar0 = sb + G.mbarOff + 16 * hw;
     if (tmaOk && !prngOnly && lane == 0) { mbarInit(mbar0, 1); mbarInit(mbar0 + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
     auto tileUsesTma = [&](int it) { return tmaOk && (it + 1) * F <= T; };
@@ -323,11 +389,11 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
             int cnt = 0;
             for (int sl = ow; sl < nsHere; sl += nOwn) cnt++;
             const unsigned bar = mbar0 + 8 * (it & 1);
-            mbarExpectTx(bar, (unsigned)(cnt * rowWords * 4));
+            mbarExpectTx(bar, (unsigned)(cnt * rowBytes));
             for (int sl = ow; sl < nsHere; sl += nOwn) {
                 const int* src = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(it * F) * A.inFrameStride;
-                const unsigned dst = smemAddr(raw_s + (size_t)(sl * 2 + (it & 1)) * rowWords);
-                if (interleavedIn) tmaLoad1D(dst, src, (unsigned)(rowWords * 4), bar);
+                const unsigned dst = sb + G.rawOff + sl * G.rawStreamBytes + (it & 1) * rowBytes;
+                if (interleavedIn) tmaLoad1D(dst, src, (unsigned)rowBytes, bar);
                 else for (int ch = 0; ch < nIn; ch++) tmaLoad1D(dst + ch * F * 4, src + (size_t)ch * A.inChStride, (unsigned)(F * 4), bar);
             }
         }
@@ -337,8 +403,9 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
     auto sourceTile = [&](int it) {
         const int f0 = it * F;
         if (f0 >= T) return;
-        if (hw == 0 && lane < nsHere) {
-            int* row = tpdf_s + lane * G.tpdfPitch + (it & 3) * F;
+        if (G.debugSkip & 1) { issueTile(it + 2); return; }
+        if (hw == 0 && lane < nsHere && !(G.debugSkip & 2)) {
+            int* row = tpdf_s + lane * TP + (it & 3) * F;
             const int n = min(F, T - f0);
             if (hasCalc) {
                 for (int j = 0; j < n; j++) {
@@ -353,81 +420,134 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
         if (nSrc == 0 || prngOnly) return;
         const bool staged = tileUsesTma(it);
         if (staged) mbarWait(mbar0 + 8 * (it & 1), (unsigned)((it >> 1) & 1));
-        for (int u = lane; u < F; u += 32) {
-            const int f = f0 + u;
-            if (f >= T) continue;
-            for (int sl = ow; sl < nsHere; sl += nOwn) {
-                const int* in = staged ? raw_s + (size_t)(sl * 2 + (it & 1)) * rowWords + u * rawFS
-                                       : A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)f * A.inFrameStride;
-                const int cs = staged ? rawCS : A.inChStride;
-                for (int k = 0; k < nSrc; k++) {
-                    const ChainDesc& d = P.chains[P.h.srcChain[k]];
-                    const long long X = chainSource(P, d, in, cs);
-                    x_s[(size_t)(sl * nSrc + k) * G.xPitch + (it & 1) * F + u] = (int)(X >> kMantBQ);
+        if (lane < F && f0 + lane < T) {
+            unsigned xa = sb + G.xOff + ow * G.xStreamBytes + ((it & 1) * F + lane) * 4;
+            unsigned ra = sb + G.rawOff + ow * G.rawStreamBytes + (it & 1) * rowBytes + lane * rawFB;
+            for (int sl = ow; sl < nsHere; sl += nOwn, xa += nOwn * G.xStreamBytes, ra += nOwn * G.rawStreamBytes) {
+                const int* in = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(f0 + lane) * A.inFrameStride;
+                // flattened source tables with static indices: constant-bank operands, no descriptor loads
+#pragma unroll
+                for (int k = 0; k < kFastTab; k++) {
+                    if (k >= nSrc) break;                    // early exit: no chain of skipped-iteration tests
+                    {
+                        long long X;
+                        if (P.h.sKind[k] == SRC_LOAD_MUX) {
+                            const ChainDesc& d = P.chains[P.h.srcChain[k]];
+                            X = staged ? muxFromShared(P, d, ra, rawCB) : chainSource(P, d, in, A.inChStride);
+                        } else {
+                            int smp = 0;
+                            if (P.h.sCh[k] >= 0) smp = staged ? lds32(ra + P.h.sCh[k] * rawCB) : in[(size_t)P.h.sCh[k] * A.inChStride];
+                            X = (P.h.sKind[k] == SRC_LOAD_GAIN) ? mul32(smp, P.h.sArg[k]) : (long long)smp;
+                        }
+                        sts32(xa + G.srcXOff[k], q59ToS31(X));
+                    }
                 }
             }
         }
         issueTile(it + 2);                               // refill this parity's buffer two tiles ahead
     };
 
+    // ---- per-lane constants of the (frame-in-pass, channel) store mapping (interleaved output, F == 32)
+    const int nOut = P.h.nOut;
+    const bool laneOut = F == 32 && A.outChStride == 1 && A.outFrameStride == nOut && nOut <= 32;
+    const int fpp = laneOut ? 32 / nOut : 1;                  // frames per pass
+    const int fppWords = fpp * nOut;
+    const int nPass = (F + fpp - 1) / fpp;
+    constexpr int nPassMax = 16;                               // nOut <= kFastTab = 16  =>  fpp >= 2  =>  <= 16 passes
+    const int bCh = lane % nOut, bFs = lane / nOut;
+    const bool bOn = laneOut && bFs < fpp;
+    const int bChain = P.h.chainOfOut[bCh];
+    const unsigned bRow = bChain >= 0 ? (unsigned)(bChain * G.postPitch * 4) : 0u;
+    const unsigned bPos4 = (unsigned)((bFs + P.h.outOff[bCh]) * 4);
+    const int bMask = bChain >= 0 ? storeMask : 0;             // outputs no path writes read as 0
+
     // ---- sink stage of window `iw`
     auto sinkWindow = [&](int iw) {
-        if (prngOnly) return;
-        for (int sl = ow; sl < nsHere; sl += nOwn) {
-            int* st = A.state + (size_t)(s0 + sl) * W;
-            // A: step iw*F+u of every chain that needs post-processing: accumulator (or inline source) -> [gain] ->
-            //    saturate (+dither,+gain) -> post ring.  Direct chains were written by their tail lanes already.
-            for (int u = lane; u < F; u += 32) {
-                const int t = iw * F + u;
-                for (int k = 0; k < P.h.nProc; k++) {
-                    const int c = P.h.procChain[k];
-                    const ChainDesc& d = P.chains[c];
-                    const int gc = d.nsec > 0 ? d.nsec - 1 : 0;
-                    const int f = t - gc;
-                    if (f < 0 || f >= T) continue;
-                    long long X;
-                    if (d.nsec > 0) X = acc_s[(size_t)(sl * nAcc + d.accRow) * G.accPitch + (iw & 1) * F + u];
-                    else {
-                        X = chainSource(P, d, A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)f * A.inFrameStride, A.inChStride);
-                        if (d.srcKind == SRC_LOAD_MUX && f == T - 1) { st[d.muxStateOff] = (int)X; st[d.muxStateOff + 1] = (int)(X >> 32); }
+        if (prngOnly || lane >= F || (G.debugSkip & 4)) return;
+        const unsigned wmask = F == 32 ? 0xffffffffu : ((1u << (F & 31)) - 1u);
+        const int t = iw * F + lane;
+        const unsigned tpos4 = (unsigned)(t & RM) << 2, RM4 = (unsigned)RM << 2;
+        const int f = iw * F - gmax + lane;                  // the output frame this lane stores in phase B
+        const unsigned f4 = (unsigned)f << 2;
+        unsigned postA = sb + G.postOff + ow * G.postStreamBytes;
+        unsigned accA = sb + ow * G.accStreamBytes + ((iw & 1) * F + lane) * 8;
+        unsigned tpdfA = sb + G.tpdfOff + ow * G.tpdfStreamBytes;
+        for (int sl = ow; sl < nsHere; sl += nOwn, postA += nOwn * G.postStreamBytes, accA += nOwn * G.accStreamBytes, tpdfA += nOwn * G.tpdfStreamBytes) {
+            // A: step t of every chain that needs post-processing: accumulator (or inline source) -> [gain] -> saturate
+            //    (+dither, +gain) -> post ring (dsp_runtime.c:464-534, 636-640).  Direct chains were written by their tails.
+#pragma unroll
+            for (int k = 0; k < kFastTab; k++) {
+                if (k >= P.h.nProc) break;
+                {
+                    const int fk = t - P.h.pLag[k];
+                    if (fk >= 0 && fk < T) {
+                        const int flags = P.h.pFlags[k];
+                        long long X;
+                        if (flags & PF_SECTIONS) X = lds64(accA + G.pAccOff[k]);
+                        else {
+                            const ChainDesc& d = P.chains[P.h.pChain[k]];
+                            X = chainSource(P, d, A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)fk * A.inFrameStride, A.inChStride);
+                            if (d.srcKind == SRC_LOAD_MUX && fk == T - 1) {
+                                int* st = A.state + (size_t)(s0 + sl) * W;
+                                st[d.muxStateOff] = lo32(X); st[d.muxStateOff + 1] = hi32(X);
+                            }
+                        }
+                        if (flags & PF_GAIN) X = X * (long long)P.h.pGain[k];
+                        if (flags & PF_SAT_GAIN) { X >>= kMant; X = X * (long long)P.h.pSatGain[k]; }
+                        if (flags & PF_SAT_TPDF) X += tpdfScaledI(lds32(tpdfA + ((unsigned)(fk & (4 * F - 1)) << 2)), P.h.tpdfShift);
+                        const int v = (int)sat64_031(X);
+                        if (anyStale && fk == 0 && P.h.pDelayN[k] > 0 && stale_s[sl * C + P.h.pChain[k]] >= 0)
+                            A.state[(size_t)(s0 + sl) * W + P.chains[P.h.pChain[k]].delayOff + 1 + stale_s[sl * C + P.h.pChain[k]]] = v;
+                        else sts32(postA + G.pPostOff[k] + tpos4, v);
                     }
-                    if (d.hasGain) X = X * (long long)d.gainBits;
-                    if (d.satKind >= SAT_GAIN) { X >>= kMant; X = X * (long long)d.satGainBits; }
-                    if (d.satKind & 1) X += tpdfScaledI(tpdf_s[sl * G.tpdfPitch + (f & (4 * F - 1))], P.h.tpdfShift);
-                    const int v = (int)sat64_031(X);
-                    if (f == 0 && d.delayN > 0 && stale_s[sl * C + c] >= 0) st[d.delayOff + 1 + stale_s[sl * C + c]] = v;
-                    else post_s[(size_t)(sl * C + c) * G.postPitch + (t & RM)] = v;
                 }
             }
             // stale delay index on a direct chain (rare): its tail lane stored post(0) where the preloaded
             // ring[n-1] has to stay; move it to where the reference puts it (ring[idx0])
-            if (iw * F <= gmax && lane == 0)
+            if (anyStale && iw * F <= gmax && lane == 0)
                 for (int c = 0; c < C; c++) {
                     const ChainDesc& d = P.chains[c];
                     if (d.nsec > 0 && d.accRow < 0 && d.delayN > 0 && stale_s[sl * C + c] >= 0 && (d.nsec - 1) / F == iw) {
                         int* pr = post_s + (size_t)(sl * C + c) * G.postPitch + ((d.nsec - 1) & RM);
-                        st[d.delayOff + 1 + stale_s[sl * C + c]] = *pr;
+                        A.state[(size_t)(s0 + sl) * W + d.delayOff + 1 + stale_s[sl * C + c]] = *pr;
                         *pr = sfix_s[sl * C + c];
                     }
                 }
-            __syncwarp();
-            // B: frames [iw*F-gmax, +F): delayed read from the post ring + mask + store (16-byte stores when the layout allows)
-            for (int u = lane; u < F; u += 32) {
-                const int f = iw * F - gmax + u;
-                if (f < 0 || f >= T) continue;
+            __syncwarp(wmask);
+            // B: delayed read from the post ring + mask + store.
+            if (laneOut) {
+                // interleaved output: lane = (frame inside a pass, channel); the 32 lanes of a pass store one contiguous
+                // run of fpp frames.  Per-lane constants (row, lag-delay) sit in registers: no descriptor loads, no
+                // branches, and the passes are independent of each other.
+                const int fw0 = iw * F - gmax;
+                int* out = A.out + (size_t)(s0 + sl) * A.outStreamStride + (size_t)fw0 * A.outFrameStride + lane;
+                const unsigned rowA = postA + bRow;
+                const unsigned p4 = (unsigned)(fw0 << 2) + bPos4;           // 4*(step of this lane's element in pass 0)
+                if (fw0 >= 0 && fw0 + F <= T) {
+#pragma unroll
+                    for (int p = 0; p < nPassMax; p++) {
+                        if (p >= nPass) break;
+                        if (bOn && (p * fpp + bFs) < F) out[p * fppWords] = lds32(rowA + ((p4 + (unsigned)(p * fpp * 4)) & RM4)) & bMask;
+                    }
+                } else {
+                    for (int p = 0; p < nPass; p++) {
+                        const int fr = p * fpp + bFs, ff = fw0 + fr;
+                        if (bOn && fr < F && ff >= 0 && ff < T) out[p * fppWords] = lds32(rowA + ((p4 + (unsigned)(p * fpp * 4)) & RM4)) & bMask;
+                    }
+                }
+            } else if (f >= 0 && f < T) {
+                // any layout: lane = frame, 16-byte stores when the layout allows
                 int* out = A.out + (size_t)(s0 + sl) * A.outStreamStride + (size_t)f * A.outFrameStride;
-                for (int ch0 = 0; ch0 < P.h.nOut; ch0 += 4) {
+#pragma unroll
+                for (int ch0 = 0; ch0 < kFastTab; ch0 += 4) {
+                    if (ch0 >= P.h.nOut) break;
                     int val[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const int ch = ch0 + q;
-                        const int c = ch < P.h.nOut ? P.h.chainOfOut[ch] : -1;
-                        int v = 0;          // outputs no path writes read as 0 (io[] is zeroed at the start of every frame)
-                        if (c >= 0) {
-                            const ChainDesc& d = P.chains[c];
-                            const int gc = d.nsec > 0 ? d.nsec - 1 : 0;
-                            v = post_s[(size_t)(sl * C + c) * G.postPitch + ((f - d.delayN + gc) & RM)] & storeMask;
-                        }
+                        int v = 0;      // outputs no path writes read as 0 (io[] is zeroed at the start of every frame)
+                        if (ch < P.h.nOut && P.h.chainOfOut[ch] >= 0)
+                            v = lds32(postA + G.outRowOff[ch] + ((f4 + (unsigned)G.outPos4[ch]) & RM4)) & storeMask;
                         val[q] = v;
                     }
                     if (vecOut) *reinterpret_cast<int4*>(out + ch0) = make_int4(val[0], val[1], val[2], val[3]);
@@ -437,7 +557,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const Chain2Ge
                     }
                 }
             }
-            __syncwarp();
+            __syncwarp(wmask);
         }
     };
 
@@ -529,7 +649,9 @@ static int packLanes2(const ChainPlan& p, int NS, int K, ChainLane* out, int* gm
 }
 
 bool chain2Supports(const ChainPlan& plan) {
-    return plan.h.aluClass == ALU_INT64 && plan.h.nChains > 0 && plan.h.nOut > 0;
+    // the helper warps address everything through the flattened tables (plan.h: kFastTab entries each)
+    return plan.h.aluClass == ALU_INT64 && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nOut <= kFastTab &&
+           plan.h.nProc <= kFastTab && plan.h.nSrc <= kFastTab;
 }
 
 bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2Geom* geom, ChainLane* lanesOut) {
@@ -542,6 +664,8 @@ bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2G
     if (NS0 <= 0) NS0 = (nStreams + numSMs - 1) / numSMs;
     NS0 = std::max(1, std::min(NS0, 32));
     const int forceF = envInt2("AVDSP_B200_F", 0);
+    int maxDelay = 0;
+    for (int c = 0; c < C; c++) maxDelay = std::max(maxDelay, plan.chains[c].delayN);
     for (int NS = NS0; NS >= 1; NS--) {
         for (int F : {32, 16}) {
             if (forceF && F != forceF) continue;
@@ -556,20 +680,37 @@ bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2G
             Chain2Geom g{};
             g.streamsPerCta = NS; g.secPerLane = K; g.tileFrames = F; g.gmax = gm;
             g.secThreads = lt; g.helpThreads = help * 32;
-            int maxDelay = 0;
-            for (int c = 0; c < C; c++) maxDelay = std::max(maxDelay, plan.chains[c].delayN);
+            g.helpersFirst = envInt2("AVDSP_B200_HELPFIRST", 0);
+            g.debugSkip = envInt2("AVDSP_B200_DEBUG_SKIP", 0);     // timing experiments only: 1 source, 2 PRNG, 4 sink are skipped (wrong output)
             int R = 2 * F;
             while (R < 2 * F + gm + maxDelay) R <<= 1;      // tails write tile i while the sink still reads window i-1
             g.postRing = R;
             g.xPitch = 2 * F + 1; g.accPitch = 2 * F + 1; g.postPitch = R + 1; g.tpdfPitch = 4 * F + 1;
-            size_t bytes = (size_t)NS * plan.h.nAcc * g.accPitch * 8 +
-                           ((size_t)NS * plan.h.nSrc * g.xPitch + (size_t)slots * g.postPitch + (size_t)NS * g.tpdfPitch + 3 * slots) * 4;
+            g.accStreamBytes = plan.h.nAcc * g.accPitch * 8;
+            g.xStreamBytes = plan.h.nSrc * g.xPitch * 4;
+            g.postStreamBytes = C * g.postPitch * 4;
+            g.tpdfStreamBytes = g.tpdfPitch * 4;
+            g.rawStreamBytes = 2 * F * plan.h.nIn * 4;
+            size_t bytes = (size_t)NS * g.accStreamBytes;
+            g.xOff = (int)bytes;    bytes += (size_t)NS * g.xStreamBytes;
+            g.postOff = (int)bytes; bytes += (size_t)NS * g.postStreamBytes;
+            g.tpdfOff = (int)bytes; bytes += (size_t)NS * g.tpdfStreamBytes;
+            g.ridxOff = (int)bytes; bytes += (size_t)3 * slots * 4;
+            g.ckOff = (int)bytes;   bytes += (size_t)6 * K * lt * 4;        // section lanes' tile-start checkpoints
             bytes = (bytes + 15) & ~(size_t)15;
             g.mbarOff = (int)bytes; bytes += (size_t)help * 2 * 8;
             bytes = (bytes + 127) & ~(size_t)127;
             g.rawOff = plan.h.nSrc > 0 ? (int)bytes : 0;          // input tiles staged by TMA (only cascades read them)
-            if (plan.h.nSrc > 0) bytes += (size_t)NS * 2 * F * plan.h.nIn * 4;
+            if (plan.h.nSrc > 0) bytes += (size_t)NS * g.rawStreamBytes;
             g.smemBytes = bytes + 16;
+            for (int k = 0; k < kFastTab; k++) {
+                const int oc = k < plan.h.nOut ? plan.h.chainOfOut[k] : -1;
+                g.outRowOff[k] = oc >= 0 ? oc * g.postPitch * 4 : 0;
+                g.outPos4[k] = plan.h.outOff[k] * 4;
+                g.pPostOff[k] = k < plan.h.nProc ? plan.h.pChain[k] * g.postPitch * 4 : 0;
+                g.pAccOff[k] = (k < plan.h.nProc && plan.h.pAccRow[k] >= 0) ? plan.h.pAccRow[k] * g.accPitch * 8 : 0;
+                g.srcXOff[k] = k * g.xPitch * 4;
+            }
             if (g.secThreads + g.helpThreads <= 1024 && g.smemBytes <= 226 * 1024) {
                 *geom = g;
                 if (lanesOut) packLanes2(plan, NS, K, lanesOut, nullptr);

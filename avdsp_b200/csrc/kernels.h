@@ -60,9 +60,21 @@ struct Chain2Geom {
     int gmax;              // largest frame offset of a cascade tail (longest cascade - 1)
     int secThreads;        // threads that own sections (multiple of 32, may be 0)
     int helpThreads;       // source / sink / dither threads (multiple of 32, >= 32)
+    int helpersFirst;      // 1: helper warps get the low warp ids
+    int debugSkip;         // timing experiments only (AVDSP_B200_DEBUG_SKIP): bit0 skip sources, bit1 skip PRNG, bit2 skip sink
     int postRing;          // R: post ring length in steps (power of two >= F + gmax + longest delay)
     int xPitch, accPitch, postPitch, tpdfPitch;   // shared-memory row pitches (elements)
     int mbarOff, rawOff;   // byte offsets of the helper warps' mbarriers / the TMA-staged input tiles (0: none)
+    // shared-memory map in BYTES (acc ring at 0) and per-stream block sizes, so that the helper warps form
+    // every address with adds on constants instead of recomputing products of geometry values
+    int xOff, postOff, tpdfOff, ridxOff, ckOff;
+    int accStreamBytes, xStreamBytes, postStreamBytes, tpdfStreamBytes, rawStreamBytes;
+    // byte offsets inside one stream's block, by STATIC index (constant-bank operands):
+    int outRowOff[kFastTab];   // output channel j  -> its chain's post row
+    int outPos4[kFastTab];     // output channel j  -> 4*(cascade lag - delay)
+    int pPostOff[kFastTab];    // post-processed chain k -> its post row
+    int pAccOff[kFastTab];     // post-processed chain k -> its acc row
+    int srcXOff[kFastTab];     // source k -> its x row
     size_t smemBytes;
 };
 struct Chain2Args {

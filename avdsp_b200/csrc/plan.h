@@ -80,6 +80,8 @@ struct GenericPlan {
 constexpr int kMaxChains     = 48;
 constexpr int kMaxChainPool  = 2560;
 constexpr int kMaxChainStores = 4;
+constexpr int kFastTab       = 16;     // entries of the flattened helper tables (chain2 handles programs within them)
+enum { PF_SECTIONS = 1, PF_GAIN = 2, PF_SAT_TPDF = 4, PF_SAT_GAIN = 8 };
 
 enum ChainSrc : int { SRC_LOAD = 0, SRC_LOAD_GAIN = 1, SRC_LOAD_MUX = 2 };
 enum ChainSat : int { SAT_PLAIN = 0, SAT_TPDF = 1, SAT_GAIN = 2, SAT_TPDF_GAIN = 3 };
@@ -118,6 +120,11 @@ struct ChainHeader {
     int32_t nProc;                                  // chains the sink has to post-process (everything but direct chains)
     int32_t procChain[kMaxChains];
     int32_t chainOfOut[kIoSlots];                   // output channel -> chain (or -1: channel never written => 0)
+    int32_t outOff[kIoSlots];                       // output channel -> (cascade lag - delay): frame f is read from post-ring step f+outOff
+    // flattened copies of the descriptors the helper warps touch every tile, indexed by small STATIC indices so
+    // that they become constant-bank operands (no loads, no registers): post-processed chains and sources 0..7
+    int32_t pChain[kFastTab], pLag[kFastTab], pAccRow[kFastTab], pFlags[kFastTab], pGain[kFastTab], pSatGain[kFastTab], pDelayN[kFastTab];
+    int32_t sKind[kFastTab], sCh[kFastTab], sArg[kFastTab];
 };
 
 struct ChainPlan {
