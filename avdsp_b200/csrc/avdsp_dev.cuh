@@ -39,6 +39,15 @@ __device__ __forceinline__ long long sat64_031(long long a) {
     if (a < -lim) return (long long)0xFFFFFFFF80000000ull;
     return a >> kMant;
 }
+// the same as a 32-bit result, decided on the high word only: a >= 2^59 <=> hi >= 2^27, a < -2^59 <=> hi < -2^27
+// (one funnel shift + two compare/select pairs instead of two 64-bit comparisons)
+__device__ __forceinline__ int sat64_031_s32(long long a) {
+    const int lo = lo32(a), hi = hi32(a);
+    int v = (int)__funnelshift_r((unsigned)lo, (unsigned)hi, kMant);
+    v = hi >= (1 << (kMant - 1)) ? 0x7FFFFFFF : v;
+    v = hi < -(1 << (kMant - 1)) ? (int)0x80000000 : v;
+    return v;
+}
 
 // checkbiquadsat (dsp_biquadSTD.h:25-32): test on the high word only; the negative side clamps one
 // high-word step early (hi <= 1-2^27).

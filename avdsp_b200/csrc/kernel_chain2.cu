@@ -185,6 +185,23 @@ __device__ __forceinline__ long long muxFromShared(const ChainPlan& P, const Cha
     return X;
 }
 
+// Phase B of the sink for interleaved output with NOUT (power of two) channels: 32/NOUT frames per pass.
+template <int F, int NOUT>
+__device__ __forceinline__ void storePasses(int* __restrict__ out, unsigned rowA, unsigned p4, unsigned RM4, int mask,
+                                            bool clean, int fw0, int fs, int T) {
+    constexpr int FPP = 32 / NOUT, NPASS = F / FPP;
+    if (clean) {
+#pragma unroll
+        for (int p = 0; p < NPASS; p++) out[p * 32] = lds32(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4)) & mask;
+    } else {
+#pragma unroll 1
+        for (int p = 0; p < NPASS; p++) {
+            const int ff = fw0 + p * FPP + fs;
+            if (ff >= 0 && ff < T) out[p * 32] = lds32(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4)) & mask;
+        }
+    }
+}
+
 template <int K, int F>
 __global__ void __launch_bounds__(1024, 1)
 k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_constant__ Chain2Geom G) {
@@ -447,15 +464,15 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         issueTile(it + 2);                               // refill this parity's buffer two tiles ahead
     };
 
+    bool simpleA = !anyStale && !(G.debugSkip & 8);             // all post-processed chains are cascade -> SAT0DB_TPDF
+    for (int k = 0; k < P.h.nProc && k < kFastTab; k++) simpleA = simpleA && P.h.pFlags[k] == (PF_SECTIONS | PF_SAT_TPDF);
+    const bool tpdfUp = P.h.tpdfShift >= 0;                    // warp-uniform: the dither is shifted up (usual) or down
+    const int tpdfSh = (tpdfUp ? P.h.tpdfShift : -P.h.tpdfShift) & 63;
     // ---- per-lane constants of the (frame-in-pass, channel) store mapping (interleaved output, F == 32)
     const int nOut = P.h.nOut;
-    const bool laneOut = F == 32 && A.outChStride == 1 && A.outFrameStride == nOut && nOut <= 32;
+    const bool laneOut = F == 32 && A.outChStride == 1 && A.outFrameStride == nOut && nOut <= 16 && (nOut & (nOut - 1)) == 0;
     const int fpp = laneOut ? 32 / nOut : 1;                  // frames per pass
-    const int fppWords = fpp * nOut;
-    const int nPass = (F + fpp - 1) / fpp;
-    constexpr int nPassMax = 16;                               // nOut <= kFastTab = 16  =>  fpp >= 2  =>  <= 16 passes
     const int bCh = lane % nOut, bFs = lane / nOut;
-    const bool bOn = laneOut && bFs < fpp;
     const int bChain = P.h.chainOfOut[bCh];
     const unsigned bRow = bChain >= 0 ? (unsigned)(bChain * G.postPitch * 4) : 0u;
     const unsigned bPos4 = (unsigned)((bFs + P.h.outOff[bCh]) * 4);
@@ -475,9 +492,20 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         for (int sl = ow; sl < nsHere; sl += nOwn, postA += nOwn * G.postStreamBytes, accA += nOwn * G.accStreamBytes, tpdfA += nOwn * G.tpdfStreamBytes) {
             // A: step t of every chain that needs post-processing: accumulator (or inline source) -> [gain] -> saturate
             //    (+dither, +gain) -> post ring (dsp_runtime.c:464-534, 636-640).  Direct chains were written by their tails.
+            if (simpleA && iw * F >= gmax && (iw + 1) * F <= T) {
+                // common case, branch-free: every post-processed chain is cascade -> SAT0DB_TPDF and the window is interior
+#pragma unroll
+                for (int k = 0; k < kFastTab; k++) {
+                    if (k >= P.h.nProc) break;
+                    long long X = lds64(accA + G.pAccOff[k]);
+                    const long long tv = lds32(tpdfA + ((unsigned)((t - P.h.pLag[k]) & (4 * F - 1)) << 2));
+                    X += tpdfUp ? (long long)((unsigned long long)tv << tpdfSh) : (tv >> tpdfSh);
+                    sts32(postA + G.pPostOff[k] + tpos4, sat64_031_s32(X));
+                }
+            } else
 #pragma unroll
             for (int k = 0; k < kFastTab; k++) {
-                if (k >= P.h.nProc) break;
+                if (k >= P.h.nProc || (G.debugSkip & 8)) break;
                 {
                     const int fk = t - P.h.pLag[k];
                     if (fk >= 0 && fk < T) {
@@ -494,8 +522,11 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         }
                         if (flags & PF_GAIN) X = X * (long long)P.h.pGain[k];
                         if (flags & PF_SAT_GAIN) { X >>= kMant; X = X * (long long)P.h.pSatGain[k]; }
-                        if (flags & PF_SAT_TPDF) X += tpdfScaledI(lds32(tpdfA + ((unsigned)(fk & (4 * F - 1)) << 2)), P.h.tpdfShift);
-                        const int v = (int)sat64_031(X);
+                        if (flags & PF_SAT_TPDF) {
+                            const long long tv = lds32(tpdfA + ((unsigned)(fk & (4 * F - 1)) << 2));
+                            X += tpdfUp ? (long long)((unsigned long long)tv << tpdfSh) : (tv >> tpdfSh);      // dspTpdfApply, dsp_tpdf.h:141-145
+                        }
+                        const int v = sat64_031_s32(X);
                         if (anyStale && fk == 0 && P.h.pDelayN[k] > 0 && stale_s[sl * C + P.h.pChain[k]] >= 0)
                             A.state[(size_t)(s0 + sl) * W + P.chains[P.h.pChain[k]].delayOff + 1 + stale_s[sl * C + P.h.pChain[k]]] = v;
                         else sts32(postA + G.pPostOff[k] + tpos4, v);
@@ -515,25 +546,22 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 }
             __syncwarp(wmask);
             // B: delayed read from the post ring + mask + store.
-            if (laneOut) {
-                // interleaved output: lane = (frame inside a pass, channel); the 32 lanes of a pass store one contiguous
-                // run of fpp frames.  Per-lane constants (row, lag-delay) sit in registers: no descriptor loads, no
-                // branches, and the passes are independent of each other.
+            if (G.debugSkip & 16) {
+            } else if (laneOut) {
+                // interleaved output, power-of-two channel count: lane = (frame inside a pass, channel); the 32 lanes of a
+                // pass store one contiguous 128-byte run.  Per-lane constants (row, lag-delay) sit in registers and the
+                // pass geometry is a template constant: a pass is add / and / add / LDS / and / STG with immediate offsets.
                 const int fw0 = iw * F - gmax;
                 int* out = A.out + (size_t)(s0 + sl) * A.outStreamStride + (size_t)fw0 * A.outFrameStride + lane;
                 const unsigned rowA = postA + bRow;
-                const unsigned p4 = (unsigned)(fw0 << 2) + bPos4;           // 4*(step of this lane's element in pass 0)
-                if (fw0 >= 0 && fw0 + F <= T) {
-#pragma unroll
-                    for (int p = 0; p < nPassMax; p++) {
-                        if (p >= nPass) break;
-                        if (bOn && (p * fpp + bFs) < F) out[p * fppWords] = lds32(rowA + ((p4 + (unsigned)(p * fpp * 4)) & RM4)) & bMask;
-                    }
-                } else {
-                    for (int p = 0; p < nPass; p++) {
-                        const int fr = p * fpp + bFs, ff = fw0 + fr;
-                        if (bOn && fr < F && ff >= 0 && ff < T) out[p * fppWords] = lds32(rowA + ((p4 + (unsigned)(p * fpp * 4)) & RM4)) & bMask;
-                    }
+                const unsigned p4 = (unsigned)(fw0 << 2) + bPos4;           // 4*(post-ring step of this lane's element in pass 0)
+                const bool clean = fw0 >= 0 && fw0 + F <= T;
+                switch (nOut) {
+                case 1:  storePasses<F, 1>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                case 2:  storePasses<F, 2>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                case 4:  storePasses<F, 4>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                case 8:  storePasses<F, 8>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                default: storePasses<F, 16>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
                 }
             } else if (f >= 0 && f < T) {
                 // any layout: lane = frame, 16-byte stores when the layout allows
