@@ -416,6 +416,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         }
     };
 
+    bool simpleSrc = true;                                  // every source is LOAD_GAIN of a fed input
+    for (int k = 0; k < nSrc && k < kFastTab; k++) simpleSrc = simpleSrc && P.h.sKind[k] == SRC_LOAD_GAIN && P.h.sCh[k] >= 0;
     // ---- source stage of tile `it`: frames [it*F, it*F+F) -> x ring (one value per distinct source), dither values
     auto sourceTile = [&](int it) {
         const int f0 = it * F;
@@ -442,6 +444,16 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
             unsigned ra = sb + G.rawOff + ow * G.rawStreamBytes + (it & 1) * rowBytes + lane * rawFB;
             for (int sl = ow; sl < nsHere; sl += nOwn, xa += nOwn * G.xStreamBytes, ra += nOwn * G.rawStreamBytes) {
                 const int* in = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(f0 + lane) * A.inFrameStride;
+                if (simpleSrc && staged) {
+                    // common case, branch-free: LOAD_GAIN sources read from the TMA-staged tile
+#pragma unroll
+                    for (int k = 0; k < kFastTab; k++) {
+                        if (k >= nSrc) break;
+                        const int smp = lds32(ra + (interleavedIn ? (unsigned)(P.h.sCh[k] * 4) : (unsigned)(P.h.sCh[k] * F * 4)));
+                        sts32(xa + G.srcXOff[k], q59ToS31(mul32(smp, P.h.sArg[k])));
+                    }
+                    continue;
+                }
                 // flattened source tables with static indices: constant-bank operands, no descriptor loads
 #pragma unroll
                 for (int k = 0; k < kFastTab; k++) {
