@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -49,17 +50,18 @@ __global__ void k_init_state(int* __restrict__ state, int W, int auxOff, int mem
     for (int k = 0; k < 2 * nMem; k++) st[memOff + k] = memInit[k];
 }
 
-// integer-pipe microbenchmark: 8 independent chains of DATA-DEPENDENT mad.wide.s32 per thread (the
-// multiplicand is the running accumulator's low word, so nothing can be hoisted or strength-reduced)
+// integer-pipe microbenchmark: 8 independent chains of DATA-DEPENDENT accumulating IMAD.WIDE per thread (the
+// multiplicand is the running accumulator's low word, so nothing can be hoisted or strength-reduced).  Same
+// kernel as tools/microbench_int.cu mode 0; SASS: one IMAD.WIDE R, R, R, R per MAC.
+__device__ __forceinline__ int peakLo32(long long v) { int l, h2; asm("mov.b64 {%0,%1}, %2;" : "=r"(l), "=r"(h2) : "l"(v)); (void)h2; return l; }
 __global__ void __launch_bounds__(256) k_int_peak(long long* out, int iters, int a0, int b0) {
     long long acc[8];
     const int b = b0 + (int)blockIdx.x;
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = a0 + k + (int)threadIdx.x;
+    for (int k = 0; k < 8; k++) acc[k] = (long long)(a0 + k + (int)threadIdx.x) * 0x100000001ll;
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-            asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((int)acc[k]), "r"(b));
+        for (int k = 0; k < 8; k++) acc[k] = acc[k] + (long long)peakLo32(acc[k]) * (long long)b;
     }
     long long s = 0;
 #pragma unroll
@@ -91,6 +93,7 @@ struct avdsp_b200 {
     int* slotIn[kSlots] = {nullptr, nullptr, nullptr};
     int* slotOut[kSlots] = {nullptr, nullptr, nullptr};
     size_t slotInWords = 0, slotOutWords = 0;
+    cudaEvent_t evIn[kSlots] = {nullptr, nullptr, nullptr}, evKernel[kSlots] = {nullptr, nullptr, nullptr}, evOut[kSlots] = {nullptr, nullptr, nullptr};
     std::string trace;
 };
 
@@ -177,6 +180,9 @@ static void freeAll(avdsp_b200* h) {
         if (h->slotIn[k]) cudaFree(h->slotIn[k]);
         if (h->slotOut[k]) cudaFree(h->slotOut[k]);
         if (h->slotStream[k]) cudaStreamDestroy(h->slotStream[k]);
+        if (h->evIn[k]) cudaEventDestroy(h->evIn[k]);
+        if (h->evKernel[k]) cudaEventDestroy(h->evKernel[k]);
+        if (h->evOut[k]) cudaEventDestroy(h->evOut[k]);
     }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -271,18 +277,19 @@ const char* avdsp_b200_trace(const avdsp_b200_t* h) { return h ? h->trace.c_str(
 // One launch over streams [first, first+n) with device buffers.  coreSel/plan override serve the
 // dspRuntime_<fmt> compatibility path.
 static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int layout, int first, int n,
-                       cudaStream_t stream, int coreSel = -1, const GenericPlan* planOverride = nullptr) {
+                       cudaStream_t stream, int coreSel = -1, const GenericPlan* planOverride = nullptr, int cap = 0) {
     if (nFrames == 0 || n == 0) return 0;
     const GenericPlan& G = planOverride ? *planOverride : h->L.gen;
     const PlanHeader& P = G.h;
     const int nIn = P.nIn, nOut = P.nOut;
+    if (cap <= 0) cap = nFrames;            // frames the buffers are laid out for (>= nFrames: staging slots are reused for a shorter last chunk)
     long long inSS, outSS; int inFS, inCS, outFS, outCS;
     if (layout == AVDSP_B200_INTERLEAVED) {
-        inSS = (long long)nFrames * nIn; inFS = nIn; inCS = 1;
-        outSS = (long long)nFrames * nOut; outFS = nOut; outCS = 1;
+        inSS = (long long)cap * nIn; inFS = nIn; inCS = 1;
+        outSS = (long long)cap * nOut; outFS = nOut; outCS = 1;
     } else if (layout == AVDSP_B200_PLANAR) {
-        inSS = (long long)nFrames * nIn; inFS = 1; inCS = nFrames;
-        outSS = (long long)nFrames * nOut; outFS = 1; outCS = nFrames;
+        inSS = (long long)cap * nIn; inFS = 1; inCS = cap;
+        outSS = (long long)cap * nOut; outFS = 1; outCS = cap;
     } else return setErr(AVDSP_B200_ERR_ARG, "unknown layout");
     int* st = h->dState + (size_t)first * P.stateWords;
     const bool chainOrder = h->period == 0 && coreSel < 0 && !planOverride;
@@ -329,7 +336,12 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
 
 static int ensureSlots(avdsp_b200* h, size_t inWords, size_t outWords) {
     for (int k = 0; k < avdsp_b200::kSlots; k++)
-        if (!h->slotStream[k]) CU(cudaStreamCreateWithFlags(&h->slotStream[k], cudaStreamNonBlocking));
+        if (!h->slotStream[k]) {
+            CU(cudaStreamCreateWithFlags(&h->slotStream[k], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&h->evIn[k], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->evKernel[k], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->evOut[k], cudaEventDisableTiming));
+        }
     if (inWords > h->slotInWords) {
         for (int k = 0; k < avdsp_b200::kSlots; k++) { if (h->slotIn[k]) cudaFree(h->slotIn[k]); h->slotIn[k] = nullptr; }
         for (int k = 0; k < avdsp_b200::kSlots; k++) CU(cudaMalloc(&h->slotIn[k], inWords * 4));
@@ -371,29 +383,52 @@ int avdsp_b200_process(avdsp_b200_t* h, const void* in, void* out, int nFrames, 
         return 0;
     }
     if (memspace != AVDSP_B200_HOST) return setErr(AVDSP_B200_ERR_ARG, "unknown memspace");
-    // Host buffers: streams are independent and both layouts are stream-major, so the batch is cut into
-    // groups of streams that flow through kSlots staging buffers: copy-in, kernel and copy-out of
-    // successive groups overlap on separate CUDA streams (PCIe both directions + SMs busy at once).
+    // Host buffers.  The time loop of a launch is sequential, so cutting the batch by streams would only shrink
+    // the grid; the batch is cut in TIME instead: chunk c of every stream is copied in (one strided 2-D DMA),
+    // processed by one launch over all streams, and copied out, through kSlots staging buffers.  Three CUDA
+    // streams (copy-in, compute, copy-out) linked by events keep PCIe in both directions and the SMs busy at
+    // once; launches stay in order on the compute stream because chunk c+1 continues chunk c's state.
     const PlanHeader& P = h->L.gen.h;
     if ((!in && P.nIn) || (!out && P.nOut)) return setErr(AVDSP_B200_ERR_ARG, "NULL buffer");
-    const size_t inPer = (size_t)nFrames * P.nIn, outPer = (size_t)nFrames * P.nOut;   // words per stream
-    const size_t perStream = std::max<size_t>(inPer + outPer, 1);
-    size_t grp = std::max<size_t>(1, ((size_t)64 << 20) / perStream);                 // ~256 MB per group
-    grp = std::min<size_t>(grp, (size_t)h->nStreams);
-    if ((size_t)h->nStreams > grp && grp >= 64) grp = grp / 32 * 32;
-    const int r0 = ensureSlots(h, std::max<size_t>(grp * inPer, 1), std::max<size_t>(grp * outPer, 1));
+    const size_t S = (size_t)h->nStreams;
+    const size_t perFrame = std::max<size_t>((size_t)(P.nIn + P.nOut) * S, 1);       // words per frame over all streams
+    long long chunk = (long long)(((size_t)96 << 20) / perFrame);                     // ~384 MB of PCM per chunk
+    chunk = std::max<long long>(256, chunk / 256 * 256);
+    if (const char* ev = getenv("AVDSP_B200_HOST_CHUNK")) { const long long v = atoll(ev); if (v > 0) chunk = v; }   // tests: force several chunks
+    if (chunk > nFrames) chunk = nFrames;
+    const int r0 = ensureSlots(h, std::max<size_t>(S * chunk * P.nIn, 1), std::max<size_t>(S * chunk * P.nOut, 1));
     if (r0 < 0) return r0;
+    cudaStream_t sIn = h->slotStream[0], sK = h->slotStream[1], sOut = h->slotStream[2];
     const int32_t* hin = (const int32_t*)in; int32_t* hout = (int32_t*)out;
+    // rows of the 2-D copies: one per stream (interleaved) or per (stream, channel) (planar)
+    const bool il = layout == AVDSP_B200_INTERLEAVED;
+    if (!il && layout != AVDSP_B200_PLANAR) return setErr(AVDSP_B200_ERR_ARG, "unknown layout");
+    const size_t inRows = il ? S : S * P.nIn, outRows = il ? S : S * P.nOut;
+    const size_t inRowW = il ? P.nIn : 1, outRowW = il ? P.nOut : 1;                   // words per frame inside a row
     int slot = 0;
-    for (size_t s0 = 0; s0 < (size_t)h->nStreams; s0 += grp, slot = (slot + 1) % avdsp_b200::kSlots) {
-        const size_t n = std::min(grp, (size_t)h->nStreams - s0);
-        cudaStream_t cs = h->slotStream[slot];
-        if (inPer) CU(cudaMemcpyAsync(h->slotIn[slot], hin + s0 * inPer, n * inPer * 4, cudaMemcpyHostToDevice, cs));
-        const int r = launchRange(h, h->slotIn[slot], h->slotOut[slot], nFrames, layout, (int)s0, (int)n, cs);
+    for (long long f0 = 0; f0 < nFrames; f0 += chunk, slot = (slot + 1) % avdsp_b200::kSlots) {
+        const int nf = (int)std::min<long long>(chunk, nFrames - f0);
+        // slot reuse: the copy-in may overwrite slotIn only after the launch that read it, and the launch may overwrite
+        // slotOut only after its copy-out
+        CU(cudaStreamWaitEvent(sIn, h->evKernel[slot], 0));
+        if (P.nIn)
+            CU(cudaMemcpy2DAsync(h->slotIn[slot], (size_t)chunk * inRowW * 4, hin + (size_t)f0 * inRowW, (size_t)nFrames * inRowW * 4,
+                                 (size_t)nf * inRowW * 4, inRows, cudaMemcpyHostToDevice, sIn));
+        CU(cudaEventRecord(h->evIn[slot], sIn));
+        CU(cudaStreamWaitEvent(sK, h->evIn[slot], 0));
+        CU(cudaStreamWaitEvent(sK, h->evOut[slot], 0));
+        const int r = launchRange(h, h->slotIn[slot], h->slotOut[slot], nf, layout, 0, h->nStreams, sK, -1, nullptr, (int)chunk);
         if (r < 0) return r;
-        if (outPer) CU(cudaMemcpyAsync(hout + s0 * outPer, h->slotOut[slot], n * outPer * 4, cudaMemcpyDeviceToHost, cs));
+        CU(cudaEventRecord(h->evKernel[slot], sK));
+        CU(cudaStreamWaitEvent(sOut, h->evKernel[slot], 0));
+        if (P.nOut)
+            CU(cudaMemcpy2DAsync(hout + (size_t)f0 * outRowW, (size_t)nFrames * outRowW * 4, h->slotOut[slot], (size_t)chunk * outRowW * 4,
+                                 (size_t)nf * outRowW * 4, outRows, cudaMemcpyDeviceToHost, sOut));
+        CU(cudaEventRecord(h->evOut[slot], sOut));
     }
-    for (int k = 0; k < avdsp_b200::kSlots; k++) CU(cudaStreamSynchronize(h->slotStream[k]));
+    CU(cudaStreamSynchronize(sOut));
+    CU(cudaStreamSynchronize(sK));
+    CU(cudaStreamSynchronize(sIn));
     return 0;
 }
 

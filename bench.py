@@ -116,7 +116,7 @@ def run_reference(args, wl):
         return
     cores = os.cpu_count() or 1
     # bounded sample of the workload per step: one stream per host core, `fr` frames each (~1-2 s per step)
-    fr = min(T, 400000) if args.frames is None else args.frames
+    fr = 1500000 if args.frames is None else args.frames       # bounded sample: ~0.6 s per host thread per step
     for _ in range(args.warmup):
         cpu_reference_rate(prog, fmt, fs, max(1000, fr // 20), cores)
     tot_frames, tot_s, kind, n_out = 0.0, 0.0, "reference", 8
@@ -260,7 +260,7 @@ def main():
     cpu = None
     if not args.no_cpu:
         cores = os.cpu_count() or 1
-        fr = 400000
+        fr = 3000000                    # ~1-1.5 s per host thread, ~20 core-seconds in total
         r = cpu_reference_rate(prog, fmt, fs, fr, cores)
         cpu = {"value": r["frames_per_s"] * r["n_out"] / 1e6, "unit": "Msps", "cores": r["cores"], "kind": r["kind"],
                "sample": f"{r['workers']} streams x {fr} frames of the same program and PCM recipe, one stream per host thread, "

@@ -155,6 +155,21 @@ def _plugin_program():
     return a.end()
 
 
+def test_host_path_time_chunk_pipeline(oracle_lib, monkeypatch):
+    """avdsp_b200_process with HOST buffers cuts the call into time chunks (copy-in / launch / copy-out pipeline):
+    forcing small, ragged chunks must not change a bit, in both layouts."""
+    w = load_program("c2_testrpi_xover_f2_192k")
+    S, T = 19, 701
+    x = synth.pcm("full", S, T, 2, 192000)
+    ys, _ = oracle_run(oracle_lib, w, 2, 192000, x, np.zeros(S, np.int32), 31)
+    monkeypatch.setenv("AVDSP_B200_HOST_CHUNK", "96")
+    ex = Executor(w, 192000, 2, S)
+    assert np.array_equal(ex.process(x), ys)
+    ex2 = Executor(w, 192000, 2, S)
+    yp = ex2.process(np.ascontiguousarray(x.transpose(0, 2, 1)), layout=PLANAR)
+    assert np.array_equal(yp.transpose(0, 2, 1), ys)
+
+
 def test_plugin_order_mode(oracle_lib):
     """core-major loop nest of linux/avdsp_plugin.c:95-142 with a given period."""
     fs, S, T, period = 48000, 3, 500, 128
