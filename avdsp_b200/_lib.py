@@ -17,7 +17,7 @@ SYMBOLS = [
     "dspRuntime_2", "dspRuntime_3", "dspRuntime_4", "dspRuntime_5", "dspRuntime_6",
     "dspQNM", "dspQM64", "dspQM32", "dspOpcodeText",
     "avdsp_b200_create", "avdsp_b200_destroy", "avdsp_b200_reset", "avdsp_b200_io_map",
-    "avdsp_b200_process", "avdsp_b200_process_async", "avdsp_b200_process_range",
+    "avdsp_b200_process", "avdsp_b200_process_async", "avdsp_b200_process_range", "avdsp_b200_process_pcm",
     "avdsp_b200_set_order", "avdsp_b200_set_kernel", "avdsp_b200_last_kernel", "avdsp_b200_launch_count",
     "avdsp_b200_reload_params", "avdsp_b200_state_words", "avdsp_b200_data_size", "avdsp_b200_aux_offset",
     "avdsp_b200_mem_offset", "avdsp_b200_num_mem", "avdsp_b200_mem_word", "avdsp_b200_get_state",
@@ -57,6 +57,7 @@ def lib():
     L.avdsp_b200_io_map.argtypes = [vp, pi, pi, pi, pi]
     L.avdsp_b200_process.argtypes = [vp, vp, vp, ci, ci, ci]
     L.avdsp_b200_process_async.argtypes = [vp, vp, vp, ci, ci, vp]
+    L.avdsp_b200_process_pcm.argtypes = [vp, vp, ci, vp, ci, ci]
     L.avdsp_b200_process_range.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp]
     L.avdsp_b200_set_order.argtypes = [vp, ci]
     L.avdsp_b200_set_kernel.argtypes = [vp, ci]

@@ -69,6 +69,16 @@ __global__ void __launch_bounds__(256) k_int_peak(long long* out, int iters, int
     if (s == 0x123456789abcdefll) out[0] = s;     // practically never true; keeps the chains alive
 }
 
+// ALSA sample formats -> s.31 (linux/avdsp_plugin.c:109-121)
+__global__ void k_widen_pcm(const unsigned char* __restrict__ src, int fmt, int* __restrict__ dst, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v;
+    if (fmt == AVDSP_B200_PCM_S16) v = (int)((const short*)src)[i] << 16;
+    else { const unsigned char* p = src + 3 * i; v = (int)(((unsigned)p[0] << 8) | ((unsigned)p[1] << 16) | ((unsigned)p[2] << 24)); }
+    dst[i] = v;
+}
+
 struct avdsp_b200 {
     int device = 0, numSMs = 148;
     int nStreams = 0;
@@ -94,6 +104,7 @@ struct avdsp_b200 {
     int* slotOut[kSlots] = {nullptr, nullptr, nullptr};
     size_t slotInWords = 0, slotOutWords = 0;
     cudaEvent_t evIn[kSlots] = {nullptr, nullptr, nullptr}, evKernel[kSlots] = {nullptr, nullptr, nullptr}, evOut[kSlots] = {nullptr, nullptr, nullptr};
+    void* pcmRaw = nullptr; int* pcmIn = nullptr; int* pcmOut = nullptr; size_t pcmRawBytes = 0, pcmInWords = 0, pcmOutWords = 0;
     std::string trace;
 };
 
@@ -176,6 +187,9 @@ static void freeAll(avdsp_b200* h) {
     if (h->dSeeds) cudaFree(h->dSeeds);
     if (h->dLanes) cudaFree(h->dLanes);
     if (h->dLanes2) cudaFree(h->dLanes2);
+    if (h->pcmRaw) cudaFree(h->pcmRaw);
+    if (h->pcmIn) cudaFree(h->pcmIn);
+    if (h->pcmOut) cudaFree(h->pcmOut);
     for (int k = 0; k < avdsp_b200::kSlots; k++) {
         if (h->slotIn[k]) cudaFree(h->slotIn[k]);
         if (h->slotOut[k]) cudaFree(h->slotOut[k]);
@@ -429,6 +443,37 @@ int avdsp_b200_process(avdsp_b200_t* h, const void* in, void* out, int nFrames, 
     CU(cudaStreamSynchronize(sOut));
     CU(cudaStreamSynchronize(sK));
     CU(cudaStreamSynchronize(sIn));
+    return 0;
+}
+
+int avdsp_b200_process_pcm(avdsp_b200_t* h, const void* in, int pcmFormat, void* out, int nFrames, int memspace) {
+    if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
+    if (pcmFormat == AVDSP_B200_PCM_S32) return avdsp_b200_process(h, in, out, nFrames, AVDSP_B200_INTERLEAVED, memspace);
+    if (pcmFormat != AVDSP_B200_PCM_S16 && pcmFormat != AVDSP_B200_PCM_S24_3LE) return setErr(AVDSP_B200_ERR_ARG, "unknown PCM format");
+    if (nFrames < 0) return setErr(AVDSP_B200_ERR_ARG, "negative frame count");
+    if (nFrames == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    const PlanHeader& P = h->L.gen.h;
+    const size_t nIn = (size_t)h->nStreams * nFrames * P.nIn, nOut = (size_t)h->nStreams * nFrames * P.nOut;
+    const size_t rawBytes = nIn * (pcmFormat == AVDSP_B200_PCM_S16 ? 2 : 3);
+    if (nIn > h->pcmInWords) { if (h->pcmIn) cudaFree(h->pcmIn); h->pcmIn = nullptr; CU(cudaMalloc(&h->pcmIn, std::max<size_t>(nIn, 1) * 4)); h->pcmInWords = nIn; }
+    const unsigned char* raw = (const unsigned char*)in;
+    if (memspace == AVDSP_B200_HOST) {
+        if (rawBytes > h->pcmRawBytes) { if (h->pcmRaw) cudaFree(h->pcmRaw); h->pcmRaw = nullptr; CU(cudaMalloc(&h->pcmRaw, std::max<size_t>(rawBytes, 1))); h->pcmRawBytes = rawBytes; }
+        if (nOut > h->pcmOutWords) { if (h->pcmOut) cudaFree(h->pcmOut); h->pcmOut = nullptr; CU(cudaMalloc(&h->pcmOut, std::max<size_t>(nOut, 1) * 4)); h->pcmOutWords = nOut; }
+        CU(cudaMemcpyAsync(h->pcmRaw, in, rawBytes, cudaMemcpyHostToDevice, h->stream));
+        raw = (const unsigned char*)h->pcmRaw;
+    } else if (memspace != AVDSP_B200_DEVICE) return setErr(AVDSP_B200_ERR_ARG, "unknown memspace");
+    if (nIn) {
+        k_widen_pcm<<<(unsigned)((nIn + 255) / 256), 256, 0, h->stream>>>(raw, pcmFormat, h->pcmIn, nIn);
+        CU(cudaGetLastError());
+        h->launches++;
+    }
+    int* dout = memspace == AVDSP_B200_HOST ? h->pcmOut : (int*)out;
+    const int r = launchRange(h, h->pcmIn, dout, nFrames, AVDSP_B200_INTERLEAVED, 0, h->nStreams, h->stream);
+    if (r < 0) return r;
+    if (memspace == AVDSP_B200_HOST && nOut) CU(cudaMemcpyAsync(out, h->pcmOut, nOut * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

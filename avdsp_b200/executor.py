@@ -16,6 +16,7 @@ from . import _lib
 INTERLEAVED, PLANAR = 0, 1
 HOST, DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CHAIN, KERNEL_CHAIN_V1 = 0, 1, 2, 3
+PCM_S32, PCM_S16, PCM_S24_3LE = 0, 1, 2
 KERNEL_NAMES = {0: "none", 1: "generic", 2: "chain", 3: "chain_v1"}
 
 
@@ -137,6 +138,14 @@ class Executor:
         y = torch.empty(so, dtype=torch.int32, device=x.device) if out is None else out
         stream = torch.cuda.current_stream(x.device).cuda_stream
         _check(self._L.avdsp_b200_process_async(self._h, x.data_ptr(), y.data_ptr(), n_frames, layout, stream))
+        return y
+
+    def process_pcm(self, raw: np.ndarray, pcm_format: int, n_frames: int) -> np.ndarray:
+        """ALSA sample formats (linux/avdsp_plugin.c:109-121): raw = interleaved S16_LE (int16 array) or S24_3LE
+        (uint8 array, 3 bytes per sample) or S32 frames of all streams; returns int32 [S, T, nOut]."""
+        raw = np.ascontiguousarray(raw)
+        y = np.empty((self.n_streams, n_frames, self.n_out), dtype=np.int32)
+        _check(self._L.avdsp_b200_process_pcm(self._h, raw.ctypes.data, pcm_format, y.ctypes.data, n_frames, HOST))
         return y
 
     def process_pinned(self, x_host, y_host, layout: int = INTERLEAVED):

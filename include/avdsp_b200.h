@@ -118,6 +118,12 @@ int  avdsp_b200_process_async(avdsp_b200_t *, const void *in, void *out, int nFr
 int  avdsp_b200_process_range(avdsp_b200_t *, const void *in, void *out, int nFrames, int layout,
                               int firstStream, int nStreams, void *cudaStream);
 
+/* The ALSA plugin's input formats (linux/avdsp_plugin.c:109-121): interleaved S16_LE / S24_3LE / S32_LE frames are
+ * widened to s.31 on the device (S16: <<16; S24_3LE: b0<<8 | b1<<16 | b2<<24), output is always S32 (:138, :364).
+ * in: nStreams*nFrames*nIn samples of `pcmFormat`, interleaved; out: nStreams*nFrames*nOut int32. Synchronous. */
+enum { AVDSP_B200_PCM_S32 = 0, AVDSP_B200_PCM_S16 = 1, AVDSP_B200_PCM_S24_3LE = 2 };
+int  avdsp_b200_process_pcm(avdsp_b200_t *, const void *in, int pcmFormat, void *out, int nFrames, int memspace);
+
 /* period == 0: canonical order.  period > 0: the ALSA plugin's core-major loop nest with this period
  * (avdsp_plugin.c:95-98), fresh io[] per (core, frame). */
 int  avdsp_b200_set_order(avdsp_b200_t *, int period);

@@ -170,6 +170,22 @@ def test_host_path_time_chunk_pipeline(oracle_lib, monkeypatch):
     assert np.array_equal(yp.transpose(0, 2, 1), ys)
 
 
+def test_alsa_sample_formats(oracle_lib):
+    """S16_LE / S24_3LE input widened like linux/avdsp_plugin.c:109-121, S32 out."""
+    from avdsp_b200.executor import PCM_S16, PCM_S24_3LE
+    w = load_program("c2_testrpi_xover_f2_192k")
+    S, T = 3, 300
+    x32 = synth.pcm("full", S, T, 2, 192000)
+    x16 = (x32 >> 16).astype(np.int16)
+    y16, _ = oracle_run(oracle_lib, w, 2, 192000, x16.astype(np.int32) << 16, np.zeros(S, np.int32), 31)
+    assert np.array_equal(Executor(w, 192000, 2, S).process_pcm(x16, PCM_S16, T), y16)
+    x24 = x32 & ~0xFF                                   # 24 significant bits
+    b = np.empty(x24.shape + (3,), np.uint8)
+    b[..., 0] = (x24 >> 8) & 0xFF; b[..., 1] = (x24 >> 16) & 0xFF; b[..., 2] = (x24 >> 24) & 0xFF
+    y24, _ = oracle_run(oracle_lib, w, 2, 192000, x24, np.zeros(S, np.int32), 31)
+    assert np.array_equal(Executor(w, 192000, 2, S).process_pcm(b, PCM_S24_3LE, T), y24)
+
+
 def test_plugin_order_mode(oracle_lib):
     """core-major loop nest of linux/avdsp_plugin.c:95-142 with a given period."""
     fs, S, T, period = 48000, 3, 500, 128
