@@ -94,6 +94,10 @@ struct avdsp_b200 {
     ChainLane* dLanes2 = nullptr;
     Chain2Geom geom2{};
     bool chain2Usable = false;      // kernel_chain2.cu (v2: warp-specialised, the default)
+    MixPlan mix{};
+    bool mixUsable = false;         // kernel_mix.cu (time-parallel: programs without biquads)
+    unsigned* dJump = nullptr; int jumpL = -1;      // PRNG jump matrix for segments of jumpL draws
+    int* dTpdf = nullptr; size_t tpdfWords = 0;     // scratch dither values of a launch
     int period = 0, kernelSel = AVDSP_B200_KERNEL_AUTO, lastKernel = 0;
     long long launches = 0;
     cudaStream_t stream = nullptr;          // for the synchronous calls
@@ -137,8 +141,11 @@ static int uploadPlanData(avdsp_b200* h) {
             h->chain2Usable = true;
         }
     }
+    h->mixUsable = false;
+    if (L.chainOk) { std::string why; h->mixUsable = buildMixPlan(L.chain, &h->mix, &why); }
     char line[320];
     h->trace = L.trace;
+    if (h->mixUsable) h->trace += "time-parallel mix kernel: usable (no biquad in any path)\n";
     if (h->chain2Usable) {
         snprintf(line, sizeof line, "chain kernel v2 geometry: %d streams/CTA, %d sections/lane, tile %d frames, gmax %d, %d section threads + %d helper threads, %d sources, %zu B smem\n",
                  h->geom2.streamsPerCta, h->geom2.secPerLane, h->geom2.tileFrames, h->geom2.gmax, h->geom2.secThreads, h->geom2.helpThreads, L.chain.h.nSrc, h->geom2.smemBytes);
@@ -187,6 +194,8 @@ static void freeAll(avdsp_b200* h) {
     if (h->dSeeds) cudaFree(h->dSeeds);
     if (h->dLanes) cudaFree(h->dLanes);
     if (h->dLanes2) cudaFree(h->dLanes2);
+    if (h->dJump) cudaFree(h->dJump);
+    if (h->dTpdf) cudaFree(h->dTpdf);
     if (h->pcmRaw) cudaFree(h->pcmRaw);
     if (h->pcmIn) cudaFree(h->pcmIn);
     if (h->pcmOut) cudaFree(h->pcmOut);
@@ -271,7 +280,7 @@ int avdsp_b200_set_order(avdsp_b200_t* h, int period) {
     h->period = period; return 0;
 }
 int avdsp_b200_set_kernel(avdsp_b200_t* h, int which) {
-    if (!h || which < 0 || which > 3) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
+    if (!h || which < 0 || which > 4) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
     h->kernelSel = which; return 0;
 }
 int avdsp_b200_last_kernel(const avdsp_b200_t* h) { return h ? h->lastKernel : 0; }
@@ -313,10 +322,39 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         else if (h->chain2Usable) use = AVDSP_B200_KERNEL_CHAIN;
         else if (h->chainUsable) use = AVDSP_B200_KERNEL_CHAIN_V1;
     }
+    if (chainOrder && h->mixUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_MIX)) use = AVDSP_B200_KERNEL_MIX;
+    if (h->kernelSel == AVDSP_B200_KERNEL_MIX && use != AVDSP_B200_KERNEL_MIX)
+        return setErr(AVDSP_B200_ERR_UNSUPPORTED, "mix kernel requested but the program has biquads or does not map to independent paths");
     if ((h->kernelSel == AVDSP_B200_KERNEL_CHAIN || h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1) && use == AVDSP_B200_KERNEL_GENERIC)
         return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel requested but this program/order does not map to it: " + h->L.chainWhyNot);
     cudaError_t e;
-    if (use == AVDSP_B200_KERNEL_CHAIN) {
+    if (use == AVDSP_B200_KERNEL_MIX) {
+        MixArgs A{};
+        A.in = in; A.out = out; A.state = st;
+        A.nStreams = n; A.nFrames = nFrames;
+        A.inStreamStride = inSS; A.outStreamStride = outSS;
+        A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
+        A.vecIn = inCS == 1 && inFS == nIn && (inSS & 3) == 0 && ((size_t)in & 15) == 0;
+        A.vecOut = outCS == 1 && (nOut & 3) == 0 && (outFS & 3) == 0 && (outSS & 3) == 0 && ((size_t)out & 15) == 0;
+        const int J = nFrames >= 1024 ? 16 : 1;
+        const int Lseg = J > 1 ? (nFrames - 1) / J : nFrames;
+        if (h->mix.hasCalc || h->mix.anyTpdf) {
+            const size_t need = (size_t)n * nFrames;
+            if (need > h->tpdfWords) { if (h->dTpdf) cudaFree(h->dTpdf); h->dTpdf = nullptr; CU(cudaMalloc(&h->dTpdf, need * 4)); h->tpdfWords = need; }
+            if (!h->dJump) CU(cudaMalloc(&h->dJump, 128 * 4 * sizeof(unsigned)));
+            if (h->jumpL != Lseg) {
+                std::vector<unsigned> m(128 * 4);
+                mixJumpMatrix(2ll * Lseg, m.data());         // one TPDF value = two xoshiro128+ steps
+                CU(cudaMemcpyAsync(h->dJump, m.data(), m.size() * 4, cudaMemcpyHostToDevice, stream));
+                CU(cudaStreamSynchronize(stream));
+                h->jumpL = Lseg;
+            }
+        }
+        A.tpdfBuf = h->dTpdf;
+        e = launchMix(h->mix, A, h->dJump, J, Lseg, h->numSMs, stream);
+        h->lastKernel = AVDSP_B200_KERNEL_MIX;
+        h->launches += 2;                                    // prng + main + tail (one is counted below)
+    } else if (use == AVDSP_B200_KERNEL_CHAIN) {
         Chain2Args A{};
         A.in = in; A.out = out; A.state = st; A.lanes = h->dLanes2;
         A.nStreams = n; A.nFrames = nFrames;

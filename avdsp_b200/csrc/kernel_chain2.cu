@@ -545,14 +545,15 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                     }
                 }
             }
-            // stale delay index on a direct chain (rare): its tail lane stored post(0) where the preloaded
-            // ring[n-1] has to stay; move it to where the reference puts it (ring[idx0])
+            // stale delay index on a cascade (rare): the tail lane stored a value where the preloaded ring[n-1] has to stay
             if (anyStale && iw * F <= gmax && lane == 0)
                 for (int c = 0; c < C; c++) {
                     const ChainDesc& d = P.chains[c];
-                    if (d.nsec > 0 && d.accRow < 0 && d.delayN > 0 && stale_s[sl * C + c] >= 0 && (d.nsec - 1) / F == iw) {
+                    if (d.nsec > 0 && d.delayN > 0 && stale_s[sl * C + c] >= 0 && (d.nsec - 1) / F == iw) {
+                        // every tail lane stores its y1 at the slot of frame 0; a direct chain's is the real post(0)
+                        // (a post-processed chain's post(0) was sent to ring[idx0] by stage A above)
                         int* pr = post_s + (size_t)(sl * C + c) * G.postPitch + ((d.nsec - 1) & RM);
-                        A.state[(size_t)(s0 + sl) * W + d.delayOff + 1 + stale_s[sl * C + c]] = *pr;
+                        if (d.accRow < 0) A.state[(size_t)(s0 + sl) * W + d.delayOff + 1 + stale_s[sl * C + c]] = *pr;
                         *pr = sfix_s[sl * C + c];
                     }
                 }

@@ -1,0 +1,319 @@
+// kernel_mix.cu -- time-parallel executor for programs WITHOUT recurrences: every signal path is
+//     source (LOAD / LOAD_GAIN / LOAD_MUX) -> [GAIN] -> SAT0DB[_TPDF][_GAIN] -> [DELAY] -> STORE
+// (matrix mixers, routers, delay/gain/dither programs: config C5).  Fixed point (DSP_FORMAT 2), bit-exact.
+//
+// With no biquad in the path the only things that tie frame n to frame n-1 are (a) the delay lines -- a pure
+// shift: the output of frame f is the saturated value of frame f-n -- and (b) the dither PRNG (xoshiro128+,
+// runtime/dsp_tpdf.h:35-49), which is LINEAR over GF(2) and can therefore be jumped ahead.  So time is not a
+// loop here: the launch is cut into (stream, tile of FT frames) CTAs that stream PCM through shared memory at
+// HBM speed; this is the "pure HBM-bound path" (64 B of PCM per frame for the 8x8 mixer).
+//
+//   k_mix_prng : per stream, J threads each jump to the start of their time segment with a precomputed
+//                2L-step transition matrix (128x128 bits) and generate the TPDF values of the segment
+//                (dspTpdfCalc, runtime/dsp_tpdf.h:103-130) into a scratch buffer; the last one leaves the PRNG /
+//                TPDF state where the reference would (per-stream aux words + the TPDF_CALC data word).
+//   k_mix_main : lane = output frame.  A CTA stages the input window [f0-maxDelay, f0+FT) (interleaved PCM is
+//                one contiguous run) and the matching dither values, then every output channel evaluates ITS
+//                chain at frame f-delay: dense gain-matrix row x 8 inputs (16-byte shared loads, accumulating
+//                IMAD.WIDE), gain / dither / saturate, mask, and the frame's outputs leave as 16-byte stores.
+//                Each saturated value is computed exactly once (by the output frame that needs it).
+//                Frames f < delay read the reference's ring from the state block (previous launch).
+//   k_mix_tail : writes the state the reference would hold after T frames: the last `delay` saturated values of
+//                every path in ring layout + ring index (dsp_runtime.c:769-794), the last LOAD_MUX value (:893-896).
+#include "avdsp_dev.cuh"
+#include "kernels.h"
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace avdsp {
+
+__device__ __forceinline__ unsigned mixSmem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// ---------------------------------------------------------------------------------------------------------
+// saturated s.31 value ("post") of output channel `ch`'s chain at frame fd, from PCM given as a pointer to
+// channel 0 of that frame (global or shared), and the dither value of that frame
+__device__ __forceinline__ long long mixSourceDense(const MixPlan& M, int ch, const int* __restrict__ fr) {
+    // dense gain-matrix row (LOAD / LOAD_GAIN are rows with a single non-zero, LOAD is handled by the caller)
+    const int* g = M.mat + M.oMatRow[ch];
+    long long X = 0;
+#pragma unroll 4
+    for (int k = 0; k < M.nInPad; k++) X = mac32(X, fr[k], g[k]);
+    return X;
+}
+__device__ __forceinline__ int mixFinish(const MixPlan& M, int flags, int gainBits, int satGainBits, long long X, int tv) {
+    if (flags & PF_GAIN) X = X * (long long)gainBits;
+    if (flags & PF_SAT_GAIN) { X >>= kMant; X = X * (long long)satGainBits; }
+    if (flags & PF_SAT_TPDF) X += tpdfScaledI(tv, M.tpdfShift);
+    return sat64_031_s32(X);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_mix_prng(const __grid_constant__ MixPlan M, int* __restrict__ state, int* __restrict__ tpdfBuf, const unsigned* __restrict__ jump,
+           int nStreams, int T, int J, int L) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = gid / J, j = gid - s * J;
+    if (s >= nStreams) return;
+    int* aux = state + (size_t)s * M.stateWords + M.auxOff;
+    unsigned st[4] = {(unsigned)aux[AUX_S0], (unsigned)aux[AUX_S1], (unsigned)aux[AUX_S2], (unsigned)aux[AUX_S3]};
+    int tpdfValue = aux[AUX_TPDF_VALUE], tpdfRandom = aux[AUX_TPDF_RANDOM];
+    const int dith = aux[AUX_DITHER];
+    int* row = tpdfBuf + (size_t)s * T;
+    if (!M.hasCalc) {                        // no TPDF_CALC in the program: the value never changes
+        for (int f = j * L; f < min(T, (j + 1) * L); f++) row[f] = tpdfValue;
+        return;
+    }
+    // first frame after a reset with another dither width: table switch, no draw, X=0, nothing stored (dsp_runtime.c:539-544)
+    const int q = (dith != M.tpdfDither) ? 1 : 0;
+    // segment j covers draws [j*L, (j+1)*L) = frames [j*L+q, (j+1)*L+q); the last segment runs to the end
+    for (int a = 0; a < j; a++) {            // jump: state <- Mseg * state  (columns of Mseg, XOR of the selected ones)
+        unsigned n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll 1
+        for (int w = 0; w < 4; w++) {
+            unsigned bits = st[w];
+            while (bits) {
+                const int b = __ffs(bits) - 1; bits &= bits - 1;
+                const uint4 c = reinterpret_cast<const uint4*>(jump)[w * 32 + b];
+                n0 ^= c.x; n1 ^= c.y; n2 ^= c.z; n3 ^= c.w;
+            }
+        }
+        st[0] = n0; st[1] = n1; st[2] = n2; st[3] = n3;
+    }
+    Prng g = {st[0], st[1], st[2], st[3]};
+    const int d0 = j * L, d1 = (j == J - 1) ? (T - q) : min(T - q, (j + 1) * L);
+    if (j == 0 && q && T > 0) row[0] = tpdfValue;
+    for (int d = d0; d < d1; d++) { tpdfValue = tpdfDraw(g, tpdfRandom); row[d + q] = tpdfValue; }
+    if (j == J - 1) {
+        aux[AUX_S0] = g.s0; aux[AUX_S1] = g.s1; aux[AUX_S2] = g.s2; aux[AUX_S3] = g.s3;
+        aux[AUX_TPDF_VALUE] = tpdfValue; aux[AUX_TPDF_RANDOM] = tpdfRandom; aux[AUX_DITHER] = M.tpdfDither;
+        if (T - q > 0) {                     // TPDF_CALC leaves its last value (as an ALU word) in the data area (dsp_runtime.c:541-543)
+            int* qd = state + (size_t)s * M.stateWords + M.tpdfDataOff;
+            qd[0] = tpdfValue; qd[1] = tpdfValue >> 31;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMixThreads = 256;
+
+__global__ void __launch_bounds__(kMixThreads, 2)
+k_mix_main(const __grid_constant__ MixPlan M, const MixArgs A) {
+    extern __shared__ __align__(16) int smem_mix[];
+    const int FT = A.tileFrames, W = M.stateWords, T = A.nFrames;
+    const int nInPad = M.nInPad;
+    const int s = blockIdx.y, f0 = blockIdx.x * FT;
+    const int nf = min(FT, T - f0);
+    const int w0 = max(0, f0 - M.maxDelay) & ~3;             // first staged frame (multiple of 4: 16-byte aligned rows)
+    const int nw = f0 + nf - w0;                             // staged frames
+    int* pcm_s = smem_mix;                                   // [nw][nInPad]
+    int* tpdf_s = smem_mix + (size_t)A.winFrames * nInPad;   // [nw]
+    const int* in = A.in + (size_t)s * A.inStreamStride;
+    // ---- stage the window (interleaved PCM: nw*nIn contiguous words)
+    if (nInPad == M.nIn && A.vecIn) {
+        const int4* src = reinterpret_cast<const int4*>(in + (size_t)w0 * M.nIn);
+        int4* dst = reinterpret_cast<int4*>(pcm_s);
+        const int n4 = nw * M.nIn / 4;
+        for (int i = threadIdx.x; i < n4; i += kMixThreads) dst[i] = __ldg(src + i);
+        for (int i = n4 * 4 + threadIdx.x; i < nw * M.nIn; i += kMixThreads) pcm_s[i] = in[(size_t)w0 * M.nIn + i];
+    } else {
+        for (int i = threadIdx.x; i < nw * nInPad; i += kMixThreads) {
+            const int fr = i / nInPad, k = i - fr * nInPad;
+            pcm_s[i] = k < M.nIn ? in[(size_t)(w0 + fr) * A.inFrameStride + (size_t)k * A.inChStride] : 0;
+        }
+    }
+    if (M.anyTpdf) {
+        const int* tb = A.tpdfBuf + (size_t)s * T + w0;
+        for (int i = threadIdx.x; i < nw; i += kMixThreads) tpdf_s[i] = tb[i];
+    }
+    __syncthreads();
+
+    const int* st = A.state + (size_t)s * W;
+    const bool vecOut = A.vecOut != 0;
+    for (int u = threadIdx.x; u < nf; u += kMixThreads) {
+        const int f = f0 + u;
+        int* out = A.out + (size_t)s * A.outStreamStride + (size_t)f * A.outFrameStride;
+#pragma unroll
+        for (int ch0 = 0; ch0 < kFastTab; ch0 += 4) {
+            if (ch0 >= M.nOut) break;
+            int val[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int ch = ch0 + q;
+                int v = 0;                               // outputs no path writes read as 0
+                if (ch < M.nOut && M.oChain[ch] >= 0) {
+                    const int n = M.oDelay[ch];
+                    const int fd = f - n;
+                    bool fromRing = fd < 0;
+                    int ridx = 0;
+                    if (n > 0 && f <= n) {               // frames served by the reference's ring (previous launch), dsp_runtime.c:769-794
+                        const int idx0 = st[M.oDelayOff[ch]];
+                        if (idx0 >= n || idx0 < 0) {     // stale index: used once, then the ring restarts at 0
+                            fromRing = true; ridx = (f == 0) ? idx0 : f - 1;
+                        } else if (fd < 0) ridx = (idx0 + f) % n;
+                    }
+                    if (fromRing) v = st[M.oDelayOff[ch] + 1 + ridx];
+                    else {
+                        const int* fr = pcm_s + (size_t)(fd - w0) * nInPad;
+                        const int flags = M.oFlags[ch];
+                        long long X;
+                        if (M.oKind[ch] == SRC_LOAD) X = M.oSrcCh[ch] >= 0 ? (long long)fr[M.oSrcCh[ch]] : 0ll;
+                        else X = mixSourceDense(M, ch, fr);
+                        v = mixFinish(M, flags, M.oGain[ch], M.oSatGain[ch], X, (flags & PF_SAT_TPDF) ? tpdf_s[fd - w0] : 0);
+                    }
+                    v &= M.storeMask;
+                }
+                val[q] = v;
+            }
+            if (vecOut) *reinterpret_cast<int4*>(out + ch0) = make_int4(val[0], val[1], val[2], val[3]);
+            else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (ch0 + q < M.nOut) out[(size_t)(ch0 + q) * A.outChStride] = val[q];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// state after T frames: delay rings + indices, last mux values.  One CTA per stream; chain c's ring is written
+// by frames j in [T-n, T) at position (idx_eff + j) mod n.
+__global__ void __launch_bounds__(128)
+k_mix_tail(const __grid_constant__ MixPlan M, const MixArgs A) {
+    const int s = blockIdx.x, T = A.nFrames, W = M.stateWords;
+    int* st = A.state + (size_t)s * W;
+    const int* in = A.in + (size_t)s * A.inStreamStride;
+    const int* tb = A.tpdfBuf ? A.tpdfBuf + (size_t)s * T : nullptr;
+    __shared__ int fr_s[128][kFastTab];
+    for (int c = 0; c < M.nChains; c++) {
+        const int ch = M.cOut[c];                // an output channel fed by chain c (carries its flattened descriptor)
+        const int n = M.cDelay[c];
+        const bool mux = M.cMuxOff[c] >= 0;
+        if (n <= 0 && !mux) continue;
+        const int idx0 = n > 0 ? st[M.cDelayOff[c]] : 0;
+        const bool stale = n > 0 && (idx0 >= n || idx0 < 0);
+        const int idxEff = stale ? n - 1 : idx0;
+        const int lo = max(stale ? 1 : 0, T - n);
+        __syncthreads();                         // everyone has read idx0 before lane 0 rewrites it below
+        // frames lo..T-1 (ring) and, for a stale index, frame 0 (goes to ring[idx0]); frame T-1 for the mux word
+        const int first = (n > 0) ? lo : T - 1;
+        for (int j0 = first; j0 < T; j0 += 128) {
+            const int j = j0 + threadIdx.x;
+            if (j < T) {
+                int* fr = fr_s[threadIdx.x];
+                for (int k = 0; k < M.nInPad; k++) fr[k] = k < M.nIn ? in[(size_t)j * A.inFrameStride + (size_t)k * A.inChStride] : 0;
+                long long X;
+                if (M.oKind[ch] == SRC_LOAD) X = M.oSrcCh[ch] >= 0 ? (long long)fr[M.oSrcCh[ch]] : 0ll;
+                else X = mixSourceDense(M, ch, fr);
+                if (mux && j == T - 1) { st[M.cMuxOff[c]] = lo32(X); st[M.cMuxOff[c] + 1] = hi32(X); }
+                if (n > 0) {
+                    const int flags = M.oFlags[ch];
+                    const int v = mixFinish(M, flags, M.oGain[ch], M.oSatGain[ch], X, ((flags & PF_SAT_TPDF) && tb) ? tb[j] : 0);
+                    st[M.cDelayOff[c] + 1 + (int)(((long long)idxEff + j) % n)] = v;
+                }
+            }
+        }
+        if (stale && T >= 1 && threadIdx.x == 0) {
+            int* fr = fr_s[0];
+            for (int k = 0; k < M.nInPad; k++) fr[k] = k < M.nIn ? in[(size_t)k * A.inChStride] : 0;
+            long long X;
+            if (M.oKind[ch] == SRC_LOAD) X = M.oSrcCh[ch] >= 0 ? (long long)fr[M.oSrcCh[ch]] : 0ll;
+            else X = mixSourceDense(M, ch, fr);
+            const int flags = M.oFlags[ch];
+            st[M.cDelayOff[c] + 1 + idx0] = mixFinish(M, flags, M.oGain[ch], M.oSatGain[ch], X, ((flags & PF_SAT_TPDF) && tb) ? tb[0] : 0);
+        }
+        __syncthreads();
+        if (n > 0 && T > 0 && threadIdx.x == 0) st[M.cDelayOff[c]] = (int)(((long long)idxEff + T) % n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// xoshiro128+ transition matrix over GF(2), as 128 columns of 128 bits (uint4 each), raised to the n-th power
+static void xoStep(unsigned s[4]) {
+    const unsigned t = s[1] << 9;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = (s[3] << 11) | (s[3] >> 21);
+}
+struct BitMat { unsigned col[128][4]; };
+static void matVec(const BitMat& m, const unsigned v[4], unsigned r[4]) {
+    r[0] = r[1] = r[2] = r[3] = 0;
+    for (int i = 0; i < 128; i++) if ((v[i >> 5] >> (i & 31)) & 1u) for (int w = 0; w < 4; w++) r[w] ^= m.col[i][w];
+}
+static void matMul(const BitMat& a, const BitMat& b, BitMat& out) { for (int i = 0; i < 128; i++) matVec(a, b.col[i], out.col[i]); }
+
+void mixJumpMatrix(long long steps, unsigned* out /*[128*4]*/) {
+    BitMat base, acc, tmp;
+    for (int i = 0; i < 128; i++) {
+        unsigned s[4] = {0, 0, 0, 0}; s[i >> 5] = 1u << (i & 31);
+        xoStep(s); memcpy(base.col[i], s, 16);
+        for (int w = 0; w < 4; w++) acc.col[i][w] = (w == (i >> 5)) ? (1u << (i & 31)) : 0u;      // identity
+    }
+    while (steps > 0) {
+        if (steps & 1) { matMul(base, acc, tmp); acc = tmp; }
+        matMul(base, base, tmp); base = tmp;
+        steps >>= 1;
+    }
+    memcpy(out, acc.col, sizeof acc.col);
+}
+
+bool buildMixPlan(const ChainPlan& P, MixPlan* M, std::string* why) {
+    auto no = [&](const char* w) { if (why) *why = w; return false; };
+    if (P.h.aluClass != ALU_INT64) return no("fixed point only");
+    if (P.h.nChains <= 0 || P.h.nChains > kFastTab || P.h.nOut <= 0 || P.h.nOut > kFastTab || P.h.nIn > kFastTab) return no("more than 16 paths / channels");
+    memset(M, 0, sizeof *M);
+    M->nIn = P.h.nIn; M->nOut = P.h.nOut; M->nChains = P.h.nChains;
+    M->nInPad = std::max(4, (P.h.nIn + 3) & ~3);
+    M->stateWords = P.h.stateWords; M->auxOff = P.h.auxOff;
+    M->hasCalc = P.h.hasTpdfCalc; M->tpdfDither = P.h.tpdfDither; M->tpdfDataOff = P.h.tpdfDataOff; M->tpdfShift = P.h.tpdfShift;
+    M->storeMask = (int)(0xFFFFFFFFu << ((32 - P.h.storeDither) & 31));
+    for (int c = 0; c < P.h.nChains; c++) {
+        const ChainDesc& d = P.chains[c];
+        if (d.nsec != 0) return no("a path has biquad sections");
+        M->cDelay[c] = d.delayN; M->cDelayOff[c] = d.delayOff; M->cMuxOff[c] = d.srcKind == SRC_LOAD_MUX ? d.muxStateOff : -1;
+        M->cOut[c] = d.nStores > 0 ? d.storeCh[0] : 0;
+        M->maxDelay = std::max(M->maxDelay, d.delayN);
+        if (d.satKind & 1) M->anyTpdf = 1;
+        // dense gain row
+        int* row = M->mat + c * kFastTab;
+        if (d.srcKind == SRC_LOAD_MUX) {
+            for (int k = 0; k < d.srcCh; k++) {
+                const int ch = P.pool[d.srcArg + 2 * k], g = P.pool[d.srcArg + 2 * k + 1];
+                if (ch < 0) continue;                    // input the host does not feed: reads 0
+                if (row[ch] != 0) return no("a LOAD_MUX lists the same input twice");
+                row[ch] = g;
+            }
+        } else if (d.srcKind == SRC_LOAD_GAIN) { if (d.srcCh >= 0) row[d.srcCh] = d.srcArg; }
+    }
+    for (int ch = 0; ch < kFastTab; ch++) {
+        const int c = ch < P.h.nOut ? P.h.chainOfOut[ch] : -1;
+        M->oChain[ch] = c;
+        if (c < 0) continue;
+        const ChainDesc& d = P.chains[c];
+        M->oDelay[ch] = d.delayN; M->oDelayOff[ch] = d.delayOff;
+        M->oFlags[ch] = (d.hasGain ? PF_GAIN : 0) | ((d.satKind & 1) ? PF_SAT_TPDF : 0) | (d.satKind >= SAT_GAIN ? PF_SAT_GAIN : 0);
+        M->oGain[ch] = d.gainBits; M->oSatGain[ch] = d.satGainBits;
+        M->oKind[ch] = d.srcKind; M->oSrcCh[ch] = d.srcCh; M->oMatRow[ch] = c * kFastTab;
+    }
+    return true;
+}
+
+cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J, int L, int numSMs, cudaStream_t stream) {
+    (void)numSMs;
+    const int S = A.nStreams, T = A.nFrames;
+    if (M.anyTpdf || M.hasCalc) {
+        const int th = 128, total = S * J;
+        k_mix_prng<<<(total + th - 1) / th, th, 0, stream>>>(M, A.state, A.tpdfBuf, dJump, S, T, J, L);
+    }
+    // tile length: window (FT + maxDelay) x nInPad words + dither values, two CTAs per SM
+    int FT = 2048;
+    auto smemFor = [&](int ft) { return (size_t)(ft + M.maxDelay + 4) * (M.nInPad + 1) * 4; };
+    while (FT > 256 && smemFor(FT) > 100 * 1024) FT >>= 1;
+    A.tileFrames = FT; A.winFrames = FT + M.maxDelay + 4;
+    const size_t smem = smemFor(FT);
+    cudaError_t e = cudaFuncSetAttribute(k_mix_main, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((T + FT - 1) / FT, S);
+    k_mix_main<<<grid, kMixThreads, smem, stream>>>(M, A);
+    k_mix_tail<<<S, 128, 0, stream>>>(M, A);
+    return cudaGetLastError();
+}
+
+} // namespace avdsp

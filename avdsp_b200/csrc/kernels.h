@@ -1,6 +1,7 @@
 // kernels.h -- launch interfaces of the CUDA kernels (host side of kernel_*.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <string>
 #include "plan.h"
 
 namespace avdsp {
@@ -88,5 +89,31 @@ struct Chain2Args {
 bool chain2Supports(const ChainPlan& plan);
 bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2Geom* geom, ChainLane* lanesOut /*[1024]*/);
 cudaError_t launchChain2(const ChainPlan& plan, const Chain2Geom& geom, const Chain2Args& args, cudaStream_t stream);
+
+// ---- time-parallel mixer / delay / dither kernel (kernel_mix.cu) -----------------------------------
+// Everything the three kernels need, flattened by OUTPUT channel (static indices -> constant-bank operands).
+struct MixPlan {
+    int nIn, nOut, nChains, nInPad;
+    int stateWords, auxOff;
+    int hasCalc, tpdfDither, tpdfDataOff, tpdfShift, anyTpdf;
+    int storeMask, maxDelay;
+    int cDelay[kFastTab], cDelayOff[kFastTab], cMuxOff[kFastTab], cOut[kFastTab];      // per chain
+    int oChain[kFastTab], oDelay[kFastTab], oDelayOff[kFastTab], oFlags[kFastTab], oGain[kFastTab], oSatGain[kFastTab],
+        oKind[kFastTab], oSrcCh[kFastTab], oMatRow[kFastTab];                           // per output channel
+    int mat[kFastTab * kFastTab];                                                        // dense gain rows [chain][input]
+};
+struct MixArgs {
+    const int* in;  int* out;
+    int* state;
+    int* tpdfBuf;               // [nStreams][nFrames] dither values of this launch (scratch)
+    int nStreams, nFrames;
+    long long inStreamStride, outStreamStride;
+    int inFrameStride, inChStride, outFrameStride, outChStride;
+    int vecIn, vecOut;          // 16-byte paths usable (interleaved + aligned)
+    int tileFrames, winFrames;  // filled by launchMix
+};
+bool buildMixPlan(const ChainPlan& plan, MixPlan* out, std::string* why);
+void mixJumpMatrix(long long steps, unsigned* out /*[128*4]*/);
+cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J, int L, int numSMs, cudaStream_t stream);
 
 } // namespace avdsp

@@ -89,7 +89,8 @@ enum { AVDSP_B200_INTERLEAVED = 0,     /* [stream][frame][channel]  (what ALSA h
 enum { AVDSP_B200_HOST = 0, AVDSP_B200_DEVICE = 1 };
 /* kernel selection (diagnostics and tests; AUTO is the product behaviour) */
 enum { AVDSP_B200_KERNEL_AUTO = 0, AVDSP_B200_KERNEL_GENERIC = 1, AVDSP_B200_KERNEL_CHAIN = 2,
-       AVDSP_B200_KERNEL_CHAIN_V1 = 3 /* the earlier tile-synchronous chain kernel, kept for A/B runs */ };
+       AVDSP_B200_KERNEL_CHAIN_V1 = 3 /* the earlier tile-synchronous chain kernel, kept for A/B runs */,
+       AVDSP_B200_KERNEL_MIX = 4      /* time-parallel kernel for programs without biquads (mixers, delays, dither) */ };
 
 /* Load + validate + lower a program (dspRuntimeInit + dspRuntimeReset for nStreams independent
  * instances).  prog: progWords little-endian 32-bit words exactly as written by dspcreate (.bin).

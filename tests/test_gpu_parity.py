@@ -118,10 +118,11 @@ def test_kernels_agree_and_can_alternate():
 
 
 def test_chain_kernel_is_selected_for_the_benchmark_programs():
-    for prog, fs in (("c2_testrpi_xover_f2_192k", 192000), ("c5_mixer8x8_f2_192k", 192000), ("c3_peq16_f2_48k", 48000)):
+    for prog, fs, kern in (("c2_testrpi_xover_f2_192k", 192000, "chain"), ("c5_mixer8x8_f2_192k", 192000, "mix"),
+                           ("c3_peq16_f2_48k", 48000, "chain")):
         ex = Executor(load_program(prog), fs, 2, 64)
         ex.process(synth.pcm("noise", 64, 64, ex.n_in, fs))
-        assert ex.last_kernel == "chain", ex.trace
+        assert ex.last_kernel == kern, ex.trace
     ex = Executor(load_program("c1_crossover2x2lfe_f2_48k"), 48000, 2, 4)   # MEM hand-off, X/Y dataflow
     ex.process(synth.pcm("noise", 4, 64, ex.n_in, 48000))
     assert ex.last_kernel == "generic"
@@ -252,6 +253,53 @@ def test_reload_params_live_patch(oracle_lib):
         assert np.array_equal(y0[s], a) and np.array_equal(y1[s], b)
 
 
+def _delay_param_program(with_biquad: bool):
+    """LOAD_GAIN -> [BIQUADS] -> SAT0DB_TPDF -> DELAY(us from a PARAM word) -> STORE, twice, + TPDF_CALC.
+    Returns (words, [word index of each delay PARAM])."""
+    from oracle import wire
+    a = wire.Asm(fmt=2, fmin=48000, fmax=48000)
+    a.core(); a.tpdf_calc(22)
+    a.param()
+    bq = a.biquad_sections([[wire.rbj_peak(48000, 900.0, 1.2, 1.4)], [wire.rbj_peak(48000, 3000.0, 0.8, 0.7)]]) if with_biquad else None
+    d0 = a.delay_param(3000, 1500, 48000)
+    d1 = a.delay_param(3000, 400, 48000)
+    for ch, dp in ((0, d0), (1, d1)):
+        a.load_gain(8 + ch, 0.6)
+        if with_biquad:
+            a.biquads(bq)
+        a.sat0db_tpdf()
+        a.delay(dp)
+        a.store(ch)
+    return a.end(), [d0, d1]
+
+
+@pytest.mark.parametrize("with_biquad", [False, True])
+@pytest.mark.parametrize("kernel", [KERNEL_GENERIC, KERNEL_AUTO])
+def test_delay_time_patched_mid_stream(oracle_lib, with_biquad, kernel):
+    """Host shortens / lengthens a delay PARAM mid-stream: the ring index can become stale (>= new length), which the
+    reference uses once and then wraps (dsp_runtime.c:769-794).  All kernels must follow it bit for bit."""
+    w, dps = _delay_param_program(with_biquad)
+    fs, S, T = 48000, 5, 333
+    x = synth.pcm("full", S, 3 * T, 2, fs)
+    ex = Executor(w, fs, 2, S, seeds=np.arange(S, dtype=np.int32))
+    ex.set_kernel(kernel)
+    orcs = [oracle_lib.Oracle(w, 2, fs, seed=s) for s in range(S)]
+    words = w.copy()
+    for part, (us0, us1) in enumerate(((1500, 400), (200, 2900), (2500, 0))):
+        for dp, us in zip(dps, (us0, us1)):
+            words[dp] = (int(words[dp]) & ~0xFFFF) | us
+        ex.reload_params(words)
+        xs = np.ascontiguousarray(x[:, part * T:(part + 1) * T])
+        y = ex.process(xs)
+        for s in range(S):
+            for dp, us in zip(dps, (us0, us1)):
+                orcs[s].code[dp] = words[dp]
+            assert np.array_equal(y[s], orcs[s].process(xs[s])), (part, s, ex.last_kernel)
+    for s in (0, S - 1):
+        st = ex.get_state(s)
+        assert np.array_equal(st[: ex.data_size], orcs[s].data), (s, ex.last_kernel)
+
+
 def test_state_roundtrip_and_reset():
     w = load_program("c5_mixer8x8_f2_192k")
     S, T = 4, 700
@@ -293,7 +341,7 @@ def test_full_width_batch_properties(oracle_lib, prog, fs, S, T):
     x1 = synth.pcm("noise", 1, T, ex.n_in, fs)
     x = np.ascontiguousarray(np.broadcast_to(x1, (S, T, ex.n_in)))
     y = ex.process(x)
-    assert ex.last_kernel == "chain"
+    assert ex.last_kernel in ("chain", "mix")
     assert (y == y[0:1]).all()
     o = oracle_lib.Oracle(w, 2, fs, seed=0)
     assert np.array_equal(y[0], o.process(x1[0]))
