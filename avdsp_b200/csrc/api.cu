@@ -336,7 +336,7 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
         A.vecIn = inCS == 1 && inFS == nIn && (inSS & 3) == 0 && ((size_t)in & 15) == 0;
         A.vecOut = outCS == 1 && (nOut & 3) == 0 && (outFS & 3) == 0 && (outSS & 3) == 0 && ((size_t)out & 15) == 0;
-        const int J = nFrames >= 1024 ? 16 : 1;
+        const int J = nFrames >= 4096 ? 64 : (nFrames >= 1024 ? 16 : 1);
         const int Lseg = J > 1 ? (nFrames - 1) / J : nFrames;
         if (h->mix.hasCalc || h->mix.anyTpdf) {
             const size_t need = (size_t)n * nFrames;

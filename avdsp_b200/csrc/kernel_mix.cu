@@ -23,6 +23,7 @@
 #include "avdsp_dev.cuh"
 #include "kernels.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -35,10 +36,25 @@ __device__ __forceinline__ unsigned mixSmem(const void* p) { return (unsigned)__
 // channel 0 of that frame (global or shared), and the dither value of that frame
 __device__ __forceinline__ long long mixSourceDense(const MixPlan& M, int ch, const int* __restrict__ fr) {
     // dense gain-matrix row (LOAD / LOAD_GAIN are rows with a single non-zero, LOAD is handled by the caller)
-    const int* g = M.mat + M.oMatRow[ch];
+    const int* g = M.mat + ch * kFastTab;
     long long X = 0;
 #pragma unroll 4
     for (int k = 0; k < M.nInPad; k++) X = mac32(X, fr[k], g[k]);
+    return X;
+}
+// the same with everything static: `ch` and NP are compile-time, so the gains are constant-bank operands of the
+// IMAD.WIDEs and the frame's inputs arrive as 16-byte shared loads
+template <int NP>
+__device__ __forceinline__ long long mixSourceDenseT(const MixPlan& M, const int ch, const int* __restrict__ fr) {
+    long long X = 0;
+#pragma unroll
+    for (int k4 = 0; k4 < NP; k4 += 4) {
+        const int4 v = *reinterpret_cast<const int4*>(fr + k4);
+        X = mac32(X, v.x, M.mat[ch * kFastTab + k4 + 0]);
+        X = mac32(X, v.y, M.mat[ch * kFastTab + k4 + 1]);
+        X = mac32(X, v.z, M.mat[ch * kFastTab + k4 + 2]);
+        X = mac32(X, v.w, M.mat[ch * kFastTab + k4 + 3]);
+    }
     return X;
 }
 __device__ __forceinline__ int mixFinish(const MixPlan& M, int flags, int gainBits, int satGainBits, long long X, int tv) {
@@ -83,7 +99,16 @@ k_mix_prng(const __grid_constant__ MixPlan M, int* __restrict__ state, int* __re
     Prng g = {st[0], st[1], st[2], st[3]};
     const int d0 = j * L, d1 = (j == J - 1) ? (T - q) : min(T - q, (j + 1) * L);
     if (j == 0 && q && T > 0) row[0] = tpdfValue;
-    for (int d = d0; d < d1; d++) { tpdfValue = tpdfDraw(g, tpdfRandom); row[d + q] = tpdfValue; }
+    int d = d0;
+    // scalar stores up to a 16-byte boundary, then four values per store (adjacent threads are a whole segment apart)
+    for (; d < d1 && (((size_t)(row + d + q)) & 15); d++) { tpdfValue = tpdfDraw(g, tpdfRandom); row[d + q] = tpdfValue; }
+    for (; d + 4 <= d1; d += 4) {
+        int4 v;
+        v.x = tpdfDraw(g, tpdfRandom); v.y = tpdfDraw(g, tpdfRandom); v.z = tpdfDraw(g, tpdfRandom); v.w = tpdfDraw(g, tpdfRandom);
+        tpdfValue = v.w;
+        *reinterpret_cast<int4*>(row + d + q) = v;
+    }
+    for (; d < d1; d++) { tpdfValue = tpdfDraw(g, tpdfRandom); row[d + q] = tpdfValue; }
     if (j == J - 1) {
         aux[AUX_S0] = g.s0; aux[AUX_S1] = g.s1; aux[AUX_S2] = g.s2; aux[AUX_S3] = g.s3;
         aux[AUX_TPDF_VALUE] = tpdfValue; aux[AUX_TPDF_RANDOM] = tpdfRandom; aux[AUX_DITHER] = M.tpdfDither;
@@ -97,11 +122,12 @@ k_mix_prng(const __grid_constant__ MixPlan M, int* __restrict__ state, int* __re
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kMixThreads = 256;
 
-__global__ void __launch_bounds__(kMixThreads, 2)
+template <int NP>
+__global__ void __launch_bounds__(kMixThreads, 4)
 k_mix_main(const __grid_constant__ MixPlan M, const MixArgs A) {
     extern __shared__ __align__(16) int smem_mix[];
     const int FT = A.tileFrames, W = M.stateWords, T = A.nFrames;
-    const int nInPad = M.nInPad;
+    constexpr int nInPad = NP;
     const int s = blockIdx.y, f0 = blockIdx.x * FT;
     const int nf = min(FT, T - f0);
     const int w0 = max(0, f0 - M.maxDelay) & ~3;             // first staged frame (multiple of 4: 16-byte aligned rows)
@@ -130,6 +156,38 @@ k_mix_main(const __grid_constant__ MixPlan M, const MixArgs A) {
 
     const int* st = A.state + (size_t)s * W;
     const bool vecOut = A.vecOut != 0;
+    if (M.uniform && f0 > M.maxDelay && vecOut) {
+        // interior tile of a uniform program (every output: dense row -> SAT0DB_TPDF_GAIN-class finish, same flags):
+        // no ring reads, no per-channel decisions; delays are byte offsets from the constant bank
+        const bool up = M.tpdfShift >= 0;
+        const int sh = (up ? M.tpdfShift : -M.tpdfShift) & 63;
+        const int flags = M.uFlags;
+        for (int u = threadIdx.x; u < nf; u += kMixThreads) {
+            const int f = f0 + u;
+            const char* frB = reinterpret_cast<const char*>(pcm_s) + (size_t)(f - w0) * (NP * 4);
+            const char* tpB = reinterpret_cast<const char*>(tpdf_s) + (size_t)(f - w0) * 4;
+            int* out = A.out + (size_t)s * A.outStreamStride + (size_t)f * A.outFrameStride;
+#pragma unroll
+            for (int ch0 = 0; ch0 < kFastTab; ch0 += 4) {
+                if (ch0 >= M.nOut) break;
+                int val[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int ch = ch0 + q;
+                    long long X = mixSourceDenseT<NP>(M, ch, reinterpret_cast<const int*>(frB - M.oDelayPcmBytes[ch]));
+                    if (flags & PF_GAIN) X = X * (long long)M.oGain[ch];
+                    if (flags & PF_SAT_GAIN) { X >>= kMant; X = X * (long long)M.oSatGain[ch]; }
+                    if (flags & PF_SAT_TPDF) {
+                        const long long tv = *reinterpret_cast<const int*>(tpB - M.oDelayBytes[ch]);
+                        X += up ? (long long)((unsigned long long)tv << sh) : (tv >> sh);
+                    }
+                    val[q] = sat64_031_s32(X) & M.storeMask;
+                }
+                *reinterpret_cast<int4*>(out + ch0) = make_int4(val[0], val[1], val[2], val[3]);
+            }
+        }
+        return;
+    }
     for (int u = threadIdx.x; u < nf; u += kMixThreads) {
         const int f = f0 + u;
         int* out = A.out + (size_t)s * A.outStreamStride + (size_t)f * A.outFrameStride;
@@ -158,7 +216,7 @@ k_mix_main(const __grid_constant__ MixPlan M, const MixArgs A) {
                         const int flags = M.oFlags[ch];
                         long long X;
                         if (M.oKind[ch] == SRC_LOAD) X = M.oSrcCh[ch] >= 0 ? (long long)fr[M.oSrcCh[ch]] : 0ll;
-                        else X = mixSourceDense(M, ch, fr);
+                        else X = mixSourceDenseT<NP>(M, ch, fr);
                         v = mixFinish(M, flags, M.oGain[ch], M.oSatGain[ch], X, (flags & PF_SAT_TPDF) ? tpdf_s[fd - w0] : 0);
                     }
                     v &= M.storeMask;
@@ -264,6 +322,7 @@ bool buildMixPlan(const ChainPlan& P, MixPlan* M, std::string* why) {
     M->stateWords = P.h.stateWords; M->auxOff = P.h.auxOff;
     M->hasCalc = P.h.hasTpdfCalc; M->tpdfDither = P.h.tpdfDither; M->tpdfDataOff = P.h.tpdfDataOff; M->tpdfShift = P.h.tpdfShift;
     M->storeMask = (int)(0xFFFFFFFFu << ((32 - P.h.storeDither) & 31));
+    std::vector<std::vector<int>> chainRow(kFastTab, std::vector<int>(kFastTab, 0));
     for (int c = 0; c < P.h.nChains; c++) {
         const ChainDesc& d = P.chains[c];
         if (d.nsec != 0) return no("a path has biquad sections");
@@ -272,7 +331,7 @@ bool buildMixPlan(const ChainPlan& P, MixPlan* M, std::string* why) {
         M->maxDelay = std::max(M->maxDelay, d.delayN);
         if (d.satKind & 1) M->anyTpdf = 1;
         // dense gain row
-        int* row = M->mat + c * kFastTab;
+        int* row = chainRow[c].data();
         if (d.srcKind == SRC_LOAD_MUX) {
             for (int k = 0; k < d.srcCh; k++) {
                 const int ch = P.pool[d.srcArg + 2 * k], g = P.pool[d.srcArg + 2 * k + 1];
@@ -290,7 +349,17 @@ bool buildMixPlan(const ChainPlan& P, MixPlan* M, std::string* why) {
         M->oDelay[ch] = d.delayN; M->oDelayOff[ch] = d.delayOff;
         M->oFlags[ch] = (d.hasGain ? PF_GAIN : 0) | ((d.satKind & 1) ? PF_SAT_TPDF : 0) | (d.satKind >= SAT_GAIN ? PF_SAT_GAIN : 0);
         M->oGain[ch] = d.gainBits; M->oSatGain[ch] = d.satGainBits;
-        M->oKind[ch] = d.srcKind; M->oSrcCh[ch] = d.srcCh; M->oMatRow[ch] = c * kFastTab;
+        M->oKind[ch] = d.srcKind; M->oSrcCh[ch] = d.srcCh; M->oMatRow[ch] = ch * kFastTab;
+        memcpy(M->mat + ch * kFastTab, chainRow[c].data(), sizeof(int) * kFastTab);     // gain rows are stored per OUTPUT channel
+    }
+    // "uniform" programs take the branch-free interior path: every output channel is written, by a dense-row chain
+    // (LOAD_GAIN / LOAD_MUX), all with the same post-processing flags
+    M->uniform = (P.h.nOut & 3) == 0;
+    M->uFlags = M->oFlags[0];
+    for (int ch = 0; ch < P.h.nOut; ch++) {
+        if (M->oChain[ch] < 0 || M->oKind[ch] == SRC_LOAD || M->oFlags[ch] != M->uFlags) M->uniform = 0;
+        M->oDelayBytes[ch] = M->oDelay[ch] * 4;
+        M->oDelayPcmBytes[ch] = M->oDelay[ch] * M->nInPad * 4;
     }
     return true;
 }
@@ -303,15 +372,21 @@ cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J,
         k_mix_prng<<<(total + th - 1) / th, th, 0, stream>>>(M, A.state, A.tpdfBuf, dJump, S, T, J, L);
     }
     // tile length: window (FT + maxDelay) x nInPad words + dither values, two CTAs per SM
-    int FT = 2048;
+    // several CTAs per SM so that one tile's load phase overlaps the others' arithmetic (override: AVDSP_B200_MIX_FT)
+    int FT = 1024;
     auto smemFor = [&](int ft) { return (size_t)(ft + M.maxDelay + 4) * (M.nInPad + 1) * 4; };
-    while (FT > 256 && smemFor(FT) > 100 * 1024) FT >>= 1;
+    while (FT > 256 && smemFor(FT) > 72 * 1024) FT >>= 1;
+    if (const char* ev = getenv("AVDSP_B200_MIX_FT")) { const int v = atoi(ev); if (v >= 64 && smemFor(v) <= 200 * 1024) FT = v; }
     A.tileFrames = FT; A.winFrames = FT + M.maxDelay + 4;
     const size_t smem = smemFor(FT);
-    cudaError_t e = cudaFuncSetAttribute(k_mix_main, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     dim3 grid((T + FT - 1) / FT, S);
-    k_mix_main<<<grid, kMixThreads, smem, stream>>>(M, A);
+    cudaError_t e = cudaSuccess;
+#define LAUNCH_MIX(NPP) do { \
+        e = cudaFuncSetAttribute(k_mix_main<NPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e; \
+        k_mix_main<NPP><<<grid, kMixThreads, smem, stream>>>(M, A); } while (0)
+    if (M.nInPad == 4) LAUNCH_MIX(4); else if (M.nInPad == 8) LAUNCH_MIX(8); else if (M.nInPad == 12) LAUNCH_MIX(12); else LAUNCH_MIX(16);
+#undef LAUNCH_MIX
     k_mix_tail<<<S, 128, 0, stream>>>(M, A);
     return cudaGetLastError();
 }

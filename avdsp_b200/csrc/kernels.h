@@ -99,7 +99,8 @@ struct MixPlan {
     int storeMask, maxDelay;
     int cDelay[kFastTab], cDelayOff[kFastTab], cMuxOff[kFastTab], cOut[kFastTab];      // per chain
     int oChain[kFastTab], oDelay[kFastTab], oDelayOff[kFastTab], oFlags[kFastTab], oGain[kFastTab], oSatGain[kFastTab],
-        oKind[kFastTab], oSrcCh[kFastTab], oMatRow[kFastTab];                           // per output channel
+        oKind[kFastTab], oSrcCh[kFastTab], oMatRow[kFastTab], oDelayBytes[kFastTab], oDelayPcmBytes[kFastTab];   // per output channel
+    int uniform, uFlags;                                                                // all outputs: dense row + the same flags
     int mat[kFastTab * kFastTab];                                                        // dense gain rows [chain][input]
 };
 struct MixArgs {

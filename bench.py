@@ -207,7 +207,8 @@ def main():
     barrier()
     total_ms = e0.elapsed_time(e1)
     launches = ex.launch_count - l0
-    kernel_ms = sum(a.elapsed_time(b) for a, b in evs) / max(launches, 1)
+    launches_per_step = max(launches // max(args.steps, 1), 1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in evs) / max(args.steps, 1)      # all launches of one step (1 for the chain kernel, 3 for the mix path)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -256,7 +257,7 @@ def main():
                 tot += float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
         traffic = tot or None
     hbm = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-           "traffic": traffic, "peak_source": peak_src, "kernel": f"k_{ex.last_kernel}", "kernel_ms": kernel_ms,
+           "traffic": traffic, "peak_source": peak_src, "kernel": f"k_{ex.last_kernel}", "kernel_ms": kernel_ms, "launches_per_step": launches_per_step,
            "algorithmic_bytes_per_launch": alg_bytes}
     hbm["frac"] = hbm["achieved"] / hbm["peak"]
     int_peak = avdsp_b200.measure_int_peak(local, 4096)
