@@ -335,7 +335,8 @@ void buildChainPlan(Lowered* L) {
     for (int i = 0; i < c.h.nChains; i++) {
         ChainDesc& d = c.chains[i];
         const bool direct = d.nsec > 0 && !d.hasGain && d.satKind == SAT_PLAIN;
-        d.accRow = (d.nsec > 0 && !direct) ? c.h.nAcc++ : -1;
+        // (the float class needs no 64-bit accumulator ring: its tails leave the float accumulator in the post ring)
+        d.accRow = (d.nsec > 0 && !direct && c.h.aluClass == ALU_INT64) ? c.h.nAcc++ : -1;
         if (!direct) c.h.procChain[c.h.nProc++] = i;
     }
     for (int k = 0; k < kFastTab; k++) {

@@ -162,6 +162,78 @@ __device__ __forceinline__ void laneStepPred(Lane2<K>& L, int xin, int t, int g0
     }
 }
 
+// ---- DSP_FORMAT 3 (float ALU, int32 samples): dsp_calc_biquads_float, runtime/dsp_biquadSTD.h:84-119.
+// acc += x*b0; += x1*b1; += x2*b2; += y1*(a1); += y2*a2 in THIS order, every product truncated
+// (dspMulFloatFloat, runtime/dsp_ieee754.h:336-375 == mul.rz.ftz.f32 except when the product underflows next to
+// 2^-126, where the reference flushes one binade earlier: an error of at most 2^-125, 95 bits below the s.31
+// LSB -- the stated tolerance of this kernel; tests require identical s.31 output), every sum rounded to nearest.
+// No saturation inside a float cascade.
+template <int K>
+struct Lane2F {
+    float acc[K], x1[K], x2[K], y1[K], y2[K];
+    float b0[K], b1[K], b2[K], a1[K], a2[K];
+};
+template <int K>
+__device__ __forceinline__ void laneStepF(Lane2F<K>& L, float xin) {
+    float in[K];
+    in[0] = xin;
+#pragma unroll
+    for (int j = 1; j < K; j++) in[j] = L.y1[j - 1];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        float acc = L.acc[j];
+        acc = __fadd_rn(acc, mulFF_fast(in[j], L.b0[j]));
+        acc = __fadd_rn(acc, mulFF_fast(L.x1[j], L.b1[j]));
+        acc = __fadd_rn(acc, mulFF_fast(L.x2[j], L.b2[j]));
+        acc = __fadd_rn(acc, mulFF_fast(L.y1[j], L.a1[j]));
+        acc = __fadd_rn(acc, mulFF_fast(L.y2[j], L.a2[j]));
+        L.acc[j] = acc;
+        L.x2[j] = L.x1[j]; L.x1[j] = in[j];
+        L.y2[j] = L.y1[j]; L.y1[j] = acc;
+    }
+}
+template <int K>
+__device__ __forceinline__ void laneStepPredF(Lane2F<K>& L, float xin, int t, int g0, int T) {
+    float in[K];
+    in[0] = xin;
+#pragma unroll
+    for (int j = 1; j < K; j++) in[j] = L.y1[j - 1];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        if ((unsigned)(t - g0 - j) < (unsigned)T) {
+            float acc = L.acc[j];
+            acc = __fadd_rn(acc, mulFF_fast(in[j], L.b0[j]));
+            acc = __fadd_rn(acc, mulFF_fast(L.x1[j], L.b1[j]));
+            acc = __fadd_rn(acc, mulFF_fast(L.x2[j], L.b2[j]));
+            acc = __fadd_rn(acc, mulFF_fast(L.y1[j], L.a1[j]));
+            acc = __fadd_rn(acc, mulFF_fast(L.y2[j], L.a2[j]));
+            L.acc[j] = acc;
+            L.x2[j] = L.x1[j]; L.x1[j] = in[j];
+            L.y2[j] = L.y1[j]; L.y1[j] = acc;
+        }
+    }
+}
+// float-class source from GLOBAL memory (sample formats 3/4: int32 samples): dsp_runtime.c:565-607, 871-897
+__device__ __forceinline__ float chainSourceF(const ChainPlan& P, const ChainDesc& d, const int* __restrict__ in, int chStride) {
+    if (d.srcKind == SRC_LOAD_MUX) {
+        float X = 0.0f;
+        for (int k = 0; k < d.srcCh; k++) {
+            const int ch = P.pool[d.srcArg + 2 * k], gain = P.pool[d.srcArg + 2 * k + 1];
+            X = __fadd_rn(X, mulFF(i2fScaled(ch >= 0 ? in[(size_t)ch * chStride] : 0, 31), __int_as_float(gain)));
+        }
+        return X;
+    }
+    const float t = i2fScaled(d.srcCh >= 0 ? in[(size_t)d.srcCh * chStride] : 0, 31);
+    return (d.srcKind == SRC_LOAD_GAIN) ? mulFF(t, __int_as_float(d.srcArg)) : t;
+}
+// float-class post-processing of one accumulator: [GAIN] -> SAT0DB[_GAIN][_TPDF] (dsp_runtime.c:464-534, 636-640)
+__device__ __forceinline__ float finishF(float X, int flags, int gainBits, int satGainBits, int tv, int dither) {
+    if (flags & PF_GAIN) X = __fmul_rn(X, __int_as_float(gainBits));
+    if (flags & PF_SAT_GAIN) X = mulFF(X, __int_as_float(satGainBits));
+    if (flags & PF_SAT_TPDF) X = __fadd_rn(X, i2fScaled(tv, 31 + dither - 1));
+    return satF(X);
+}
+
 // source value of a chain for one frame from GLOBAL memory: LOAD / LOAD_GAIN / LOAD_MUX (dsp_runtime.c:565-607, 871-897)
 __device__ __forceinline__ long long chainSource(const ChainPlan& P, const ChainDesc& d, const int* __restrict__ in, int chStride) {
     if (d.srcKind == SRC_LOAD_MUX) {
@@ -185,24 +257,30 @@ __device__ __forceinline__ long long muxFromShared(const ChainPlan& P, const Cha
     return X;
 }
 
+// post-ring word -> s.31 sample: fixed point stores it as such; the float class stores the (possibly not yet saturated)
+// float and converts here (dspSaturateFloat0db + dsps31Float0DB, runtime/dsp_ieee754.h:60-83,170-184)
+template <int CLS> __device__ __forceinline__ int postToS31(int v) {
+    if (CLS == ALU_F32) return f2s31(satF(__int_as_float(v)));
+    return v;
+}
 // Phase B of the sink for interleaved output with NOUT (power of two) channels: 32/NOUT frames per pass.
-template <int F, int NOUT>
+template <int F, int NOUT, int CLS>
 __device__ __forceinline__ void storePasses(int* __restrict__ out, unsigned rowA, unsigned p4, unsigned RM4, int mask,
                                             bool clean, int fw0, int fs, int T) {
     constexpr int FPP = 32 / NOUT, NPASS = F / FPP;
     if (clean) {
 #pragma unroll
-        for (int p = 0; p < NPASS; p++) out[p * 32] = lds32(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4)) & mask;
+        for (int p = 0; p < NPASS; p++) out[p * 32] = postToS31<CLS>(lds32(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
     } else {
 #pragma unroll 1
         for (int p = 0; p < NPASS; p++) {
             const int ff = fw0 + p * FPP + fs;
-            if (ff >= 0 && ff < T) out[p * 32] = lds32(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4)) & mask;
+            if (ff >= 0 && ff < T) out[p * 32] = postToS31<CLS>(lds32(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
         }
     }
 }
 
-template <int K, int F>
+template <int K, int F, int CLS>
 __global__ void __launch_bounds__(1024, 1)
 k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_constant__ Chain2Geom G) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -218,7 +296,77 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
     const int RM = G.postRing - 1;
     constexpr int XP = 2 * F + 1, AP = 2 * F + 1, TP = 4 * F + 1;        // row pitches (elements) of x / acc / tpdf rings
 
-    if (tid < G.secThreads) {
+    if (CLS == ALU_F32 && tid < G.secThreads) {
+        // =========================================================================== section warps, float ALU
+        int* x_s = reinterpret_cast<int*>(smem_raw + G.xOff);
+        int* post_s = reinterpret_cast<int*>(smem_raw + G.postOff);
+        Lane2F<K> L;
+        const ChainLane e = A.lanes[tid];
+        const bool live = e.slot >= 0 && e.slot / C < nsHere;
+        const bool head = (e.flags & 1) != 0, tail = (e.flags & 2) != 0;
+        const int g0 = e.firstSec;
+        const int slot = e.slot < 0 ? 0 : e.slot;
+        int* stLane = nullptr;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            L.acc[k] = L.x1[k] = L.x2[k] = L.y1[k] = L.y2[k] = 0.0f;
+            L.b0[k] = L.b1[k] = L.b2[k] = L.a1[k] = L.a2[k] = 0.0f;
+        }
+        const ChainDesc& d = P.chains[slot % C];
+        if (live) {
+            stLane = A.state + (size_t)(s0 + slot / C) * W;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int sec = g0 + k;
+                const int* cf = P.pool + d.coefOff + 5 * sec;
+                L.b0[k] = __int_as_float(cf[0]); L.b1[k] = __int_as_float(cf[1]); L.b2[k] = __int_as_float(cf[2]);
+                L.a1[k] = __int_as_float(cf[3]); L.a2[k] = __int_as_float(cf[4]);
+                const int* q = stLane + P.pool[d.secStateOff + sec];        // [acc, -, x1, x2, y1, y2] (dsp_biquadSTD.h:84-119)
+                L.acc[k] = __int_as_float(q[0]);
+                L.x1[k] = __int_as_float(q[2]); L.x2[k] = __int_as_float(q[3]); L.y1[k] = __int_as_float(q[4]); L.y2[k] = __int_as_float(q[5]);
+            }
+        }
+        const int* xrow = x_s + (size_t)((slot / C) * nSrc + max(d.srcId, 0)) * XP;
+        int* prow = post_s + (size_t)slot * G.postPitch;
+        for (int i = 0; i < nTiles; i++) {
+            barSync(kBarFull + (i & 1), nAll);
+            const int* xs = xrow + (i & 1) * F;
+            const int t0 = i * F;
+            int* ps = prow + (t0 & RM);
+            if (t0 >= gmax && t0 + F <= T) {
+#pragma unroll 1
+                for (int j0 = 0; j0 < F; j0 += UNR) {
+#pragma unroll
+                    for (int jj = 0; jj < UNR; jj++) {
+                        const int j = j0 + jj;
+                        float x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
+                        if (head) x = __int_as_float(xs[j]);
+                        laneStepF<K>(L, x);
+                        if (tail) ps[j] = __float_as_int(L.acc[K - 1]);     // the sink saturates / converts (satF is idempotent)
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < F; j++) {
+                    float x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
+                    if (head) x = __int_as_float(xs[j]);
+                    laneStepPredF<K>(L, x, t0 + j, g0, T);
+                    if (tail && (unsigned)(t0 + j - g0 - (K - 1)) < (unsigned)T) ps[j] = __float_as_int(L.acc[K - 1]);
+                }
+            }
+            barArrive(kBarDone + (i & 1), nAll);
+        }
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                int* q = stLane + P.pool[d.secStateOff + g0 + k];
+                q[0] = __float_as_int(L.acc[k]);
+                q[2] = __float_as_int(L.x1[k]); q[3] = __float_as_int(L.x2[k]); q[4] = __float_as_int(L.y1[k]); q[5] = __float_as_int(L.y2[k]);
+            }
+        }
+        return;
+    }
+    if (CLS == ALU_INT64 && tid < G.secThreads) {
         // =========================================================================== section warps
         long long* acc_s = reinterpret_cast<long long*>(smem_raw);
         int* x_s = reinterpret_cast<int*>(smem_raw + G.xOff);
@@ -450,8 +598,14 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                     for (int k = 0; k < kFastTab; k++) {
                         if (k >= nSrc) break;
                         const int smp = lds32(ra + (interleavedIn ? (unsigned)(P.h.sCh[k] * 4) : (unsigned)(P.h.sCh[k] * F * 4)));
-                        sts32(xa + G.srcXOff[k], q59ToS31(mul32(smp, P.h.sArg[k])));
+                        if (CLS == ALU_F32) sts32(xa + G.srcXOff[k], __float_as_int(mulFF(i2fScaled(smp, 31), __int_as_float(P.h.sArg[k]))));
+                        else sts32(xa + G.srcXOff[k], q59ToS31(mul32(smp, P.h.sArg[k])));
                     }
+                    continue;
+                }
+                if (CLS == ALU_F32) {            // float class, any source kind: straight from global memory
+                    for (int k = 0; k < nSrc; k++)
+                        sts32(xa + (unsigned)(k * XP * 4), __float_as_int(chainSourceF(P, P.chains[P.h.srcChain[k]], in, A.inChStride)));
                     continue;
                 }
                 // flattened source tables with static indices: constant-bank operands, no descriptor loads
@@ -476,7 +630,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         issueTile(it + 2);                               // refill this parity's buffer two tiles ahead
     };
 
-    bool simpleA = !anyStale && !(G.debugSkip & 8);             // all post-processed chains are cascade -> SAT0DB_TPDF
+    bool simpleA = CLS == ALU_INT64 && !anyStale && !(G.debugSkip & 8);             // all post-processed chains are cascade -> SAT0DB_TPDF
     for (int k = 0; k < P.h.nProc && k < kFastTab; k++) simpleA = simpleA && P.h.pFlags[k] == (PF_SECTIONS | PF_SAT_TPDF);
     const bool tpdfUp = P.h.tpdfShift >= 0;                    // warp-uniform: the dither is shifted up (usual) or down
     const int tpdfSh = (tpdfUp ? P.h.tpdfShift : -P.h.tpdfShift) & 63;
@@ -490,6 +644,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
     const unsigned bPos4 = (unsigned)((bFs + P.h.outOff[bCh]) * 4);
     const int bMask = bChain >= 0 ? storeMask : 0;             // outputs no path writes read as 0
 
+    auto isProc = [&](int c) { for (int k = 0; k < P.h.nProc; k++) if (P.h.procChain[k] == c) return true; return false; };
     // ---- sink stage of window `iw`
     auto sinkWindow = [&](int iw) {
         if (prngOnly || lane >= F || (G.debugSkip & 4)) return;
@@ -504,7 +659,29 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         for (int sl = ow; sl < nsHere; sl += nOwn, postA += nOwn * G.postStreamBytes, accA += nOwn * G.accStreamBytes, tpdfA += nOwn * G.tpdfStreamBytes) {
             // A: step t of every chain that needs post-processing: accumulator (or inline source) -> [gain] -> saturate
             //    (+dither, +gain) -> post ring (dsp_runtime.c:464-534, 636-640).  Direct chains were written by their tails.
-            if (simpleA && iw * F >= gmax && (iw + 1) * F <= T) {
+            if (CLS == ALU_F32) {
+                // float class: the tail lanes left the cascade's accumulator (float bits) in the post ring; chains with
+                // gain / dither are finished in place, the others are saturated and converted by stage B
+                for (int k = 0; k < P.h.nProc; k++) {
+                    const int c = P.h.procChain[k];
+                    const ChainDesc& d = P.chains[c];
+                    const int fk = t - (d.nsec > 0 ? d.nsec - 1 : 0);
+                    if (fk < 0 || fk >= T) continue;
+                    const unsigned pa = postA + (unsigned)(c * G.postPitch * 4) + tpos4;
+                    float X;
+                    if (d.nsec > 0) X = __int_as_float(lds32(pa));
+                    else {
+                        X = chainSourceF(P, d, A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)fk * A.inFrameStride, A.inChStride);
+                        if (d.srcKind == SRC_LOAD_MUX && fk == T - 1) A.state[(size_t)(s0 + sl) * W + d.muxStateOff] = __float_as_int(X);
+                    }
+                    const int flags = (d.hasGain ? PF_GAIN : 0) | ((d.satKind & 1) ? PF_SAT_TPDF : 0) | (d.satKind >= SAT_GAIN ? PF_SAT_GAIN : 0);
+                    const int tv = (flags & PF_SAT_TPDF) ? lds32(tpdfA + ((unsigned)(fk & (4 * F - 1)) << 2)) : 0;
+                    const int v = __float_as_int(finishF(X, flags, d.gainBits, d.satGainBits, tv, P.h.storeDither));
+                    if (anyStale && fk == 0 && d.delayN > 0 && stale_s[sl * C + c] >= 0)
+                        A.state[(size_t)(s0 + sl) * W + d.delayOff + 1 + stale_s[sl * C + c]] = v;
+                    else sts32(pa, v);
+                }
+            } else if (simpleA && iw * F >= gmax && (iw + 1) * F <= T) {
                 // common case, branch-free: every post-processed chain is cascade -> SAT0DB_TPDF and the window is interior
 #pragma unroll
                 for (int k = 0; k < kFastTab; k++) {
@@ -553,7 +730,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         // every tail lane stores its y1 at the slot of frame 0; a direct chain's is the real post(0)
                         // (a post-processed chain's post(0) was sent to ring[idx0] by stage A above)
                         int* pr = post_s + (size_t)(sl * C + c) * G.postPitch + ((d.nsec - 1) & RM);
-                        if (d.accRow < 0) A.state[(size_t)(s0 + sl) * W + d.delayOff + 1 + stale_s[sl * C + c]] = *pr;
+                        if (d.accRow < 0 && !(CLS == ALU_F32 && isProc(c)))
+                            A.state[(size_t)(s0 + sl) * W + d.delayOff + 1 + stale_s[sl * C + c]] = CLS == ALU_F32 ? __float_as_int(satF(__int_as_float(*pr))) : *pr;
                         *pr = sfix_s[sl * C + c];
                     }
                 }
@@ -570,11 +748,11 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 const unsigned p4 = (unsigned)(fw0 << 2) + bPos4;           // 4*(post-ring step of this lane's element in pass 0)
                 const bool clean = fw0 >= 0 && fw0 + F <= T;
                 switch (nOut) {
-                case 1:  storePasses<F, 1>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
-                case 2:  storePasses<F, 2>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
-                case 4:  storePasses<F, 4>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
-                case 8:  storePasses<F, 8>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
-                default: storePasses<F, 16>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                case 1:  storePasses<F, 1, CLS>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                case 2:  storePasses<F, 2, CLS>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                case 4:  storePasses<F, 4, CLS>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                case 8:  storePasses<F, 8, CLS>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                default: storePasses<F, 16, CLS>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
                 }
             } else if (f >= 0 && f < T) {
                 // any layout: lane = frame, 16-byte stores when the layout allows
@@ -617,7 +795,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         auxp[AUX_TPDF_VALUE] = tpdfValue; auxp[AUX_TPDF_RANDOM] = tpdfRandom; auxp[AUX_DITHER] = dith;
         if (drew) {   // TPDF_CALC leaves its last value (as an ALU word) in the data area (dsp_runtime.c:541-543)
             int* q = A.state + (size_t)(s0 + lane) * W + P.h.tpdfDataOff;
-            q[0] = tpdfValue; q[1] = tpdfValue >> 31;
+            if (CLS == ALU_F32) q[0] = __float_as_int(i2fScaled(tpdfValue, 31));
+            else { q[0] = tpdfValue; q[1] = tpdfValue >> 31; }
         }
     }
     if (prngOnly || T <= 0) return;
@@ -628,8 +807,9 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
             const ChainDesc& d = P.chains[c];
             // last LOAD_MUX value of chains with sections stays in the data area (dsp_runtime.c:893-896)
             if (d.srcKind == SRC_LOAD_MUX && d.nsec > 0 && lane == 0) {
-                const long long X = chainSource(P, d, A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(T - 1) * A.inFrameStride, A.inChStride);
-                st[d.muxStateOff] = (int)X; st[d.muxStateOff + 1] = (int)(X >> 32);
+                const int* fr = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(T - 1) * A.inFrameStride;
+                if (CLS == ALU_F32) st[d.muxStateOff] = __float_as_int(chainSourceF(P, d, fr, A.inChStride));
+                else { const long long X = chainSource(P, d, fr, A.inChStride); st[d.muxStateOff] = (int)X; st[d.muxStateOff + 1] = (int)(X >> 32); }
             }
             // delay line back to the reference's ring layout: frame j sits at position (idx0+j) mod n
             const int n = d.delayN;
@@ -640,7 +820,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
             int* ring = st + d.delayOff + 1;
             for (int k = lane; k < n; k += 32) {
                 const int j = T - n + k;                                     // frames T-n .. T-1 (virtual ones included)
-                ring[(int)(((long long)idx0 + j + n) % n)] = prow[(j + gc) & RM];
+                const int pv = prow[(j + gc) & RM];       // float class: direct chains still hold the unsaturated accumulator
+                ring[(int)(((long long)idx0 + j + n) % n)] = CLS == ALU_F32 ? __float_as_int(satF(__int_as_float(pv))) : pv;
             }
             if (lane == 0) st[d.delayOff] = (int)(((long long)idx0 + T) % n);
         }
@@ -691,7 +872,7 @@ static int packLanes2(const ChainPlan& p, int NS, int K, ChainLane* out, int* gm
 
 bool chain2Supports(const ChainPlan& plan) {
     // the helper warps address everything through the flattened tables (plan.h: kFastTab entries each)
-    return plan.h.aluClass == ALU_INT64 && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nOut <= kFastTab &&
+    return (plan.h.aluClass == ALU_INT64 || plan.h.aluClass == ALU_F32) && plan.h.sampleInt && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nOut <= kFastTab &&
            plan.h.nProc <= kFastTab && plan.h.nSrc <= kFastTab;
 }
 
@@ -767,9 +948,15 @@ cudaError_t launchChain2(const ChainPlan& plan, const Chain2Geom& geom, const Ch
     const int threads = geom.secThreads + geom.helpThreads;
     cudaError_t e = cudaSuccess;
 #define LAUNCH2(KK, FF) do { \
-    e = cudaFuncSetAttribute(k_chain2<KK, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geom.smemBytes); \
-    if (e != cudaSuccess) return e; \
-    k_chain2<KK, FF><<<blocks, threads, geom.smemBytes, stream>>>(plan, args, geom); } while (0)
+    if (plan.h.aluClass == ALU_F32) { \
+        e = cudaFuncSetAttribute(k_chain2<KK, FF, ALU_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geom.smemBytes); \
+        if (e != cudaSuccess) return e; \
+        k_chain2<KK, FF, ALU_F32><<<blocks, threads, geom.smemBytes, stream>>>(plan, args, geom); \
+    } else { \
+        e = cudaFuncSetAttribute(k_chain2<KK, FF, ALU_INT64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geom.smemBytes); \
+        if (e != cudaSuccess) return e; \
+        k_chain2<KK, FF, ALU_INT64><<<blocks, threads, geom.smemBytes, stream>>>(plan, args, geom); \
+    } } while (0)
     const int key = geom.secPerLane * 100 + geom.tileFrames;
     switch (key) {
     case 432: LAUNCH2(4, 32); break;

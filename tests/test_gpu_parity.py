@@ -54,13 +54,17 @@ def test_golden_vectors_auto_kernel(name):
     """Whatever kernel AUTO picks (the fused chain kernel where the program maps to it) must give the
     reference's bits for fixed point; float formats through the chain kernel: see tolerance test."""
     v = load_vector(name)
-    if v["fmt"] != 2:
-        pytest.skip("float formats: covered by test_float_formats_auto_kernel")
     w = load_program(v["program"])
     ex = Executor(w, v["fs"], v["fmt"], 1, seeds=[v["seed"]], dither=v["dither"])
     y = ex.process(v["x"][None])[0]
     assert np.array_equal(y, v["y"]), f"{name} ({ex.last_kernel}): {np.count_nonzero(y != v['y'])} samples differ"
-    assert np.array_equal(ex.get_state(0)[: ex.data_size], v["data"]), f"{name} ({ex.last_kernel}): state differs"
+    got, exp = ex.get_state(0)[: ex.data_size], v["data"]
+    if v["fmt"] == 3 and ex.last_kernel == "chain":        # float chain kernel: state tolerance 2^-100 (see multi-stream test)
+        d = np.nonzero(got != exp)[0]
+        if d.size:
+            assert np.abs(got[d].view(np.float32).astype(np.float64) - exp[d].view(np.float32).astype(np.float64)).max() <= 2.0 ** -100
+    else:
+        assert np.array_equal(got, exp), f"{name} ({ex.last_kernel}): state differs"
 
 
 @pytest.mark.parametrize("prog,fmt,fs", CASES)
@@ -74,13 +78,17 @@ def test_parity_vs_oracle_multi_stream(oracle_lib, prog, fmt, fs, kernel):
     x = gen(fmt)("full" if fmt == 2 else "noise", S, T, ex.n_in, fs)
     ys, sts = oracle_run(oracle_lib, w, fmt, fs, x, seeds, 24)
     y = ex.process(x)
-    if fmt != 2 and ex.last_kernel == "chain":
-        pytest.skip("float chain kernel: tolerance test")
     bad = np.count_nonzero(y != ys)
     assert bad == 0, f"{prog} [{ex.last_kernel}]: {bad}/{y.size} samples differ"
     for s in (0, 1, S - 1):
         got, exp = ex.get_state(s), expected_state(ex, sts[s])
         diff = np.nonzero(got != exp)[0]
+        if fmt != 2 and ex.last_kernel == "chain" and diff.size:
+            # float chain kernel: products use mul.rz.ftz.f32; the reference flushes products next to 2^-126 one binade
+            # earlier (dsp_ieee754.h:336-375).  Stated tolerance on float state words: 2^-100 absolute; s.31 outputs exact.
+            err = np.abs(got[diff].view(np.float32).astype(np.float64) - exp[diff].view(np.float32).astype(np.float64))
+            assert err.max() <= 2.0 ** -100, f"{prog} stream {s}: float state differs by {err.max()}"
+            continue
         assert diff.size == 0, f"{prog} [{ex.last_kernel}] stream {s}: state words {diff[:8]} differ"
 
 
@@ -119,8 +127,8 @@ def test_kernels_agree_and_can_alternate():
 
 def test_chain_kernel_is_selected_for_the_benchmark_programs():
     for prog, fs, kern in (("c2_testrpi_xover_f2_192k", 192000, "chain"), ("c5_mixer8x8_f2_192k", 192000, "mix"),
-                           ("c3_peq16_f2_48k", 48000, "chain")):
-        ex = Executor(load_program(prog), fs, 2, 64)
+                           ("c3_peq16_f2_48k", 48000, "chain"), ("c3_peq16_f3_48k", 48000, "chain")):
+        ex = Executor(load_program(prog), fs, 3 if "_f3_" in prog else 2, 64)
         ex.process(synth.pcm("noise", 64, 64, ex.n_in, fs))
         assert ex.last_kernel == kern, ex.trace
     ex = Executor(load_program("c1_crossover2x2lfe_f2_48k"), 48000, 2, 4)   # MEM hand-off, X/Y dataflow
