@@ -38,6 +38,8 @@ WORKLOADS = {
            "C5 8x8 matrix mixer + per-channel delays + gain/TPDF dither, int64 fixed point, 192 kHz"),
     "c3": ("c3_peq16_f2_48k", 2, 48000, 65536, 4096, 160,
            "C3 16-section parametric EQ per channel x2 (fixed-point encoding), 48 kHz"),
+    "c3f": ("c3_peq16_f3_48k", 3, 48000, 65536, 4096, 160,
+            "C3 16-section parametric EQ per channel x2, float format (DSP_FORMAT 3), 48 kHz"),
 }
 
 
