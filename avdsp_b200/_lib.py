@@ -22,7 +22,7 @@ SYMBOLS = [
     "avdsp_b200_reload_params", "avdsp_b200_state_words", "avdsp_b200_data_size", "avdsp_b200_aux_offset",
     "avdsp_b200_mem_offset", "avdsp_b200_num_mem", "avdsp_b200_mem_word", "avdsp_b200_get_state",
     "avdsp_b200_set_state", "avdsp_b200_num_streams", "avdsp_b200_num_cores", "avdsp_b200_trace",
-    "avdsp_b200_last_error", "avdsp_b200_measure_int_peak",
+    "avdsp_b200_last_error", "avdsp_b200_measure_int_peak", "avdsp_b200_measure_f32_peak",
 ]
 
 _lib = None
@@ -76,6 +76,8 @@ def lib():
     L.avdsp_b200_last_error.restype = C.c_char_p
     L.avdsp_b200_measure_int_peak.argtypes = [ci, ci]
     L.avdsp_b200_measure_int_peak.restype = C.c_double
+    L.avdsp_b200_measure_f32_peak.argtypes = [ci, ci, ci]
+    L.avdsp_b200_measure_f32_peak.restype = C.c_double
     # reference entry points
     L.dspRuntimeInit.argtypes = [vp, ci, ci, ci, ci]
     L.dspRuntimeReset.argtypes = [ci, ci, ci]

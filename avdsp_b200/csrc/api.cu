@@ -69,6 +69,51 @@ __global__ void __launch_bounds__(256) k_int_peak(long long* out, int iters, int
     if (s == 0x123456789abcdefll) out[0] = s;     // practically never true; keeps the chains alive
 }
 
+// float-pipe microbenchmark for the FP32 roofline of the float kernels: 8 independent chains per thread of the
+// reference's non-fused MAC, acc = add.rn(acc, mul.rz.ftz(x, c)) -- scalar (FMUL + FADD) or packed (FMUL2 + FADD2,
+// two MACs per instruction pair).  Counts MACs.
+template <int PACKED>
+__global__ void __launch_bounds__(256) k_f32_peak(float* out, int iters, float c0) {
+    const float c = c0 + 1e-7f * (float)blockIdx.x;
+    if constexpr (PACKED == 0) {
+        float acc[8], x[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { acc[k] = 0.f; x[k] = 1e-3f * (float)(k + 1 + (int)threadIdx.x); }
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                float p; asm volatile("mul.rz.ftz.f32 %0, %1, %2;" : "=f"(p) : "f"(x[k]), "f"(c));
+                asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(acc[k]) : "f"(p));
+            }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += acc[k];
+        if (s == 123.456f) out[0] = s;
+    } else {
+        unsigned long long acc[8], x[8], cc;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float a = 1e-3f * (float)(k + 1 + (int)threadIdx.x);
+            asm("mov.b64 %0, {%1, %1};" : "=l"(x[k]) : "f"(a));
+            acc[k] = 0ull;
+        }
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                unsigned long long p;
+                asm volatile("mul.rz.ftz.f32x2 %0, %1, %2;" : "=l"(p) : "l"(x[k]), "l"(cc));
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc[k]) : "l"(p));
+            }
+        }
+        unsigned long long s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s ^= acc[k];
+        if (s == 0x123456789abcdefull) out[0] = 1.f;
+    }
+}
+
 // ALSA sample formats -> s.31 (linux/avdsp_plugin.c:109-121)
 __global__ void k_widen_pcm(const unsigned char* __restrict__ src, int fmt, int* __restrict__ dst, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,6 +141,7 @@ struct avdsp_b200 {
     bool chain2Usable = false;      // kernel_chain2.cu (v2: warp-specialised, the default)
     MixPlan mix{};
     bool mixUsable = false;         // kernel_mix.cu (time-parallel: programs without biquads)
+    bool firUsable = false;         // kernel_fir.cu (time-parallel FIR paths)
     unsigned* dJump = nullptr; int jumpL = -1;      // PRNG jump matrix for segments of jumpL draws
     int* dTpdf = nullptr; size_t tpdfWords = 0;     // scratch dither values of a launch
     int period = 0, kernelSel = AVDSP_B200_KERNEL_AUTO, lastKernel = 0;
@@ -143,8 +189,13 @@ static int uploadPlanData(avdsp_b200* h) {
     }
     h->mixUsable = false;
     if (L.chainOk) { std::string why; h->mixUsable = buildMixPlan(L.chain, &h->mix, &why); }
+    h->firUsable = L.firOk;
     char line[320];
     h->trace = L.trace;
+    if (h->firUsable) {
+        snprintf(line, sizeof line, "time-parallel FIR kernel: usable (%d paths, longest impulse %d taps)\n", L.fir.nPaths, L.fir.maxLen);
+        h->trace += line;
+    } else if (!L.firs.empty()) h->trace += "FIR kernel not used: " + L.firWhyNot + "\n";
     if (h->mixUsable) h->trace += "time-parallel mix kernel: usable (no biquad in any path)\n";
     if (h->chain2Usable) {
         snprintf(line, sizeof line, "chain kernel v2 geometry: %d streams/CTA, %d sections/lane, tile %d frames, gmax %d, %d section threads + %d helper threads, %d sources, %zu B smem\n",
@@ -280,7 +331,7 @@ int avdsp_b200_set_order(avdsp_b200_t* h, int period) {
     h->period = period; return 0;
 }
 int avdsp_b200_set_kernel(avdsp_b200_t* h, int which) {
-    if (!h || which < 0 || which > 4) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
+    if (!h || which < 0 || which > 5) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
     h->kernelSel = which; return 0;
 }
 int avdsp_b200_last_kernel(const avdsp_b200_t* h) { return h ? h->lastKernel : 0; }
@@ -323,12 +374,25 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         else if (h->chainUsable) use = AVDSP_B200_KERNEL_CHAIN_V1;
     }
     if (chainOrder && h->mixUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_MIX)) use = AVDSP_B200_KERNEL_MIX;
+    if (chainOrder && h->firUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_FIR)) use = AVDSP_B200_KERNEL_FIR;
+    if (h->kernelSel == AVDSP_B200_KERNEL_FIR && use != AVDSP_B200_KERNEL_FIR)
+        return setErr(AVDSP_B200_ERR_UNSUPPORTED, "FIR kernel requested but this program/order does not map to it: " + h->L.firWhyNot);
     if (h->kernelSel == AVDSP_B200_KERNEL_MIX && use != AVDSP_B200_KERNEL_MIX)
         return setErr(AVDSP_B200_ERR_UNSUPPORTED, "mix kernel requested but the program has biquads or does not map to independent paths");
     if ((h->kernelSel == AVDSP_B200_KERNEL_CHAIN || h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1) && use == AVDSP_B200_KERNEL_GENERIC)
         return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel requested but this program/order does not map to it: " + h->L.chainWhyNot);
     cudaError_t e;
-    if (use == AVDSP_B200_KERNEL_MIX) {
+    if (use == AVDSP_B200_KERNEL_FIR) {
+        FirArgs A{};
+        A.in = in; A.out = out; A.state = st; A.bigPool = h->dBig;
+        A.nStreams = n; A.nFrames = nFrames;
+        A.inStreamStride = inSS; A.outStreamStride = outSS;
+        A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
+        int nl = 0;
+        e = launchFir(h->L.fir, A, h->numSMs, stream, &nl);
+        h->lastKernel = AVDSP_B200_KERNEL_FIR;
+        h->launches += nl - 1;
+    } else if (use == AVDSP_B200_KERNEL_MIX) {
         MixArgs A{};
         A.in = in; A.out = out; A.state = st;
         A.nStreams = n; A.nFrames = nFrames;
@@ -559,6 +623,28 @@ double avdsp_b200_measure_int_peak(int device, int iters) {
         float ms = 0; cudaEventElapsedTime(&ms, a, b);
         const double rate = (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
         best = std::max(best, rate);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    return best;
+}
+
+double avdsp_b200_measure_f32_peak(int device, int iters, int packed) {
+    if (cudaSetDevice(device) != cudaSuccess) { setErr(AVDSP_B200_ERR_CUDA, "no CUDA device"); return 0.0; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0.0;
+    float* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return 0.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(a);
+        if (packed) k_f32_peak<1><<<blocks, threads>>>(d, iters, 0.37f); else k_f32_peak<0><<<blocks, threads>>>(d, iters, 0.37f);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) { best = 0.0; break; }
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        const double rate = (double)blocks * threads * 8.0 * (packed ? 2.0 : 1.0) * iters / (ms * 1e-3);
+        if (rep) best = std::max(best, rate);
     }
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
     return best;

@@ -355,6 +355,59 @@ void buildChainPlan(Lowered* L) {
     }
 }
 
+// ---- FIR path recognition (kernel_fir.cu) ---------------------------------------------------------
+// LOAD|LOAD_GAIN -> FIR(convolution) -> [GAIN] -> SAT0DB|SAT0DB_GAIN -> STORE+ , any number of such paths per core.
+void buildFirPlan(Lowered* L) {
+    const GenericPlan& g = L->gen;
+    FirPlan& f = L->fir;
+    memset(&f, 0, sizeof f);
+    f.aluClass = g.h.aluClass; f.nIn = g.h.nIn; f.nOut = g.h.nOut; f.stateWords = g.h.stateWords;
+    f.storeMask = (int32_t)(0xFFFFFFFFu << ((32 - g.h.defaultDither) & 31));     // dspTpdfPrepare, dsp_tpdf.h:55-80
+    if (L->firs.empty()) throw ChainFail{"no DSP_FIR in the program"};
+    if (g.h.aluClass == ALU_F64 || !g.h.sampleInt) throw ChainFail{"FIR kernels cover DSP_FORMAT 2 and 3; formats 4..6 run on the generic executor"};
+    int inChOfSlot[kIoSlots], outChOfSlot[kIoSlots], owner[kIoSlots];
+    for (int k = 0; k < kIoSlots; k++) { inChOfSlot[k] = outChOfSlot[k] = -1; owner[k] = -1; }
+    for (int k = 0; k < g.h.nIn; k++)  inChOfSlot[g.h.inIdx[k]] = k;
+    for (int k = 0; k < g.h.nOut; k++) outChOfSlot[g.h.outIdx[k]] = k;
+    uint32_t written = 0;
+    for (int i = 0; i < g.h.nOps; i++) if (g.ops[i].op == OP_STORE) written |= 1u << g.ops[i].a;
+    for (int core = 0; core < g.h.nCores; core++) {
+        int i = g.h.coreStart[core]; const int e = g.h.coreStart[core + 1];
+        while (i < e) {
+            if (f.nPaths >= kMaxFirPaths) throw ChainFail{"more than kMaxFirPaths FIR paths"};
+            FirPath& d = f.paths[f.nPaths];
+            const MicroOp& s = g.ops[i];
+            if (s.op != OP_LOAD && s.op != OP_LOAD_GAIN) throw ChainFail{"a path does not start with LOAD / LOAD_GAIN"};
+            if ((written >> s.a) & 1u) throw ChainFail{"an input slot is also written by the program"};
+            d.srcKind = s.op == OP_LOAD ? SRC_LOAD : SRC_LOAD_GAIN; d.srcCh = inChOfSlot[s.a]; d.srcArg = s.b;
+            i++;
+            if (i >= e || g.ops[i].op != OP_FIR || g.ops[i].n != 1) throw ChainFail{"a path has no FIR convolution right after its load"};
+            d.stateOff = g.ops[i].a; d.tapsOff = g.ops[i].b; d.length = g.ops[i].c;
+            if (d.length > kMaxFirTaps) throw ChainFail{"impulse longer than kMaxFirTaps"};
+            if (d.length > f.maxLen) f.maxLen = d.length;
+            i++;
+            if (i < e && g.ops[i].op == OP_GAIN) { d.flags |= PF_GAIN; d.gainBits = g.ops[i].a; i++; }
+            if (i >= e) throw ChainFail{"a path ends without saturation/store"};
+            if (g.ops[i].op == OP_SAT0DB_GAIN) { d.flags |= PF_SAT_GAIN; d.satGainBits = g.ops[i].a; }
+            else if (g.ops[i].op != OP_SAT0DB) throw ChainFail{"a FIR path has an opcode the FIR kernels do not fuse"};
+            i++;
+            if (i >= e || g.ops[i].op != OP_STORE) throw ChainFail{"a path does not end with STORE"};
+            while (i < e && g.ops[i].op == OP_STORE) {
+                if (d.nStores >= kMaxChainStores) throw ChainFail{"too many STOREs on one path"};
+                const int ch = outChOfSlot[g.ops[i].a];
+                if (ch < 0) throw ChainFail{"STORE to a slot outside the declared outputs"};
+                if (owner[ch] >= 0) throw ChainFail{"two paths store to the same output"};
+                owner[ch] = f.nPaths;
+                d.storeCh[d.nStores++] = ch;
+                i++;
+            }
+            f.nPaths++;
+        }
+    }
+    if (f.nPaths == 0) throw ChainFail{"no signal path"};
+    for (int k = 0; k < g.h.nOut; k++) if (owner[k] < 0) f.unwritten[f.nUnwritten++] = k;
+}
+
 void lowerAll(Lowered* L) {
     Ctx cx; cx.L = L; cx.w = L->words.data(); cx.total = L->totalLength;
     cx.delayFactor = (uint32_t)(4294.967296 * (double)L->fs);      // dsp_runtime.c:81-90
@@ -389,6 +442,8 @@ void lowerAll(Lowered* L) {
 
     try { buildChainPlan(L); L->chainOk = true; L->chainWhyNot.clear(); }
     catch (const ChainFail& f) { L->chainOk = false; L->chainWhyNot = f.why; }
+    try { buildFirPlan(L); L->firOk = true; L->firWhyNot.clear(); }
+    catch (const ChainFail& f) { L->firOk = false; L->firWhyNot = f.why; }
 
     // lowering trace (the B200 counterpart of the reference's DSP_PRINTF>=2 opcode trace)
     char line[160];

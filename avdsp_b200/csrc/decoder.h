@@ -28,6 +28,9 @@ struct Lowered {
     ChainPlan chain{};
     std::vector<int32_t> bigPool;        // FIR taps / data tables (device: HBM)
     std::vector<FirDesc> firs;
+    bool firOk = false;                  // program maps to the time-parallel FIR kernels (kernel_fir.cu)
+    std::string firWhyNot;
+    FirPlan fir{};
     // MEM words (LOAD_MEM / STORE_MEM targets inside the code area)
     std::vector<int> memWord;            // code word index of each slot
     // human readable trace of the lowering (replaces the reference's DSP_PRINTF=2 opcode trace)

@@ -259,12 +259,14 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
         case OP_FIR: {
             int* s = st + m.a;
             if (m.n == 0) {                                   // plain delay of m.b samples, stores X>>28
-                int idx = s[0];
+                // dsp_runtime.c:943 reads/writes the ring index through the dspALU_SP_t pointer: a float in formats 3..6
+                int idx;
+                if constexpr (CLS == ALU_INT64) idx = s[0]; else idx = (int)__int_as_float(s[0]);
                 const SPT old = ldSP<CLS>(s + 1 + idx);
                 if constexpr (CLS == ALU_INT64) s[1 + idx] = (int)(X >> kMant); else stSP<CLS>(s + 1 + idx, (SPT)X);
                 X = old;
                 idx++; if (idx >= m.b) idx = 0;
-                s[0] = idx;
+                if constexpr (CLS == ALU_INT64) s[0] = idx; else s[0] = __float_as_int((float)idx);
             } else {
                 const int* taps = big + m.b;
                 if constexpr (CLS == ALU_INT64) {            // intended semantics, see DESIGN.md "FIR"

@@ -117,4 +117,16 @@ bool buildMixPlan(const ChainPlan& plan, MixPlan* out, std::string* why);
 void mixJumpMatrix(long long steps, unsigned* out /*[128*4]*/);
 cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J, int L, int numSMs, cudaStream_t stream);
 
+// ---- time-parallel FIR kernels (kernel_fir.cu) ---------------------------------------------------
+struct FirArgs {
+    const int* in;  int* out;
+    int* state;
+    const int* bigPool;         // taps (Q4.28 ints or float bits)
+    int nStreams, nFrames;
+    long long inStreamStride, outStreamStride;
+    int inFrameStride, inChStride, outFrameStride, outChStride;
+};
+// exact kernels: int64 accumulation (any order is exact) / float in the reference's tap order
+cudaError_t launchFir(const FirPlan& plan, const FirArgs& args, int numSMs, cudaStream_t stream, int* launches);
+
 } // namespace avdsp

@@ -141,4 +141,24 @@ struct FirDesc {
     int32_t stateOff;    // data-area offset of the delay line (length words)
 };
 
+// Programs made only of paths   LOAD|LOAD_GAIN -> FIR (convolution) -> [GAIN] -> SAT0DB[_GAIN] -> STORE(s)
+// (room-correction / linear-phase crossover programs: BASELINE config C4) run on the time-parallel FIR
+// kernels (kernel_fir.cu) instead of the per-frame interpreter.
+constexpr int kMaxFirPaths = 16;
+constexpr int kMaxFirTaps  = 8192;
+struct FirPath {
+    int32_t srcKind, srcCh, srcArg;      // ChainSrc; INPUT CHANNEL number (-1: reads 0); LOAD_GAIN gain bits
+    int32_t tapsOff, length, stateOff;   // FirDesc
+    int32_t flags, gainBits, satGainBits;// PF_GAIN / PF_SAT_GAIN
+    int32_t nStores, storeCh[kMaxChainStores];   // OUTPUT CHANNEL numbers
+};
+struct FirPlan {
+    int32_t aluClass, nPaths, nIn, nOut;
+    int32_t stateWords, storeMask;
+    int32_t maxLen;                      // longest impulse
+    int32_t nUnwritten;                  // output channels no path stores to (they read 0)
+    int32_t unwritten[kIoSlots];
+    FirPath paths[kMaxFirPaths];
+};
+
 } // namespace avdsp

@@ -15,9 +15,9 @@ from . import _lib
 
 INTERLEAVED, PLANAR = 0, 1
 HOST, DEVICE = 0, 1
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CHAIN, KERNEL_CHAIN_V1, KERNEL_MIX = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CHAIN, KERNEL_CHAIN_V1, KERNEL_MIX, KERNEL_FIR = 0, 1, 2, 3, 4, 5
 PCM_S32, PCM_S16, PCM_S24_3LE = 0, 1, 2
-KERNEL_NAMES = {0: "none", 1: "generic", 2: "chain", 3: "chain_v1", 4: "mix"}
+KERNEL_NAMES = {0: "none", 1: "generic", 2: "chain", 3: "chain_v1", 4: "mix", 5: "fir"}
 
 
 class AvdspError(RuntimeError):
@@ -160,3 +160,8 @@ class Executor:
 def measure_int_peak(device: int = 0, iters: int = 4096) -> float:
     """mad.wide.s32 per second the whole device sustains (denominator of the INT-pipe roofline)."""
     return float(_lib.lib().avdsp_b200_measure_int_peak(device, iters))
+
+
+def measure_f32_peak(device: int = 0, iters: int = 4096, packed: bool = False) -> float:
+    """Non-fused float MACs (mul.rz.ftz + add.rn) per second the whole device sustains (FP32-pipe roofline)."""
+    return float(_lib.lib().avdsp_b200_measure_f32_peak(device, iters, 1 if packed else 0))

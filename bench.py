@@ -40,6 +40,10 @@ WORKLOADS = {
            "C3 16-section parametric EQ per channel x2 (fixed-point encoding), 48 kHz"),
     "c3f": ("c3_peq16_f3_48k", 3, 48000, 65536, 4096, 160,
             "C3 16-section parametric EQ per channel x2, float format (DSP_FORMAT 3), 48 kHz"),
+    "c4": ("c4_fir4096_f2_48k", 2, 48000, 1024, 65536, 8192,
+           "C4 4096-tap room-correction FIR per channel x2, fixed point (direct tiled, int64 accumulation), 48 kHz"),
+    "c4f": ("c4_fir4096_f3_48k", 3, 48000, 1024, 65536, 8192,
+            "C4 4096-tap room-correction FIR per channel x2, float format (DSP_FORMAT 3, reference tap order), 48 kHz"),
 }
 
 
@@ -90,7 +94,10 @@ def cpu_reference_rate(prog, fmt, fs, frames, workers, streams_per_worker=1):
     /root/reference by oracle/Makefile); falls back to the C restatement (oracle/liboracle_avdsp.so)."""
     refdir = os.path.join(ROOT, "oracle", "_ref")
     exe, lib = os.path.join(refdir, "refbench"), os.path.join(refdir, f"libavdspruntime{fmt}.so")
-    if os.path.exists(exe) and os.path.exists(lib):
+    # fixed-point DSP_FIR: the reference's int kernel is not a convolution (SURVEY.md App. C #3) and does a fraction of the
+    # work, so timing it would be meaningless: the oracle restatement ("port", one core) is the CPU baseline there
+    broken_ref = fmt == 2 and "fir" in prog
+    if os.path.exists(exe) and os.path.exists(lib) and not broken_ref:
         out = subprocess.run([exe, lib, prog_file(prog), str(fmt), str(fs), str(workers), str(streams_per_worker), str(frames)],
                              capture_output=True, text=True, timeout=900)
         if out.returncode == 0:
@@ -118,7 +125,7 @@ def run_reference(args, wl):
         return
     cores = os.cpu_count() or 1
     # bounded sample of the workload per step: one stream per host core, `fr` frames each (~1-2 s per step)
-    fr = 1500000 if args.frames is None else args.frames       # bounded sample: ~0.6 s per host thread per step
+    fr = max(1500000 * 240 // wl[5] // 1000 * 1000, 1000) if args.frames is None else args.frames   # bounded sample: ~0.6 s per host thread per step
     for _ in range(args.warmup):
         cpu_reference_rate(prog, fmt, fs, max(1000, fr // 20), cores)
     tot_frames, tot_s, kind, n_out = 0.0, 0.0, "reference", 8
@@ -262,17 +269,25 @@ def main():
            "traffic": traffic, "peak_source": peak_src, "kernel": f"k_{ex.last_kernel}", "kernel_ms": kernel_ms, "launches_per_step": launches_per_step,
            "algorithmic_bytes_per_launch": alg_bytes}
     hbm["frac"] = hbm["achieved"] / hbm["peak"]
-    int_peak = avdsp_b200.measure_int_peak(local, 4096)
     alg_macs = float(S) * T * macs
-    roof_int = {"bound": "int_pipe", "achieved": alg_macs / (kernel_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
-                "unit": "T mad.wide.s32/s", "peak_source": "measured live (avdsp_b200_measure_int_peak)",
-                "algorithmic_macs_per_launch": alg_macs}
+    if fmt == 2:
+        int_peak = avdsp_b200.measure_int_peak(local, 4096)
+        roof_int = {"bound": "int_pipe", "achieved": alg_macs / (kernel_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
+                    "unit": "T mad.wide.s32/s", "peak_source": "measured live (avdsp_b200_measure_int_peak)",
+                    "algorithmic_macs_per_launch": alg_macs}
+    else:
+        # DSP_FORMAT 3: a MAC is a truncating multiply + a rounded add (no FMA: the reference rounds each product)
+        int_peak = avdsp_b200.measure_f32_peak(local, 4096, False)
+        packed = avdsp_b200.measure_f32_peak(local, 4096, True)
+        roof_int = {"bound": "fp32_pipe", "achieved": alg_macs / (kernel_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
+                    "unit": "T (mul.rz + add.rn)/s", "peak_source": "measured live (avdsp_b200_measure_f32_peak, scalar FMUL+FADD)",
+                    "peak_packed_f32x2": packed / 1e12, "algorithmic_macs_per_launch": alg_macs}
     roof_int["frac"] = roof_int["achieved"] / roof_int["peak"] if int_peak else None
 
     cpu = None
     if not args.no_cpu:
         cores = os.cpu_count() or 1
-        fr = 3000000                    # ~1-1.5 s per host thread, ~20 core-seconds in total
+        fr = max(3000000 * 240 // macs // 1000 * 1000, 2000)     # ~1-1.5 s per host thread, ~20 core-seconds in total
         r = cpu_reference_rate(prog, fmt, fs, fr, cores)
         cpu = {"value": r["frames_per_s"] * r["n_out"] / 1e6, "unit": "Msps", "cores": r["cores"], "kind": r["kind"],
                "sample": f"{r['workers']} streams x {fr} frames of the same program and PCM recipe, one stream per host thread, "
@@ -286,7 +301,7 @@ def main():
                        "l2": f"inputs+outputs {alg_bytes / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)",
                        "kernel": ex.last_kernel, "frames_per_s": frames_job / (total_ms * 1e-3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": hbm, "roofline_int": roof_int, "cpu_baseline": cpu}
+            "roofline": hbm, ("roofline_int" if fmt == 2 else "roofline_fp32"): roof_int, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

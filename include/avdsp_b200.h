@@ -90,7 +90,8 @@ enum { AVDSP_B200_HOST = 0, AVDSP_B200_DEVICE = 1 };
 /* kernel selection (diagnostics and tests; AUTO is the product behaviour) */
 enum { AVDSP_B200_KERNEL_AUTO = 0, AVDSP_B200_KERNEL_GENERIC = 1, AVDSP_B200_KERNEL_CHAIN = 2,
        AVDSP_B200_KERNEL_CHAIN_V1 = 3 /* the earlier tile-synchronous chain kernel, kept for A/B runs */,
-       AVDSP_B200_KERNEL_MIX = 4      /* time-parallel kernel for programs without biquads (mixers, delays, dither) */ };
+       AVDSP_B200_KERNEL_MIX = 4      /* time-parallel kernel for programs without biquads (mixers, delays, dither) */,
+       AVDSP_B200_KERNEL_FIR = 5      /* time-parallel tiled DSP_FIR kernels (runtime/dsp_firSTD.h, dsp_runtime.c:928-969) */ };
 
 /* Load + validate + lower a program (dspRuntimeInit + dspRuntimeReset for nStreams independent
  * instances).  prog: progWords little-endian 32-bit words exactly as written by dspcreate (.bin).
@@ -160,6 +161,10 @@ const char *avdsp_b200_last_error(void);
 /* Integer-pipe microbenchmark used for the INT roofline: runs `iters` dependent-free mad.wide.s32
  * per thread on the whole device and returns the achieved rate in mad.wide/s (0 on failure). */
 double avdsp_b200_measure_int_peak(int device, int iters);
+/* Float-pipe microbenchmark used for the FP32 roofline of the DSP_FORMAT 3 kernels: the reference's non-fused
+ * multiply-accumulate (truncating multiply, runtime/dsp_ieee754.h:336-375, then a rounded add) as mul.rz.ftz.f32 +
+ * add.rn.f32 (packed = 0) or mul.rz.ftz.f32x2 + add.rn.f32x2 (packed = 1); returns MACs per second. */
+double avdsp_b200_measure_f32_peak(int device, int iters, int packed);
 
 #ifdef __cplusplus
 }

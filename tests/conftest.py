@@ -80,4 +80,14 @@ CASES = [
     ("ref_dacdiy1", 2, 192000),
     ("ref_dsptest1", 3, 48000),
     ("ref_dac8prodsp", 2, 96000),
+    # DSP_FIR (C4): 4096-tap room-correction paths, and a small multi-rate program (convolution / plain delay / skipped)
+    ("c4_fir4096_f2_48k", 2, 48000),
+    ("c4_fir4096_f3_48k", 3, 48000),
+    ("c4s_fir_f2_multifs", 2, 48000),
+    ("c4s_fir_f2_multifs", 2, 96000),
+    ("c4s_fir_f3_multifs", 3, 48000),
+    ("c4s_fir_f3_multifs", 3, 96000),
+    ("c4s_fir_f4_multifs", 4, 48000),
+    ("c4s_fir_f5_multifs", 5, 48000),
+    ("c4s_fir_f6_multifs", 6, 88200),
 ]

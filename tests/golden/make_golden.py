@@ -49,6 +49,60 @@ PROGRAMS = {
 MUST_MATCH = {"ref_crossoverLV6": "crossoverLV6.bin", "ref_dacdiy1": "dacdiy1.bin",
               "ref_dsptest1": "dsptest1.bin", "ref_dac8prodsp": "dac8prodsp.h"}
 
+
+
+def fir_taps(n, seed):
+    """Room-correction-like impulse: a main tap followed by exponentially decaying noise; sum(|c|) ~ 1.3."""
+    r = np.random.default_rng(seed)
+    k = np.arange(n)
+    c = r.standard_normal(n) * np.exp(-k / (n / 6.0))
+    c *= 0.6 / np.abs(c).sum()
+    c[0] += 0.7
+    return c.astype(np.float32)
+
+
+def fir_program(fmt, lens, fmin=48000, fmax=48000, nch=2, variants=None):
+    """C4: one core per channel, LOAD_GAIN -> FIR -> SAT0DB -> STORE, ALSA io convention (in 8+k, out k).
+    Assembled with oracle/wire.py in the layout the RUNTIME decodes (dsp_runtime.c:928-969) because the reference
+    encoder's dsp_FIR emission is broken.  lens[k][fsIndex] = taps of channel k at that fs,
+    ('delay', n) for the plain-delay form, or None (FIR skipped at that fs)."""
+    a = wire.Asm(fmt=fmt, fmin=fmin, fmax=fmax)
+    for k in range(nch):
+        a.core()
+        a.param()
+        imps = []
+        for fi, ln in enumerate(lens[k]):
+            if ln is None or isinstance(ln, tuple):
+                imps.append(ln)
+            else:
+                t = fir_taps(ln, 1000 * k + fi + 17)
+                imps.append([wire.q28(float(v)) for v in t] if fmt == 2 else [float(v) for v in t])
+        where = a.fir_impulses(imps)
+        mx = max([(l[1] + 1) if isinstance(l, tuple) else (l or 0) for l in lens[k]] + [1])
+        a.load_gain(8 + k, 0.9 - 0.2 * k)
+        a.fir(where, mx)
+        if variants and variants[k] == "gain":
+            a.gain(1.25)
+            a.sat0db()
+        elif variants and variants[k] == "satgain":
+            a.sat0db_gain(0.8)
+        else:
+            a.sat0db()
+        a.store(k)
+        if variants and variants[k] == "gain":
+            a.store(nch + k)
+    return a.end()
+
+
+# programs assembled here (no reference encoder involved): name -> (DSP_FORMAT, builder)
+ASM_PROGRAMS = {}
+for _f in (2, 3):
+    ASM_PROGRAMS[f"c4_fir4096_f{_f}_48k"] = (_f, lambda f=_f: fir_program(f, [[4096], [4096]]))
+for _f in (2, 3, 4, 5, 6):
+    # two sampling rates: 48k convolution (ragged lengths), 96k: channel 0 plain delay, channel 1 skipped
+    ASM_PROGRAMS[f"c4s_fir_f{_f}_multifs"] = (_f, lambda f=_f: fir_program(
+        f, [[100, None, ("delay", 37)], [33, None, None]], fmin=48000, fmax=96000, variants=["gain", "satgain"]))
+
 # vector name -> (program, DSP_FORMAT, fs, seed, defaultDither, stimulus, frames)
 VECTORS = {}
 for stim in ("noise", "full", "impulse", "sine"):
@@ -66,10 +120,18 @@ VECTORS["lv6_96k"] = ("ref_crossoverLV6", 2, 96000, 11, 31, "full", 1024)
 VECTORS["dacdiy1_192k"] = ("ref_dacdiy1", 2, 192000, 0, 24, "noise", 1024)
 VECTORS["dacdiy1_48k"] = ("ref_dacdiy1", 2, 48000, 5, 31, "sine", 1024)
 VECTORS["dsptest1_48k"] = ("ref_dsptest1", 3, 48000, 0, 26, "noise", 1024)
+# DSP_FIR: the reference's FLOAT kernel is a correct direct form (dsp_firSTD.h:38-52) -> golden vectors for formats 3..6;
+# its fixed-point kernel is not a convolution -> no golden for format 2 (oracle-defined semantics)
+for fmt in (3, 4, 5, 6):
+    VECTORS[f"c4s_f{fmt}_48k_noise"] = (f"c4s_fir_f{fmt}_multifs", fmt, 48000, 0, 31, "noise", 512)
+    VECTORS[f"c4s_f{fmt}_96k_full"] = (f"c4s_fir_f{fmt}_multifs", fmt, 96000, 0, 24, "full", 256)
+VECTORS["c4_f3_noise"] = ("c4_fir4096_f3_48k", 3, 48000, 0, 31, "noise", 640)
 VECTORS["dac8prodsp_96k"] = ("ref_dac8prodsp", 2, 96000, 0, 24, "noise", 1024)
 
 
 def prog_path(name):
+    if name in ASM_PROGRAMS:
+        return os.path.join(PROGDIR, name + ".bin")
     kind = PROGRAMS[name][1]
     return os.path.join(PROGDIR, name + (".bin" if kind == "bin" else ".h"))
 
@@ -97,9 +159,20 @@ def make_programs():
         print(f"  wrote {os.path.relpath(out, ROOT)} ({os.path.getsize(out)} bytes)")
 
 
+def make_asm_programs():
+    os.makedirs(PROGDIR, exist_ok=True)
+    for name, (fmt, build) in ASM_PROGRAMS.items():
+        w = build()
+        w.astype("<i4").tofile(prog_path(name))
+        print(f"  wrote {os.path.relpath(prog_path(name), ROOT)} ({w.size * 4} bytes, assembled)")
+
+
 def make_vectors():
     os.makedirs(VECDIR, exist_ok=True)
+    only = sys.argv[1:]          # optional name prefixes: regenerate just those vectors (npz files are not byte-reproducible)
     for vname, (prog, fmt, fs, seed, dither, stim, frames) in VECTORS.items():
+        if only and not any(vname.startswith(o) for o in only):
+            continue
         w = load_prog(prog)
         ins, outs = wire.io_maps(w)
         gen = synth.pcm_float if fmt >= 5 else synth.pcm
@@ -116,5 +189,7 @@ def make_vectors():
 if __name__ == "__main__":
     if not os.path.exists(os.path.join(REFDIR, "dspcreate")):
         raise SystemExit("oracle/_ref is not built: run `make -C oracle` where /root/reference exists")
-    make_programs()
+    if not sys.argv[1:]:
+        make_programs()
+    make_asm_programs()
     make_vectors()

@@ -131,6 +131,12 @@ def test_chain_kernel_is_selected_for_the_benchmark_programs():
         ex = Executor(load_program(prog), fs, 3 if "_f3_" in prog else 2, 64)
         ex.process(synth.pcm("noise", 64, 64, ex.n_in, fs))
         assert ex.last_kernel == kern, ex.trace
+    for prog, fmt, fs, kern in (("c4_fir4096_f2_48k", 2, 48000, "fir"), ("c4_fir4096_f3_48k", 3, 48000, "fir"),
+                                ("c4s_fir_f3_multifs", 3, 48000, "fir"), ("c4s_fir_f3_multifs", 3, 96000, "generic"),
+                                ("c4s_fir_f4_multifs", 4, 48000, "generic")):
+        ex = Executor(load_program(prog), fs, fmt, 8)
+        ex.process(synth.pcm("noise", 8, 64, ex.n_in, fs))
+        assert ex.last_kernel == kern, ex.trace
     ex = Executor(load_program("c1_crossover2x2lfe_f2_48k"), 48000, 2, 4)   # MEM hand-off, X/Y dataflow
     ex.process(synth.pcm("noise", 4, 64, ex.n_in, 48000))
     assert ex.last_kernel == "generic"
@@ -360,3 +366,52 @@ def test_full_width_batch_properties(oracle_lib, prog, fs, S, T):
     for s in (0, 1, 31, 32, 1000, S - 1):
         o = oracle_lib.Oracle(w, 2, fs, seed=s)
         assert np.array_equal(ys[s], o.process(xs[s])), s
+
+
+@pytest.mark.parametrize("prog,fmt", [("c4_fir4096_f3_48k", 3), ("c4s_fir_f3_multifs", 3), ("c4_fir4096_f2_48k", 2)])
+def test_fir_kernel_periods_and_kernel_switches(oracle_lib, prog, fmt):
+    """DSP_FIR through the time-parallel kernel: ALSA-period sized calls, calls shorter than the impulse, a switch to the
+    generic interpreter and back (shared delay-line layout), all against one oracle run.  Float format 3 included:
+    outputs AND the delay line must be identical (reference tap order, truncated products)."""
+    from avdsp_b200 import KERNEL_FIR
+    w = load_program(prog)
+    fs, S, T = 48000, 5, 2600
+    x = synth.pcm("full", S, T, 2, fs)
+    seeds = np.arange(S, dtype=np.int32)
+    ys, sts = oracle_run(oracle_lib, w, fmt, fs, x, seeds, 31)
+    ex = Executor(w, fs, fmt, S, seeds=seeds)
+    cuts = [0, 1, 3, 11, 300, 1324, 1325, 2349, T]
+    parts = []
+    for i, (c0, c1) in enumerate(zip(cuts, cuts[1:])):
+        ex.set_kernel(KERNEL_GENERIC if i == 4 else KERNEL_FIR)
+        parts.append(ex.process(np.ascontiguousarray(x[:, c0:c1])))
+    y = np.concatenate(parts, axis=1)
+    assert np.array_equal(y, ys), np.count_nonzero(y != ys)
+    for s in (0, S - 1):
+        assert np.array_equal(ex.get_state(s), expected_state(ex, sts[s])), s
+    # planar layout, one call
+    ex2 = Executor(w, fs, fmt, S, seeds=seeds)
+    yp = ex2.process(np.ascontiguousarray(x.transpose(0, 2, 1)), layout=PLANAR)
+    assert ex2.last_kernel == "fir" and np.array_equal(yp.transpose(0, 2, 1), ys)
+
+
+@pytest.mark.parametrize("prog,fmt", [("c4_fir4096_f2_48k", 2), ("c4_fir4096_f3_48k", 3)])
+def test_fir_full_width_batch_properties(oracle_lib, prog, fmt):
+    """C4 width (1024 streams, several time tiles per stream): spot streams bit-for-bit against the oracle, streams fed
+    identical PCM give identical output, and a shifted copy of the input gives the shifted output (time invariance
+    across tile boundaries; the FIR has no other state)."""
+    w = load_program(prog)
+    fs, S, T = 48000, 1024, 6144
+    xs = synth.pcm("noise", S, T, 2, fs)
+    xs[1] = xs[0]
+    D = 1000
+    xs[2, :D] = 0; xs[2, D:] = xs[0, : T - D]
+    ex = Executor(w, fs, fmt, S)
+    y = ex.process(xs)
+    assert ex.last_kernel == "fir"
+    assert np.array_equal(y[1], y[0])
+    assert np.array_equal(y[2, D:], y[0, : T - D]) and not y[2, :D].any()
+    for s in (0, 3, 517, S - 1):
+        o = oracle_lib.Oracle(w, fmt, fs, seed=0)
+        assert np.array_equal(y[s], o.process(xs[s])), s
+        assert np.array_equal(ex.get_state(s)[: ex.data_size], o.data), s
