@@ -74,15 +74,16 @@ __global__ void __launch_bounds__(256) k_int_peak(long long* out, int iters, int
 // two MACs per instruction pair).  Counts MACs.
 template <int PACKED>
 __global__ void __launch_bounds__(256) k_f32_peak(float* out, int iters, float c0) {
-    const float c = c0 + 1e-7f * (float)blockIdx.x;
+    // the multiplicand is the running accumulator, so neither instruction can be hoisted: acc += rz(acc * c), c < 0
+    const float c = c0 - 1e-7f * (float)blockIdx.x;
     if constexpr (PACKED == 0) {
-        float acc[8], x[8];
+        float acc[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { acc[k] = 0.f; x[k] = 1e-3f * (float)(k + 1 + (int)threadIdx.x); }
+        for (int k = 0; k < 8; k++) acc[k] = 1e3f * (float)(k + 1 + (int)threadIdx.x);
         for (int i = 0; i < iters; i++) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                float p; asm volatile("mul.rz.ftz.f32 %0, %1, %2;" : "=f"(p) : "f"(x[k]), "f"(c));
+                float p; asm volatile("mul.rz.ftz.f32 %0, %1, %2;" : "=f"(p) : "f"(acc[k]), "f"(c));
                 asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(acc[k]) : "f"(p));
             }
         }
@@ -91,19 +92,18 @@ __global__ void __launch_bounds__(256) k_f32_peak(float* out, int iters, float c
         for (int k = 0; k < 8; k++) s += acc[k];
         if (s == 123.456f) out[0] = s;
     } else {
-        unsigned long long acc[8], x[8], cc;
+        unsigned long long acc[8], cc;
         asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const float a = 1e-3f * (float)(k + 1 + (int)threadIdx.x);
-            asm("mov.b64 %0, {%1, %1};" : "=l"(x[k]) : "f"(a));
-            acc[k] = 0ull;
+            const float a = 1e3f * (float)(k + 1 + (int)threadIdx.x);
+            asm("mov.b64 %0, {%1, %1};" : "=l"(acc[k]) : "f"(a));
         }
         for (int i = 0; i < iters; i++) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 unsigned long long p;
-                asm volatile("mul.rz.ftz.f32x2 %0, %1, %2;" : "=l"(p) : "l"(x[k]), "l"(cc));
+                asm volatile("mul.rz.ftz.f32x2 %0, %1, %2;" : "=l"(p) : "l"(acc[k]), "l"(cc));
                 asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc[k]) : "l"(p));
             }
         }
@@ -142,6 +142,8 @@ struct avdsp_b200 {
     MixPlan mix{};
     bool mixUsable = false;         // kernel_mix.cu (time-parallel: programs without biquads)
     bool firUsable = false;         // kernel_fir.cu (time-parallel FIR paths)
+    unsigned char* dFirTaps = nullptr;              // kernel_fir_tc.cu: pre-swizzled Toeplitz taps blobs
+    unsigned char* dFirWs = nullptr; size_t firWsBytes = 0;     // ... and the packed-sample workspace
     unsigned* dJump = nullptr; int jumpL = -1;      // PRNG jump matrix for segments of jumpL draws
     int* dTpdf = nullptr; size_t tpdfWords = 0;     // scratch dither values of a launch
     int period = 0, kernelSel = AVDSP_B200_KERNEL_AUTO, lastKernel = 0;
@@ -190,6 +192,13 @@ static int uploadPlanData(avdsp_b200* h) {
     h->mixUsable = false;
     if (L.chainOk) { std::string why; h->mixUsable = buildMixPlan(L.chain, &h->mix, &why); }
     h->firUsable = L.firOk;
+    if (h->dFirTaps) { cudaFree(h->dFirTaps); h->dFirTaps = nullptr; }
+    if (h->firUsable) {
+        std::vector<unsigned char> blobs;
+        firTcBuildTaps(L.fir, L.fir.aluClass == ALU_INT64 ? FIRTC_I8 : FIRTC_TF32, L.bigPool.data(), &blobs);
+        CU(cudaMalloc(&h->dFirTaps, blobs.size()));
+        CU(cudaMemcpy(h->dFirTaps, blobs.data(), blobs.size(), cudaMemcpyHostToDevice));
+    }
     char line[320];
     h->trace = L.trace;
     if (h->firUsable) {
@@ -247,6 +256,8 @@ static void freeAll(avdsp_b200* h) {
     if (h->dLanes2) cudaFree(h->dLanes2);
     if (h->dJump) cudaFree(h->dJump);
     if (h->dTpdf) cudaFree(h->dTpdf);
+    if (h->dFirTaps) cudaFree(h->dFirTaps);
+    if (h->dFirWs) cudaFree(h->dFirWs);
     if (h->pcmRaw) cudaFree(h->pcmRaw);
     if (h->pcmIn) cudaFree(h->pcmIn);
     if (h->pcmOut) cudaFree(h->pcmOut);
@@ -331,7 +342,7 @@ int avdsp_b200_set_order(avdsp_b200_t* h, int period) {
     h->period = period; return 0;
 }
 int avdsp_b200_set_kernel(avdsp_b200_t* h, int which) {
-    if (!h || which < 0 || which > 5) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
+    if (!h || which < 0 || which > 6) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
     h->kernelSel = which; return 0;
 }
 int avdsp_b200_last_kernel(const avdsp_b200_t* h) { return h ? h->lastKernel : 0; }
@@ -375,6 +386,13 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
     }
     if (chainOrder && h->mixUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_MIX)) use = AVDSP_B200_KERNEL_MIX;
     if (chainOrder && h->firUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_FIR)) use = AVDSP_B200_KERNEL_FIR;
+    // tensor-core Toeplitz GEMM: the bit-exact int8-limb form is the default for fixed-point batches that fill a tile;
+    // the 3xTF32 form (stated tolerance) only on request
+    if (chainOrder && h->firUsable && (h->kernelSel == AVDSP_B200_KERNEL_FIR_TC ||
+        (h->kernelSel == AVDSP_B200_KERNEL_AUTO && h->L.fir.aluClass == ALU_INT64 && n >= 32 && nFrames >= 128 && h->L.fir.maxLen >= 256)))
+        use = AVDSP_B200_KERNEL_FIR_TC;
+    if (h->kernelSel == AVDSP_B200_KERNEL_FIR_TC && use != AVDSP_B200_KERNEL_FIR_TC)
+        return setErr(AVDSP_B200_ERR_UNSUPPORTED, "tensor-core FIR kernel requested but this program/order does not map to it: " + h->L.firWhyNot);
     if (h->kernelSel == AVDSP_B200_KERNEL_FIR && use != AVDSP_B200_KERNEL_FIR)
         return setErr(AVDSP_B200_ERR_UNSUPPORTED, "FIR kernel requested but this program/order does not map to it: " + h->L.firWhyNot);
     if (h->kernelSel == AVDSP_B200_KERNEL_MIX && use != AVDSP_B200_KERNEL_MIX)
@@ -382,15 +400,26 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
     if ((h->kernelSel == AVDSP_B200_KERNEL_CHAIN || h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1) && use == AVDSP_B200_KERNEL_GENERIC)
         return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel requested but this program/order does not map to it: " + h->L.chainWhyNot);
     cudaError_t e;
-    if (use == AVDSP_B200_KERNEL_FIR) {
+    if (use == AVDSP_B200_KERNEL_FIR || use == AVDSP_B200_KERNEL_FIR_TC) {
         FirArgs A{};
         A.in = in; A.out = out; A.state = st; A.bigPool = h->dBig;
         A.nStreams = n; A.nFrames = nFrames;
         A.inStreamStride = inSS; A.outStreamStride = outSS;
         A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
         int nl = 0;
-        e = launchFir(h->L.fir, A, h->numSMs, stream, &nl);
-        h->lastKernel = AVDSP_B200_KERNEL_FIR;
+        if (use == AVDSP_B200_KERNEL_FIR_TC) {
+            const int kind = h->L.fir.aluClass == ALU_INT64 ? FIRTC_I8 : FIRTC_TF32;
+            const size_t need = firTcWorkspaceBytes(h->L.fir, kind, n, nFrames);
+            if (need > h->firWsBytes) {
+                CU(cudaStreamSynchronize(stream));
+                if (h->dFirWs) cudaFree(h->dFirWs);
+                h->dFirWs = nullptr; h->firWsBytes = 0;
+                CU(cudaMalloc(&h->dFirWs, need));
+                h->firWsBytes = need;
+            }
+            e = launchFirTc(h->L.fir, kind, A, h->dFirTaps, h->dFirWs, stream, &nl);
+        } else e = launchFir(h->L.fir, A, h->numSMs, stream, &nl);
+        h->lastKernel = use;
         h->launches += nl - 1;
     } else if (use == AVDSP_B200_KERNEL_MIX) {
         MixArgs A{};
@@ -639,7 +668,7 @@ double avdsp_b200_measure_f32_peak(int device, int iters, int packed) {
     double best = 0.0;
     for (int rep = 0; rep < 4; rep++) {
         cudaEventRecord(a);
-        if (packed) k_f32_peak<1><<<blocks, threads>>>(d, iters, 0.37f); else k_f32_peak<0><<<blocks, threads>>>(d, iters, 0.37f);
+        if (packed) k_f32_peak<1><<<blocks, threads>>>(d, iters, -0.0003f); else k_f32_peak<0><<<blocks, threads>>>(d, iters, -0.0003f);
         cudaEventRecord(b);
         if (cudaEventSynchronize(b) != cudaSuccess) { best = 0.0; break; }
         float ms = 0; cudaEventElapsedTime(&ms, a, b);

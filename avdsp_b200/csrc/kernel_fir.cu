@@ -166,8 +166,15 @@ static cudaError_t launchFirT(const FirPlan& P, const FirArgs& A, cudaStream_t s
     k_fir<CLS><<<(unsigned)ctas, threads, smem, stream>>>(P, A, nTiles, H);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_fir_state<CLS><<<(unsigned)(P.nPaths * A.nStreams), 256, (size_t)P.maxLen * sizeof(int), stream>>>(P, A);
     if (launches) *launches = 2;
+    return launchFirState(P, A, stream);
+}
+
+cudaError_t launchFirState(const FirPlan& P, const FirArgs& A, cudaStream_t stream) {
+    const unsigned grid = (unsigned)(P.nPaths * A.nStreams);
+    const size_t smem = (size_t)P.maxLen * sizeof(int);
+    if (P.aluClass == ALU_INT64) k_fir_state<ALU_INT64><<<grid, 256, smem, stream>>>(P, A);
+    else k_fir_state<ALU_F32><<<grid, 256, smem, stream>>>(P, A);
     return cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <string>
+#include <vector>
 #include "plan.h"
 
 namespace avdsp {
@@ -128,5 +129,14 @@ struct FirArgs {
 };
 // exact kernels: int64 accumulation (any order is exact) / float in the reference's tap order
 cudaError_t launchFir(const FirPlan& plan, const FirArgs& args, int numSMs, cudaStream_t stream, int* launches);
+cudaError_t launchFirState(const FirPlan& plan, const FirArgs& args, cudaStream_t stream);      // delay-line update only
+
+// ---- Toeplitz-GEMM FIR on tcgen05 tensor cores (kernel_fir_tc.cu) -------------------------------------
+enum FirTcKind : int { FIRTC_I8 = 0 /* DSP_FORMAT 2: 8-bit limbs, bit-exact */, FIRTC_TF32 = 1 /* DSP_FORMAT 3: 3xTF32, stated tolerance */ };
+int firTcHistory(const FirPlan& plan);
+void firTcBuildTaps(const FirPlan& plan, int kind, const int32_t* bigPool, std::vector<unsigned char>* out);
+size_t firTcWorkspaceBytes(const FirPlan& plan, int kind, int nStreams, int nFrames);
+cudaError_t launchFirTc(const FirPlan& plan, int kind, const FirArgs& args, const unsigned char* dTaps, unsigned char* workspace,
+                        cudaStream_t stream, int* launches);
 
 } // namespace avdsp

@@ -15,9 +15,9 @@ from . import _lib
 
 INTERLEAVED, PLANAR = 0, 1
 HOST, DEVICE = 0, 1
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CHAIN, KERNEL_CHAIN_V1, KERNEL_MIX, KERNEL_FIR = 0, 1, 2, 3, 4, 5
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CHAIN, KERNEL_CHAIN_V1, KERNEL_MIX, KERNEL_FIR, KERNEL_FIR_TC = 0, 1, 2, 3, 4, 5, 6
 PCM_S32, PCM_S16, PCM_S24_3LE = 0, 1, 2
-KERNEL_NAMES = {0: "none", 1: "generic", 2: "chain", 3: "chain_v1", 4: "mix", 5: "fir"}
+KERNEL_NAMES = {0: "none", 1: "generic", 2: "chain", 3: "chain_v1", 4: "mix", 5: "fir", 6: "fir_tc"}
 
 
 class AvdspError(RuntimeError):

@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--frames", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "chain", "mix", "fir", "fir_tc"],
+                    help="force a kernel (diagnostics; the default is what the product picks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -191,6 +193,9 @@ def main():
     first = rank * S                                   # weak scaling: rank r owns streams [r*S, (r+1)*S)
     seeds = np.arange(first, first + S, dtype=np.int32)
     ex = avdsp_b200.Executor(words, fs, fmt, S, seeds=seeds, dither=31, device=local)
+    if args.kernel != "auto":
+        ex.set_kernel({"generic": avdsp_b200.KERNEL_GENERIC, "chain": avdsp_b200.KERNEL_CHAIN, "mix": avdsp_b200.KERNEL_MIX,
+                       "fir": avdsp_b200.KERNEL_FIR, "fir_tc": avdsp_b200.KERNEL_FIR_TC}[args.kernel])
     n_in, n_out = ex.n_in, ex.n_out
     x = synth.pcm_torch("noise", S, T, n_in, dev, first_stream=first)       # synthetic PCM, resident in HBM
     y = torch.empty((S, T, n_out), dtype=torch.int32, device=dev)

@@ -91,7 +91,9 @@ enum { AVDSP_B200_HOST = 0, AVDSP_B200_DEVICE = 1 };
 enum { AVDSP_B200_KERNEL_AUTO = 0, AVDSP_B200_KERNEL_GENERIC = 1, AVDSP_B200_KERNEL_CHAIN = 2,
        AVDSP_B200_KERNEL_CHAIN_V1 = 3 /* the earlier tile-synchronous chain kernel, kept for A/B runs */,
        AVDSP_B200_KERNEL_MIX = 4      /* time-parallel kernel for programs without biquads (mixers, delays, dither) */,
-       AVDSP_B200_KERNEL_FIR = 5      /* time-parallel tiled DSP_FIR kernels (runtime/dsp_firSTD.h, dsp_runtime.c:928-969) */ };
+       AVDSP_B200_KERNEL_FIR = 5      /* time-parallel tiled DSP_FIR kernels (runtime/dsp_firSTD.h, dsp_runtime.c:928-969) */,
+       AVDSP_B200_KERNEL_FIR_TC = 6   /* DSP_FIR as a Toeplitz GEMM on tcgen05 tensor cores: DSP_FORMAT 2 bit-exact (8-bit limbs, the
+                                         AUTO choice for batches), DSP_FORMAT 3 as 3xTF32 under a stated tolerance (only on request) */ };
 
 /* Load + validate + lower a program (dspRuntimeInit + dspRuntimeReset for nStreams independent
  * instances).  prog: progWords little-endian 32-bit words exactly as written by dspcreate (.bin).

@@ -408,10 +408,61 @@ def test_fir_full_width_batch_properties(oracle_lib, prog, fmt):
     xs[2, :D] = 0; xs[2, D:] = xs[0, : T - D]
     ex = Executor(w, fs, fmt, S)
     y = ex.process(xs)
-    assert ex.last_kernel == "fir"
+    assert ex.last_kernel == ("fir_tc" if fmt == 2 else "fir")      # fixed point: bit-exact tensor-core limb GEMM
     assert np.array_equal(y[1], y[0])
     assert np.array_equal(y[2, D:], y[0, : T - D]) and not y[2, :D].any()
     for s in (0, 3, 517, S - 1):
         o = oracle_lib.Oracle(w, fmt, fs, seed=0)
         assert np.array_equal(y[s], o.process(xs[s])), s
         assert np.array_equal(ex.get_state(s)[: ex.data_size], o.data), s
+
+
+def test_fir_tensor_core_int8_limbs_bit_exact(oracle_lib):
+    """DSP_FORMAT 2 FIR as a Toeplitz GEMM on tcgen05 (kind::i8, four 8-bit limbs per operand, int32 accumulators in
+    TMEM, recombined in wrapping int64): must be BIT-EXACT, outputs and delay line, for ragged stream counts (partial
+    64-stream tile), calls shorter than one 128-output block, full-scale input that saturates SAT0DB, and when
+    alternated with the scalar-pipe kernel and the interpreter."""
+    from avdsp_b200 import KERNEL_FIR, KERNEL_FIR_TC
+    for prog, S, T in (("c4_fir4096_f2_48k", 70, 1500), ("c4s_fir_f2_multifs", 5, 700)):
+        w = load_program(prog)
+        fs = 48000
+        x = synth.pcm("full", S, T, 2, fs)
+        seeds = np.arange(S, dtype=np.int32)
+        ys, sts = oracle_run(oracle_lib, w, 2, fs, x, seeds, 24)
+        ex = Executor(w, fs, 2, S, seeds=seeds, dither=24)
+        ex.set_kernel(KERNEL_FIR_TC)
+        y = ex.process(x)
+        assert ex.last_kernel == "fir_tc"
+        assert np.array_equal(y, ys), (prog, np.count_nonzero(y != ys))
+        for s in (0, S - 1):
+            assert np.array_equal(ex.get_state(s), expected_state(ex, sts[s])), (prog, s)
+        ex2 = Executor(w, fs, 2, S, seeds=seeds, dither=24)
+        cuts = [0, 1, 130, 131, 700, T] if T > 700 else [0, 1, 130, 131, T]
+        kern = [KERNEL_FIR_TC, KERNEL_FIR, KERNEL_FIR_TC, KERNEL_GENERIC, KERNEL_FIR_TC]
+        parts = []
+        for i, (c0, c1) in enumerate(zip(cuts, cuts[1:])):
+            ex2.set_kernel(kern[i])
+            parts.append(ex2.process(np.ascontiguousarray(x[:, c0:c1])))
+        assert np.array_equal(np.concatenate(parts, axis=1), ys), prog
+        assert np.array_equal(ex2.get_state(S - 1), expected_state(ex2, sts[S - 1])), prog
+
+
+def test_fir_tensor_core_tf32_stated_tolerance(oracle_lib):
+    """DSP_FORMAT 3 FIR as a 3xTF32 Toeplitz GEMM (opt-in): NOT the reference's summation order.  Stated tolerance:
+    |y - reference| <= 2^-16 of full scale (-96 dBFS) on s.31 outputs; the delay line (exact input samples) must be
+    identical.  The exact-order float kernel stays the AUTO choice."""
+    from avdsp_b200 import KERNEL_FIR_TC
+    w = load_program("c4_fir4096_f3_48k")
+    fs, S, T = 48000, 40, 1100
+    x = synth.pcm("noise", S, T, 2, fs)
+    ys, sts = oracle_run(oracle_lib, w, 3, fs, x, np.zeros(S, np.int32), 31)
+    ex = Executor(w, fs, 3, S)
+    ex.set_kernel(KERNEL_FIR_TC)
+    y = np.concatenate([ex.process(np.ascontiguousarray(x[:, :333])), ex.process(np.ascontiguousarray(x[:, 333:]))], axis=1)
+    assert ex.last_kernel == "fir_tc"
+    err = np.abs(y.astype(np.int64) - ys.astype(np.int64)).max()
+    print("3xTF32 FIR: max |err| =", err, "LSB of s.31 =", err / 2.0 ** 31, "FS")
+    assert err <= 2 ** 15, err
+    assert np.abs(ys).max() > 2 ** 28                      # the comparison is not vacuous
+    for s in (0, S - 1):
+        assert np.array_equal(ex.get_state(s), expected_state(ex, sts[s])), s
