@@ -261,33 +261,55 @@ def main():
 
     peaks, peak_src = measured_peaks()
     alg_bytes = float(S) * T * (n_in + n_out) * 4               # read every input once + write every output once
-    traffic = None          # DRAM bytes per launch from the committed `ncu --set full` capture of this exact workload
-    prof = os.path.join(ROOT, "profiles", "r1_chain2_c2_ncu_summary.txt")
-    if args.workload == "c2" and S == 4096 and T == 48000 and os.path.exists(prof):
+    # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of this exact workload + kernel
+    traffic = None
+    prof_name = {("c2", "chain"): "r1_chain2_c2", ("c5", "mix"): "r1_mix_c5", ("c4", "fir_tc"): "r1_firtc_i8_c4",
+                 ("c4f", "fir_tc"): "r1_firtc_tf32_c4f", ("c4f", "fir"): "r1_fir_f32_c4f"}.get((args.workload, ex.last_kernel))
+    prof = os.path.join(ROOT, "profiles", f"{prof_name}_ncu_summary.txt") if prof_name else None
+    if prof and S == wl[3] and T == wl[4] and os.path.exists(prof):
         tot = 0.0
         for ln in open(prof):
             f = ln.split()
             if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
         traffic = tot or None
+    common = {"traffic": traffic, "kernel": f"k_{ex.last_kernel}", "kernel_ms": kernel_ms, "launches_per_step": launches_per_step}
     hbm = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-           "traffic": traffic, "peak_source": peak_src, "kernel": f"k_{ex.last_kernel}", "kernel_ms": kernel_ms, "launches_per_step": launches_per_step,
-           "algorithmic_bytes_per_launch": alg_bytes}
+           "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, **common}
     hbm["frac"] = hbm["achieved"] / hbm["peak"]
     alg_macs = float(S) * T * macs
     if fmt == 2:
         int_peak = avdsp_b200.measure_int_peak(local, 4096)
-        roof_int = {"bound": "int_pipe", "achieved": alg_macs / (kernel_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
-                    "unit": "T mad.wide.s32/s", "peak_source": "measured live (avdsp_b200_measure_int_peak)",
-                    "algorithmic_macs_per_launch": alg_macs}
+        pipe = {"bound": "int_pipe", "achieved": alg_macs / (kernel_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
+                "unit": "T mad.wide.s32/s", "peak_source": "measured live (avdsp_b200_measure_int_peak)",
+                "algorithmic_macs_per_launch": alg_macs, **common}
     else:
         # DSP_FORMAT 3: a MAC is a truncating multiply + a rounded add (no FMA: the reference rounds each product)
         int_peak = avdsp_b200.measure_f32_peak(local, 4096, False)
         packed = avdsp_b200.measure_f32_peak(local, 4096, True)
-        roof_int = {"bound": "fp32_pipe", "achieved": alg_macs / (kernel_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
-                    "unit": "T (mul.rz + add.rn)/s", "peak_source": "measured live (avdsp_b200_measure_f32_peak, scalar FMUL+FADD)",
-                    "peak_packed_f32x2": packed / 1e12, "algorithmic_macs_per_launch": alg_macs}
-    roof_int["frac"] = roof_int["achieved"] / roof_int["peak"] if int_peak else None
+        pipe = {"bound": "fp32_pipe", "achieved": alg_macs / (kernel_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
+                "unit": "T (mul.rz + add.rn)/s", "peak_source": "measured live (avdsp_b200_measure_f32_peak, scalar FMUL+FADD)",
+                "peak_packed_f32x2": packed / 1e12, "algorithmic_macs_per_launch": alg_macs, **common}
+    pipe["frac"] = pipe["achieved"] / pipe["peak"] if int_peak else None
+    tensor = None
+    if ex.last_kernel == "fir_tc":
+        # Toeplitz GEMM on tcgen05: dense MMA operations issued per launch (kernel_fir_tc.cu geometry: 128-output blocks,
+        # Hc + 128 samples of K per block; int8: 16 limb products per MAC, TF32: 3 passes)
+        taps, paths = 4096, n_out
+        hc = (taps + 127) // 128 * 128
+        blocks = (T + 127) // 128
+        if fmt == 2:
+            tiles, ns, passes, kind, peak_tc = (S + 63) // 64, 64, 16, "int8 (kind::i8)", 2.0 * peaks["bf16_tflops"]
+        else:
+            tiles, ns, passes, kind, peak_tc = (S + 255) // 256, 256, 3, "tf32 (kind::tf32)", 0.5 * peaks["bf16_tflops"]
+        ops = 2.0 * blocks * tiles * paths * passes * 128.0 * ns * (hc + 128)
+        tensor = {"bound": "tensor", "achieved": ops / (kernel_ms * 1e-3) / 1e12, "peak": peak_tc, "unit": "TOP/s" if fmt == 2 else "TFLOP/s",
+                  "peak_source": f"{peak_src}: dense bf16 x {'2' if fmt == 2 else '0.5'} for {kind} on the same tensor datapath",
+                  "mma_ops_per_launch": ops, "useful_macs_per_launch": alg_macs,
+                  "note": "kernel_ms covers pack + GEMM + delay-line update (3 launches)", **common}
+        tensor["frac"] = tensor["achieved"] / tensor["peak"]
+    # `roofline` is the BINDING one for the workload + kernel; the HBM figure is always kept beside it
+    binding = tensor if tensor else (hbm if args.workload == "c5" else pipe)
 
     cpu = None
     if not args.no_cpu:
@@ -306,7 +328,7 @@ def main():
                        "l2": f"inputs+outputs {alg_bytes / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)",
                        "kernel": ex.last_kernel, "frames_per_s": frames_job / (total_ms * 1e-3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": hbm, ("roofline_int" if fmt == 2 else "roofline_fp32"): roof_int, "cpu_baseline": cpu}
+            "roofline": binding, "roofline_hbm": hbm, ("roofline_int" if fmt == 2 else "roofline_fp32"): pipe, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
