@@ -549,18 +549,18 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
     auto issueTile = [&](int it) {
         if (prngOnly || !tileUsesTma(it)) return;
         __syncwarp();                                    // every lane is done reading the buffer being refilled
-        if (lane == 0) {
-            fenceProxyAsync();
-            int cnt = 0;
-            for (int sl = ow; sl < nsHere; sl += nOwn) cnt++;
-            const unsigned bar = mbar0 + 8 * (it & 1);
-            mbarExpectTx(bar, (unsigned)(cnt * rowBytes));
-            for (int sl = ow; sl < nsHere; sl += nOwn) {
-                const int* src = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(it * F) * A.inFrameStride;
-                const unsigned dst = sb + G.rawOff + sl * G.rawStreamBytes + (it & 1) * rowBytes;
-                if (interleavedIn) tmaLoad1D(dst, src, (unsigned)rowBytes, bar);
-                else for (int ch = 0; ch < nIn; ch++) tmaLoad1D(dst + ch * F * 4, src + (size_t)ch * A.inChStride, (unsigned)(F * 4), bar);
-            }
+        fenceProxyAsync();
+        const unsigned bar = mbar0 + 8 * (it & 1);
+        const int cnt = nsHere > ow ? (nsHere - ow + nOwn - 1) / nOwn : 0;      // streams this warp owns
+        // lane 0 posts the byte count (the phase cannot complete before this arrival, so the order against the copies
+        // below does not matter); lane j issues the copy of the warp's j-th stream -- in parallel, not in a lane-0 loop
+        if (lane == 0) mbarExpectTx(bar, (unsigned)(cnt * rowBytes));
+        for (int j = lane; j < cnt; j += 32) {
+            const int sl = ow + j * nOwn;
+            const int* src = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(it * F) * A.inFrameStride;
+            const unsigned dst = sb + G.rawOff + sl * G.rawStreamBytes + (it & 1) * rowBytes;
+            if (interleavedIn) tmaLoad1D(dst, src, (unsigned)rowBytes, bar);
+            else for (int ch = 0; ch < nIn; ch++) tmaLoad1D(dst + ch * F * 4, src + (size_t)ch * A.inChStride, (unsigned)(F * 4), bar);
         }
     };
 
