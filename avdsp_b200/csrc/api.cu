@@ -429,15 +429,16 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
         A.vecIn = inCS == 1 && inFS == nIn && (inSS & 3) == 0 && ((size_t)in & 15) == 0;
         A.vecOut = outCS == 1 && (nOut & 3) == 0 && (outFS & 3) == 0 && (outSS & 3) == 0 && ((size_t)out & 15) == 0;
-        const int J = nFrames >= 4096 ? 64 : (nFrames >= 1024 ? 16 : 1);
-        const int Lseg = J > 1 ? (nFrames - 1) / J : nFrames;
+        int J = 1, Lseg = nFrames;
+        mixPrngSegments(h->mix, A, h->numSMs, &J, &Lseg);
         if (h->mix.hasCalc || h->mix.anyTpdf) {
             const size_t need = (size_t)n * nFrames;
             if (need > h->tpdfWords) { if (h->dTpdf) cudaFree(h->dTpdf); h->dTpdf = nullptr; CU(cudaMalloc(&h->dTpdf, need * 4)); h->tpdfWords = need; }
-            if (!h->dJump) CU(cudaMalloc(&h->dJump, 128 * 4 * sizeof(unsigned)));
+            constexpr int kJumpLevels = kMixJumpLevels;       // thread j applies M^(2L * 2^b) for the bits b set in j
+            if (!h->dJump) CU(cudaMalloc(&h->dJump, kJumpLevels * 128 * 4 * sizeof(unsigned)));
             if (h->jumpL != Lseg) {
-                std::vector<unsigned> m(128 * 4);
-                mixJumpMatrix(2ll * Lseg, m.data());         // one TPDF value = two xoshiro128+ steps
+                std::vector<unsigned> m(kJumpLevels * 128 * 4);
+                for (int b = 0; b < kJumpLevels; b++) mixJumpMatrix((2ll * Lseg) << b, m.data() + b * 128 * 4);   // one TPDF value = two xoshiro128+ steps
                 CU(cudaMemcpyAsync(h->dJump, m.data(), m.size() * 4, cudaMemcpyHostToDevice, stream));
                 CU(cudaStreamSynchronize(stream));
                 h->jumpL = Lseg;
@@ -446,7 +447,7 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         A.tpdfBuf = h->dTpdf;
         e = launchMix(h->mix, A, h->dJump, J, Lseg, h->numSMs, stream);
         h->lastKernel = AVDSP_B200_KERNEL_MIX;
-        h->launches += 2;                                    // prng + main + tail (one is counted below)
+        h->launches += (J == 256) ? 0 : 2;                   // prng + main + tail (one is counted below); fused: one kernel
     } else if (use == AVDSP_B200_KERNEL_CHAIN) {
         Chain2Args A{};
         A.in = in; A.out = out; A.state = st; A.lanes = h->dLanes2;

@@ -65,33 +65,35 @@ __device__ __forceinline__ int mixFinish(const MixPlan& M, int flags, int gainBi
 }
 
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_mix_prng(const __grid_constant__ MixPlan M, int* __restrict__ state, int* __restrict__ tpdfBuf, const unsigned* __restrict__ jump,
-           int nStreams, int T, int J, int L) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = gid / J, j = gid - s * J;
-    if (s >= nStreams) return;
+// segment j of J of stream s: jump to the segment's first draw, generate its dither values, leave the state (last segment)
+__device__ __forceinline__ void mixPrngSegment(const MixPlan& M, int* __restrict__ state, int* __restrict__ tpdfBuf,
+                                               const unsigned* __restrict__ jump, int s, int j, int T, int J, int L) {
     int* aux = state + (size_t)s * M.stateWords + M.auxOff;
     unsigned st[4] = {(unsigned)aux[AUX_S0], (unsigned)aux[AUX_S1], (unsigned)aux[AUX_S2], (unsigned)aux[AUX_S3]};
     int tpdfValue = aux[AUX_TPDF_VALUE], tpdfRandom = aux[AUX_TPDF_RANDOM];
     const int dith = aux[AUX_DITHER];
     int* row = tpdfBuf + (size_t)s * T;
     if (!M.hasCalc) {                        // no TPDF_CALC in the program: the value never changes
-        for (int f = j * L; f < min(T, (j + 1) * L); f++) row[f] = tpdfValue;
+        for (int f = j * L; f < ((j == J - 1) ? T : min(T, (j + 1) * L)); f++) row[f] = tpdfValue;   // the last segment runs to the end
         return;
     }
     // first frame after a reset with another dither width: table switch, no draw, X=0, nothing stored (dsp_runtime.c:539-544)
     const int q = (dith != M.tpdfDither) ? 1 : 0;
     // segment j covers draws [j*L, (j+1)*L) = frames [j*L+q, (j+1)*L+q); the last segment runs to the end
-    for (int a = 0; a < j; a++) {            // jump: state <- Mseg * state  (columns of Mseg, XOR of the selected ones)
+    // jump to the segment start: state <- Mseg^j * state, with Mseg^(2^b) precomputed per level b (columns of the matrix,
+    // XOR of those selected by the state's bits; branch-free so that the lanes of a warp stay together)
+    for (int lv = 0; (j >> lv) != 0; lv++) {
+        if (!((j >> lv) & 1)) continue;
+        const uint4* cols = reinterpret_cast<const uint4*>(jump) + lv * 128;
         unsigned n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll 1
         for (int w = 0; w < 4; w++) {
-            unsigned bits = st[w];
-            while (bits) {
-                const int b = __ffs(bits) - 1; bits &= bits - 1;
-                const uint4 c = reinterpret_cast<const uint4*>(jump)[w * 32 + b];
-                n0 ^= c.x; n1 ^= c.y; n2 ^= c.z; n3 ^= c.w;
+            const unsigned bits = st[w];
+#pragma unroll 8
+            for (int b = 0; b < 32; b++) {
+                const uint4 c = __ldg(cols + w * 32 + b);
+                const unsigned m = 0u - ((bits >> b) & 1u);
+                n0 ^= c.x & m; n1 ^= c.y & m; n2 ^= c.z & m; n3 ^= c.w & m;
             }
         }
         st[0] = n0; st[1] = n1; st[2] = n2; st[3] = n3;
@@ -117,6 +119,14 @@ k_mix_prng(const __grid_constant__ MixPlan M, int* __restrict__ state, int* __re
             qd[0] = tpdfValue; qd[1] = tpdfValue >> 31;
         }
     }
+}
+__global__ void __launch_bounds__(128)
+k_mix_prng(const __grid_constant__ MixPlan M, int* __restrict__ state, int* __restrict__ tpdfBuf, const unsigned* __restrict__ jump,
+           int nStreams, int T, int J, int L) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = gid / J, j = gid - s * J;
+    if (s >= nStreams) return;
+    mixPrngSegment(M, state, tpdfBuf, jump, s, j, T, J, L);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -229,6 +239,175 @@ k_mix_main(const __grid_constant__ MixPlan M, const MixArgs A) {
                 for (int q = 0; q < 4; q++) if (ch0 + q < M.nOut) out[(size_t)(ch0 + q) * A.outChStride] = val[q];
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_mix_stream: the same arithmetic organised per STREAM instead of per (stream, tile): a CTA walks its stream's
+// frames in time order, 256 frames per step.  Phase A (lane = frame g): read the frame's PCM once (16-byte loads,
+// coalesced), evaluate EVERY output channel's chain on it -- dense gain row (constant-bank operands), gain, dither,
+// saturate -- and park the saturated values in a shared-memory ring [channel][frame mod R].  Phase B (lane = output
+// frame f): channel ch reads its ring row at f - delay_ch (conflict-free: consecutive lanes, consecutive words), masks,
+// and the frame leaves as 16-byte stores.  Every input frame is read from HBM once and mixed once; the ring IS the
+// set of delay lines (it is primed from the reference's rings in the state block, dsp_runtime.c:769-794, including
+// the stale-index case), so delays cost one shared load per output sample.  One barrier per step: the ring holds
+// maxDelay + 2 steps of frames, so phase A of the next step never overwrites what phase B still reads.
+// Streams can be cut into time segments when there are too few of them; a segment recomputes maxDelay frames of warm-up.
+constexpr int kStreamThreads = 256;
+
+template <int NP, int FLAGS>          // FLAGS >= 0: the program's uniform finish flags at compile time (common programs), -1: read at run time
+__global__ void __launch_bounds__(kStreamThreads, 3)
+k_mix_stream(const __grid_constant__ MixPlan M, const MixArgs A, const int nSeg, const int segFrames, const int ringMask,
+             const unsigned* __restrict__ jump, const int prngL /* > 0: this CTA generates its stream's dither first */, const int fusedTail) {
+    extern __shared__ __align__(16) int post_s[];            // [nOut][R]
+    constexpr int FT = kStreamThreads;
+    const int R = ringMask + 1;
+    const int tid = (int)threadIdx.x;
+    const int s = (int)blockIdx.x / nSeg, seg = (int)blockIdx.x - s * nSeg;
+    const int T = A.nFrames;
+    const int fa = seg * segFrames, fb = min(T, fa + segFrames);
+    if (fa >= fb) return;
+    const int* st = A.state + (size_t)s * M.stateWords;
+    const int4* in4 = reinterpret_cast<const int4*>(A.in + (size_t)s * A.inStreamStride);
+    const int* tb = M.anyTpdf ? A.tpdfBuf + (size_t)s * T : nullptr;
+    int* out = A.out + (size_t)s * A.outStreamStride;
+    const int warm = (M.maxDelay + FT - 1) / FT * FT;
+    const int g0 = max(0, fa - warm);
+    if (prngL > 0) {
+        // one stream per CTA (nSeg == 1): the CTA's 256 threads generate the stream's dither values (256 jump-ahead
+        // segments) into the scratch row right before using them, so the row is still in L2 when phase A reads it
+        mixPrngSegment(M, A.state, A.tpdfBuf, jump, s, tid, T, FT, prngL);
+        __syncthreads();
+    }
+    unsigned staleMask = 0;
+    if (g0 == 0) {
+        // prime the ring with what the reference's delay rings hold: frame f < n outputs ring[(idx0 + f) % n]; a stale
+        // index (>= n after the host shortened the delay) is used once, then the ring restarts at 0
+#pragma unroll 1
+        for (int ch = 0; ch < M.nOut; ch++) {
+            const int n = M.oDelay[ch];
+            if (n <= 0) continue;
+            const int off = M.oDelayOff[ch];
+            const int idx0 = st[off];
+            const bool stale = idx0 >= n || idx0 < 0;
+            if (stale) staleMask |= 1u << ch;
+            int* row = post_s + ch * R;
+            for (int i = tid; i < n; i += FT) {
+                int v;
+                if (stale) v = i == 0 ? st[off + 1 + idx0] : st[off + i];
+                else { int r = idx0 + i; if (r >= n) r -= n; v = st[off + 1 + r]; }
+                row[(i - n) & ringMask] = v;
+            }
+        }
+    }
+    const bool up = M.tpdfShift >= 0;
+    const int sh = (up ? M.tpdfShift : -M.tpdfShift) & 63;
+    const int flags = FLAGS >= 0 ? FLAGS : M.uFlags;
+    int4 cur[NP / 4];
+    int ctv = 0;
+    {
+        const int g = g0 + tid;
+        if (g < fb) {
+#pragma unroll
+            for (int q = 0; q < NP / 4; q++) cur[q] = __ldg(in4 + (size_t)g * (NP / 4) + q);
+            if (tb) ctv = __ldg(tb + g);
+        }
+    }
+    for (int gt = g0; gt < fb; gt += FT) {
+        const int g = gt + tid;
+        // ---- phase A: all chains of frame g
+        if (g < fb) {
+            const int* v = reinterpret_cast<const int*>(cur);
+            int* slotp = post_s + (g & ringMask);
+            long long dq = 0;                                 // the frame's dither, scaled once for all channels (dspTpdfApply)
+            if (flags & PF_SAT_TPDF) { const long long tv = ctv; dq = up ? (long long)((unsigned long long)tv << sh) : (tv >> sh); }
+#pragma unroll
+            for (int ch = 0; ch < kFastTab; ch++) {
+                if (ch >= M.nOut) break;
+                long long X = 0;
+#pragma unroll
+                for (int k = 0; k < NP; k++) X = mac32(X, v[k], M.mat[ch * kFastTab + k]);
+                if (flags & PF_GAIN) X = X * (long long)M.oGain[ch];
+                if (flags & PF_SAT_GAIN) { X >>= kMant; X = X * (long long)M.oSatGain[ch]; }
+                X += dq;
+                slotp[ch * R] = sat64_031_s32(X);
+            }
+            if (g == 0 && staleMask) {                        // stale ring index: frame n still outputs ring[n-1], not post[0]
+                for (int ch = 0; ch < M.nOut; ch++)
+                    if ((staleMask >> ch) & 1u) slotp[ch * R] = st[M.oDelayOff[ch] + M.oDelay[ch]];
+            }
+        }
+        // ---- prefetch the next step's frame while this one drains
+        int4 nxt[NP / 4];
+        int ntv = 0;
+        {
+            const int gn = g + FT;
+            if (gn < fb) {
+#pragma unroll
+                for (int q = 0; q < NP / 4; q++) nxt[q] = __ldg(in4 + (size_t)gn * (NP / 4) + q);
+                if (tb) ntv = __ldg(tb + gn);
+            }
+        }
+        __syncthreads();
+        // ---- phase B: output frame f = g gathers every channel at its own delay
+        if (g >= fa && g < fb) {
+            int* o = out + (size_t)g * A.outFrameStride;
+#pragma unroll
+            for (int ch0 = 0; ch0 < kFastTab; ch0 += 4) {
+                if (ch0 >= M.nOut) break;
+                int val[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) val[q] = post_s[(ch0 + q) * R + ((g - M.oDelay[ch0 + q]) & ringMask)] & M.storeMask;
+                *reinterpret_cast<int4*>(o + ch0) = make_int4(val[0], val[1], val[2], val[3]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NP / 4; q++) cur[q] = nxt[q];
+        ctv = ntv;
+    }
+    if (!fusedTail) return;
+    // ---- state after T frames, straight from the ring (nSeg == 1): the reference's delay rings hold the last n saturated
+    // values of every path at (idx + j) mod n, the ring index has advanced by T (dsp_runtime.c:769-794), and LOAD_MUX
+    // leaves its last 64-bit value in the data area (:893-896).  Same arithmetic as k_mix_tail.
+    __syncthreads();
+    int* stw = A.state + (size_t)s * M.stateWords;
+    for (int c = 0; c < M.nChains; c++) {
+        const int ch = M.cOut[c];
+        const int n = M.cDelay[c];
+        if (M.cMuxOff[c] >= 0 && tid == 0 && T > 0) {
+            const int4* fr4 = in4 + (size_t)(T - 1) * (NP / 4);
+            long long X = 0;
+            for (int q = 0; q < NP / 4; q++) {
+                const int4 v = fr4[q];
+                X = mac32(X, v.x, M.mat[ch * kFastTab + 4 * q + 0]); X = mac32(X, v.y, M.mat[ch * kFastTab + 4 * q + 1]);
+                X = mac32(X, v.z, M.mat[ch * kFastTab + 4 * q + 2]); X = mac32(X, v.w, M.mat[ch * kFastTab + 4 * q + 3]);
+            }
+            stw[M.cMuxOff[c]] = lo32(X); stw[M.cMuxOff[c] + 1] = hi32(X);
+        }
+        if (n <= 0) continue;
+        const int off = M.cDelayOff[c];
+        const int idx0 = stw[off];
+        const bool stale = idx0 >= n || idx0 < 0;
+        const int idxEff = stale ? n - 1 : idx0;
+        const int lo = max(stale ? 1 : 0, T - n);
+        __syncthreads();                                   // everyone has read idx0 (and the stale slot) before it is rewritten
+        const int* row = post_s + ch * R;
+        for (int j = lo + tid; j < T; j += FT) {
+            int v = row[j & ringMask];
+            stw[off + 1 + (int)(((long long)idxEff + j) % n)] = v;
+        }
+        if (stale && T >= 1 && tid == 0) {                  // frame 0's own value went to ring[idx0] (the ring slot of frame 0 holds the override)
+            const int4* fr4 = in4;
+            long long X = 0;
+            for (int q = 0; q < NP / 4; q++) {
+                const int4 v = fr4[q];
+                X = mac32(X, v.x, M.mat[ch * kFastTab + 4 * q + 0]); X = mac32(X, v.y, M.mat[ch * kFastTab + 4 * q + 1]);
+                X = mac32(X, v.z, M.mat[ch * kFastTab + 4 * q + 2]); X = mac32(X, v.w, M.mat[ch * kFastTab + 4 * q + 3]);
+            }
+            stw[off + 1 + idx0] = mixFinish(M, M.oFlags[ch], M.oGain[ch], M.oSatGain[ch], X, ((M.oFlags[ch] & PF_SAT_TPDF) && tb) ? tb[0] : 0);
+        }
+        __syncthreads();
+        if (T > 0 && tid == 0) stw[off] = (int)(((long long)idxEff + T) % n);
     }
 }
 
@@ -364,12 +543,60 @@ bool buildMixPlan(const ChainPlan& P, MixPlan* M, std::string* why) {
     return true;
 }
 
-cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J, int L, int numSMs, cudaStream_t stream) {
-    (void)numSMs;
+// per-stream kernel usable?  (uniform program, interleaved + aligned PCM, ring fits); *nSeg = time segments per stream
+static bool mixStreamPath(const MixPlan& M, const MixArgs& A, int numSMs, int* nSegOut, int* segFramesOut, int* ringFramesOut) {
+    int ringFrames = 1;
+    while (ringFrames < M.maxDelay + 2 * kStreamThreads) ringFrames <<= 1;
+    if (!(M.uniform && A.vecIn && A.vecOut && M.nIn == M.nInPad && (size_t)M.nOut * ringFrames * 4 <= 200 * 1024) || getenv("AVDSP_B200_MIX_TILED")) return false;
     const int S = A.nStreams, T = A.nFrames;
-    if (M.anyTpdf || M.hasCalc) {
+    int nSeg = 1;                                            // cut streams into time segments only when there are few of them
+    const int want = 6 * numSMs;
+    const int minSeg = std::max(4 * M.maxDelay, 8 * kStreamThreads);
+    if (S < want) nSeg = std::max(1, std::min((want + S - 1) / S, T / minSeg));
+    const int segFrames = ((T + nSeg - 1) / nSeg + kStreamThreads - 1) / kStreamThreads * kStreamThreads;
+    *nSegOut = (T + segFrames - 1) / segFrames; *segFramesOut = segFrames; *ringFramesOut = ringFrames;
+    return true;
+}
+// dither PRNG segmentation of a launch: J jump-ahead segments of L draws per stream.  J == kStreamThreads means the
+// per-stream kernel generates the values itself (one stream per CTA)
+void mixPrngSegments(const MixPlan& M, const MixArgs& A, int numSMs, int* J, int* L) {
+    int nSeg, segFrames, ringFrames;
+    const int T = A.nFrames;
+    if (mixStreamPath(M, A, numSMs, &nSeg, &segFrames, &ringFrames) && nSeg == 1 && T >= 8 * kStreamThreads && !getenv("AVDSP_B200_MIX_SPLIT_PRNG")) *J = kStreamThreads;
+    else *J = T >= 4096 ? 64 : (T >= 1024 ? 16 : 1);
+    *L = *J > 1 ? (T - 1) / *J : T;
+}
+
+cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J, int L, int numSMs, cudaStream_t stream) {
+    const int S = A.nStreams, T = A.nFrames;
+    const bool fusedPrng = J == kStreamThreads;
+    if ((M.anyTpdf || M.hasCalc) && !fusedPrng) {
         const int th = 128, total = S * J;
         k_mix_prng<<<(total + th - 1) / th, th, 0, stream>>>(M, A.state, A.tpdfBuf, dJump, S, T, J, L);
+    }
+    cudaError_t e = cudaSuccess;
+    // uniform programs (every output: dense row + the same finish) on interleaved, 16-byte aligned PCM: per-stream kernel
+    int nSeg = 1, segFrames = 0, ringFrames = 0;
+    if (mixStreamPath(M, A, numSMs, &nSeg, &segFrames, &ringFrames)) {
+        const size_t ringBytes = (size_t)M.nOut * ringFrames * 4;
+        const int prngL = (fusedPrng && (M.anyTpdf || M.hasCalc)) ? L : 0;
+        const int fusedTail = nSeg == 1 && !getenv("AVDSP_B200_MIX_SPLIT_TAIL");
+#define LAUNCH_STREAM2(NPP, FL) do { \
+            e = cudaFuncSetAttribute(k_mix_stream<NPP, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes); \
+            if (e != cudaSuccess) return e; \
+            k_mix_stream<NPP, FL><<<(unsigned)(S * nSeg), kStreamThreads, ringBytes, stream>>>(M, A, nSeg, segFrames, ringFrames - 1, dJump, prngL, fusedTail); } while (0)
+#define LAUNCH_STREAM(NPP) do { \
+            if (M.uFlags == (PF_SAT_TPDF | PF_SAT_GAIN)) LAUNCH_STREAM2(NPP, PF_SAT_TPDF | PF_SAT_GAIN); \
+            else if (M.uFlags == PF_SAT_TPDF) LAUNCH_STREAM2(NPP, PF_SAT_TPDF); \
+            else if (M.uFlags == 0) LAUNCH_STREAM2(NPP, 0); \
+            else LAUNCH_STREAM2(NPP, -1); } while (0)
+        if (M.nInPad == 4) LAUNCH_STREAM(4); else if (M.nInPad == 8) LAUNCH_STREAM(8); else if (M.nInPad == 12) LAUNCH_STREAM(12); else LAUNCH_STREAM(16);
+#undef LAUNCH_STREAM2
+#undef LAUNCH_STREAM
+        e = cudaGetLastError();
+        if (e != cudaSuccess || fusedTail) return e;
+        k_mix_tail<<<S, 128, 0, stream>>>(M, A);
+        return cudaGetLastError();
     }
     // tile length: window (FT + maxDelay) x nInPad words + dither values, two CTAs per SM
     // several CTAs per SM so that one tile's load phase overlaps the others' arithmetic (override: AVDSP_B200_MIX_FT)
@@ -380,7 +607,6 @@ cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J,
     A.tileFrames = FT; A.winFrames = FT + M.maxDelay + 4;
     const size_t smem = smemFor(FT);
     dim3 grid((T + FT - 1) / FT, S);
-    cudaError_t e = cudaSuccess;
 #define LAUNCH_MIX(NPP) do { \
         e = cudaFuncSetAttribute(k_mix_main<NPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e; \

@@ -466,3 +466,50 @@ def test_fir_tensor_core_tf32_stated_tolerance(oracle_lib):
     assert np.abs(ys).max() > 2 ** 28                      # the comparison is not vacuous
     for s in (0, S - 1):
         assert np.array_equal(ex.get_state(s), expected_state(ex, sts[s])), s
+
+
+def _uniform_delay_program():
+    """Four outputs, every path LOAD_MUX/LOAD_GAIN -> SAT0DB_TPDF_GAIN -> DELAY(us from a PARAM word) -> STORE + TPDF_CALC:
+    a 'uniform' program, i.e. what the per-stream mix kernel takes.  Returns (words, delay PARAM word indices)."""
+    from oracle import wire
+    a = wire.Asm(fmt=2, fmin=48000, fmax=48000)
+    a.core(); a.tpdf_calc(23)
+    a.param()
+    dps = [a.delay_param(4000, us, 48000) for us in (1500, 400, 0, 3900)]
+    tabs = [a.mux_table([(8 + (k + j) % 4, 0.3 - 0.1 * j) for j in range(3)]) for k in range(4)]
+    for ch in range(4):
+        a.load_mux(tabs[ch])
+        a.sat0db_tpdf_gain(0.9 - 0.1 * ch)
+        a.delay(dps[ch])
+        a.store(ch)
+    return a.end(), dps
+
+
+def test_stream_mix_kernel_stale_delays_and_state(oracle_lib):
+    """Per-stream mix kernel (uniform program): delay times patched mid-stream (stale ring indices, zero-length delays),
+    many streams (one CTA per stream: in-kernel dither generation + in-kernel state write-back) and few streams
+    (time segments + the separate tail kernel), against the oracle: outputs and every state word."""
+    w, dps = _uniform_delay_program()
+    fs = 48000
+    for S, T in ((900, 2304), (3, 9000), (5, 333)):
+        x = synth.pcm("full", S, 3 * T, 4, fs)
+        seeds = np.arange(S, dtype=np.int32)
+        ex = Executor(w, fs, 2, S, seeds=seeds)
+        pick = sorted({0, 1, S // 2, S - 1})
+        orcs = {s: oracle_lib.Oracle(w, 2, fs, seed=s) for s in pick}
+        words = w.copy()
+        for part, uss in enumerate(((1500, 400, 0, 3900), (200, 3000, 700, 0), (3999, 1, 5, 100))):
+            for dp, us in zip(dps, uss):
+                words[dp] = (int(words[dp]) & ~0xFFFF) | us
+            ex.reload_params(words)
+            xs = np.ascontiguousarray(x[:, part * T:(part + 1) * T])
+            y = ex.process(xs)
+            assert ex.last_kernel == "mix"
+            for s in pick:
+                for dp, us in zip(dps, uss):
+                    orcs[s].code[dp] = words[dp]
+                assert np.array_equal(y[s], orcs[s].process(xs[s])), (S, part, s)
+        for s in pick:
+            st = ex.get_state(s)
+            assert np.array_equal(st[: ex.data_size], orcs[s].data), (S, s)
+            assert np.array_equal(st[ex.aux_offset: ex.aux_offset + 7], orcs[s].aux()[:7]), (S, s)
