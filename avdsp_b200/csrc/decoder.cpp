@@ -384,6 +384,16 @@ void buildFirPlan(Lowered* L) {
             if (i >= e || g.ops[i].op != OP_FIR || g.ops[i].n != 1) throw ChainFail{"a path has no FIR convolution right after its load"};
             d.stateOff = g.ops[i].a; d.tapsOff = g.ops[i].b; d.length = g.ops[i].c;
             if (d.length > kMaxFirTaps) throw ChainFail{"impulse longer than kMaxFirTaps"};
+            if (g.h.aluClass == ALU_F32) {
+                // the float kernels multiply with mul.rz.ftz.f32, which equals the reference's dspMulFloatFloat (dsp_ieee754.h:336-375)
+                // except for products next to 2^-126 (the reference flushes one binade earlier).  |x| >= 2^-31 * |gain| for s.31
+                // samples, so with |tap| >= 2^-60 and |gain| >= 2^-30 no product can get there; anything smaller (but non-zero)
+                // sends the program to the interpreter, which restates the reference's multiply bit by bit
+                auto tiny = [](int32_t bits, int minExp) { const int e = (int)(((uint32_t)bits >> 23) & 255u); return e != 0 && e < 127 + minExp; };
+                for (int k = 0; k < d.length; k++)
+                    if (tiny(L->bigPool[d.tapsOff + k], -60)) throw ChainFail{"a float tap is smaller than 2^-60: kept on the interpreter for exact underflow behaviour"};
+                if (d.srcKind == SRC_LOAD_GAIN && tiny(d.srcArg, -30)) throw ChainFail{"LOAD_GAIN gain smaller than 2^-30 in front of a float FIR"};
+            }
             if (d.length > f.maxLen) f.maxLen = d.length;
             i++;
             if (i < e && g.ops[i].op == OP_GAIN) { d.flags |= PF_GAIN; d.gainBits = g.ops[i].a; i++; }

@@ -12,8 +12,9 @@
 //   * DSP_FORMAT 2: int32 x int32 -> int64 accumulation wraps mod 2^64, so any order is bit-exact; the MAC is one
 //     accumulating IMAD.WIDE (quarter rate on sm_100a: the integer-pipe roofline of this kernel);
 //   * DSP_FORMAT 3: the reference's order is kept per output (taps ascending), each product truncated
-//     (dspMulFloatFloat == mul.rz.ftz.f32, see avdsp_dev.cuh), each sum rounded to nearest: bit-exact; the eight
-//     outputs of a thread are eight independent dependency chains;
+//     (dspMulFloatFloat == mul.rz.ftz.f32 away from the underflow range, see avdsp_dev.cuh; the decoder only routes
+//     programs here whose taps / gains keep every product above 2^-121), each sum rounded to nearest: bit-exact; the
+//     eight outputs of a thread are eight independent dependency chains;
 //   * k_fir_state then rewrites the delay line once per launch (st[i] = x[T-1-i], older entries shifted by T).
 // The fixed-point semantics are the INTENDED ones (the reference's dsp_calc_fir_int is not a convolution,
 // SURVEY.md App. C #3): same structure as the float kernel on int32 x int32 -> int64, x = ALU >> 28.

@@ -3,7 +3,7 @@
 // A long FIR shared by many streams IS a dense contraction:  Y[o, s] = sum_j C[o, j] * X[j, s]  with C[o, j] = c[o - j]
 // (the taps as a banded Toeplitz matrix, identical for every stream and every output block) and X[j, s] = x_s[j]
 // (time x streams).  One CTA computes a 128-output x NS-stream block: M = 128 output samples, N = NS streams,
-// K = the Hc + 128 input samples that block can see, walked in stages of 128 bytes of K.
+// K = the Hc + 128 input samples that block can see, walked in stages of 128 (int8) or 64 (TF32) bytes of K.
 //
 //   * KIND_I8 -- DSP_FORMAT 2, BIT-EXACT.  int32 taps and samples are split into four 8-bit limbs (top limb signed,
 //     the others unsigned): x = sum_i x_i 2^(8i).  The 16 limb products run as kind::i8 MMAs with int32 accumulators
@@ -16,7 +16,8 @@
 //     (AVDSP_B200_KERNEL_FIR_TC); the exact float kernel (kernel_fir.cu) stays the default.
 //
 // Operands reach shared memory as 1-D bulk copies (cp.async.bulk + mbarrier) of blobs that are ALREADY in the
-// canonical K-major SWIZZLE_128B layout the MMA descriptors expect: the taps blobs are built once on the host when the
+// canonical K-major swizzled layout the MMA descriptors expect (SWIZZLE_128B for the int8 planes, 2 stages of 96 KB;
+// SWIZZLE_64B for TF32, 4 stages of 48 KB -- measured: 8.35 vs 8.81 ms and 5.10 vs 5.32 ms per C4 step): the taps blobs are built once on the host when the
 // program is loaded (firTcBuildTaps), the sample blobs by k_firtc_pack (PCM -> LOAD/LOAD_GAIN -> limbs / hi+lo, with
 // the delay-line history in front).  Warp roles: warp 0 producer, warp 1 MMA issuer (one elected thread) + TMEM
 // allocation, warps 2-5 epilogue (tcgen05.ld -> registers -> global).
@@ -30,16 +31,37 @@ namespace avdsp {
 namespace {
 
 constexpr int kTcM = 128;                 // outputs per block
-constexpr int kStageBytes = 98304;        // A planes + B planes of one K stage
-constexpr int kTcStages = 2;
+constexpr int kTcSmem = 196608;           // operand ring: kStages x (A planes + B planes of one K stage)
 constexpr int kTcThreads = 192;
+#ifndef AVDSP_FIRTC_ROWB_I8
+#define AVDSP_FIRTC_ROWB_I8 128
+#endif
+#ifndef AVDSP_FIRTC_ROWB_TF32
+#define AVDSP_FIRTC_ROWB_TF32 64
+#endif
 
+// rowB: bytes of K per operand row and stage = the swizzle span (128: SWIZZLE_128B, 64: SWIZZLE_64B).  Shorter rows mean
+// smaller stages and a deeper bulk-copy pipeline for the same shared memory (-DAVDSP_FIRTC_ROWB_I8/_TF32=64|128 for A/B runs).
 template <int KIND> struct TcCfg;
-template <> struct TcCfg<FIRTC_I8>   { static constexpr int planes = 4, NS = 64,  E = 128, elemBytes = 1, nAcc = 7, tmemCols = 512; };
-template <> struct TcCfg<FIRTC_TF32> { static constexpr int planes = 2, NS = 256, E = 32,  elemBytes = 4, nAcc = 1, tmemCols = 256; };
+template <> struct TcCfg<FIRTC_I8> {
+    static constexpr int planes = 4, NS = 64, elemBytes = 1, nAcc = 7, tmemCols = 512, rowB = AVDSP_FIRTC_ROWB_I8;
+};
+template <> struct TcCfg<FIRTC_TF32> {
+    static constexpr int planes = 2, NS = 256, elemBytes = 4, nAcc = 1, tmemCols = 256, rowB = AVDSP_FIRTC_ROWB_TF32;
+};
+template <int KIND> struct TcGeo {
+    typedef TcCfg<KIND> C;
+    static constexpr int E = C::rowB / C::elemBytes;                       // samples of K per stage
+    static constexpr int aBlob = kTcM * C::rowB, bBlob = C::NS * C::rowB;  // one plane of one stage
+    static constexpr int stageBytes = C::planes * (aBlob + bBlob);
+    static constexpr int stages = kTcSmem / stageBytes;
+};
 
-__host__ __device__ __forceinline__ unsigned sw128(unsigned row, unsigned byteInRow) {     // offset inside a [rows][128 B] tile
-    return (row >> 3) * 1024u + (row & 7u) * 128u + ((((byteInRow >> 4) ^ row) & 7u) << 4) + (byteInRow & 15u);
+// byte offset of (row, byteInRow) inside a [rows][rowB] K-major tile in the canonical swizzled layout: 8-row atoms of
+// 8*rowB bytes; the 16-byte chunk index is XORed with the row bits the hardware swizzle uses (Swizzle<3,4,3> / <2,4,3>)
+__host__ __device__ __forceinline__ unsigned swz(unsigned rowB, unsigned row, unsigned b) {
+    if (rowB == 128) return (row >> 3) * 1024u + (row & 7u) * 128u + ((((b >> 4) ^ row) & 7u) << 4) + (b & 15u);
+    return (row >> 3) * 512u + (row & 7u) * 64u + ((((b >> 4) ^ (row >> 1)) & 3u) << 4) + (b & 15u);
 }
 
 __device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -55,9 +77,12 @@ __device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::b
 __device__ __forceinline__ void tcFenceAfter()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcCommit(unsigned bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory"); }
 
-// shared-memory matrix descriptor, K-major SWIZZLE_128B: rows 128 B apart inside an 8-row atom, atoms 1024 B apart
+// shared-memory matrix descriptor, K-major, swizzled: rows rowB bytes apart inside an 8-row atom, atoms 8*rowB bytes apart
+// (SBO), version 1 (sm_100), layout type 2 = SWIZZLE_128B / 4 = SWIZZLE_64B
+template <int ROWB>
 __device__ __forceinline__ unsigned long long smemDesc(unsigned addr) {
-    return (unsigned long long)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+    constexpr unsigned long long sbo = (8ull * ROWB) >> 4, lt = ROWB == 128 ? 2ull : 4ull;
+    return (unsigned long long)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (lt << 61);
 }
 template <int KIND>
 __device__ __forceinline__ void mma(unsigned dTmem, unsigned long long aDesc, unsigned long long bDesc, unsigned idesc, unsigned accumulate) {
@@ -132,13 +157,14 @@ k_firtc_pack(const __grid_constant__ FirPlan P, const FirArgs A, unsigned char* 
             else { const int si = -1 - t; if (si < d.length) x[k] = st[si]; }
         }
     }
+    typedef TcGeo<KIND> G;
     const int e = 4 * q;
-    const int nTimeTiles = (Hc + Tpad) / C::E;
-    const size_t blobBytes = (size_t)C::NS * 128;
-    const unsigned inTile = sw128((unsigned)row, (unsigned)((e % C::E) * C::elemBytes));
+    const int nTimeTiles = (Hc + Tpad) / G::E;
+    const size_t blobBytes = (size_t)G::bBlob;
+    const unsigned inTile = swz(C::rowB, (unsigned)row, (unsigned)((e % G::E) * C::elemBytes));
 #pragma unroll
     for (int pl = 0; pl < C::planes; pl++) {
-        unsigned char* blob = ws + ((((size_t)path * C::planes + pl) * nStreamTiles + tile) * nTimeTiles + e / C::E) * blobBytes;
+        unsigned char* blob = ws + ((((size_t)path * C::planes + pl) * nStreamTiles + tile) * nTimeTiles + e / G::E) * blobBytes;
         if constexpr (KIND == FIRTC_I8) {
             const unsigned w = ((unsigned)(x[0] >> (8 * pl)) & 255u) | (((unsigned)(x[1] >> (8 * pl)) & 255u) << 8) |
                                (((unsigned)(x[2] >> (8 * pl)) & 255u) << 16) | (((unsigned)(x[3] >> (8 * pl)) & 255u) << 24);
@@ -163,16 +189,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 k_firtc(const __grid_constant__ FirPlan P, const FirArgs A, const unsigned char* __restrict__ taps, const unsigned char* __restrict__ ws,
         const int Hc, const int Tpad, const int nStreamTiles) {
     typedef TcCfg<KIND> C;
+    typedef TcGeo<KIND> G;
+    constexpr int kTcStages = G::stages, kStageBytes = G::stageBytes;
     extern __shared__ __align__(1024) unsigned char tc_sm[];
     __shared__ __align__(8) unsigned long long bars[2 * kTcStages + 1];
     __shared__ unsigned tmemBase;
     const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
     const int Q = (int)blockIdx.x, tile = (int)blockIdx.y, path = (int)blockIdx.z;
-    const int nStages = (Hc + kTcM) / C::E;
-    const int nTimeTiles = (Hc + Tpad) / C::E;
+    const int nStages = (Hc + kTcM) / G::E;
+    const int nTimeTiles = (Hc + Tpad) / G::E;
     const unsigned smBase = (smemAddr(tc_sm) + 1023u) & ~1023u;
     const unsigned barFull = smemAddr(&bars[0]), barEmpty = smemAddr(&bars[kTcStages]), barAcc = smemAddr(&bars[2 * kTcStages]);
-    constexpr unsigned aBlob = 16384, bBlob = (unsigned)C::NS * 128;
+    constexpr unsigned aBlob = G::aBlob, bBlob = G::bBlob;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kTcStages; s++) { mbarInit(barFull + 8 * s, 1); mbarInit(barEmpty + 8 * s, 1); }
@@ -194,7 +222,7 @@ k_firtc(const __grid_constant__ FirPlan P, const FirArgs A, const unsigned char*
             const unsigned char* aSrc = taps + (size_t)path * C::planes * nStages * aBlob;
             const unsigned char* bSrc = ws + (((size_t)path * C::planes) * nStreamTiles + tile) * nTimeTiles * (size_t)bBlob;
             const size_t bPlaneStride = (size_t)nStreamTiles * nTimeTiles * bBlob;
-            const int tau0 = Q * (kTcM / C::E);
+            const int tau0 = Q * (kTcM / G::E);
             for (int st = 0; st < nStages; st++) {
                 const int slot = st % kTcStages;
                 mbarWait(barEmpty + 8 * slot, (((unsigned)st / kTcStages) & 1u) ^ 1u);
@@ -216,7 +244,7 @@ k_firtc(const __grid_constant__ FirPlan P, const FirArgs A, const unsigned char*
                 tcFenceAfter();
                 const unsigned aBase = smBase + (unsigned)slot * kStageBytes, bBase = aBase + C::planes * aBlob;
 #pragma unroll
-                for (int ks = 0; ks < 4; ks++) {                              // 128 B of K per stage = 4 MMAs of 32 B
+                for (int ks = 0; ks < C::rowB / 32; ks++) {                   // rowB bytes of K per stage = rowB/32 MMAs of 32 B
                     if constexpr (KIND == FIRTC_I8) {
 #pragma unroll
                         for (int i = 0; i < 4; i++)
@@ -224,15 +252,15 @@ k_firtc(const __grid_constant__ FirPlan P, const FirArgs A, const unsigned char*
                             for (int j = 0; j < 4; j++) {
                                 const int s = i + j;
                                 const bool first = st == 0 && ks == 0 && i == (s > 3 ? s - 3 : 0);
-                                mma<KIND>(tmem + (unsigned)(s * C::NS), smemDesc(aBase + i * aBlob + ks * 32), smemDesc(bBase + j * bBlob + ks * 32),
+                                mma<KIND>(tmem + (unsigned)(s * C::NS), smemDesc<C::rowB>(aBase + i * aBlob + ks * 32), smemDesc<C::rowB>(bBase + j * bBlob + ks * 32),
                                           instrDesc<KIND>(i == 3, j == 3), first ? 0u : 1u);
                             }
                     } else {
                         const unsigned id = instrDesc<KIND>(0, 0);
                         // small terms first: lo*hi, hi*lo, then hi*hi
-                        mma<KIND>(tmem, smemDesc(aBase + aBlob + ks * 32), smemDesc(bBase + ks * 32), id, (st == 0 && ks == 0) ? 0u : 1u);
-                        mma<KIND>(tmem, smemDesc(aBase + ks * 32), smemDesc(bBase + bBlob + ks * 32), id, 1u);
-                        mma<KIND>(tmem, smemDesc(aBase + ks * 32), smemDesc(bBase + ks * 32), id, 1u);
+                        mma<KIND>(tmem, smemDesc<C::rowB>(aBase + aBlob + ks * 32), smemDesc<C::rowB>(bBase + ks * 32), id, (st == 0 && ks == 0) ? 0u : 1u);
+                        mma<KIND>(tmem, smemDesc<C::rowB>(aBase + ks * 32), smemDesc<C::rowB>(bBase + bBlob + ks * 32), id, 1u);
+                        mma<KIND>(tmem, smemDesc<C::rowB>(aBase + ks * 32), smemDesc<C::rowB>(bBase + ks * 32), id, 1u);
                     }
                 }
                 tcCommit(barEmpty + 8 * slot);             // frees the smem slot when these MMAs have read it
@@ -296,23 +324,27 @@ k_firtc(const __grid_constant__ FirPlan P, const FirArgs A, const unsigned char*
 // ---- host side ------------------------------------------------------------------------------------------------------
 int firTcHistory(const FirPlan& P) { return (P.maxLen + 127) & ~127; }
 
-// Taps as pre-swizzled A blobs: A[m, k] = c[m + Hc - k] for stage st = k / E, one [128 rows x 128 B] blob per (path, plane, stage)
+static int firTcRowB(int kind) { return kind == FIRTC_I8 ? TcCfg<FIRTC_I8>::rowB : TcCfg<FIRTC_TF32>::rowB; }
+
+// Taps as pre-swizzled A blobs: A[m, k] = c[m + Hc - k] for stage st = k / E, one [128 rows x rowB] blob per (path, plane, stage)
 void firTcBuildTaps(const FirPlan& P, int kind, const int32_t* bigPool, std::vector<unsigned char>* out) {
     const int Hc = firTcHistory(P);
-    const int planes = kind == FIRTC_I8 ? 4 : 2, E = kind == FIRTC_I8 ? 128 : 32, eb = kind == FIRTC_I8 ? 1 : 4;
+    const int rowB = firTcRowB(kind);
+    const int planes = kind == FIRTC_I8 ? 4 : 2, eb = kind == FIRTC_I8 ? 1 : 4, E = rowB / eb;
     const int nStages = (Hc + kTcM) / E;
-    out->assign((size_t)P.nPaths * planes * nStages * 16384, 0);
+    const size_t blobBytes = (size_t)kTcM * rowB;
+    out->assign((size_t)P.nPaths * planes * nStages * blobBytes, 0);
     for (int p = 0; p < P.nPaths; p++) {
         const FirPath& d = P.paths[p];
         for (int pl = 0; pl < planes; pl++)
             for (int st = 0; st < nStages; st++) {
-                unsigned char* blob = out->data() + (((size_t)p * planes + pl) * nStages + st) * 16384;
+                unsigned char* blob = out->data() + (((size_t)p * planes + pl) * nStages + st) * blobBytes;
                 for (int m = 0; m < kTcM; m++)
                     for (int kk = 0; kk < E; kk++) {
                         const int idx = m + Hc - (st * E + kk);
                         if (idx < 0 || idx >= d.length) continue;
                         const int32_t c = bigPool[d.tapsOff + idx];
-                        unsigned char* dst = blob + sw128((unsigned)m, (unsigned)(kk * eb));
+                        unsigned char* dst = blob + swz((unsigned)rowB, (unsigned)m, (unsigned)(kk * eb));
                         if (kind == FIRTC_I8) *dst = (unsigned char)((uint32_t)(c >> (8 * pl)) & 255u);
                         else {
                             const int32_t hi = c & (int32_t)0xFFFFE000;
@@ -341,7 +373,7 @@ static cudaError_t launchFirTcT(const FirPlan& P, const FirArgs& A, const unsign
     k_firtc_pack<KIND><<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(P, A, ws, Hc, Tpad, tiles);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const size_t smem = (size_t)kTcStages * kStageBytes + 1024;
+    const size_t smem = (size_t)TcGeo<KIND>::stages * TcGeo<KIND>::stageBytes + 1024;
     e = cudaFuncSetAttribute(k_firtc<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (tiles > 65535 || P.nPaths > 65535) return cudaErrorInvalidConfiguration;
