@@ -321,16 +321,24 @@ k_mix_stream(const __grid_constant__ MixPlan M, const MixArgs A, const int nSeg,
             int* slotp = post_s + (g & ringMask);
             long long dq = 0;                                 // the frame's dither, scaled once for all channels (dspTpdfApply)
             if (flags & PF_SAT_TPDF) { const long long tv = ctv; dq = up ? (long long)((unsigned long long)tv << sh) : (tv >> sh); }
+            // four channels at a time: four independent accumulation chains keep the quarter-rate IMAD.WIDE pipe fed
+            // (one chain alone waits ~6 cycles between dependent MACs)
 #pragma unroll
-            for (int ch = 0; ch < kFastTab; ch++) {
-                if (ch >= M.nOut) break;
-                long long X = 0;
+            for (int ch0 = 0; ch0 < kFastTab; ch0 += 4) {
+                if (ch0 >= M.nOut) break;                     // uniform programs have nOut % 4 == 0
+                long long X[4] = {0, 0, 0, 0};
 #pragma unroll
-                for (int k = 0; k < NP; k++) X = mac32(X, v[k], M.mat[ch * kFastTab + k]);
-                if (flags & PF_GAIN) X = X * (long long)M.oGain[ch];
-                if (flags & PF_SAT_GAIN) { X >>= kMant; X = X * (long long)M.oSatGain[ch]; }
-                X += dq;
-                slotp[ch * R] = sat64_031_s32(X);
+                for (int k = 0; k < NP; k++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) X[q] = mac32(X[q], v[k], M.mat[(ch0 + q) * kFastTab + k]);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    long long Y = X[q];
+                    if (flags & PF_GAIN) Y = Y * (long long)M.oGain[ch0 + q];
+                    if (flags & PF_SAT_GAIN) { Y >>= kMant; Y = Y * (long long)M.oSatGain[ch0 + q]; }
+                    Y += dq;
+                    slotp[(ch0 + q) * R] = sat64_031_s32(Y);
+                }
             }
             if (g == 0 && staleMask) {                        // stale ring index: frame n still outputs ring[n-1], not post[0]
                 for (int ch = 0; ch < M.nOut; ch++)
