@@ -445,9 +445,10 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
             }
         }
         A.tpdfBuf = h->dTpdf;
-        e = launchMix(h->mix, A, h->dJump, J, Lseg, h->numSMs, stream);
+        int nl = 1;
+        e = launchMix(h->mix, A, h->dJump, J, Lseg, h->numSMs, stream, &nl);
         h->lastKernel = AVDSP_B200_KERNEL_MIX;
-        h->launches += (J == 256) ? 0 : 2;                   // prng + main + tail (one is counted below); fused: one kernel
+        h->launches += nl - 1;                               // one is counted below
     } else if (use == AVDSP_B200_KERNEL_CHAIN) {
         Chain2Args A{};
         A.in = in; A.out = out; A.state = st; A.lanes = h->dLanes2;

@@ -575,10 +575,13 @@ void mixPrngSegments(const MixPlan& M, const MixArgs& A, int numSMs, int* J, int
     *L = *J > 1 ? (T - 1) / *J : T;
 }
 
-cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J, int L, int numSMs, cudaStream_t stream) {
+cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J, int L, int numSMs, cudaStream_t stream, int* launches) {
     const int S = A.nStreams, T = A.nFrames;
     const bool fusedPrng = J == kStreamThreads;
+    int nl = 0;
+    if (launches) *launches = 0;
     if ((M.anyTpdf || M.hasCalc) && !fusedPrng) {
+        nl++;
         const int th = 128, total = S * J;
         k_mix_prng<<<(total + th - 1) / th, th, 0, stream>>>(M, A.state, A.tpdfBuf, dJump, S, T, J, L);
     }
@@ -602,6 +605,7 @@ cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J,
 #undef LAUNCH_STREAM2
 #undef LAUNCH_STREAM
         e = cudaGetLastError();
+        if (launches) *launches = nl + (fusedTail ? 1 : 2);
         if (e != cudaSuccess || fusedTail) return e;
         k_mix_tail<<<S, 128, 0, stream>>>(M, A);
         return cudaGetLastError();
@@ -622,6 +626,7 @@ cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J,
     if (M.nInPad == 4) LAUNCH_MIX(4); else if (M.nInPad == 8) LAUNCH_MIX(8); else if (M.nInPad == 12) LAUNCH_MIX(12); else LAUNCH_MIX(16);
 #undef LAUNCH_MIX
     k_mix_tail<<<S, 128, 0, stream>>>(M, A);
+    if (launches) *launches = nl + 2;
     return cudaGetLastError();
 }
 

@@ -118,7 +118,7 @@ bool buildMixPlan(const ChainPlan& plan, MixPlan* out, std::string* why);
 void mixJumpMatrix(long long steps, unsigned* out /*[128*4]*/);
 constexpr int kMixJumpLevels = 8;                 // up to 256 jump-ahead segments per stream: level b holds M^(2L * 2^b)
 void mixPrngSegments(const MixPlan& M, const MixArgs& A, int numSMs, int* J, int* L);
-cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J, int L, int numSMs, cudaStream_t stream);
+cudaError_t launchMix(const MixPlan& M, MixArgs A, const unsigned* dJump, int J, int L, int numSMs, cudaStream_t stream, int* launches);
 
 // ---- time-parallel FIR kernels (kernel_fir.cu) ---------------------------------------------------
 struct FirArgs {
