@@ -513,3 +513,17 @@ def test_stream_mix_kernel_stale_delays_and_state(oracle_lib):
             st = ex.get_state(s)
             assert np.array_equal(st[: ex.data_size], orcs[s].data), (S, s)
             assert np.array_equal(st[ex.aux_offset: ex.aux_offset + 7], orcs[s].aux()[:7]), (S, s)
+
+
+def test_c1_ten_seconds_of_stereo_pcm(oracle_lib):
+    """BASELINE.json configs[0]: the stereo 2-way LR4 crossover (crossover2x2lfe, 3 io hand-offs through MEM words) over
+    10 s of synthetic 48 kHz stereo PCM, one stream: bit-exact plumbing against the oracle, outputs and data area."""
+    w = load_program("c1_crossover2x2lfe_f2_48k")
+    fs, T = 48000, 480000
+    x = synth.pcm("noise", 1, T, 2, fs)
+    o = oracle_lib.Oracle(w, 2, fs, seed=0, dither=31)
+    yo = o.process(x[0])
+    ex = Executor(w, fs, 2, 1, seeds=[0], dither=31)
+    y = np.concatenate([ex.process(np.ascontiguousarray(x[:, c0:c0 + 96000])) for c0 in range(0, T, 96000)], axis=1)
+    assert np.array_equal(y[0], yo)
+    assert np.array_equal(ex.get_state(0)[: ex.data_size], o.data)
