@@ -138,6 +138,13 @@ __device__ __forceinline__ float i2fScaled(int x, int shift) {
     e += 127 + 23 - shift;
     return __uint_as_float((acc & 0x7FFFFFu) | ((unsigned)e << 23));
 }
+// the same conversion for shift = 31 on the hardware converter: cvt.rz.f32.s32 truncates the magnitude exactly like the
+// reference's right shifts for |x| < 2^31, and the scale by 2^-31 is exact; INT_MIN (where the reference's shift cap
+// leaves an unnormalised mantissa) takes the restatement
+__device__ __forceinline__ float i2f31Fast(int x) {
+    if (__builtin_expect(x == (int)0x80000000, 0)) return i2fScaled(x, 31);
+    return __fmul_rz(__int2float_rz(x), 4.656612873077393e-10f);
+}
 // dspIntToDoubleScaled (:252-295): exact
 __device__ __forceinline__ double i2dScaled(int x, int shift) {
     if (x == 0) return 0.0;
@@ -161,6 +168,15 @@ __device__ __forceinline__ int f2s31(float f) {
     if (n > 0) m >>= (n & 31); else m = 0x7FFFFFFFu;
     if (u & 0x80000000u) m = 0u - m;
     return (int)m;
+}
+// f2s31(satF(f)) for |f| in [2^-31, 1): the mantissa shift is a plain truncation there, i.e. cvt.rzi of f * 2^31 (exact
+// scale through the exponent field); everything else (zeros/denormals, |f| >= 1, the x86 shift-count wrap below 2^-31)
+// takes the restatement
+__device__ __forceinline__ float satF(float f);
+__device__ __forceinline__ int f2s31SatFast(int bits) {
+    const unsigned e = ((unsigned)bits >> 23) & 255u;
+    if (__builtin_expect(e - 96u < 31u, 1)) return __float2int_rz(__int_as_float(bits + (31 << 23)));
+    return f2s31(satF(__int_as_float(bits)));
 }
 __device__ __forceinline__ int d2s31(double d) {
     const unsigned long long u = (unsigned long long)__double_as_longlong(d);

@@ -192,6 +192,41 @@ __device__ __forceinline__ void laneStepF(Lane2F<K>& L, float xin) {
         L.y2[j] = L.y1[j]; L.y1[j] = acc;
     }
 }
+// K = 2 interior steps with the two sections of the lane packed into f32x2 operands (sm_100a: FMUL2.FTZ.RZ / FADD2): the
+// same per-element arithmetic in half the issue slots -- the float lane-step is issue-bound, not FP32-pipe-bound.
+struct Lane2FP { unsigned long long acc, x1, x2, y1, y2, b0, b1, b2, a1, a2; };
+__device__ __forceinline__ unsigned long long packF2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float loF2(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); (void)hi; return lo; }
+__device__ __forceinline__ float hiF2(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); (void)lo; return hi; }
+__device__ __forceinline__ unsigned long long macF2(unsigned long long acc, unsigned long long a, unsigned long long b) {
+    unsigned long long p;
+    asm("mul.rz.ftz.f32x2 %0, %1, %2;" : "=l"(p) : "l"(a), "l"(b));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(acc), "l"(p));
+    return acc;
+}
+__device__ __forceinline__ void packLane(const Lane2F<2>& L, Lane2FP& Q) {
+    Q.acc = packF2(L.acc[0], L.acc[1]); Q.x1 = packF2(L.x1[0], L.x1[1]); Q.x2 = packF2(L.x2[0], L.x2[1]);
+    Q.y1 = packF2(L.y1[0], L.y1[1]); Q.y2 = packF2(L.y2[0], L.y2[1]);
+    Q.b0 = packF2(L.b0[0], L.b0[1]); Q.b1 = packF2(L.b1[0], L.b1[1]); Q.b2 = packF2(L.b2[0], L.b2[1]);
+    Q.a1 = packF2(L.a1[0], L.a1[1]); Q.a2 = packF2(L.a2[0], L.a2[1]);
+}
+__device__ __forceinline__ void unpackLane(const Lane2FP& Q, Lane2F<2>& L) {
+    L.acc[0] = loF2(Q.acc); L.acc[1] = hiF2(Q.acc); L.x1[0] = loF2(Q.x1); L.x1[1] = hiF2(Q.x1); L.x2[0] = loF2(Q.x2); L.x2[1] = hiF2(Q.x2);
+    L.y1[0] = loF2(Q.y1); L.y1[1] = hiF2(Q.y1); L.y2[0] = loF2(Q.y2); L.y2[1] = hiF2(Q.y2);
+}
+__device__ __forceinline__ void laneStepFP(Lane2FP& Q, float xin) {
+    const unsigned long long in = packF2(xin, loF2(Q.y1));           // section 1 works on section 0's previous output
+    unsigned long long acc = Q.acc;
+    acc = macF2(acc, in, Q.b0);
+    acc = macF2(acc, Q.x1, Q.b1);
+    acc = macF2(acc, Q.x2, Q.b2);
+    acc = macF2(acc, Q.y1, Q.a1);
+    acc = macF2(acc, Q.y2, Q.a2);
+    Q.acc = acc;
+    Q.x2 = Q.x1; Q.x1 = in;
+    Q.y2 = Q.y1; Q.y1 = acc;
+}
+
 template <int K>
 __device__ __forceinline__ void laneStepPredF(Lane2F<K>& L, float xin, int t, int g0, int T) {
     float in[K];
@@ -260,7 +295,7 @@ __device__ __forceinline__ long long muxFromShared(const ChainPlan& P, const Cha
 // post-ring word -> s.31 sample: fixed point stores it as such; the float class stores the (possibly not yet saturated)
 // float and converts here (dspSaturateFloat0db + dsps31Float0DB, runtime/dsp_ieee754.h:60-83,170-184)
 template <int CLS> __device__ __forceinline__ int postToS31(int v) {
-    if (CLS == ALU_F32) return f2s31(satF(__int_as_float(v)));
+    if (CLS == ALU_F32) return f2s31SatFast(v);
     return v;
 }
 // Phase B of the sink for interleaved output with NOUT (power of two) channels: 32/NOUT frames per pass.
@@ -334,6 +369,22 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
             const int t0 = i * F;
             int* ps = prow + (t0 & RM);
             if (t0 >= gmax && t0 + F <= T) {
+                if constexpr (K == 2) {
+                    Lane2FP Q;
+                    packLane(L, Q);
+#pragma unroll 1
+                    for (int j0 = 0; j0 < F; j0 += UNR) {
+#pragma unroll
+                        for (int jj = 0; jj < UNR; jj++) {
+                            const int j = j0 + jj;
+                            float x = __shfl_up_sync(0xffffffffu, hiF2(Q.y1), 1);
+                            if (head) x = __int_as_float(xs[j]);
+                            laneStepFP(Q, x);
+                            if (tail) ps[j] = __float_as_int(hiF2(Q.acc));
+                        }
+                    }
+                    unpackLane(Q, L);
+                } else {
 #pragma unroll 1
                 for (int j0 = 0; j0 < F; j0 += UNR) {
 #pragma unroll
@@ -344,6 +395,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         laneStepF<K>(L, x);
                         if (tail) ps[j] = __float_as_int(L.acc[K - 1]);     // the sink saturates / converts (satF is idempotent)
                     }
+                }
                 }
             } else {
 #pragma unroll 1
@@ -598,7 +650,14 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                     for (int k = 0; k < kFastTab; k++) {
                         if (k >= nSrc) break;
                         const int smp = lds32(ra + (interleavedIn ? (unsigned)(P.h.sCh[k] * 4) : (unsigned)(P.h.sCh[k] * F * 4)));
-                        if (CLS == ALU_F32) sts32(xa + G.srcXOff[k], __float_as_int(mulFF(i2fScaled(smp, 31), __int_as_float(P.h.sArg[k]))));
+                        if (CLS == ALU_F32) {
+                            // LOAD_GAIN in the float class: hardware convert + mul.rz.ftz when the host checked that no product
+                            // can reach the underflow range (G.floatFast: every gain in [2^-30, 2^30]), else the restatement
+                            float xf = G.floatFast ? mulFF_fast(i2f31Fast(smp), __int_as_float(P.h.sArg[k]))
+                                                   : mulFF(i2fScaled(smp, 31), __int_as_float(P.h.sArg[k]));
+                            if (smp == 0) xf = 0.0f;                   // the reference's product of a zero is +0, never -0
+                            sts32(xa + G.srcXOff[k], __float_as_int(xf));
+                        }
                         else sts32(xa + G.srcXOff[k], q59ToS31(mul32(smp, P.h.sArg[k])));
                     }
                     continue;
@@ -904,6 +963,13 @@ bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2G
             g.secThreads = lt; g.helpThreads = help * 32;
             g.helpersFirst = envInt2("AVDSP_B200_HELPFIRST", 0);
             g.debugSkip = envInt2("AVDSP_B200_DEBUG_SKIP", 0);     // timing experiments only: 1 source, 2 PRNG, 4 sink are skipped (wrong output)
+            g.floatFast = 1;                                       // float class: every LOAD_GAIN gain within [2^-30, 2^30] (or exactly 0)
+            for (int k = 0; k < plan.h.nSrc && k < kFastTab; k++)
+                if (plan.h.sKind[k] == SRC_LOAD_GAIN) {
+                    const int ex = (int)(((uint32_t)plan.h.sArg[k] >> 23) & 255u);
+                    if (ex != 0 && (ex < 127 - 30 || ex > 127 + 30)) g.floatFast = 0;
+                }
+            if (envInt2("AVDSP_B200_FLOAT_EXACT_HELPERS", 0)) g.floatFast = 0;
             int R = 2 * F;
             while (R < 2 * F + gm + maxDelay) R <<= 1;      // tails write tile i while the sink still reads window i-1
             g.postRing = R;

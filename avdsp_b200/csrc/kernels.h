@@ -63,6 +63,7 @@ struct Chain2Geom {
     int secThreads;        // threads that own sections (multiple of 32, may be 0)
     int helpThreads;       // source / sink / dither threads (multiple of 32, >= 32)
     int helpersFirst;      // 1: helper warps get the low warp ids
+    int floatFast;         // float class: LOAD_GAIN sources may use the hardware convert + mul.rz.ftz (gains checked on the host)
     int debugSkip;         // timing experiments only (AVDSP_B200_DEBUG_SKIP): bit0 skip sources, bit1 skip PRNG, bit2 skip sink
     int postRing;          // R: post ring length in steps (power of two >= F + gmax + longest delay)
     int xPitch, accPitch, postPitch, tpdfPitch;   // shared-memory row pitches (elements)
