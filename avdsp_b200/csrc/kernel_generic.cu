@@ -10,6 +10,8 @@
 // the faster systolic kernel (kernel_chain.cu) instead; this one is the always-correct path.
 #include "avdsp_dev.cuh"
 #include "kernels.h"
+#include <algorithm>
+#include <cstdlib>
 
 namespace avdsp {
 
@@ -18,20 +20,33 @@ template <> struct AluT<ALU_INT64> { typedef long long T; typedef int SP; static
 template <> struct AluT<ALU_F32>   { typedef float T;     typedef float SP; static constexpr int W = 1; };
 template <> struct AluT<ALU_F64>   { typedef double T;    typedef float SP; static constexpr int W = 2; };
 
-template <int CLS> __device__ __forceinline__ typename AluT<CLS>::T ldA(const int* p) {
+// Per-stream state is addressed through a strided pointer: stride 1 when the lane works on its block in HBM, stride
+// blockDim when the CTA staged its streams' blocks in shared memory word-interleaved ([word][lane]: conflict-free, and
+// no more 32-sector uncoalesced global accesses per state word -- the lanes' blocks are stateWords apart in HBM).
+template <typename T> struct SPtr {
+    T* p; int s;
+    __device__ __forceinline__ SPtr operator+(int k) const { return SPtr{p + (ptrdiff_t)k * s, s}; }
+    __device__ __forceinline__ T& operator[](int k) const { return p[(ptrdiff_t)k * s]; }
+    __device__ __forceinline__ T& operator*() const { return *p; }
+    __device__ __forceinline__ SPtr& operator+=(int k) { p += (ptrdiff_t)k * s; return *this; }
+    template <typename U> __device__ __forceinline__ SPtr<U> as() const { return SPtr<U>{reinterpret_cast<U*>(p), s}; }
+};
+typedef SPtr<int> SPi;
+
+template <int CLS, typename Ptr> __device__ __forceinline__ typename AluT<CLS>::T ldA(Ptr p) {
     if constexpr (CLS == ALU_INT64) return (long long)(((unsigned long long)(unsigned)p[1] << 32) | (unsigned)p[0]);
     else if constexpr (CLS == ALU_F32) return __int_as_float(p[0]);
     else return __longlong_as_double((long long)(((unsigned long long)(unsigned)p[1] << 32) | (unsigned)p[0]));
 }
-template <int CLS> __device__ __forceinline__ void stA(int* p, typename AluT<CLS>::T v) {
+template <int CLS, typename Ptr> __device__ __forceinline__ void stA(Ptr p, typename AluT<CLS>::T v) {
     if constexpr (CLS == ALU_INT64) { p[0] = (int)v; p[1] = (int)(v >> 32); }
     else if constexpr (CLS == ALU_F32) { p[0] = __float_as_int(v); }
     else { const long long b = __double_as_longlong(v); p[0] = (int)b; p[1] = (int)(b >> 32); }
 }
-template <int CLS> __device__ __forceinline__ typename AluT<CLS>::SP ldSP(const int* p) {
+template <int CLS, typename Ptr> __device__ __forceinline__ typename AluT<CLS>::SP ldSP(Ptr p) {
     if constexpr (CLS == ALU_INT64) return p[0]; else return __int_as_float(p[0]);
 }
-template <int CLS> __device__ __forceinline__ void stSP(int* p, typename AluT<CLS>::SP v) {
+template <int CLS, typename Ptr> __device__ __forceinline__ void stSP(Ptr p, typename AluT<CLS>::SP v) {
     if constexpr (CLS == ALU_INT64) p[0] = v; else p[0] = __float_as_int(v);
 }
 // parameter word -> value
@@ -79,7 +94,7 @@ struct StreamRegs { Prng g; int tpdfValue, tpdfRandom, dither; };
 // memory (stride = blockDim.x), `st` its state block in HBM.
 template <int CLS>
 __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, int* __restrict__ io, const int ios,
-                                        int* __restrict__ st, const int* __restrict__ big, StreamRegs& R) {
+                                        const SPi st, const int* __restrict__ big, StreamRegs& R) {
     typedef typename AluT<CLS>::T ALU;
     typedef typename AluT<CLS>::SP SPT;
     constexpr int AW = AluT<CLS>::W;
@@ -206,7 +221,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             break;
         case OP_DELAY_1: { Y = X; const ALU t = ldA<CLS>(st + m.a); stA<CLS>(st + m.a, X); X = t; break; }
         case OP_DELAY: {
-            int* d = st + m.a;
+            SPi d = st + m.a;
             int idx = d[0];
             const SPT old = ldSP<CLS>(d + 1 + idx);
             stSP<CLS>(d + 1 + idx, (SPT)X);
@@ -215,7 +230,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             d[0] = idx;
             break; }
         case OP_DELAY_DP: {
-            int* d = st + m.a;
+            SPi d = st + m.a;
             int idx = d[0];
             const ALU old = ldA<CLS>(d + 1 + idx * AW);
             stA<CLS>(d + 1 + idx * AW, X);
@@ -224,7 +239,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             d[0] = idx;
             break; }
         case OP_BIQUADS: {
-            int* s = st + m.a;
+            SPi s = st + m.a;
             const int* cf = P.pool + m.b;
             if constexpr (CLS == ALU_INT64) {
                 int xn = (int)(X >> kMantBQ);
@@ -257,7 +272,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             }
             break; }
         case OP_FIR: {
-            int* s = st + m.a;
+            SPi s = st + m.a;
             if (m.n == 0) {                                   // plain delay of m.b samples, stores X>>28
                 // dsp_runtime.c:943 reads/writes the ring index through the dspALU_SP_t pointer: a float in formats 3..6
                 int idx;
@@ -288,7 +303,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             break; }
         case OP_DATA_TABLE: {
             const int* q = P.pool + m.a;                      // gain, div, size, idxOff, tableOff
-            int* ip = st + q[3];
+            SPi ip = st + q[3];
             int idx = *ip;
             const int raw = big[q[4] + idx];
             idx += q[1]; if (idx >= q[2]) idx -= q[2];
@@ -300,7 +315,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             }
             break; }
         case OP_DCBLOCK: {
-            int* ap = st + m.a; int* sp = ap + AW;
+            SPi ap = st + m.a; SPi sp = ap + AW;
             if constexpr (CLS == ALU_INT64) {
                 int xn = (int)(X >> kMant);
                 const int prevX = sp[0]; sp[0] = xn;
@@ -323,7 +338,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             }
             break; }
         case OP_DITHER: {
-            int* e = st + m.a;
+            SPi e = st + m.a;
             ALU t0 = ldA<CLS>(e); const ALU t1 = ldA<CLS>(e + AW), t2 = ldA<CLS>(e + 2 * AW);
             X = X + t0;
             if constexpr (CLS == ALU_INT64) t0 >>= 1; else if constexpr (CLS == ALU_F32) t0 = shiftF(t0, -1); else t0 = shiftD(t0, -1);
@@ -334,7 +349,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             stA<CLS>(e, s0 - X);
             break; }
         case OP_DITHER_NS2: {
-            int* e = st + m.a;
+            SPi e = st + m.a;
             const SPT e0 = ldSP<CLS>(e), e1 = ldSP<CLS>(e + 1), e2 = ldSP<CLS>(e + 2);
             macc<CLS>(X, e0, par<CLS>(P.pool[m.b]));
             macc<CLS>(X, e1, par<CLS>(P.pool[m.b + 1]));
@@ -346,12 +361,12 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             if constexpr (CLS == ALU_INT64) e[0] = (int)(s0 >> kMant); else stSP<CLS>(e, (SPT)s0);
             break; }
         case OP_RMS: {
-            unsigned* d = (unsigned*)(st + m.a);
+            SPtr<unsigned> d = (st + m.a).as<unsigned>();
             const unsigned delay = (unsigned)m.b;
             const unsigned counter = d[0] + 1;
             const unsigned maxCounter = (unsigned)P.pool[m.c];
             const int factor = P.pool[m.c + 1];
-            int* sumsq = (int*)(d + 5); int* avg = sumsq + AW;
+            SPi sumsq = (d + 5).as<int>(); SPi avg = sumsq + AW;
             if constexpr (CLS == ALU_INT64) {
                 if (factor > 0) { const int sv = (int)(((long long)(int)X * factor) >> 32); X = ldA<CLS>(sumsq); X = mac32(X, sv, sv); }
                 else { const int sx = (int)(((long long)(int)X * factor) >> 32), sy = (int)(((long long)(int)Y * factor) >> 32);
@@ -360,7 +375,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             if (counter >= maxCounter) {
                 if (delay) {
                     unsigned idx = d[1];
-                    int* line = sumsq + 2 * AW + (int)idx * AW;
+                    SPi line = sumsq + (2 * AW + (int)idx * AW);
                     const ALU old = ldA<CLS>(line);
                     stA<CLS>(line, X);
                     X = X - old; X = X + ldA<CLS>(avg);
@@ -390,7 +405,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             break; }
         case OP_DISTRIB: {
             const int size = m.b;
-            int* d = st + m.c; int* tab = d + 1;
+            SPi d = st + m.c; SPi tab = d + 1;
             int idx = d[0];
             const int middle = size >> 1;
             const SPT sv = (SPT)X;
@@ -408,7 +423,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             else IO(m.a) = sampleInt ? v : __float_as_int(i2fScaled(v, 31));
             break; }
         case OP_DIRAC: case OP_SQUAREWAVE: {
-            int* cp = st + m.a;
+            SPi cp = st + m.a;
             int counter = *cp;
             if (m.op == OP_DIRAC) {
                 if (counter == 0) { if constexpr (CLS == ALU_INT64) X = mul32(0x7FFFFFFF, m.b); else X = (ALU)__int_as_float(m.b); }
@@ -436,13 +451,17 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
 template <int CLS>
 __global__ void __launch_bounds__(kGenericThreads)
 k_generic(const __grid_constant__ GenericPlan P, const GenericArgs A) {
-    extern __shared__ int io_s[];                       // [kIoSlots][blockDim.x]
+    extern __shared__ int io_s[];                       // [kIoSlots][blockDim.x], then (staged) [stateWords][blockDim.x]
     const int ios = blockDim.x;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.nStreams) return;
     int* io = io_s + threadIdx.x;
-    int* st = A.state + (size_t)s * P.h.stateWords;
-    const int* aux = st + P.h.auxOff;
+    int* gst = A.state + (size_t)s * P.h.stateWords;
+    // longer launches work on a shared-memory copy of the state blocks ([word][lane]); each lane moves its own block
+    const bool staged = A.stageState != 0;
+    const SPi st = staged ? SPi{io_s + kIoSlots * ios + threadIdx.x, ios} : SPi{gst, 1};
+    if (staged) for (int w = 0; w < P.h.stateWords; w++) st[w] = gst[w];
+    const SPi aux = st + P.h.auxOff;
     StreamRegs R;
     R.g.s0 = aux[AUX_S0]; R.g.s1 = aux[AUX_S1]; R.g.s2 = aux[AUX_S2]; R.g.s3 = aux[AUX_S3];
     R.tpdfValue = aux[AUX_TPDF_VALUE]; R.tpdfRandom = aux[AUX_TPDF_RANDOM]; R.dither = aux[AUX_DITHER];
@@ -477,20 +496,37 @@ k_generic(const __grid_constant__ GenericPlan P, const GenericArgs A) {
                 }
         }
     }
-    int* auxw = st + P.h.auxOff;
+    const SPi auxw = st + P.h.auxOff;
     auxw[AUX_S0] = R.g.s0; auxw[AUX_S1] = R.g.s1; auxw[AUX_S2] = R.g.s2; auxw[AUX_S3] = R.g.s3;
     auxw[AUX_TPDF_VALUE] = R.tpdfValue; auxw[AUX_TPDF_RANDOM] = R.tpdfRandom; auxw[AUX_DITHER] = R.dither;
+    if (staged) for (int w = 0; w < P.h.stateWords; w++) gst[w] = st[w];
 }
 
 cudaError_t launchGeneric(const GenericPlan& plan, const GenericArgs& args, cudaStream_t stream) {
-    const int threads = args.nStreams >= 4 * kGenericThreads ? kGenericThreads : 32;
-    const int blocks = (args.nStreams + threads - 1) / threads;
-    const size_t smem = (size_t)threads * kIoSlots * sizeof(int);
-    switch (plan.h.aluClass) {
-    case ALU_INT64: k_generic<ALU_INT64><<<blocks, threads, smem, stream>>>(plan, args); break;
-    case ALU_F32:   k_generic<ALU_F32><<<blocks, threads, smem, stream>>>(plan, args); break;
-    default:        k_generic<ALU_F64><<<blocks, threads, smem, stream>>>(plan, args); break;
+    GenericArgs A = args;
+    int threads = A.nStreams >= 4 * kGenericThreads ? kGenericThreads : 32;
+    // stage the state blocks in shared memory when the launch is long enough to pay for the two copies and a warp's
+    // blocks fit: as many threads per CTA as ~96 KB allow (more CTAs per SM beat wider CTAs: the lanes are latency-bound)
+    A.stageState = 0;
+    const size_t perLane = (size_t)(kIoSlots + plan.h.stateWords) * sizeof(int);
+    if (A.nFrames >= 32 && perLane * 32 <= 200 * 1024 && !getenv("AVDSP_B200_GENERIC_NO_STAGE")) {
+        A.stageState = 1;
+        int t = (int)((96 * 1024) / perLane) / 32 * 32;
+        threads = std::max(32, std::min(threads, t));
     }
+    const int blocks = (A.nStreams + threads - 1) / threads;
+    const size_t smem = (size_t)threads * (A.stageState ? perLane : kIoSlots * sizeof(int));
+    cudaError_t e = cudaSuccess;
+#define LAUNCH_G(CLS) do { \
+        e = cudaFuncSetAttribute(k_generic<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)); \
+        if (e != cudaSuccess) return e; \
+        k_generic<CLS><<<blocks, threads, smem, stream>>>(plan, A); } while (0)
+    switch (plan.h.aluClass) {
+    case ALU_INT64: LAUNCH_G(ALU_INT64); break;
+    case ALU_F32:   LAUNCH_G(ALU_F32); break;
+    default:        LAUNCH_G(ALU_F64); break;
+    }
+#undef LAUNCH_G
     return cudaGetLastError();
 }
 

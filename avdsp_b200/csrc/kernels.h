@@ -20,6 +20,7 @@ struct GenericArgs {
     int inFrameStride, inChStride, outFrameStride, outChStride;
     int coreSel;                // -1: all cores; k: only core k (0-based)  -- dspRuntime_<fmt> compat path
     int period;                 // 0: canonical order; >0: ALSA plugin order with this period
+    int stageState;             // filled by launchGeneric: the CTA works on a shared-memory copy of its streams' state blocks
     unsigned coreInMask[kMaxCores], coreOutMask[kMaxCores];
 };
 cudaError_t launchGeneric(const GenericPlan& plan, const GenericArgs& args, cudaStream_t stream);
