@@ -54,7 +54,7 @@ __device__ __forceinline__ int firFinish(const FirPath& d, typename FirNum<CLS>:
         float X = acc;
         if (d.flags & PF_GAIN) X = __fmul_rn(X, __int_as_float(d.gainBits));
         if (d.flags & PF_SAT_GAIN) X = mulFF(X, __int_as_float(d.satGainBits));
-        return f2s31(satF(X)) & mask;
+        return f2s31SatFast(__float_as_int(X)) & mask;
     }
 }
 

@@ -126,7 +126,7 @@ __device__ __forceinline__ int tcFinishI(const FirPath& d, long long X, int mask
 __device__ __forceinline__ int tcFinishF(const FirPath& d, float X, int mask) {
     if (d.flags & PF_GAIN) X = __fmul_rn(X, __int_as_float(d.gainBits));
     if (d.flags & PF_SAT_GAIN) X = mulFF(X, __int_as_float(d.satGainBits));
-    return f2s31(satF(X)) & mask;
+    return f2s31SatFast(__float_as_int(X)) & mask;      // hardware convert for |X| in [2^-31, 1), the restatement otherwise
 }
 
 // ---- pack: PCM (+ delay-line history) -> pre-swizzled B blobs ---------------------------------------------------
