@@ -73,6 +73,11 @@ __device__ __forceinline__ void tmaLoad1D(unsigned dst, const void* src, unsigne
 __device__ __forceinline__ void mbarWait(unsigned bar, unsigned parity) {
     asm volatile("{\n.reg .pred P1;\nTCW_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra TCW_DONE;\nbra TCW_LOOP;\nTCW_DONE:\n}" :: "r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool electOne() {
+    unsigned pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcFenceAfter()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcCommit(unsigned bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory"); }
@@ -236,12 +241,13 @@ k_firtc(const __grid_constant__ FirPlan P, const FirArgs A, const unsigned char*
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            for (int st = 0; st < nStages; st++) {
-                const int slot = st % kTcStages;
-                mbarWait(barFull + 8 * slot, ((unsigned)st / kTcStages) & 1u);
-                tcFenceAfter();
+        // ===== MMA issuer: the WHOLE warp walks the stages (uniform control flow) and one elected lane issues, so that
+        // ptxas emits bare UTC*MMA instructions instead of an elect/branch wrapper around each of them =====
+        for (int st = 0; st < nStages; st++) {
+            const int slot = st % kTcStages;
+            mbarWait(barFull + 8 * slot, ((unsigned)st / kTcStages) & 1u);
+            tcFenceAfter();
+            if (electOne()) {
                 const unsigned aBase = smBase + (unsigned)slot * kStageBytes, bBase = aBase + C::planes * aBlob;
 #pragma unroll
                 for (int ks = 0; ks < C::rowB / 32; ks++) {                   // rowB bytes of K per stage = rowB/32 MMAs of 32 B
@@ -264,8 +270,9 @@ k_firtc(const __grid_constant__ FirPlan P, const FirArgs A, const unsigned char*
                     }
                 }
                 tcCommit(barEmpty + 8 * slot);             // frees the smem slot when these MMAs have read it
+                if (st == nStages - 1) tcCommit(barAcc);   // accumulators complete
             }
-            tcCommit(barAcc);                               // accumulators complete
+            __syncwarp();
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
