@@ -245,13 +245,35 @@ void buildChainPlan(Lowered* L) {
 
     for (int core = 0; core < g.h.nCores; core++) {
         int i = g.h.coreStart[core], e = g.h.coreStart[core + 1];
+        auto takeRaw = [&]() {
+            // DSP_LOAD_STORE (dsp_runtime.c:738-747): raw io[out] = io[in] copies; each pair is a pass-through path
+            const MicroOp& s = g.ops[i];
+            for (int k = 0; k < s.n; k++) {
+                if (c.h.nChains >= kMaxChains) throw ChainFail{"more than kMaxChains signal paths"};
+                ChainDesc& d = c.chains[c.h.nChains];
+                memset(&d, 0, sizeof d);
+                d.muxStateOff = -1; d.delayOff = -1; d.srcId = -1; d.accRow = -1;
+                d.srcKind = SRC_RAW; d.srcCh = (int16_t)inputCh(g.pool[s.a + 2 * k]);
+                const int ch = outChOfSlot[g.pool[s.a + 2 * k + 1]];
+                if (ch < 0) throw ChainFail{"LOAD_STORE to a slot outside the declared outputs"};
+                if (c.h.chainOfOut[ch] >= 0) throw ChainFail{"two paths store to the same output"};
+                c.h.chainOfOut[ch] = c.h.nChains;
+                d.storeCh[d.nStores++] = (uint8_t)ch;
+                c.h.nChains++; c.h.nRaw++;
+            }
+            i++;
+        };
+        // core 1 may compute the frame's dither after raw copies (the DAC8PRO firmware does): LOAD_STORE neither uses the
+        // TPDF value nor the STORE mask, so TPDF_CALC behind them is still "at the start of the frame" for everything else
+        while (core == 0 && i < e && g.ops[i].op == OP_LOAD_STORE && c.h.nChains == c.h.nRaw && !c.h.hasTpdfCalc) takeRaw();
         if (i < e && g.ops[i].op == OP_TPDF_CALC) {
-            if (core != 0 || c.h.nChains != 0 || c.h.hasTpdfCalc) throw ChainFail{"TPDF_CALC not at the very start of core 1"};
+            if (core != 0 || c.h.nChains != c.h.nRaw || c.h.hasTpdfCalc) throw ChainFail{"TPDF_CALC not at the very start of core 1"};
             c.h.hasTpdfCalc = 1; c.h.tpdfDither = g.ops[i].a; c.h.tpdfDataOff = g.ops[i].b;
             c.h.storeDither = g.ops[i].a;
             i++;
         }
         while (i < e) {
+            if (g.ops[i].op == OP_LOAD_STORE) { takeRaw(); continue; }
             if (c.h.nChains >= kMaxChains) throw ChainFail{"more than kMaxChains signal paths"};
             ChainDesc& d = c.chains[c.h.nChains];
             memset(&d, 0, sizeof d);

@@ -931,7 +931,7 @@ static int packLanes2(const ChainPlan& p, int NS, int K, ChainLane* out, int* gm
 
 bool chain2Supports(const ChainPlan& plan) {
     // the helper warps address everything through the flattened tables (plan.h: kFastTab entries each)
-    return (plan.h.aluClass == ALU_INT64 || plan.h.aluClass == ALU_F32) && plan.h.sampleInt && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nOut <= kFastTab &&
+    return (plan.h.aluClass == ALU_INT64 || plan.h.aluClass == ALU_F32) && plan.h.sampleInt && plan.h.nRaw == 0 && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nOut <= kFastTab &&
            plan.h.nProc <= kFastTab && plan.h.nSrc <= kFastTab;
 }
 

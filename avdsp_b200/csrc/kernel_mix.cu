@@ -225,6 +225,10 @@ k_mix_main(const __grid_constant__ MixPlan M, const MixArgs A) {
                         const int* fr = pcm_s + (size_t)(fd - w0) * nInPad;
                         const int flags = M.oFlags[ch];
                         long long X;
+                        if (M.oKind[ch] == SRC_RAW) {        // DSP_LOAD_STORE: the sample itself, no saturation, no STORE mask
+                            val[q] = M.oSrcCh[ch] >= 0 ? fr[M.oSrcCh[ch]] : 0;
+                            continue;
+                        }
                         if (M.oKind[ch] == SRC_LOAD) X = M.oSrcCh[ch] >= 0 ? (long long)fr[M.oSrcCh[ch]] : 0ll;
                         else X = mixSourceDenseT<NP>(M, ch, fr);
                         v = mixFinish(M, flags, M.oGain[ch], M.oSatGain[ch], X, (flags & PF_SAT_TPDF) ? tpdf_s[fd - w0] : 0);
@@ -544,7 +548,7 @@ bool buildMixPlan(const ChainPlan& P, MixPlan* M, std::string* why) {
     M->uniform = (P.h.nOut & 3) == 0;
     M->uFlags = M->oFlags[0];
     for (int ch = 0; ch < P.h.nOut; ch++) {
-        if (M->oChain[ch] < 0 || M->oKind[ch] == SRC_LOAD || M->oFlags[ch] != M->uFlags) M->uniform = 0;
+        if (M->oChain[ch] < 0 || M->oKind[ch] == SRC_LOAD || M->oKind[ch] == SRC_RAW || M->oFlags[ch] != M->uFlags) M->uniform = 0;
         M->oDelayBytes[ch] = M->oDelay[ch] * 4;
         M->oDelayPcmBytes[ch] = M->oDelay[ch] * M->nInPad * 4;
     }

@@ -83,7 +83,8 @@ constexpr int kMaxChainStores = 4;
 constexpr int kFastTab       = 16;     // entries of the flattened helper tables (chain2 handles programs within them)
 enum { PF_SECTIONS = 1, PF_GAIN = 2, PF_SAT_TPDF = 4, PF_SAT_GAIN = 8 };
 
-enum ChainSrc : int { SRC_LOAD = 0, SRC_LOAD_GAIN = 1, SRC_LOAD_MUX = 2 };
+enum ChainSrc : int { SRC_LOAD = 0, SRC_LOAD_GAIN = 1, SRC_LOAD_MUX = 2,
+                      SRC_RAW = 3 /* a DSP_LOAD_STORE pair: the output is the input sample, untouched (no saturation, no STORE mask) */ };
 enum ChainSat : int { SAT_PLAIN = 0, SAT_TPDF = 1, SAT_GAIN = 2, SAT_TPDF_GAIN = 3 };
 
 struct ChainDesc {
@@ -116,6 +117,7 @@ struct ChainHeader {
     int32_t nSrc;                                   // distinct sources among chains that have sections
     int32_t srcChain[kMaxChains];                   // a chain that carries source k's description
     int32_t nUnwritten;                             // output channels no path stores to (they read 0)
+    int32_t nRaw;                                   // DSP_LOAD_STORE pass-through paths (only the mix kernels take them)
     int32_t nAcc;                                   // acc-ring rows per stream
     int32_t nProc;                                  // chains the sink has to post-process (everything but direct chains)
     int32_t procChain[kMaxChains];

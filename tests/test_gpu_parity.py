@@ -127,6 +127,7 @@ def test_kernels_agree_and_can_alternate():
 
 def test_chain_kernel_is_selected_for_the_benchmark_programs():
     for prog, fs, kern in (("c2_testrpi_xover_f2_192k", 192000, "chain"), ("c5_mixer8x8_f2_192k", 192000, "mix"),
+                           ("ref_dac8prodsp", 96000, "mix"),      # the DAC8PRO firmware program: raw LOAD_STORE copies + dithered gains
                            ("c3_peq16_f2_48k", 48000, "chain"), ("c3_peq16_f3_48k", 48000, "chain")):
         ex = Executor(load_program(prog), fs, 3 if "_f3_" in prog else 2, 64)
         ex.process(synth.pcm("noise", 64, 64, ex.n_in, fs))
