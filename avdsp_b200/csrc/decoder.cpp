@@ -243,6 +243,23 @@ void buildChainPlan(Lowered* L) {
         return inChOfSlot[slot];
     };
 
+    // the path being built (chain index nChains) stores to output channel ch; a later path of the frame that stores to the
+    // same slot wins: the earlier STORE is dead (its path still runs for its state)
+    auto claimOutput = [&](int ch, ChainDesc& d) {
+        const int owner = c.h.chainOfOut[ch];
+        if (owner == c.h.nChains) return;
+        if (owner >= 0) {
+            ChainDesc& o = c.chains[owner];
+            int w = 0;
+            for (int k = 0; k < o.nStores; k++) if (o.storeCh[k] != ch) o.storeCh[w++] = o.storeCh[k];
+            o.nStores = (uint8_t)w;
+        }
+        c.h.chainOfOut[ch] = c.h.nChains;
+        d.storeCh[d.nStores++] = (uint8_t)ch;
+    };
+    struct MemProducer { int srcKind, srcCh, srcArg, consumers; std::vector<int> secOff; std::vector<int32_t> coefs; };
+    std::vector<std::pair<int, MemProducer>> producers;          // keyed by the MEM word's state offset
+    auto findProducer = [&](int memOff) -> MemProducer* { for (auto& pr : producers) if (pr.first == memOff) return &pr.second; return nullptr; };
     for (int core = 0; core < g.h.nCores; core++) {
         int i = g.h.coreStart[core], e = g.h.coreStart[core + 1];
         auto takeRaw = [&]() {
@@ -256,9 +273,7 @@ void buildChainPlan(Lowered* L) {
                 d.srcKind = SRC_RAW; d.srcCh = (int16_t)inputCh(g.pool[s.a + 2 * k]);
                 const int ch = outChOfSlot[g.pool[s.a + 2 * k + 1]];
                 if (ch < 0) throw ChainFail{"LOAD_STORE to a slot outside the declared outputs"};
-                if (c.h.chainOfOut[ch] >= 0) throw ChainFail{"two paths store to the same output"};
-                c.h.chainOfOut[ch] = c.h.nChains;
-                d.storeCh[d.nStores++] = (uint8_t)ch;
+                claimOutput(ch, d);
                 c.h.nChains++; c.h.nRaw++;
             }
             i++;
@@ -285,11 +300,19 @@ void buildChainPlan(Lowered* L) {
                 d.srcKind = SRC_LOAD_MUX; d.srcCh = (int16_t)s.n; d.muxStateOff = s.b;
                 d.srcArg = c.h.nPool;
                 for (int k = 0; k < s.n; k++) { chainPool(c, inputCh(g.pool[s.a + 2 * k])); chainPool(c, g.pool[s.a + 2 * k + 1]); }
-            } else throw ChainFail{"a signal path does not start with LOAD / LOAD_GAIN / LOAD_MUX"};
-            i++;
-            d.coefOff = c.h.nPool;
+            }
             std::vector<int> secOff;
             std::vector<int32_t> coefs;
+            if (s.op == OP_LOAD_MEM) {
+                // a cascade continued from an earlier core through a MEM word: inline the producer (same frame, canonical order:
+                // the consumer's BIQUADS sees x = MEM >> 28 = the producer's last y, exactly as if the sections were consecutive)
+                MemProducer* pr = findProducer(s.a);
+                if (!pr) throw ChainFail{"LOAD_MEM of a word no earlier cascade of the frame stored"};
+                d.srcKind = (uint8_t)pr->srcKind; d.srcCh = (int16_t)pr->srcCh; d.srcArg = pr->srcArg;
+                secOff = pr->secOff; coefs = pr->coefs; pr->consumers++;
+            } else if (s.op != OP_LOAD && s.op != OP_LOAD_GAIN && s.op != OP_LOAD_MUX)
+                throw ChainFail{"a signal path does not start with LOAD / LOAD_GAIN / LOAD_MUX"};
+            i++;
             while (i < e && g.ops[i].op == OP_BIQUADS) {
                 for (int k = 0; k < g.ops[i].n; k++) {
                     secOff.push_back(g.ops[i].a + 6 * k);
@@ -297,6 +320,16 @@ void buildChainPlan(Lowered* L) {
                 }
                 i++;
             }
+            if (i < e && g.ops[i].op == OP_STORE_MEM) {
+                // producer half of such a cascade: no output of its own
+                if (g.h.aluClass != ALU_INT64 || secOff.empty() || d.srcKind == SRC_LOAD_MUX || findProducer(g.ops[i].a) || (int)producers.size() >= kMaxMemCopy)
+                    throw ChainFail{"STORE_MEM the chain kernels cannot inline"};
+                MemProducer pr{d.srcKind, d.srcCh, d.srcArg, 0, secOff, coefs};
+                producers.emplace_back(g.ops[i].a, pr);
+                i++;
+                continue;
+            }
+            d.coefOff = c.h.nPool;
             for (int32_t v : coefs) chainPool(c, v);
             d.secStateOff = c.h.nPool;
             for (int v : secOff) chainPool(c, v);
@@ -317,9 +350,7 @@ void buildChainPlan(Lowered* L) {
                 if (d.nStores >= kMaxChainStores) throw ChainFail{"too many STOREs on one path"};
                 int ch = outChOfSlot[g.ops[i].a];
                 if (ch < 0) throw ChainFail{"STORE to a slot outside the declared outputs"};
-                if (c.h.chainOfOut[ch] >= 0) throw ChainFail{"two paths store to the same output"};
-                c.h.chainOfOut[ch] = c.h.nChains;
-                d.storeCh[d.nStores++] = (uint8_t)ch;
+                claimOutput(ch, d);
                 i++;
             }
             if (d.nsec > c.h.maxSec) c.h.maxSec = d.nsec;
@@ -328,6 +359,10 @@ void buildChainPlan(Lowered* L) {
         }
     }
     if (c.h.nChains == 0) throw ChainFail{"no signal path"};
+    for (auto& pr : producers) {
+        if (pr.second.consumers == 0) throw ChainFail{"a STORE_MEM cascade nobody loads"};
+        c.h.memCopyDst[c.h.nMemCopy] = pr.first; c.h.memCopySrc[c.h.nMemCopy] = pr.second.secOff.back(); c.h.nMemCopy++;
+    }
     c.h.tpdfShift = kMant - c.h.storeDither + 1;
     // deduplicate the sources of chains that have sections: crossovers feed several cascades from the same
     // LOAD_GAIN (same input, same gain), so their x values are computed and staged once per frame
@@ -367,7 +402,8 @@ void buildChainPlan(Lowered* L) {
         if (k < c.h.nProc) {
             const ChainDesc& d = c.chains[c.h.procChain[k]];
             c.h.pChain[k] = c.h.procChain[k]; c.h.pLag[k] = d.nsec > 0 ? d.nsec - 1 : 0; c.h.pAccRow[k] = d.accRow;
-            c.h.pFlags[k] = (d.nsec > 0 ? PF_SECTIONS : 0) | (d.hasGain ? PF_GAIN : 0) | ((d.satKind & 1) ? PF_SAT_TPDF : 0) | (d.satKind >= SAT_GAIN ? PF_SAT_GAIN : 0);
+            c.h.pFlags[k] = (d.nsec > 0 ? PF_SECTIONS : 0) | (d.hasGain ? PF_GAIN : 0) | ((d.satKind & 1) ? PF_SAT_TPDF : 0) | (d.satKind >= SAT_GAIN ? PF_SAT_GAIN : 0) |
+                            (d.srcKind == SRC_RAW ? PF_RAW : 0);
             c.h.pGain[k] = d.gainBits; c.h.pSatGain[k] = d.satGainBits; c.h.pDelayN[k] = d.delayN;
         }
         if (k < c.h.nSrc) {

@@ -701,7 +701,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
     const int bChain = P.h.chainOfOut[bCh];
     const unsigned bRow = bChain >= 0 ? (unsigned)(bChain * G.postPitch * 4) : 0u;
     const unsigned bPos4 = (unsigned)((bFs + P.h.outOff[bCh]) * 4);
-    const int bMask = bChain >= 0 ? storeMask : 0;             // outputs no path writes read as 0
+    // outputs no path writes read as 0; DSP_LOAD_STORE copies are not masked by the STORE dither mask
+    const int bMask = bChain >= 0 ? (P.chains[bChain].srcKind == SRC_RAW ? -1 : storeMask) : 0;
 
     auto isProc = [&](int c) { for (int k = 0; k < P.h.nProc; k++) if (P.h.procChain[k] == c) return true; return false; };
     // ---- sink stage of window `iw`
@@ -774,7 +775,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                             const long long tv = lds32(tpdfA + ((unsigned)(fk & (4 * F - 1)) << 2));
                             X += tpdfUp ? (long long)((unsigned long long)tv << tpdfSh) : (tv >> tpdfSh);      // dspTpdfApply, dsp_tpdf.h:141-145
                         }
-                        const int v = sat64_031_s32(X);
+                        const int v = (flags & PF_RAW) ? lo32(X) : sat64_031_s32(X);     // LOAD_STORE: the sample itself
                         if (anyStale && fk == 0 && P.h.pDelayN[k] > 0 && stale_s[sl * C + P.h.pChain[k]] >= 0)
                             A.state[(size_t)(s0 + sl) * W + P.chains[P.h.pChain[k]].delayOff + 1 + stale_s[sl * C + P.h.pChain[k]]] = v;
                         else sts32(postA + G.pPostOff[k] + tpos4, v);
@@ -825,7 +826,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         const int ch = ch0 + q;
                         int v = 0;      // outputs no path writes read as 0 (io[] is zeroed at the start of every frame)
                         if (ch < P.h.nOut && P.h.chainOfOut[ch] >= 0)
-                            v = lds32(postA + G.outRowOff[ch] + ((f4 + (unsigned)G.outPos4[ch]) & RM4)) & storeMask;
+                            v = lds32(postA + G.outRowOff[ch] + ((f4 + (unsigned)G.outPos4[ch]) & RM4)) &
+                                (P.chains[P.h.chainOfOut[ch]].srcKind == SRC_RAW ? -1 : storeMask);
                         val[q] = v;
                     }
                     if (vecOut) *reinterpret_cast<int4*>(out + ch0) = make_int4(val[0], val[1], val[2], val[3]);
@@ -931,7 +933,7 @@ static int packLanes2(const ChainPlan& p, int NS, int K, ChainLane* out, int* gm
 
 bool chain2Supports(const ChainPlan& plan) {
     // the helper warps address everything through the flattened tables (plan.h: kFastTab entries each)
-    return (plan.h.aluClass == ALU_INT64 || plan.h.aluClass == ALU_F32) && plan.h.sampleInt && plan.h.nRaw == 0 && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nOut <= kFastTab &&
+    return (plan.h.aluClass == ALU_INT64 || plan.h.aluClass == ALU_F32) && plan.h.sampleInt && (plan.h.aluClass == ALU_INT64 || (plan.h.nRaw == 0 && plan.h.nMemCopy == 0)) && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nOut <= kFastTab &&
            plan.h.nProc <= kFastTab && plan.h.nSrc <= kFastTab;
 }
 
@@ -1009,6 +1011,14 @@ bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2G
     return false;
 }
 
+// MEM words of inlined cascades: what the producer's STORE_MEM left there = the accumulator of its last section
+__global__ void k_chain2_memfix(const __grid_constant__ ChainPlan P, int* __restrict__ state, int nStreams) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nStreams) return;
+    int* st = state + (size_t)s * P.h.stateWords;
+    for (int k = 0; k < P.h.nMemCopy; k++) { st[P.h.memCopyDst[k]] = st[P.h.memCopySrc[k]]; st[P.h.memCopyDst[k] + 1] = st[P.h.memCopySrc[k] + 1]; }
+}
+
 cudaError_t launchChain2(const ChainPlan& plan, const Chain2Geom& geom, const Chain2Args& args, cudaStream_t stream) {
     const int blocks = (args.nStreams + geom.streamsPerCta - 1) / geom.streamsPerCta;
     const int threads = geom.secThreads + geom.helpThreads;
@@ -1033,7 +1043,12 @@ cudaError_t launchChain2(const ChainPlan& plan, const Chain2Geom& geom, const Ch
     default:  LAUNCH2(1, 16); break;
     }
 #undef LAUNCH2
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e == cudaSuccess && plan.h.nMemCopy > 0 && args.nFrames > 0) {
+        k_chain2_memfix<<<(args.nStreams + 127) / 128, 128, 0, stream>>>(plan, args.state, args.nStreams);
+        e = cudaGetLastError();
+    }
+    return e;
 }
 
 } // namespace avdsp

@@ -81,7 +81,8 @@ constexpr int kMaxChains     = 48;
 constexpr int kMaxChainPool  = 2560;
 constexpr int kMaxChainStores = 4;
 constexpr int kFastTab       = 16;     // entries of the flattened helper tables (chain2 handles programs within them)
-enum { PF_SECTIONS = 1, PF_GAIN = 2, PF_SAT_TPDF = 4, PF_SAT_GAIN = 8 };
+enum { PF_SECTIONS = 1, PF_GAIN = 2, PF_SAT_TPDF = 4, PF_SAT_GAIN = 8, PF_RAW = 16 /* DSP_LOAD_STORE pass-through */ };
+constexpr int kMaxMemCopy = 8;
 
 enum ChainSrc : int { SRC_LOAD = 0, SRC_LOAD_GAIN = 1, SRC_LOAD_MUX = 2,
                       SRC_RAW = 3 /* a DSP_LOAD_STORE pair: the output is the input sample, untouched (no saturation, no STORE mask) */ };
@@ -117,7 +118,11 @@ struct ChainHeader {
     int32_t nSrc;                                   // distinct sources among chains that have sections
     int32_t srcChain[kMaxChains];                   // a chain that carries source k's description
     int32_t nUnwritten;                             // output channels no path stores to (they read 0)
-    int32_t nRaw;                                   // DSP_LOAD_STORE pass-through paths (only the mix kernels take them)
+    int32_t nRaw;                                   // DSP_LOAD_STORE pass-through paths
+    // cascades handed from one core to the next through a MEM word (source -> BIQUADS -> STORE_MEM m ... LOAD_MEM m -> BIQUADS ->
+    // ...) are inlined into their consumers; after a launch MEM m must hold what the producer stored last: the accumulator of
+    // its last section, which the section lanes leave in the data area anyway
+    int32_t nMemCopy, memCopyDst[kMaxMemCopy], memCopySrc[kMaxMemCopy];
     int32_t nAcc;                                   // acc-ring rows per stream
     int32_t nProc;                                  // chains the sink has to post-process (everything but direct chains)
     int32_t procChain[kMaxChains];

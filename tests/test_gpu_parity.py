@@ -528,3 +528,51 @@ def test_c1_ten_seconds_of_stereo_pcm(oracle_lib):
     y = np.concatenate([ex.process(np.ascontiguousarray(x[:, c0:c0 + 96000])) for c0 in range(0, T, 96000)], axis=1)
     assert np.array_equal(y[0], yo)
     assert np.array_equal(ex.get_state(0)[: ex.data_size], o.data)
+
+
+def _mem_handoff_program():
+    """What oktodac-style crossovers do: core 1 copies inputs through (LOAD_STORE, one slot twice), computes the dither and
+    runs shared pre-filters into MEM words; later cores continue those cascades per output.  One output is stored twice
+    (the later path wins), one MEM word feeds two consumers."""
+    from oracle import wire
+    a = wire.Asm(fmt=2, fmin=48000, fmax=48000)
+    a.core()
+    a.load_store([(8, 4), (9, 5), (8, 5)])
+    a.tpdf_calc(24)
+    a.param()
+    m0 = a.mem_location(); m1 = a.mem_location()
+    pre0 = a.biquad_sections([[wire.rbj_peak(48000, 300.0, 0.9, 1.3)], [wire.rbj_peak(48000, 5000.0, 0.7, 0.8)]])
+    pre1 = a.biquad_sections([[wire.rbj_peak(48000, 120.0, 1.1, 1.2)]] * 2)
+    lo = a.biquad_sections([[wire.rbj_peak(48000, 800.0, 0.7, 0.5)]] * 2)
+    hi = a.biquad_sections([[wire.rbj_peak(48000, 2500.0, 0.7, 1.6)]] * 4)
+    d0 = a.delay_param(2000, 700, 48000)
+    a.load_gain(8, 0.45); a.biquads(pre0); a.store_mem(m0)
+    a.load_gain(9, 0.45); a.biquads(pre1); a.store_mem(m1)
+    a.core()
+    a.load_mem(m0); a.biquads(lo); a.sat0db_tpdf(); a.delay(d0); a.store(0); a.store(2)
+    a.load_mem(m0); a.biquads(hi); a.sat0db(); a.store(1)
+    a.core()
+    a.load_mem(m1); a.sat0db_tpdf_gain(0.9); a.store(3)
+    a.load_mem(m1); a.biquads(lo); a.sat0db(); a.store(2)        # overwrites core 2's STORE 2
+    return a.end()
+
+
+def test_chain_kernel_inlines_mem_handoffs(oracle_lib):
+    """LOAD_STORE pass-through paths, TPDF_CALC behind them, cascades handed between cores through MEM words, dead stores:
+    the chain kernel must take the program and match the oracle bit for bit -- outputs, biquad/delay state, and the MEM
+    words the producers leave in the (mirrored) code area."""
+    w = _mem_handoff_program()
+    fs, S, T = 48000, 37, 700
+    seeds = np.arange(S, dtype=np.int32) + 3
+    x = synth.pcm("full", S, T, 2, fs)
+    ys, sts = oracle_run(oracle_lib, w, 2, fs, x, seeds, 31)
+    ex = Executor(w, fs, 2, S, seeds=seeds)
+    cuts = [0, 1, 33, 400, T]
+    y = np.concatenate([ex.process(np.ascontiguousarray(x[:, c0:c1])) for c0, c1 in zip(cuts, cuts[1:])], axis=1)
+    assert ex.last_kernel == "chain", ex.trace
+    assert np.array_equal(y, ys), np.count_nonzero(y != ys)
+    for s in (0, 5, S - 1):
+        got, exp = ex.get_state(s), expected_state(ex, sts[s])
+        assert np.array_equal(got, exp), (s, np.nonzero(got != exp)[0][:10])
+    g = Executor(w, fs, 2, S, seeds=seeds); g.set_kernel(KERNEL_GENERIC)
+    assert np.array_equal(g.process(x), ys)
