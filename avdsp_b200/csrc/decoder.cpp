@@ -335,6 +335,12 @@ void buildChainPlan(Lowered* L) {
             for (int v : secOff) chainPool(c, v);
             d.nsec = (int16_t)secOff.size();
             if (i < e && g.ops[i].op == OP_GAIN) { d.hasGain = 1; d.gainBits = g.ops[i].a; i++; }
+            if (i + 1 < e && g.ops[i].op == OP_DELAY && !d.hasGain && d.nsec > 0 && g.h.aluClass == ALU_INT64 &&
+                (g.ops[i + 1].op == OP_SAT0DB || g.ops[i + 1].op == OP_SAT0DB_TPDF || g.ops[i + 1].op == OP_SAT0DB_GAIN || g.ops[i + 1].op == OP_SAT0DB_TPDF_GAIN)) {
+                // cascade -> DELAY -> saturation: the delay ring stores (int)X, the low word of the Q59 accumulator, and hands it
+                // back sign-extended (dsp_runtime.c:769-794); the saturation stage then works on that
+                d.delayOff = g.ops[i].a; d.delayN = g.ops[i].b; d.delayFirst = 1; c.h.nDelayFirst++; i++;
+            }
             if (i >= e) throw ChainFail{"a signal path ends without saturation/store"};
             switch (g.ops[i].op) {
             case OP_SAT0DB:           d.satKind = SAT_PLAIN; break;
@@ -344,7 +350,7 @@ void buildChainPlan(Lowered* L) {
             default: throw ChainFail{"a signal path has an opcode the chain kernel does not fuse"};
             }
             i++;
-            if (i < e && g.ops[i].op == OP_DELAY) { d.delayOff = g.ops[i].a; d.delayN = g.ops[i].b; i++; }
+            if (i < e && g.ops[i].op == OP_DELAY && !d.delayFirst) { d.delayOff = g.ops[i].a; d.delayN = g.ops[i].b; i++; }
             if (i >= e || g.ops[i].op != OP_STORE) throw ChainFail{"a signal path does not end with STORE"};
             while (i < e && g.ops[i].op == OP_STORE) {
                 if (d.nStores >= kMaxChainStores) throw ChainFail{"too many STOREs on one path"};
@@ -391,7 +397,7 @@ void buildChainPlan(Lowered* L) {
     c.h.nAcc = c.h.nProc = 0;
     for (int i = 0; i < c.h.nChains; i++) {
         ChainDesc& d = c.chains[i];
-        const bool direct = d.nsec > 0 && !d.hasGain && d.satKind == SAT_PLAIN;
+        const bool direct = d.nsec > 0 && !d.hasGain && d.satKind == SAT_PLAIN && !d.delayFirst;
         // (the float class needs no 64-bit accumulator ring: its tails leave the float accumulator in the post ring)
         d.accRow = (d.nsec > 0 && !direct && c.h.aluClass == ALU_INT64) ? c.h.nAcc++ : -1;
         if (!direct) c.h.procChain[c.h.nProc++] = i;
@@ -404,6 +410,7 @@ void buildChainPlan(Lowered* L) {
             c.h.pChain[k] = c.h.procChain[k]; c.h.pLag[k] = d.nsec > 0 ? d.nsec - 1 : 0; c.h.pAccRow[k] = d.accRow;
             c.h.pFlags[k] = (d.nsec > 0 ? PF_SECTIONS : 0) | (d.hasGain ? PF_GAIN : 0) | ((d.satKind & 1) ? PF_SAT_TPDF : 0) | (d.satKind >= SAT_GAIN ? PF_SAT_GAIN : 0) |
                             (d.srcKind == SRC_RAW ? PF_RAW : 0);
+            if (d.delayFirst) c.h.pFlags[k] = PF_SECTIONS | PF_DELAY_FIRST;      // stage A only parks the accumulator's low word; the sink's stage B finishes
             c.h.pGain[k] = d.gainBits; c.h.pSatGain[k] = d.satGainBits; c.h.pDelayN[k] = d.delayN;
         }
         if (k < c.h.nSrc) {

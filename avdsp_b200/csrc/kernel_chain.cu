@@ -316,7 +316,7 @@ k_chain(const __grid_constant__ ChainPlan P, const ChainArgs A, const ChainGeom 
 
 // ------------------------------------------------------------------------------------------------
 bool chainKernelSupports(const ChainPlan& plan) {
-    return plan.h.aluClass == ALU_INT64 && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nRaw == 0 && plan.h.nMemCopy == 0;
+    return plan.h.aluClass == ALU_INT64 && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nRaw == 0 && plan.h.nMemCopy == 0 && plan.h.nDelayFirst == 0;
 }
 
 static size_t chainSmem(const ChainPlan& p, int NS, int F) {

@@ -695,7 +695,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
     const int tpdfSh = (tpdfUp ? P.h.tpdfShift : -P.h.tpdfShift) & 63;
     // ---- per-lane constants of the (frame-in-pass, channel) store mapping (interleaved output, F == 32)
     const int nOut = P.h.nOut;
-    const bool laneOut = F == 32 && A.outChStride == 1 && A.outFrameStride == nOut && nOut <= 16 && (nOut & (nOut - 1)) == 0;
+    const bool laneOut = F == 32 && A.outChStride == 1 && A.outFrameStride == nOut && nOut <= 16 && (nOut & (nOut - 1)) == 0 &&
+                         P.h.nDelayFirst == 0;            // delay-first paths are finished by the frame-per-lane form of stage B
     const int fpp = laneOut ? 32 / nOut : 1;                  // frames per pass
     const int bCh = lane % nOut, bFs = lane / nOut;
     const int bChain = P.h.chainOfOut[bCh];
@@ -775,7 +776,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                             const long long tv = lds32(tpdfA + ((unsigned)(fk & (4 * F - 1)) << 2));
                             X += tpdfUp ? (long long)((unsigned long long)tv << tpdfSh) : (tv >> tpdfSh);      // dspTpdfApply, dsp_tpdf.h:141-145
                         }
-                        const int v = (flags & PF_RAW) ? lo32(X) : sat64_031_s32(X);     // LOAD_STORE: the sample itself
+                        // LOAD_STORE: the sample itself; delay-first paths: the accumulator's low word (what the ring stores)
+                        const int v = (flags & (PF_RAW | PF_DELAY_FIRST)) ? lo32(X) : sat64_031_s32(X);
                         if (anyStale && fk == 0 && P.h.pDelayN[k] > 0 && stale_s[sl * C + P.h.pChain[k]] >= 0)
                             A.state[(size_t)(s0 + sl) * W + P.chains[P.h.pChain[k]].delayOff + 1 + stale_s[sl * C + P.h.pChain[k]]] = v;
                         else sts32(postA + G.pPostOff[k] + tpos4, v);
@@ -825,9 +827,22 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                     for (int q = 0; q < 4; q++) {
                         const int ch = ch0 + q;
                         int v = 0;      // outputs no path writes read as 0 (io[] is zeroed at the start of every frame)
-                        if (ch < P.h.nOut && P.h.chainOfOut[ch] >= 0)
-                            v = lds32(postA + G.outRowOff[ch] + ((f4 + (unsigned)G.outPos4[ch]) & RM4)) &
-                                (P.chains[P.h.chainOfOut[ch]].srcKind == SRC_RAW ? -1 : storeMask);
+                        if (ch < P.h.nOut && P.h.chainOfOut[ch] >= 0) {
+                            const ChainDesc& dc = P.chains[P.h.chainOfOut[ch]];
+                            int wv = lds32(postA + G.outRowOff[ch] + ((f4 + (unsigned)G.outPos4[ch]) & RM4));
+                            if (dc.delayFirst) {
+                                // cascade -> DELAY -> SAT0DB*: the ring value is the low word of a Q59 accumulator, handed back
+                                // sign-extended; the saturation stage (with THIS frame's dither) runs on it
+                                long long X = (long long)wv;
+                                if (dc.satKind >= SAT_GAIN) { X >>= kMant; X = X * (long long)dc.satGainBits; }
+                                if (dc.satKind & 1) {
+                                    const long long tv = lds32(tpdfA + ((unsigned)(f & (4 * F - 1)) << 2));
+                                    X += tpdfUp ? (long long)((unsigned long long)tv << tpdfSh) : (tv >> tpdfSh);
+                                }
+                                wv = sat64_031_s32(X);
+                            }
+                            v = wv & (dc.srcKind == SRC_RAW ? -1 : storeMask);
+                        }
                         val[q] = v;
                     }
                     if (vecOut) *reinterpret_cast<int4*>(out + ch0) = make_int4(val[0], val[1], val[2], val[3]);
@@ -949,6 +964,15 @@ bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2G
     const int forceF = envInt2("AVDSP_B200_F", 0);
     int maxDelay = 0;
     for (int c = 0; c < C; c++) maxDelay = std::max(maxDelay, plan.chains[c].delayN);
+    // Every feasible streams-per-CTA count is scored: time ~ waves over the SMs x (streams per CTA + 4) (the section lanes of a CTA
+    // walk their streams' frames in lock step), and the helper warps must keep up with the section warps they serve -- a CTA
+    // whose 31 warps are all section lanes leaves one warp to feed and drain 20+ streams.  Pass 0 demands enough helpers,
+    // pass 1 (only if nothing qualified) takes whatever fits.
+    bool found = false;
+    long long bestCost = 0;
+    Chain2Geom bestG{};
+    const bool forcedNS = envInt2("AVDSP_B200_NS", 0) > 0;
+    for (int pass = 0; pass < 2 && !found; pass++)
     for (int NS = NS0; NS >= 1; NS--) {
         for (int F : {32, 16}) {
             if (forceF && F != forceF) continue;
@@ -1002,13 +1026,20 @@ bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2G
                 g.srcXOff[k] = k * g.xPitch * 4;
             }
             if (g.secThreads + g.helpThreads <= 1024 && g.smemBytes <= 226 * 1024) {
-                *geom = g;
-                if (lanesOut) packLanes2(plan, NS, K, lanesOut, nullptr);
-                return true;
+                const int needHelp = lt > 0 ? std::max(2, (NS + 3) / 4) : 1;
+                if (pass == 0 && help < needHelp && !forcedNS) break;          // too few helper warps for this many streams
+                const long long ctas = (nStreams + NS - 1) / NS;
+                const long long cost = ((ctas + numSMs - 1) / numSMs) * (NS + 4);  // + a CTA's fixed cost (prologue, rings, thin warps), in streams
+                if (!found || cost < bestCost) { found = true; bestCost = cost; bestG = g; }
+                break;                                                          // F = 32 is preferred when it fits
             }
         }
+        if (found && forcedNS) break;
     }
-    return false;
+    if (!found) return false;
+    *geom = bestG;
+    if (lanesOut) packLanes2(plan, bestG.streamsPerCta, K, lanesOut, nullptr);
+    return true;
 }
 
 // MEM words of inlined cascades: what the producer's STORE_MEM left there = the accumulator of its last section

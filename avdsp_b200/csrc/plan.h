@@ -81,7 +81,8 @@ constexpr int kMaxChains     = 48;
 constexpr int kMaxChainPool  = 2560;
 constexpr int kMaxChainStores = 4;
 constexpr int kFastTab       = 16;     // entries of the flattened helper tables (chain2 handles programs within them)
-enum { PF_SECTIONS = 1, PF_GAIN = 2, PF_SAT_TPDF = 4, PF_SAT_GAIN = 8, PF_RAW = 16 /* DSP_LOAD_STORE pass-through */ };
+enum { PF_SECTIONS = 1, PF_GAIN = 2, PF_SAT_TPDF = 4, PF_SAT_GAIN = 8, PF_RAW = 16 /* DSP_LOAD_STORE pass-through */,
+       PF_DELAY_FIRST = 32 /* cascade -> DELAY -> SAT0DB*: the ring holds the low word of the accumulator, the finish runs on the delayed value */ };
 constexpr int kMaxMemCopy = 8;
 
 enum ChainSrc : int { SRC_LOAD = 0, SRC_LOAD_GAIN = 1, SRC_LOAD_MUX = 2,
@@ -103,6 +104,7 @@ struct ChainDesc {
     int32_t  gainBits;        // optional GAIN between cascade and saturation
     int32_t  satGainBits;     // SAT0DB_GAIN / SAT0DB_TPDF_GAIN
     int32_t  delayOff, delayN;// ring in the data area ([index][n samples]); delayN==0: none
+    int32_t  delayFirst;      // 1: the DELAY sits between the cascade and the saturation (osx/dacdiy1.bin)
 };
 
 struct ChainHeader {
@@ -118,6 +120,7 @@ struct ChainHeader {
     int32_t nSrc;                                   // distinct sources among chains that have sections
     int32_t srcChain[kMaxChains];                   // a chain that carries source k's description
     int32_t nUnwritten;                             // output channels no path stores to (they read 0)
+    int32_t nDelayFirst;                            // paths with the DELAY in front of the saturation (k_chain2 only)
     int32_t nRaw;                                   // DSP_LOAD_STORE pass-through paths
     // cascades handed from one core to the next through a MEM word (source -> BIQUADS -> STORE_MEM m ... LOAD_MEM m -> BIQUADS ->
     // ...) are inlined into their consumers; after a launch MEM m must hold what the producer stored last: the accumulator of
