@@ -576,3 +576,43 @@ def test_chain_kernel_inlines_mem_handoffs(oracle_lib):
         assert np.array_equal(got, exp), (s, np.nonzero(got != exp)[0][:10])
     g = Executor(w, fs, 2, S, seeds=seeds); g.set_kernel(KERNEL_GENERIC)
     assert np.array_equal(g.process(x), ys)
+
+
+def test_delay_first_paths_with_patched_delays(oracle_lib):
+    """cascade -> DELAY -> SAT0DB[_TPDF][_GAIN] -> STORE (the osx/dacdiy1.bin shape): the ring holds the low word of the Q59
+    accumulator.  Delay times are patched mid-stream (stale ring indices, a delay dropping to zero); chain kernel and
+    interpreter against the oracle, outputs and state."""
+    from oracle import wire
+    a = wire.Asm(fmt=2, fmin=48000, fmax=48000)
+    a.core(); a.tpdf_calc(22)
+    a.param()
+    bq = a.biquad_sections([[wire.rbj_peak(48000, 900.0, 1.2, 1.4)], [wire.rbj_peak(48000, 3000.0, 0.8, 0.7)]])
+    dps = [a.delay_param(3000, us, 48000) for us in (1500, 400, 2900, 50)]
+    for ch in range(4):
+        a.load_gain(8 + (ch & 1), 0.6 - 0.1 * ch)
+        a.biquads(bq)
+        a.delay(dps[ch])
+        [lambda: a.sat0db_tpdf_gain(0.9), a.sat0db_tpdf, lambda: a.sat0db_gain(0.8), a.sat0db][ch]()
+        a.store(ch)
+    w = a.end()
+    fs, S, T = 48000, 6, 333
+    x = synth.pcm("full", S, 3 * T, 2, fs)
+    for kernel in (KERNEL_AUTO, KERNEL_GENERIC):
+        ex = Executor(w, fs, 2, S, seeds=np.arange(S, dtype=np.int32))
+        ex.set_kernel(kernel)
+        orcs = [oracle_lib.Oracle(w, 2, fs, seed=s) for s in range(S)]
+        words = w.copy()
+        for part, uss in enumerate(((1500, 400, 2900, 50), (200, 2900, 0, 700), (2500, 0, 1000, 10))):
+            for dp, us in zip(dps, uss):
+                words[dp] = (int(words[dp]) & ~0xFFFF) | us
+            ex.reload_params(words)
+            xs = np.ascontiguousarray(x[:, part * T:(part + 1) * T])
+            y = ex.process(xs)
+            if kernel == KERNEL_AUTO:
+                assert ex.last_kernel == "chain", ex.trace
+            for s in range(S):
+                for dp, us in zip(dps, uss):
+                    orcs[s].code[dp] = words[dp]
+                assert np.array_equal(y[s], orcs[s].process(xs[s])), (part, s, ex.last_kernel)
+        for s in (0, S - 1):
+            assert np.array_equal(ex.get_state(s)[: ex.data_size], orcs[s].data), (s, ex.last_kernel)
