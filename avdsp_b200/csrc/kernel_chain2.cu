@@ -292,6 +292,15 @@ __device__ __forceinline__ long long muxFromShared(const ChainPlan& P, const Cha
     return X;
 }
 
+// cascade -> DELAY -> SAT0DB*: the ring value is the low word of a Q59 accumulator, handed back sign-extended
+// (dsp_runtime.c:769-794); the saturation stage (with the OUTPUT frame's dither) runs on it
+__device__ __noinline__ int delayFirstFinish(int wv, int satKind, int satGainBits, int tv, int tpdfShift) {
+    long long X = (long long)wv;
+    if (satKind >= SAT_GAIN) { X >>= kMant; X = X * (long long)satGainBits; }
+    if (satKind & 1) X += tpdfScaledI(tv, tpdfShift);
+    return sat64_031_s32(X);
+}
+
 // post-ring word -> s.31 sample: fixed point stores it as such; the float class stores the (possibly not yet saturated)
 // float and converts here (dspSaturateFloat0db + dsps31Float0DB, runtime/dsp_ieee754.h:60-83,170-184)
 template <int CLS> __device__ __forceinline__ int postToS31(int v) {
@@ -830,17 +839,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         if (ch < P.h.nOut && P.h.chainOfOut[ch] >= 0) {
                             const ChainDesc& dc = P.chains[P.h.chainOfOut[ch]];
                             int wv = lds32(postA + G.outRowOff[ch] + ((f4 + (unsigned)G.outPos4[ch]) & RM4));
-                            if (dc.delayFirst) {
-                                // cascade -> DELAY -> SAT0DB*: the ring value is the low word of a Q59 accumulator, handed back
-                                // sign-extended; the saturation stage (with THIS frame's dither) runs on it
-                                long long X = (long long)wv;
-                                if (dc.satKind >= SAT_GAIN) { X >>= kMant; X = X * (long long)dc.satGainBits; }
-                                if (dc.satKind & 1) {
-                                    const long long tv = lds32(tpdfA + ((unsigned)(f & (4 * F - 1)) << 2));
-                                    X += tpdfUp ? (long long)((unsigned long long)tv << tpdfSh) : (tv >> tpdfSh);
-                                }
-                                wv = sat64_031_s32(X);
-                            }
+                            if (dc.delayFirst)      // out of line: rare program shape, keeps the common store loop compact
+                                wv = delayFirstFinish(wv, dc.satKind, dc.satGainBits, lds32(tpdfA + ((unsigned)(f & (4 * F - 1)) << 2)), P.h.tpdfShift);
                             v = wv & (dc.srcKind == SRC_RAW ? -1 : storeMask);
                         }
                         val[q] = v;
