@@ -726,6 +726,35 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         unsigned postA = sb + G.postOff + ow * G.postStreamBytes;
         unsigned accA = sb + ow * G.accStreamBytes + ((iw & 1) * F + lane) * 8;
         unsigned tpdfA = sb + G.tpdfOff + ow * G.tpdfStreamBytes;
+        if (CLS == ALU_INT64 && simpleA && laneOut && !anyStale && iw * F >= gmax && (iw + 1) * F <= T && !(G.debugSkip & 16)) {
+            // the common window of the common program (every post-processed chain is cascade -> SAT0DB_TPDF, interleaved
+            // power-of-two outputs, interior tile, no stale ring index) as its own compact loop: nothing of the general
+            // forms below sits between its instructions (the kernel is instruction-cache sensitive)
+            const int fw0 = iw * F - gmax;
+            const unsigned p4 = (unsigned)(fw0 << 2) + bPos4;
+            for (int sl = ow; sl < nsHere; sl += nOwn, postA += nOwn * G.postStreamBytes, accA += nOwn * G.accStreamBytes, tpdfA += nOwn * G.tpdfStreamBytes) {
+#pragma unroll
+                for (int k = 0; k < kFastTab; k++) {
+                    if (k >= P.h.nProc) break;
+                    long long X = lds64(accA + G.pAccOff[k]);
+                    const long long tv = lds32(tpdfA + ((unsigned)((t - P.h.pLag[k]) & (4 * F - 1)) << 2));
+                    X += tpdfUp ? (long long)((unsigned long long)tv << tpdfSh) : (tv >> tpdfSh);
+                    sts32(postA + G.pPostOff[k] + tpos4, sat64_031_s32(X));
+                }
+                __syncwarp(wmask);
+                int* out = A.out + (size_t)(s0 + sl) * A.outStreamStride + (size_t)fw0 * A.outFrameStride + lane;
+                const unsigned rowA = postA + bRow;
+                switch (nOut) {
+                case 1:  storePasses<F, 1, CLS>(out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
+                case 2:  storePasses<F, 2, CLS>(out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
+                case 4:  storePasses<F, 4, CLS>(out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
+                case 8:  storePasses<F, 8, CLS>(out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
+                default: storePasses<F, 16, CLS>(out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
+                }
+                __syncwarp(wmask);
+            }
+            return;
+        }
         for (int sl = ow; sl < nsHere; sl += nOwn, postA += nOwn * G.postStreamBytes, accA += nOwn * G.accStreamBytes, tpdfA += nOwn * G.tpdfStreamBytes) {
             // A: step t of every chain that needs post-processing: accumulator (or inline source) -> [gain] -> saturate
             //    (+dither, +gain) -> post ring (dsp_runtime.c:464-534, 636-640).  Direct chains were written by their tails.
