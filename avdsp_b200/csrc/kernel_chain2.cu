@@ -648,7 +648,20 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         if (nSrc == 0 || prngOnly) return;
         const bool staged = tileUsesTma(it);
         if (staged) mbarWait(mbar0 + 8 * (it & 1), (unsigned)((it >> 1) & 1));
-        if (lane < F && f0 + lane < T) {
+        if (CLS == ALU_INT64 && simpleSrc && staged && lane < F && f0 + lane < T) {
+            // the common source stage (fixed point, every source LOAD_GAIN of a fed input, tile staged by TMA) as its own
+            // compact loop, apart from the general forms below
+            unsigned xa = sb + G.xOff + ow * G.xStreamBytes + ((it & 1) * F + lane) * 4;
+            unsigned ra = sb + G.rawOff + ow * G.rawStreamBytes + (it & 1) * rowBytes + lane * rawFB;
+            for (int sl = ow; sl < nsHere; sl += nOwn, xa += nOwn * G.xStreamBytes, ra += nOwn * G.rawStreamBytes) {
+#pragma unroll
+                for (int k = 0; k < kFastTab; k++) {
+                    if (k >= nSrc) break;
+                    const int smp = lds32(ra + (interleavedIn ? (unsigned)(P.h.sCh[k] * 4) : (unsigned)(P.h.sCh[k] * F * 4)));
+                    sts32(xa + G.srcXOff[k], q59ToS31(mul32(smp, P.h.sArg[k])));
+                }
+            }
+        } else if (lane < F && f0 + lane < T) {
             unsigned xa = sb + G.xOff + ow * G.xStreamBytes + ((it & 1) * F + lane) * 4;
             unsigned ra = sb + G.rawOff + ow * G.rawStreamBytes + (it & 1) * rowBytes + lane * rawFB;
             for (int sl = ow; sl < nsHere; sl += nOwn, xa += nOwn * G.xStreamBytes, ra += nOwn * G.rawStreamBytes) {
