@@ -648,7 +648,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         if (nSrc == 0 || prngOnly) return;
         const bool staged = tileUsesTma(it);
         if (staged) mbarWait(mbar0 + 8 * (it & 1), (unsigned)((it >> 1) & 1));
-        if (CLS == ALU_INT64 && simpleSrc && staged && lane < F && f0 + lane < T) {
+        if (simpleSrc && staged && lane < F && f0 + lane < T) {
             // the common source stage (fixed point, every source LOAD_GAIN of a fed input, tile staged by TMA) as its own
             // compact loop, apart from the general forms below
             unsigned xa = sb + G.xOff + ow * G.xStreamBytes + ((it & 1) * F + lane) * 4;
@@ -658,7 +658,14 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 for (int k = 0; k < kFastTab; k++) {
                     if (k >= nSrc) break;
                     const int smp = lds32(ra + (interleavedIn ? (unsigned)(P.h.sCh[k] * 4) : (unsigned)(P.h.sCh[k] * F * 4)));
-                    sts32(xa + G.srcXOff[k], q59ToS31(mul32(smp, P.h.sArg[k])));
+                    if (CLS == ALU_F32) {
+                        // LOAD_GAIN in the float class: hardware convert + mul.rz.ftz when the host checked that no product
+                        // can reach the underflow range (G.floatFast: every gain in [2^-30, 2^30]), else the restatement
+                        float xf = G.floatFast ? mulFF_fast(i2f31Fast(smp), __int_as_float(P.h.sArg[k]))
+                                               : mulFF(i2fScaled(smp, 31), __int_as_float(P.h.sArg[k]));
+                        if (smp == 0) xf = 0.0f;                       // the reference's product of a zero is +0, never -0
+                        sts32(xa + G.srcXOff[k], __float_as_int(xf));
+                    } else sts32(xa + G.srcXOff[k], q59ToS31(mul32(smp, P.h.sArg[k])));
                 }
             }
         } else if (lane < F && f0 + lane < T) {
@@ -739,22 +746,25 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         unsigned postA = sb + G.postOff + ow * G.postStreamBytes;
         unsigned accA = sb + ow * G.accStreamBytes + ((iw & 1) * F + lane) * 8;
         unsigned tpdfA = sb + G.tpdfOff + ow * G.tpdfStreamBytes;
-        if (CLS == ALU_INT64 && simpleA && laneOut && !anyStale && iw * F >= gmax && (iw + 1) * F <= T && !(G.debugSkip & 16)) {
+        if (((CLS == ALU_INT64 && simpleA) || (CLS == ALU_F32 && P.h.nProc == 0)) && laneOut && !anyStale && iw * F >= gmax && (iw + 1) * F <= T &&
+            !(G.debugSkip & 16)) {
             // the common window of the common program (every post-processed chain is cascade -> SAT0DB_TPDF, interleaved
             // power-of-two outputs, interior tile, no stale ring index) as its own compact loop: nothing of the general
             // forms below sits between its instructions (the kernel is instruction-cache sensitive)
             const int fw0 = iw * F - gmax;
             const unsigned p4 = (unsigned)(fw0 << 2) + bPos4;
             for (int sl = ow; sl < nsHere; sl += nOwn, postA += nOwn * G.postStreamBytes, accA += nOwn * G.accStreamBytes, tpdfA += nOwn * G.tpdfStreamBytes) {
+                if (CLS == ALU_INT64) {
 #pragma unroll
-                for (int k = 0; k < kFastTab; k++) {
-                    if (k >= P.h.nProc) break;
-                    long long X = lds64(accA + G.pAccOff[k]);
-                    const long long tv = lds32(tpdfA + ((unsigned)((t - P.h.pLag[k]) & (4 * F - 1)) << 2));
-                    X += tpdfUp ? (long long)((unsigned long long)tv << tpdfSh) : (tv >> tpdfSh);
-                    sts32(postA + G.pPostOff[k] + tpos4, sat64_031_s32(X));
+                    for (int k = 0; k < kFastTab; k++) {
+                        if (k >= P.h.nProc) break;
+                        long long X = lds64(accA + G.pAccOff[k]);
+                        const long long tv = lds32(tpdfA + ((unsigned)((t - P.h.pLag[k]) & (4 * F - 1)) << 2));
+                        X += tpdfUp ? (long long)((unsigned long long)tv << tpdfSh) : (tv >> tpdfSh);
+                        sts32(postA + G.pPostOff[k] + tpos4, sat64_031_s32(X));
+                    }
+                    __syncwarp(wmask);
                 }
-                __syncwarp(wmask);
                 int* out = A.out + (size_t)(s0 + sl) * A.outStreamStride + (size_t)fw0 * A.outFrameStride + lane;
                 const unsigned rowA = postA + bRow;
                 switch (nOut) {
