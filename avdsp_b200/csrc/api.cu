@@ -139,6 +139,9 @@ struct avdsp_b200 {
     ChainLane* dLanes2 = nullptr;
     Chain2Geom geom2{};
     bool chain2Usable = false;      // kernel_chain2.cu (v2: warp-specialised, the default)
+    Chain3Geom geom3{};
+    bool chain3Usable = false;      // kernel_chain3.cu (v3: one cascade per lane; the common crossover / EQ shape at batch width)
+    int lastChainVariant = 0;       // 2 / 3: which chain kernel the last AVDSP_B200_KERNEL_CHAIN launch used
     MixPlan mix{};
     bool mixUsable = false;         // kernel_mix.cu (time-parallel: programs without biquads)
     bool firUsable = false;         // kernel_fir.cu (time-parallel FIR paths)
@@ -189,6 +192,7 @@ static int uploadPlanData(avdsp_b200* h) {
             h->chain2Usable = true;
         }
     }
+    h->chain3Usable = h->chain2Usable && planChain3Geometry(L.chain, h->nStreams, h->numSMs, &h->geom3);
     h->mixUsable = false;
     if (L.chainOk) { std::string why; h->mixUsable = buildMixPlan(L.chain, &h->mix, &why); }
     h->firUsable = L.firOk;
@@ -209,6 +213,17 @@ static int uploadPlanData(avdsp_b200* h) {
     if (h->chain2Usable) {
         snprintf(line, sizeof line, "chain kernel v2 geometry: %d streams/CTA, %d sections/lane, tile %d frames, gmax %d, %d section threads + %d helper threads, %d sources, %zu B smem\n",
                  h->geom2.streamsPerCta, h->geom2.secPerLane, h->geom2.tileFrames, h->geom2.gmax, h->geom2.secThreads, h->geom2.helpThreads, L.chain.h.nSrc, h->geom2.smemBytes);
+        h->trace += line;
+    }
+    if (h->chain3Usable) {
+        snprintf(line, sizeof line, "chain kernel v3 geometry: %d streams/CTA (lane = one cascade part of one stream), %d cascade warps of <= %d sections + 1 dither warp + %d store warps, largest lag %d frames, row ring %d steps, %zu B smem; parts (chain:first+n@base):",
+                 h->geom3.streamsPerCta, h->geom3.nCascade, h->geom3.maxSec, h->geom3.nStore, h->geom3.gmax, h->geom3.postRing, h->geom3.smemBytes);
+        h->trace += line;
+        for (int w = 0; w < h->geom3.nCascade; w++) {
+            snprintf(line, sizeof line, " %d:%d+%d@%d", h->geom3.warpChain[w], h->geom3.warpFirstSec[w], h->geom3.warpNsec[w], h->geom3.warpBase[w]);
+            h->trace += line;
+        }
+        snprintf(line, sizeof line, "\n");
         h->trace += line;
     }
     if (h->chainUsable)
@@ -342,10 +357,11 @@ int avdsp_b200_set_order(avdsp_b200_t* h, int period) {
     h->period = period; return 0;
 }
 int avdsp_b200_set_kernel(avdsp_b200_t* h, int which) {
-    if (!h || which < 0 || which > 6) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
+    if (!h || which < 0 || which > AVDSP_B200_KERNEL_CHAIN_V3) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
     h->kernelSel = which; return 0;
 }
 int avdsp_b200_last_kernel(const avdsp_b200_t* h) { return h ? h->lastKernel : 0; }
+int avdsp_b200_last_chain_variant(const avdsp_b200_t* h) { return (h && h->lastKernel == AVDSP_B200_KERNEL_CHAIN) ? h->lastChainVariant : 0; }
 long long avdsp_b200_launch_count(const avdsp_b200_t* h) { return h ? h->launches : 0; }
 int avdsp_b200_state_words(const avdsp_b200_t* h) { return h ? h->L.gen.h.stateWords : 0; }
 int avdsp_b200_data_size(const avdsp_b200_t* h) { return h ? h->L.gen.h.dataSize : 0; }
@@ -397,7 +413,8 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         return setErr(AVDSP_B200_ERR_UNSUPPORTED, "FIR kernel requested but this program/order does not map to it: " + h->L.firWhyNot);
     if (h->kernelSel == AVDSP_B200_KERNEL_MIX && use != AVDSP_B200_KERNEL_MIX)
         return setErr(AVDSP_B200_ERR_UNSUPPORTED, "mix kernel requested but the program has biquads or does not map to independent paths");
-    if ((h->kernelSel == AVDSP_B200_KERNEL_CHAIN || h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1) && use == AVDSP_B200_KERNEL_GENERIC)
+    if ((h->kernelSel == AVDSP_B200_KERNEL_CHAIN || h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1 || h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V2 ||
+         h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V3) && use == AVDSP_B200_KERNEL_GENERIC)
         return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel requested but this program/order does not map to it: " + h->L.chainWhyNot);
     cudaError_t e;
     if (use == AVDSP_B200_KERNEL_FIR || use == AVDSP_B200_KERNEL_FIR_TC) {
@@ -455,7 +472,17 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         A.nStreams = n; A.nFrames = nFrames;
         A.inStreamStride = inSS; A.outStreamStride = outSS;
         A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
-        e = launchChain2(h->L.chain, h->geom2, A, stream);
+        // v3 (one whole cascade per lane) wants a lane per stream: it is the choice at batch width (>= 16 streams per SM);
+        // everything else -- and every program shape outside v3's -- runs on v2
+        const bool v3Ok = h->chain3Usable && use == AVDSP_B200_KERNEL_CHAIN;
+        static const int envChain3 = [] { const char* v = getenv("AVDSP_B200_CHAIN3"); return (v && *v) ? atoi(v) : -1; }();
+        bool v3 = v3Ok && h->kernelSel != AVDSP_B200_KERNEL_CHAIN_V2 &&
+                  (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V3 || envChain3 == 1 || (envChain3 != 0 && h->geom3.streamsPerCta >= 16 && nFrames >= 64));
+        if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V3 && !v3)
+            return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel v3 requested but the program shape does not map to it");
+        if (v3) e = launchChain3(h->L.chain, h->geom3, A, stream);
+        else e = launchChain2(h->L.chain, h->geom2, A, stream);
+        h->lastChainVariant = v3 ? 3 : 2;
         h->lastKernel = AVDSP_B200_KERNEL_CHAIN;
     } else if (use == AVDSP_B200_KERNEL_CHAIN_V1) {
         ChainArgs A{};

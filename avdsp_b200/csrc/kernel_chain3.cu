@@ -1,0 +1,710 @@
+// kernel_chain3.cu -- register-resident cascade executor for the common crossover / EQ program shape
+//     LOAD | LOAD_GAIN -> biquad cascade (1..8 sections) -> SAT0DB | SAT0DB_TPDF -> [DELAY] -> STORE(s)
+// Fixed point (DSP_FORMAT 2), bit-exact (dsp_calc_biquads_int, runtime/dsp_biquadSTD.h:25-77; dsp_runtime.c:464-491,
+// 565-633, 769-794, 827-849).  Programs outside this shape run on k_chain2 (kernel_chain2.cu).
+//
+// Why a second chain kernel.  k_chain2 gives a lane two sections and links the lanes of a cascade with shuffles; the
+// 32x32+64 IMAD.WIDE issues at 1/4 rate and every other ALU instruction next to it costs real time
+// (tools/microbench_mix.cu), and k_chain2 spends 13 such instructions per 10 MACs in the section loop plus 36 % of all
+// instructions in helper warps that move samples between rings.  Here
+//   * a lane owns ONE WHOLE CASCADE of one stream: accumulators, histories and coefficients of all its sections stay
+//     in registers for the whole launch -- no shuffles, no x / accumulator rings.  Per section and frame:
+//     5 accumulating IMAD.WIDE + 1 funnel shift + 1 VIADDMNMX (sticky saturation record);
+//   * the sections of a lane are SKEWED IN TIME (section k works on frame t-k at step t), so the K section updates of a
+//     step are independent chains and a single warp keeps the quarter-rate pipe busy (an un-skewed cascade is one long
+//     dependent chain MAC -> shift -> MAC ...: measured 390 cycles per frame for 8 sections).  Exact, because section k
+//     of frame n only needs section k-1 of the same frame.  The input history of section k+1 is the output history of
+//     section k, so a section keeps (acc, y1, y2, y3) only; the reference's separate x1/x2 words are honoured on the
+//     first two frames of a launch and rebuilt at its end.  Launch edges (pipeline fill / drain) run a predicated form;
+//   * a warp = one chain (or one PART of a chain) x up to 32 streams, so a warp's work is uniform.  One warp issues an
+//     IMAD.WIDE every ~6.7 cycles at best, two per sub-partition reach 4.8, three or more ~4.5 (tools/microbench_warps.cu),
+//     and a warp that finishes its tile early leaves its neighbour alone with the pipe -- so long cascades are cut into
+//     parts of <= 4 sections that run as separate warps (C2: 14 warps of 3 or 4 sections, 12 sections per
+//     sub-partition).  A part hands its output to the next part through a shared-memory row, one tile later (the consumer
+//     part runs F + lag frames behind and waits on a per-part tile counter), so parts never synchronise inside a tile;
+//   * the lane reads its input sample straight from the staged PCM tile (cp.async.bulk + mbarrier, issued two tiles
+//     ahead by the helper warp; plain copies when the caller's buffer is not 16-byte friendly), applies LOAD_GAIN
+//     itself, finishes SAT0DB / SAT0DB_TPDF itself and parks the s.31 value in a shared-memory post ring that doubles
+//     as the delay line;
+//   * helper warps: warp C runs the per-stream xoshiro128+ (lane = stream) one tile ahead and stages the input; the
+//     store warps read the post ring at frame - delay, apply the STORE mask and write 128-byte coalesced runs;
+//   * saturation (checkbiquadsat fires on the accumulator's high word): tiles run optimistically and are replayed from
+//     a shared-memory checkpoint with the exact per-section clamp when the sticky record fired (as in k_chain2).
+//
+// Ring bookkeeping (F = 32 frames per tile; lag of a warp = its step offset `base` + its sections - 1; gmax = largest lag):
+//   row ring  [warp][stream][R] by STEP: the tail of warp w writes at step t the value of frame t - lag_w, i.e. frame f
+//             sits at (f + lag_w) mod R; R >= 2F + gmax + longest delay (power of two).  Final parts park the finished
+//             s.31 output there (the post ring = the delay line), the other parts their last section's y for the next part
+//   tpdf ring [stream][4F]       by frame (the dither warp runs one tile ahead)
+//   window i = frames [iF - gmax, (i+1)F - gmax): every chain has finished them when tile i is done.
+#include "avdsp_dev.cuh"
+#include "kernels.h"
+#include <algorithm>
+#include <cstdlib>
+
+namespace avdsp {
+namespace {
+
+constexpr int F3 = 32;                  // steps per tile
+constexpr int TP3 = 4 * F3 + 1;         // tpdf ring pitch (words)
+constexpr int kBarFull3 = 1;            // +parity: inputs of tile i ready and the post ring has room (helpers arrive, cascades wait)
+constexpr int kBarDone3 = 3;            // +parity: cascade warps finished tile i (cascades arrive, helpers wait)
+#ifndef AVDSP_UNR3
+#define AVDSP_UNR3 4
+#endif
+constexpr unsigned kSatBias3  = (1u << (kMantBQ - 1)) - 2u;     // in range <=> (unsigned)(hi + bias) <= limit
+constexpr unsigned kSatLimit3 = (1u << kMantBQ) - 3u;           // (checkbiquadsat, runtime/dsp_biquadSTD.h:25-32)
+
+// named barriers are warp-aligned: reconverge first (lanes take different paths around the per-stream work)
+__device__ __forceinline__ void barSync3(int id, int n)   { __syncwarp(); asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void barArrive3(int id, int n) { __syncwarp(); asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ unsigned smemAddr3(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lds3(unsigned a) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts3(unsigned a, int v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void mbarInit3(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx3(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tmaLoad3(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbarWait3(unsigned bar, unsigned parity) {
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "WAIT3_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE3_%=;\n"
+                 "bra WAIT3_%=;\n"
+                 "DONE3_%=:\n"
+                 "}" :: "r"(bar), "r"(parity) : "memory");
+}
+
+// One cascade in registers, sections skewed in time.  y1/y2/y3[k]: the three most recent outputs of section k (y1 newest);
+// section k+1 takes them as its input, x1 and x2.  X1/X2: input history of section 0.  rx1/rx2: the reference's own x1/x2
+// words of sections >= 1 as loaded from the state block (they stand in for outputs older than this launch).
+template <int NSEC>
+struct Casc {
+    long long acc[NSEC];
+    int y1[NSEC], y2[NSEC], y3[NSEC];
+    int X1, X2;
+    int rx1[NSEC], rx2[NSEC];
+    int b0[NSEC], b1[NSEC], b2[NSEC], a1[NSEC], a2[NSEC];
+};
+
+// one step, every section active, OPTIMISTIC: no clamp, only the sticky record of the largest biased high word.
+// Returns the accumulator of the last section (frame t - (NSEC-1)).
+template <int NSEC>
+__device__ __forceinline__ long long cascStep(Casc<NSEC>& L, int xin, unsigned& w0, unsigned& w1) {
+    long long acc[NSEC];
+    // the NSEC updates are independent: written operand-major so that dependent MACs sit NSEC instructions apart
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) acc[k] = mac32(L.acc[k], k ? L.y2[k - 1] : L.X1, L.b1[k]);
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) acc[k] = mac32(acc[k], k ? L.y3[k - 1] : L.X2, L.b2[k]);
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) acc[k] = mac32(acc[k], L.y1[k], L.a1[k]);
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) acc[k] = mac32(acc[k], L.y2[k], L.a2[k]);
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) acc[k] = mac32(acc[k], k ? L.y1[k - 1] : xin, L.b0[k]);
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) {
+        if (k & 1) w1 = max(w1, (unsigned)hi32(acc[k]) + kSatBias3);
+        else       w0 = max(w0, (unsigned)hi32(acc[k]) + kSatBias3);
+        L.acc[k] = acc[k];
+        L.y3[k] = L.y2[k]; L.y2[k] = L.y1[k]; L.y1[k] = q59ToS31(acc[k]);
+    }
+    L.X2 = L.X1; L.X1 = xin;
+    return acc[NSEC - 1];
+}
+// the same step with the reference's clamp, for any step of the launch: section k commits only when its frame t-k lies in
+// [0,T); on the first two frames of a launch the reference's x1/x2 words stand in for outputs older than the launch
+template <int NSEC>
+__device__ __forceinline__ long long cascStepExact(Casc<NSEC>& L, int xin, int t, int T) {
+    int in[NSEC], x1[NSEC], x2[NSEC];
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) {
+        const int f = t - k;
+        in[k] = k ? L.y1[k - 1] : xin;
+        x1[k] = k ? (f == 0 ? L.rx1[k] : L.y2[k - 1]) : L.X1;
+        x2[k] = k ? (f == 0 ? L.rx2[k] : (f == 1 ? L.rx1[k] : L.y3[k - 1])) : L.X2;
+    }
+    long long last = 0;
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) {
+        if ((unsigned)(t - k) < (unsigned)T) {
+            long long acc = L.acc[k];
+            acc = mac32(acc, x1[k], L.b1[k]);
+            acc = mac32(acc, x2[k], L.b2[k]);
+            acc = mac32(acc, L.y1[k], L.a1[k]);
+            acc = mac32(acc, L.y2[k], L.a2[k]);
+            acc = mac32(acc, in[k], L.b0[k]);
+            acc = biquadSat(acc);
+            L.acc[k] = acc;
+            L.y3[k] = L.y2[k]; L.y2[k] = L.y1[k]; L.y1[k] = q59ToS31(acc);
+            if (k == NSEC - 1) last = acc;
+        }
+    }
+    if ((unsigned)t < (unsigned)T) { L.X2 = L.X1; L.X1 = xin; }
+    return last;
+}
+
+// SAT0DB_TPDF on the cascade's accumulator (dsp_runtime.c:478-491, dspTpdfApply runtime/dsp_tpdf.h:141-145)
+__device__ __forceinline__ int finishTpdf3(long long acc, int tv, bool up, int sh) {
+    const long long t = tv;
+    acc += up ? (long long)((unsigned long long)t << sh) : (t >> sh);
+    return sat64_031_s32(acc);
+}
+
+// ------------------------------------------------------------------------------------------------ cascade warps
+// MODE bit 0: the source is LOAD_GAIN with gain 1.0 (x = the sample itself); bit 1: SAT0DB_TPDF finish
+template <int NSEC, int MODE, bool CKREG>
+__device__ __forceinline__ void cascadeWarp(const ChainPlan& P, const Chain2Args& A, const Chain3Geom& G, unsigned char* smem,
+                                            int w, int lane) {
+    constexpr int LAG = NSEC - 1;
+    const int NS = G.streamsPerCta, W = P.h.stateWords, T = A.nFrames;
+    const int s0 = blockIdx.x * NS, nsHere = min(NS, A.nStreams - s0);
+    const int c = G.warpChain[w];
+    const ChainDesc& d = P.chains[c];
+    const int sec0 = G.warpFirstSec[w];                     // this warp owns sections [sec0, sec0 + NSEC) of chain c
+    const int base = G.warpBase[w];                         // step offset: section k of the warp works on frame t - base - k at step t
+    const int LAGA = base + LAG;                            // the warp's tail finishes frame t - LAGA at step t
+    const int srcWarp = G.warpSrc[w];                       // -1: the staged PCM tile; else the warp whose row feeds this part
+    const bool fin = G.warpFinal[w] != 0;                   // last part of its chain: SAT0DB[_TPDF], delay line, post ring
+    const bool live = lane < nsHere;
+    const int sl = min(lane, NS - 1);                       // idle lanes shadow the last stream's shared-memory rows (reads only)
+    const int RM = G.postRing - 1;
+    const unsigned RM4 = (unsigned)RM << 2, TM4 = (unsigned)(4 * F3 - 1) << 2;
+    const unsigned sb = smemAddr3(smem);
+    const unsigned postRow = sb + (unsigned)G.warpRowOff[w] + (unsigned)(sl * G.warpPitch[w]) * 4u;
+    const unsigned srcRow = sb + (unsigned)G.warpRowOff[max(srcWarp, 0)] + (unsigned)(sl * G.warpPitch[max(srcWarp, 0)]) * 4u;
+    volatile int* tileDone = reinterpret_cast<volatile int*>(smem + G.doneOff);       // [warp]: tiles finished
+    const unsigned tpdfRow = sb + G.tpdfOff + (unsigned)(sl * TP3) * 4u;
+    const unsigned rawRow = sb + G.rawOff + (unsigned)(sl * G.rawPitchBytes) + (unsigned)d.srcCh * 4u;
+    const unsigned fb = (unsigned)P.h.nIn * 4u;              // bytes per frame in a staged tile
+    const unsigned mbar = sb + G.mbarOff;
+    // LOAD: X = the sample, the cascade takes X >> 28; a later part takes the previous part's y as it is (1.0 in Q4.28)
+    const int gain = srcWarp >= 0 ? (1 << kMant) : (d.srcKind == SRC_LOAD_GAIN ? d.srcArg : 1);
+    const bool tpdfUp = P.h.tpdfShift >= 0;
+    const int tpdfSh = (tpdfUp ? P.h.tpdfShift : -P.h.tpdfShift) & 63;
+    const bool wantTpdf = fin && (d.satKind & 1) != 0;
+    int* st = A.state + (size_t)(s0 + (live ? lane : 0)) * W;
+
+    Casc<NSEC> L;
+    L.X1 = L.X2 = 0;
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) {
+        const int* cf = P.pool + d.coefOff + 5 * (sec0 + k);
+        L.b0[k] = cf[0]; L.b1[k] = cf[1]; L.b2[k] = cf[2]; L.a1[k] = cf[3]; L.a2[k] = cf[4];
+        L.acc[k] = 0; L.y1[k] = L.y2[k] = L.y3[k] = L.rx1[k] = L.rx2[k] = 0;
+        if (live) {
+            const int* q = st + P.pool[d.secStateOff + sec0 + k];   // [acc_lo, acc_hi, x1, x2, y1, y2] (dsp_biquadSTD.h:45)
+            L.acc[k] = (long long)(((unsigned long long)(unsigned)q[1] << 32) | (unsigned)q[0]);
+            L.rx1[k] = q[2]; L.rx2[k] = q[3]; L.y1[k] = q[4]; L.y2[k] = q[5];
+            if (k == 0) { L.X1 = q[2]; L.X2 = q[3]; }
+        }
+    }
+    // delay line (dsp_runtime.c:769-794): ring of n samples, frame f swaps with position (idx0+f) mod n, so the output of frame
+    // f is the post value of frame f-n.  The post ring IS the delay line: the n samples the reference ring holds are preloaded
+    // as "virtual frames" -n..-1.  A stale index idx0 >= n (delay shortened by reload_params) is used once by the reference
+    // and then wraps to 0: frame 0 swaps with ring[idx0], frames >= 1 behave like idx0 = n-1 (same handling as k_chain2).
+    const int n = fin ? d.delayN : 0;
+    int idx0 = 0, staleIdx = -1;
+    if (live && n > 0) {
+        const int* ring = st + d.delayOff + 1;
+        idx0 = st[d.delayOff];
+        const bool stale = idx0 >= n || idx0 < 0;
+        for (int k = 0; k < n; k++) {
+            const int v = !stale ? ring[(idx0 + k) % n] : (k == 0 ? ring[idx0] : ring[k - 1]);
+            sts3(postRow + ((unsigned)((k - n + LAGA) & RM) << 2), v);
+        }
+        if (stale) { sts3(postRow + ((unsigned)(LAGA & RM) << 2), ring[n - 1]); staleIdx = idx0; idx0 = n - 1; }   // takes the place of post(0)
+    }
+    const bool anyStale = __any_sync(0xffffffffu, staleIdx >= 0);
+    int* ck = reinterpret_cast<int*>(smem + G.ckOff) + (w * 32 + lane);               // [5*maxSec+2 words][cascade threads]
+    const int CKP = G.nCascade * 32;
+    const int nTiles = (T + G.gmax + F3 - 1) / F3;
+
+    for (int i = 0; i < nTiles; i++) {
+        barSync3(kBarFull3 + (i & 1), G.threads);
+        const int t0 = i * F3;
+        unsigned ra, rstep;                                 // this tile's input: address of step t0, bytes per step
+        if (srcWarp < 0) {
+            if (G.tma && t0 + F3 <= T) mbarWait3(mbar + 8u * (unsigned)(i & 1), (unsigned)((i >> 1) & 1));
+            ra = rawRow + (unsigned)(i & 1) * (unsigned)G.rawStageBytes; rstep = fb;
+        } else {
+            // the previous part wrote the steps of its tile i-1 into its row: wait until it has finished that tile
+            if (i > 0) { while (tileDone[srcWarp] < i) { } __threadfence_block(); __syncwarp(); }
+            ra = srcRow + (unsigned)(((i + 2) % 3) * F3) * 4u; rstep = 4u;       // hand-over rows hold three tiles: slot = tile mod 3
+        }
+        const int tl0 = t0 - base;                          // local step of the tile's first step
+        // interior tile: every section of the lane is active on every step, the input tile is complete
+        bool exact = !(tl0 >= LAG + 2 && tl0 + F3 <= T && !(anyStale && tl0 <= LAG));
+        if (!exact) {
+            // checkpoint (registers for short parts, else shared memory: the LSU is idle in this loop), optimistic tile, one
+            // vote, rare exact replay
+            long long cAcc[CKREG ? NSEC : 1]; int cY1[CKREG ? NSEC : 1], cY2[CKREG ? NSEC : 1], cY3[CKREG ? NSEC : 1], cX1 = 0, cX2 = 0;
+            if (CKREG) {
+#pragma unroll
+                for (int k = 0; k < NSEC; k++) { cAcc[CKREG ? k : 0] = L.acc[k]; cY1[CKREG ? k : 0] = L.y1[k]; cY2[CKREG ? k : 0] = L.y2[k]; cY3[CKREG ? k : 0] = L.y3[k]; }
+                cX1 = L.X1; cX2 = L.X2;
+            } else {
+#pragma unroll
+                for (int k = 0; k < NSEC; k++) {
+                    ck[(5 * k + 0) * CKP] = lo32(L.acc[k]); ck[(5 * k + 1) * CKP] = hi32(L.acc[k]);
+                    ck[(5 * k + 2) * CKP] = L.y1[k]; ck[(5 * k + 3) * CKP] = L.y2[k]; ck[(5 * k + 4) * CKP] = L.y3[k];
+                }
+                ck[(5 * NSEC) * CKP] = L.X1; ck[(5 * NSEC + 1) * CKP] = L.X2;
+            }
+            unsigned w0 = 0, w1 = 0;
+            unsigned rj = ra;
+            unsigned pj = postRow + (fin ? ((unsigned)(t0 & RM) << 2) : (unsigned)((i % 3) * F3) * 4u);
+            unsigned tj = (unsigned)((t0 - LAGA) << 2);
+#pragma unroll 1
+            for (int j0 = 0; j0 < F3; j0 += AVDSP_UNR3) {
+#pragma unroll
+                for (int jj = 0; jj < AVDSP_UNR3; jj++) {
+                    const int smp = lds3(rj); rj += rstep;
+                    const int x = (MODE & 1) ? smp : q59ToS31(mul32(smp, gain));
+                    const long long acc = cascStep<NSEC>(L, x, w0, w1);
+                    int v;
+                    if (MODE & 2) v = finishTpdf3(acc, lds3(tpdfRow + ((tj + 4u * jj) & TM4)), tpdfUp, tpdfSh);
+                    else v = q59ToS31(acc);        // SAT0DB of a clamped accumulator is its own >> 28 (replayed exactly if a clamp fired)
+                    if (live) sts3(pj + 4u * jj, v);
+                }
+                pj += 4u * AVDSP_UNR3; tj += 4u * AVDSP_UNR3;
+            }
+            if (__any_sync(0xffffffffu, max(w0, w1) > kSatLimit3)) {
+                if (CKREG) {
+#pragma unroll
+                    for (int k = 0; k < NSEC; k++) { L.acc[k] = cAcc[CKREG ? k : 0]; L.y1[k] = cY1[CKREG ? k : 0]; L.y2[k] = cY2[CKREG ? k : 0]; L.y3[k] = cY3[CKREG ? k : 0]; }
+                    L.X1 = cX1; L.X2 = cX2;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NSEC; k++) {
+                        L.acc[k] = (long long)(((unsigned long long)(unsigned)ck[(5 * k + 1) * CKP] << 32) | (unsigned)ck[(5 * k + 0) * CKP]);
+                        L.y1[k] = ck[(5 * k + 2) * CKP]; L.y2[k] = ck[(5 * k + 3) * CKP]; L.y3[k] = ck[(5 * k + 4) * CKP];
+                    }
+                    L.X1 = ck[(5 * NSEC) * CKP]; L.X2 = ck[(5 * NSEC + 1) * CKP];
+                }
+                exact = true;
+            }
+        }
+        if (exact) {
+            // launch edges (pipeline fill / drain, partial last tile, a stale delay index at frame 0) and replays
+#pragma unroll 1
+            for (int j = 0; j < F3; j++) {
+                const int t = t0 + j, tl = t - base;
+                if (tl >= T + LAG) break;
+                if (tl < 0) continue;
+                const int smp = tl < T ? lds3(ra + (unsigned)j * rstep) : 0;
+                const int x = q59ToS31(mul32(smp, gain));
+                const long long acc = cascStepExact<NSEC>(L, x, tl, T);
+                const int f = tl - LAG;                         // the frame the last section just finished
+                if (f >= 0) {
+                    int v;
+                    if (wantTpdf) v = finishTpdf3(acc, lds3(tpdfRow + ((unsigned)(f << 2) & TM4)), tpdfUp, tpdfSh);
+                    else v = q59ToS31(acc);
+                    if (live) {
+                        if (f == 0 && staleIdx >= 0) st[d.delayOff + 1 + staleIdx] = v;     // the reference's swap with ring[idx0]
+                        else sts3(postRow + (fin ? ((unsigned)(t << 2) & RM4) : (unsigned)((i % 3) * F3 + j) * 4u), v);
+                    }
+                }
+            }
+        }
+        if (!fin) {                                         // the next part may read this tile's steps now
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); tileDone[w] = i + 1; }
+        }
+        barArrive3(kBarDone3 + (i & 1), G.threads);
+    }
+
+    if (live) {
+        // the pipeline is drained: every section has seen frames 0..T-1.  Back to the reference layout.
+#pragma unroll
+        for (int k = 0; k < NSEC; k++) {
+            int* q = st + P.pool[d.secStateOff + sec0 + k];
+            q[0] = lo32(L.acc[k]); q[1] = hi32(L.acc[k]);
+            if (k == 0) { q[2] = L.X1; q[3] = L.X2; }
+            else if (T >= 2) { q[2] = L.y1[k - 1]; q[3] = L.y2[k - 1]; }
+            else if (T == 1) { q[2] = L.y1[k - 1]; q[3] = L.rx1[k]; }
+            q[4] = L.y1[k]; q[5] = L.y2[k];
+        }
+        if (n > 0 && T > 0) {
+            // delay line back to the reference's ring layout: frame j sits at position (idx0+j) mod n
+            int* ring = st + d.delayOff + 1;
+            for (int k = 0; k < n; k++) {
+                const long long j = (long long)T - n + k;                    // frames T-n .. T-1 (virtual ones included)
+                ring[(int)(((long long)idx0 + j + n) % n)] = lds3(postRow + ((unsigned)(((int)j + LAGA) & RM) << 2));
+            }
+            st[d.delayOff] = (int)(((long long)idx0 + T) % n);
+        }
+    }
+}
+
+template <int NSEC, bool CKREG>
+__device__ __forceinline__ void cascadeWarpMode(const ChainPlan& P, const Chain2Args& A, const Chain3Geom& G, unsigned char* smem,
+                                                int w, int lane, int mode) {
+    switch (mode) {
+    case 0:  cascadeWarp<NSEC, 0, CKREG>(P, A, G, smem, w, lane); break;
+    case 1:  cascadeWarp<NSEC, 1, CKREG>(P, A, G, smem, w, lane); break;
+    case 2:  cascadeWarp<NSEC, 2, CKREG>(P, A, G, smem, w, lane); break;
+    default: cascadeWarp<NSEC, 3, CKREG>(P, A, G, smem, w, lane); break;
+    }
+}
+
+// store pass of one stream's window, interleaved output with NOUT (power of two) channels: 32/NOUT frames per pass, one
+// 128-byte run per pass; per-lane constants (row, lag - delay, mask) in registers
+template <int NOUT>
+__device__ __forceinline__ void storeTile3(int* __restrict__ out, unsigned rowA, unsigned p4, unsigned RM4, int mask, bool clean,
+                                           int f0, int fs, int T) {
+    constexpr int FPP = 32 / NOUT, NPASS = F3 / FPP;
+    if (clean) {
+#pragma unroll
+        for (int p = 0; p < NPASS; p++) out[p * 32] = lds3(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4)) & mask;
+    } else {
+#pragma unroll 1
+        for (int p = 0; p < NPASS; p++) {
+            const int f = f0 + p * FPP + fs;
+            if (f >= 0 && f < T) out[p * 32] = lds3(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4)) & mask;
+        }
+    }
+}
+
+// all streams of one store warp for one window: the channel-count dispatch sits outside the stream loop, the loop itself is
+// pointer bumps + the passes
+template <int NOUT>
+__device__ __forceinline__ void storeStreams3(int* __restrict__ out, size_t outStep, unsigned rowA, unsigned rowStep, int cnt, unsigned p4,
+                                              unsigned RM4, int mask, bool clean, int f0, int fs, int T) {
+#pragma unroll 1
+    for (int s = 0; s < cnt; s++, out += outStep, rowA += rowStep) storeTile3<NOUT>(out, rowA, p4, RM4, mask, clean, f0, fs, T);
+}
+
+} // namespace
+
+// MAXSEC = 8: whole cascades, up to 12 warps of 168 registers;  MAXSEC = 4: cascades cut into parts, up to 16 warps of 128
+template <int MAXSEC>
+__global__ void __launch_bounds__(MAXSEC > 4 ? kChain3MaxThreads : kChain3MaxThreadsParts, 1)
+k_chain3(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_constant__ Chain3Geom G) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int role = G.warpRole[threadIdx.x >> 5];          // >= 0: cascade warp (index); -1: dither warp; <= -2: store warp -2-k
+    if (role >= 0) {
+        const int warp = role;
+        const ChainDesc& d = P.chains[G.warpChain[warp]];
+        const bool unity = G.warpSrc[warp] >= 0 || (d.srcKind == SRC_LOAD_GAIN && d.srcArg == (1 << kMant));
+        const int mode = (unity ? 1 : 0) | ((G.warpFinal[warp] && (d.satKind & 1)) ? 2 : 0);
+        switch (G.warpNsec[warp]) {
+        case 1: cascadeWarpMode<1, (MAXSEC <= 4)>(P, A, G, smem_raw, warp, lane, mode); break;
+        case 2: cascadeWarpMode<2, (MAXSEC <= 4)>(P, A, G, smem_raw, warp, lane, mode); break;
+        case 3: cascadeWarpMode<3, (MAXSEC <= 4)>(P, A, G, smem_raw, warp, lane, mode); break;
+        case 4: cascadeWarpMode<4, (MAXSEC <= 4)>(P, A, G, smem_raw, warp, lane, mode); break;
+        default:
+            if constexpr (MAXSEC > 4) {
+                switch (G.warpNsec[warp]) {
+                case 5: cascadeWarpMode<5, (MAXSEC <= 4)>(P, A, G, smem_raw, warp, lane, mode); break;
+                case 6: cascadeWarpMode<6, (MAXSEC <= 4)>(P, A, G, smem_raw, warp, lane, mode); break;
+                case 7: cascadeWarpMode<7, (MAXSEC <= 4)>(P, A, G, smem_raw, warp, lane, mode); break;
+                default: cascadeWarpMode<8, (MAXSEC <= 4)>(P, A, G, smem_raw, warp, lane, mode); break;
+                }
+            }
+            break;
+        }
+        return;
+    }
+    // =============================================================================== helper warps
+    const int NS = G.streamsPerCta, W = P.h.stateWords, T = A.nFrames;
+    const int s0 = blockIdx.x * NS, nsHere = min(NS, A.nStreams - s0);
+    const int gmax = G.gmax;
+    const int nTiles = (T + gmax + F3 - 1) / F3;
+    const int hw = -role - 1;                               // 0: dither PRNG + input staging; 1..nStore: store warps
+    const unsigned sb = smemAddr3(smem_raw);
+    const unsigned RM4 = (unsigned)(G.postRing - 1) << 2;
+
+    if (hw == 0) {
+        // ---- per-stream dither PRNG (lane = stream; DSP_TPDF_CALC, dsp_runtime.c:537-545) one tile ahead of the cascades, and
+        // the input tiles: bulk copies two tiles ahead, or plain copies one tile ahead where the bulk copy cannot be used
+        const bool own = lane < nsHere;
+        const bool hasCalc = P.h.hasTpdfCalc != 0;
+        const int nIn = P.h.nIn;
+        Prng g = {0, 0, 0, 0}; int tpdfValue = 0, tpdfRandom = 0, dith = 0; bool drew = false;
+        int* auxp = nullptr;
+        if (own) {
+            auxp = A.state + (size_t)(s0 + lane) * W + P.h.auxOff;
+            g.s0 = auxp[AUX_S0]; g.s1 = auxp[AUX_S1]; g.s2 = auxp[AUX_S2]; g.s3 = auxp[AUX_S3];
+            tpdfValue = auxp[AUX_TPDF_VALUE]; tpdfRandom = auxp[AUX_TPDF_RANDOM]; dith = auxp[AUX_DITHER];
+        }
+        const unsigned mbar = sb + G.mbarOff;
+        const unsigned rowBytes = (unsigned)(F3 * nIn * 4);
+        if (G.tma && lane == 0) { mbarInit3(mbar, 1); mbarInit3(mbar + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+        if (lane < kChain3MaxWarps) reinterpret_cast<volatile int*>(smem_raw + G.doneOff)[lane] = 0;     // per-part tile counters
+        __syncwarp();
+        auto issueTile = [&](int it) {                      // full tiles by TMA
+            if (!G.tma || (it + 1) * F3 > T) return;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const unsigned bar = mbar + 8u * (unsigned)(it & 1);
+            if (lane == 0) mbarExpectTx3(bar, (unsigned)nsHere * rowBytes);
+            __syncwarp();
+            if (own) {
+                const int* src = A.in + (size_t)(s0 + lane) * A.inStreamStride + (size_t)(it * F3) * A.inFrameStride;
+                tmaLoad3(sb + G.rawOff + (unsigned)(it & 1) * (unsigned)G.rawStageBytes + (unsigned)(lane * G.rawPitchBytes), src, rowBytes, bar);
+            }
+        };
+        auto copyTile = [&](int it) {                       // everything else (partial last tile, planar or unaligned buffers)
+            const int f0 = it * F3;
+            if (f0 >= T || (G.tma && f0 + F3 <= T)) return;
+            const int nf = min(F3, T - f0);
+            const unsigned dst0 = sb + G.rawOff + (unsigned)(it & 1) * (unsigned)G.rawStageBytes;
+            // lane = channel-sample inside a stream's row: consecutive lanes read consecutive words of interleaved PCM
+            for (int s = 0; s < nsHere; s++) {
+                const int* src = A.in + (size_t)(s0 + s) * A.inStreamStride + (size_t)f0 * A.inFrameStride;
+                for (int e = lane; e < nf * nIn; e += 32) {
+                    const int fr = e / nIn, ch = e - fr * nIn;
+                    sts3(dst0 + (unsigned)(s * G.rawPitchBytes) + 4u * (unsigned)e, src[(size_t)fr * A.inFrameStride + (size_t)ch * A.inChStride]);
+                }
+            }
+        };
+        auto ditherTile = [&](int it) {
+            const int f0 = it * F3;
+            if (f0 >= T || !own) return;
+            const unsigned row = sb + G.tpdfOff + (unsigned)(lane * TP3 + (it & 3) * F3) * 4u;
+            const int nf = min(F3, T - f0);
+            int j = 0;
+            if (hasCalc) {
+                // a table switch on the first frame after a reset: no draw (dsp_runtime.c:539-544)
+                if (dith != P.h.tpdfDither) { dith = P.h.tpdfDither; sts3(row, tpdfValue); j = 1; }
+                if (j < nf) drew = true;
+                for (; j < nf; j++) { tpdfValue = tpdfDraw(g, tpdfRandom); sts3(row + 4u * j, tpdfValue); }
+            } else {
+                for (; j < nf; j++) sts3(row + 4u * j, tpdfValue);
+            }
+        };
+        issueTile(0);
+        issueTile(1);
+        copyTile(0);
+        ditherTile(0);
+        barArrive3(kBarFull3 + 0, G.threads);
+        for (int i = 0; i < nTiles; i++) {
+            if (i + 1 < nTiles) { copyTile(i + 1); ditherTile(i + 1); barArrive3(kBarFull3 + ((i + 1) & 1), G.threads); }
+            barSync3(kBarDone3 + (i & 1), G.threads);
+            issueTile(i + 2);                               // the cascades are done with this parity's buffer
+        }
+        if (auxp) {
+            auxp[AUX_S0] = g.s0; auxp[AUX_S1] = g.s1; auxp[AUX_S2] = g.s2; auxp[AUX_S3] = g.s3;
+            auxp[AUX_TPDF_VALUE] = tpdfValue; auxp[AUX_TPDF_RANDOM] = tpdfRandom; auxp[AUX_DITHER] = dith;
+            if (drew) {   // TPDF_CALC leaves its last value (as an ALU word) in the data area (dsp_runtime.c:541-543)
+                int* q = A.state + (size_t)(s0 + lane) * W + P.h.tpdfDataOff;
+                q[0] = tpdfValue; q[1] = tpdfValue >> 31;
+            }
+        }
+        return;
+    }
+
+    // ---- store warps: post ring at (frame + lag - delay) -> STORE mask -> global
+    const int sw = hw - 1, nSW = G.nStore;
+    const int nOut = P.h.nOut;
+    const int storeMask = ditherMask(P.h.storeDither);
+    const bool laneOut = A.outChStride == 1 && A.outFrameStride == nOut;      // interleaved: lane = (frame inside a pass, channel)
+    const int bCh = lane % nOut, bFs = lane / nOut;
+    const int bChain = P.h.chainOfOut[bCh];
+    const unsigned bRow = bChain >= 0 ? (unsigned)G.warpRowOff[G.chainRow[bChain]] : (unsigned)G.warpRowOff[G.chainRow[0]];
+    const int bOff = bChain >= 0 ? G.chainLag[bChain] - P.chains[bChain].delayN : 0;
+    const int bMask = bChain >= 0 ? storeMask : 0;          // outputs no path writes read as 0
+    barArrive3(kBarFull3 + 0, G.threads);
+    for (int i = 0; i < nTiles; i++) {
+        if (i + 1 < nTiles) barArrive3(kBarFull3 + ((i + 1) & 1), G.threads);     // window i-1 is stored: its ring span may be reused
+        barSync3(kBarDone3 + (i & 1), G.threads);
+        const int f0 = i * F3 - gmax;                       // window i
+        const bool clean = f0 >= 0 && f0 + F3 <= T;
+        if (laneOut) {
+            const unsigned p4 = (unsigned)((f0 + bFs + bOff) << 2);
+            const int cnt = nsHere > sw ? (nsHere - sw + nSW - 1) / nSW : 0;
+            int* out = A.out + (size_t)(s0 + sw) * A.outStreamStride + (long long)f0 * A.outFrameStride + lane;
+            const size_t outStep = (size_t)nSW * (size_t)A.outStreamStride;
+            const unsigned rowA = sb + bRow + (unsigned)(sw * G.postPitch) * 4u, rowStep = (unsigned)(nSW * G.postPitch) * 4u;
+            switch (nOut) {
+            case 1:  storeStreams3<1>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            case 2:  storeStreams3<2>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            case 4:  storeStreams3<4>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            case 8:  storeStreams3<8>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            case 16: storeStreams3<16>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            default: storeStreams3<32>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            }
+        } else {
+            // any other layout (planar): lane = frame, channels in a loop; consecutive lanes store consecutive frames
+            const int f = f0 + lane;
+            if (f >= 0 && f < T)
+                for (int sl = sw; sl < nsHere; sl += nSW)
+                    for (int ch = 0; ch < nOut; ch++) {
+                        const int oc = P.h.chainOfOut[ch];
+                        int v = 0;
+                        if (oc >= 0) {
+                            const int off = G.chainLag[oc] - P.chains[oc].delayN;
+                            v = lds3(sb + (unsigned)G.warpRowOff[G.chainRow[oc]] + (unsigned)(sl * G.postPitch) * 4u + ((unsigned)((f + off) << 2) & RM4)) & storeMask;
+                        }
+                        A.out[(size_t)(s0 + sl) * A.outStreamStride + (size_t)f * A.outFrameStride + (size_t)ch * A.outChStride] = v;
+                    }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int envInt3(const char* name, int dflt) { const char* v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
+
+bool chain3Supports(const ChainPlan& plan) {
+    const ChainHeader& h = plan.h;
+    if (h.aluClass != ALU_INT64 || !h.sampleInt) return false;
+    if (h.nChains <= 0 || h.nChains > kChain3MaxChains || h.nIn <= 0) return false;
+    if (h.nOut <= 0 || h.nOut > 32 || (h.nOut & (h.nOut - 1)) != 0) return false;
+    if (h.nRaw || h.nDelayFirst || h.nMemCopy) return false;
+    for (int c = 0; c < h.nChains; c++) {
+        const ChainDesc& d = plan.chains[c];
+        if (d.nsec < 1 || d.nsec > 8) return false;
+        if (d.srcKind != SRC_LOAD && d.srcKind != SRC_LOAD_GAIN) return false;
+        if (d.srcCh < 0 || d.srcCh >= h.nIn) return false;
+        if (d.hasGain || d.delayFirst) return false;
+        if (d.satKind != SAT_PLAIN && d.satKind != SAT_TPDF) return false;
+        if (d.delayN < 0) return false;
+    }
+    return true;
+}
+
+bool planChain3Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain3Geom* geom) {
+    if (!chain3Supports(plan)) return false;
+    const int C = plan.h.nChains;
+    int NS = envInt3("AVDSP_B200_NS3", 0);
+    if (NS <= 0) NS = (nStreams + numSMs - 1) / numSMs;
+    NS = std::max(1, std::min(NS, 32));
+    int maxDelay = 0;
+    for (int c = 0; c < C; c++) maxDelay = std::max(maxDelay, plan.chains[c].delayN);
+    // Two shapes: cascades cut into parts of <= 4 sections (more, equal warps: the faster shape when it fits), else whole cascades
+    for (int partMax : {envInt3("AVDSP_B200_PART3", 4), 8}) {
+        if (partMax < 1 || partMax > 8) continue;
+        struct Part { int chain, first, nsec, base, src, fin; };
+        Part parts[kChain3MaxWarps];
+        int nParts = 0, gmax = 0, maxSec = 0;
+        bool fits = true;
+        Chain3Geom g{};
+        for (int c = 0; c < C && fits; c++) {
+            const int nsec = plan.chains[c].nsec, np = (nsec + partMax - 1) / partMax;
+            if (np > 2) { fits = false; break; }            // lags beyond F + 2 * partMax would outrun the dither ring (4 tiles)
+            int first = 0, base = 0, prev = -1;
+            for (int p = 0; p < np; p++) {
+                if (nParts >= kChain3MaxWarps) { fits = false; break; }
+                const int n = nsec / np + (p < nsec % np ? 1 : 0);          // near-equal parts, the longer ones first
+                parts[nParts] = {c, first, n, base, prev, p == np - 1};
+                prev = nParts++;
+                first += n;
+                maxSec = std::max(maxSec, n);
+                gmax = std::max(gmax, base + n - 1);
+                if (p == np - 1) g.chainLag[c] = base + n - 1;
+                base += n - 1 + F3;                                       // the next part reads this part's row one tile later
+            }
+        }
+        if (!fits) continue;
+        const int maxThreads = maxSec > 4 ? kChain3MaxThreads : kChain3MaxThreadsParts;
+        g.streamsPerCta = NS;
+        g.nCascade = nParts;
+        g.gmax = gmax;
+        g.maxSec = maxSec;
+        g.nStore = std::max(1, std::min(envInt3("AVDSP_B200_SW3", 3), maxThreads / 32 - nParts - 1));
+        g.threads = (nParts + 1 + g.nStore) * 32;
+        if (g.threads > maxThreads) continue;
+        // the cascades write steps of tile i+1 while the store warps still read window i back to (its first frame - longest delay)
+        int R = 2 * F3;
+        while (R < 2 * F3 + gmax + maxDelay) R <<= 1;
+        g.postRing = R; g.postPitch = R + 1;
+        g.rawPitchBytes = F3 * plan.h.nIn * 4 + 16;         // 16-byte aligned rows, 4-bank skew between streams
+        g.rawStageBytes = NS * g.rawPitchBytes;
+        // warps -> sub-partitions (warp id % 4).  Cascade parts are packed first-fit-decreasing into four bins of equal section
+        // count (C2: 4+4+4 | 4+4+4 | 3+3+3+3 | 3+3+3+3); the dither and store warps take the slots that are left, the dither
+        // warp (the busier one) on the lightest bin.  Cascade warp index w (rows, tables) is independent of the hardware warp id.
+        {
+            const int total = nParts + 1 + g.nStore;
+            int slots[4], order[kChain3MaxWarps], binOf[kChain3MaxWarps];
+            for (int q = 0; q < 4; q++) slots[q] = (total - q + 3) / 4;   // warp ids q, q+4, ... below total
+            for (int k = 0; k < nParts; k++) order[k] = k;
+            std::stable_sort(order, order + nParts, [&](int a, int b) { return parts[a].nsec > parts[b].nsec; });
+            int sum = 0;
+            for (int k = 0; k < nParts; k++) sum += parts[k].nsec;
+            int load[4], used[4];
+            for (int capLoad = (sum + 3) / 4; ; capLoad++) {
+                bool ok = true;
+                for (int q = 0; q < 4; q++) load[q] = used[q] = 0;
+                for (int k = 0; k < nParts && ok; k++) {
+                    int q = 0;
+                    // keep 1 + nStore slots for the helper warps overall
+                    for (; q < 4; q++) if (used[q] < slots[q] && load[q] + parts[order[k]].nsec <= capLoad) break;
+                    if (q == 4) { ok = false; break; }
+                    binOf[order[k]] = q; used[q]++; load[q] += parts[order[k]].nsec;
+                }
+                if (ok) break;
+                if (capLoad > sum) break;                    // cannot happen: every part fits somewhere
+            }
+            int next[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 32; k++) g.warpRole[k] = -1;
+            int slotOf[kChain3MaxWarps];
+            // cascade index = part index k (rows follow the part order); hardware warp id = bin + 4 * position in the bin
+            for (int k = 0; k < nParts; k++) { slotOf[k] = k; g.warpRole[binOf[k] + 4 * next[binOf[k]]++] = k; }
+            for (int hk = 0; hk < 1 + g.nStore; hk++) {       // helpers: lightest bin with a free slot
+                int best = -1;
+                for (int q = 0; q < 4; q++) if (next[q] < slots[q] && (best < 0 || load[q] < load[best])) best = q;
+                if (best < 0) return false;
+                g.warpRole[best + 4 * next[best]++] = -1 - hk;
+                load[best] += 2;                             // spread the helpers
+            }
+            for (int k = 0; k < nParts; k++) {
+                const int w = slotOf[k];
+                g.warpChain[w] = parts[k].chain; g.warpFirstSec[w] = parts[k].first; g.warpNsec[w] = parts[k].nsec;
+                g.warpBase[w] = parts[k].base; g.warpSrc[w] = parts[k].src >= 0 ? slotOf[parts[k].src] : -1; g.warpFinal[w] = parts[k].fin;
+                if (parts[k].fin) g.chainRow[parts[k].chain] = w;
+            }
+        }
+        size_t bytes = 0;
+        g.postOff = 0;
+        for (int w = 0; w < nParts; w++) {                  // final parts: R-step ring (the delay line); hand-over rows: three tiles
+            g.warpPitch[w] = g.warpFinal[w] ? g.postPitch : 3 * F3 + 1;
+            g.warpRowOff[w] = (int)bytes; bytes += (size_t)NS * g.warpPitch[w] * 4;
+        }
+        g.tpdfOff = (int)bytes; bytes += (size_t)NS * TP3 * 4;
+        g.ckOff = (int)bytes;   if (maxSec > 4) bytes += (size_t)(5 * maxSec + 2) * nParts * 32 * 4;   // short parts checkpoint in registers
+        g.doneOff = (int)bytes; bytes += (size_t)kChain3MaxWarps * 4;
+        bytes = (bytes + 15) & ~(size_t)15;
+        g.mbarOff = (int)bytes; bytes += 16;
+        bytes = (bytes + 127) & ~(size_t)127;
+        g.rawOff = (int)bytes;  bytes += (size_t)2 * g.rawStageBytes;
+        g.smemBytes = bytes + 16;
+        if (g.smemBytes > 226 * 1024) continue;
+        *geom = g;
+        return true;
+    }
+    return false;
+}
+
+// bulk copies need interleaved, 16-byte friendly input rows; everything else is staged with plain copies
+static bool chain3TmaOk(const ChainPlan& plan, const Chain2Args& a) {
+    const int nIn = plan.h.nIn;
+    return a.inChStride == 1 && a.inFrameStride == nIn && ((size_t)a.in & 15) == 0 && (a.inStreamStride & 3) == 0 && ((F3 * nIn * 4) & 15) == 0;
+}
+
+cudaError_t launchChain3(const ChainPlan& plan, const Chain3Geom& geom, const Chain2Args& args, cudaStream_t stream) {
+    Chain3Geom g = geom;
+    g.tma = chain3TmaOk(plan, args) ? 1 : 0;
+    const int blocks = (args.nStreams + g.streamsPerCta - 1) / g.streamsPerCta;
+    cudaError_t e;
+    if (g.maxSec > 4) {
+        e = cudaFuncSetAttribute(k_chain3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes);
+        if (e != cudaSuccess) return e;
+        k_chain3<8><<<blocks, g.threads, g.smemBytes, stream>>>(plan, args, g);
+    } else {
+        e = cudaFuncSetAttribute(k_chain3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes);
+        if (e != cudaSuccess) return e;
+        k_chain3<4><<<blocks, g.threads, g.smemBytes, stream>>>(plan, args, g);
+    }
+    return cudaGetLastError();
+}
+
+} // namespace avdsp

@@ -93,6 +93,39 @@ bool chain2Supports(const ChainPlan& plan);
 bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2Geom* geom, ChainLane* lanesOut /*[1024]*/);
 cudaError_t launchChain2(const ChainPlan& plan, const Chain2Geom& geom, const Chain2Args& args, cudaStream_t stream);
 
+// ---- register-resident cascade kernel (kernel_chain3.cu): lane = one whole cascade of one stream ------------------
+constexpr int kChain3MaxChains = 10;        // chains of a program the kernel takes
+constexpr int kChain3MaxWarps = 16;         // cascade warps of a CTA (chains, or parts of chains)
+constexpr int kChain3MaxThreads = 384;      // whole cascades (<= 8 sections): 3 warps per sub-partition (16384 registers each) = 168 registers per thread
+constexpr int kChain3MaxThreadsParts = 512; // parts of <= 4 sections: 4 warps per sub-partition = 128 registers per thread
+struct Chain3Geom {
+    int streamsPerCta;     // NS (<= 32): lane = stream inside a cascade warp
+    int nCascade;          // cascade warps
+    int nStore;            // store warps
+    int gmax;              // largest lag of a warp's tail (sections are skewed in time, parts run a tile behind each other)
+    int maxSec;            // longest part (selects the kernel instance)
+    int threads;           // (nCascade + 1 + nStore) * 32
+    int postRing;          // R: row ring length in steps (power of two >= 2 tiles + gmax + longest delay)
+    int postPitch;         // R + 1
+    int rawPitchBytes, rawStageBytes;     // staged input tiles: bytes per stream row / per stage (2 stages)
+    int postOff, tpdfOff, ckOff, doneOff, mbarOff, rawOff;   // shared-memory map (bytes)
+    int tma;               // filled per launch: the caller's input buffer allows bulk copies (else plain staged copies)
+    // cascade warp -> what it runs (dealt so that the four sub-partitions carry equal section counts)
+    int warpChain[kChain3MaxWarps], warpFirstSec[kChain3MaxWarps], warpNsec[kChain3MaxWarps];
+    int warpBase[kChain3MaxWarps];        // step offset of the part: its section k works on frame t - base - k at step t
+    int warpSrc[kChain3MaxWarps];         // -1: the PCM tile; else the warp whose row feeds this part
+    int warpFinal[kChain3MaxWarps];       // last part of its chain
+    int warpRowOff[kChain3MaxWarps];      // byte offset of the warp's rows [stream][pitch] in shared memory
+    int warpPitch[kChain3MaxWarps];       // words per row: R + 1 (final parts: the post ring) or 3 tiles + 1 (hand-over rows)
+    int warpRole[32];                     // hardware warp id -> cascade warp index (>= 0), -1 dither warp, -2-k store warp k
+    int chainRow[kChain3MaxChains];       // chain -> row (= warp) of its final part
+    int chainLag[kChain3MaxChains];       // chain -> lag of its final part's tail
+    size_t smemBytes;
+};
+bool chain3Supports(const ChainPlan& plan);
+bool planChain3Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain3Geom* geom);
+cudaError_t launchChain3(const ChainPlan& plan, const Chain3Geom& geom, const Chain2Args& args, cudaStream_t stream);
+
 // ---- time-parallel mixer / delay / dither kernel (kernel_mix.cu) -----------------------------------
 // Everything the three kernels need, flattened by OUTPUT channel (static indices -> constant-bank operands).
 struct MixPlan {

@@ -16,6 +16,7 @@ from . import _lib
 INTERLEAVED, PLANAR = 0, 1
 HOST, DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CHAIN, KERNEL_CHAIN_V1, KERNEL_MIX, KERNEL_FIR, KERNEL_FIR_TC = 0, 1, 2, 3, 4, 5, 6
+KERNEL_CHAIN_V2, KERNEL_CHAIN_V3 = 7, 8        # force k_chain2 / k_chain3 (KERNEL_CHAIN and AUTO choose between them)
 PCM_S32, PCM_S16, PCM_S24_3LE = 0, 1, 2
 KERNEL_NAMES = {0: "none", 1: "generic", 2: "chain", 3: "chain_v1", 4: "mix", 5: "fir", 6: "fir_tc"}
 
@@ -92,6 +93,11 @@ class Executor:
     @property
     def last_kernel(self) -> str:
         return KERNEL_NAMES[self._L.avdsp_b200_last_kernel(self._h)]
+
+    @property
+    def last_chain_variant(self) -> int:
+        """2 / 3: which chain kernel (kernel_chain2.cu / kernel_chain3.cu) the last call ran, 0 if it was no chain kernel."""
+        return int(self._L.avdsp_b200_last_chain_variant(self._h))
 
     @property
     def launch_count(self) -> int:

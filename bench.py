@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--frames", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "chain", "mix", "fir", "fir_tc"],
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "chain", "chain_v2", "chain_v3", "mix", "fir", "fir_tc"],
                     help="force a kernel (diagnostics; the default is what the product picks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -195,7 +195,8 @@ def main():
     ex = avdsp_b200.Executor(words, fs, fmt, S, seeds=seeds, dither=31, device=local)
     if args.kernel != "auto":
         ex.set_kernel({"generic": avdsp_b200.KERNEL_GENERIC, "chain": avdsp_b200.KERNEL_CHAIN, "mix": avdsp_b200.KERNEL_MIX,
-                       "fir": avdsp_b200.KERNEL_FIR, "fir_tc": avdsp_b200.KERNEL_FIR_TC}[args.kernel])
+                       "fir": avdsp_b200.KERNEL_FIR, "fir_tc": avdsp_b200.KERNEL_FIR_TC,
+                       "chain_v2": avdsp_b200.KERNEL_CHAIN_V2, "chain_v3": avdsp_b200.KERNEL_CHAIN_V3}[args.kernel])
     n_in, n_out = ex.n_in, ex.n_out
     x = synth.pcm_torch("noise", S, T, n_in, dev, first_stream=first)       # synthetic PCM, resident in HBM
     y = torch.empty((S, T, n_out), dtype=torch.int32, device=dev)
@@ -263,8 +264,9 @@ def main():
     alg_bytes = float(S) * T * (n_in + n_out) * 4               # read every input once + write every output once
     # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of this exact workload + kernel
     traffic = None
-    prof_name = {("c2", "chain"): "r1_chain2_c2", ("c5", "mix"): "r1_mix_c5", ("c4", "fir_tc"): "r1_firtc_i8_c4",
-                 ("c4f", "fir_tc"): "r1_firtc_tf32_c4f", ("c4f", "fir"): "r1_fir_f32_c4f"}.get((args.workload, ex.last_kernel))
+    kname = ex.last_kernel + (str(ex.last_chain_variant) if ex.last_kernel == "chain" else "")       # chain2 / chain3
+    prof_name = {("c2", "chain2"): "r1_chain2_c2", ("c2", "chain3"): "r1_chain3_c2", ("c5", "mix"): "r1_mix_c5", ("c4", "fir_tc"): "r1_firtc_i8_c4",
+                 ("c4f", "fir_tc"): "r1_firtc_tf32_c4f", ("c4f", "fir"): "r1_fir_f32_c4f"}.get((args.workload, kname if ex.last_kernel == "chain" else ex.last_kernel))
     prof = os.path.join(ROOT, "profiles", f"{prof_name}_ncu_summary.txt") if prof_name else None
     if prof and S == wl[3] and T == wl[4] and os.path.exists(prof):
         tot = 0.0
@@ -273,7 +275,7 @@ def main():
             if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
         traffic = tot or None
-    common = {"traffic": traffic, "kernel": f"k_{ex.last_kernel}", "kernel_ms": kernel_ms, "launches_per_step": launches_per_step}
+    common = {"traffic": traffic, "kernel": f"k_{kname}", "kernel_ms": kernel_ms, "launches_per_step": launches_per_step}
     hbm = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
            "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, **common}
     hbm["frac"] = hbm["achieved"] / hbm["peak"]
@@ -326,7 +328,7 @@ def main():
             "config": {"workload": desc, "program": prog, "streams_per_gpu": S, "frames_per_step": T, "fs": fs,
                        "n_in": n_in, "n_out": n_out, "layout": "interleaved [stream][frame][channel] int32",
                        "l2": f"inputs+outputs {alg_bytes / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)",
-                       "kernel": ex.last_kernel, "frames_per_s": frames_job / (total_ms * 1e-3)},
+                       "kernel": kname, "frames_per_s": frames_job / (total_ms * 1e-3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": binding, "roofline_hbm": hbm, ("roofline_int" if fmt == 2 else "roofline_fp32"): pipe, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -93,7 +93,10 @@ enum { AVDSP_B200_KERNEL_AUTO = 0, AVDSP_B200_KERNEL_GENERIC = 1, AVDSP_B200_KER
        AVDSP_B200_KERNEL_MIX = 4      /* time-parallel kernel for programs without biquads (mixers, delays, dither) */,
        AVDSP_B200_KERNEL_FIR = 5      /* time-parallel tiled DSP_FIR kernels (runtime/dsp_firSTD.h, dsp_runtime.c:928-969) */,
        AVDSP_B200_KERNEL_FIR_TC = 6   /* DSP_FIR as a Toeplitz GEMM on tcgen05 tensor cores: DSP_FORMAT 2 bit-exact (8-bit limbs, the
-                                         AUTO choice for batches), DSP_FORMAT 3 as 3xTF32 under a stated tolerance (only on request) */ };
+                                         AUTO choice for batches), DSP_FORMAT 3 as 3xTF32 under a stated tolerance (only on request) */,
+       AVDSP_B200_KERNEL_CHAIN_V2 = 7 /* force the section-lane chain kernel (kernel_chain2.cu) */,
+       AVDSP_B200_KERNEL_CHAIN_V3 = 8 /* force the cascade-per-lane chain kernel (kernel_chain3.cu); KERNEL_CHAIN / AUTO pick between
+                                         v2 and v3 themselves (v3: common crossover / EQ shapes at batch width) */ };
 
 /* Load + validate + lower a program (dspRuntimeInit + dspRuntimeReset for nStreams independent
  * instances).  prog: progWords little-endian 32-bit words exactly as written by dspcreate (.bin).
@@ -134,6 +137,8 @@ int  avdsp_b200_set_order(avdsp_b200_t *, int period);
 int  avdsp_b200_set_kernel(avdsp_b200_t *, int which);
 /* which kernel the last process call used (AVDSP_B200_KERNEL_*) and how many kernels were launched so far */
 int  avdsp_b200_last_kernel(const avdsp_b200_t *);
+/* 2 or 3 when the last call ran a chain kernel (which of kernel_chain2.cu / kernel_chain3.cu), else 0 */
+int  avdsp_b200_last_chain_variant(const avdsp_b200_t *);
 long long avdsp_b200_launch_count(const avdsp_b200_t *);
 
 /* The host edited PARAM words (gains, delay times, biquad coefficients, bypass flags) of the loaded

@@ -1,0 +1,169 @@
+"""k_chain3 (kernel_chain3.cu: one whole biquad cascade per lane, lane = stream) against the CPU oracle through the
+C ABI.  Fixed point only, bar = BIT-EXACT: outputs and every state word (biquad accumulators and histories, delay
+rings + indices, PRNG / TPDF words).  The kernel is forced with KERNEL_CHAIN_V3 and given several streams per CTA
+through AVDSP_B200_NS3 (AUTO picks it by itself only at batch width, which test_gpu_parity's 4096-stream tests cover).
+"""
+import numpy as np
+import pytest
+
+from conftest import load_program
+from avdsp_b200 import Executor, AvdspError, synth, KERNEL_GENERIC, KERNEL_CHAIN_V2, KERNEL_CHAIN_V3, KERNEL_AUTO
+
+from test_gpu_parity import expected_state, oracle_run, _delay_param_program
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["4", "8", "2"], ids=["parts4", "whole", "parts2"])
+def _several_streams_per_cta(monkeypatch, request):
+    """Both shapes of the kernel: cascades cut into parts of <= 4 (or 2) sections that run as separate warps a tile behind each
+    other, and whole cascades per lane.  (Where the parts do not fit 16 warps the geometry falls back to whole cascades.)"""
+    monkeypatch.setenv("AVDSP_B200_NS3", "5")          # read when an Executor plans its geometry
+    monkeypatch.setenv("AVDSP_B200_PART3", request.param)
+
+
+def _v3(w, fs, S, **kw):
+    ex = Executor(w, fs, 2, S, **kw)
+    ex.set_kernel(KERNEL_CHAIN_V3)
+    return ex
+
+
+@pytest.mark.parametrize("prog,fs", [("c2_testrpi_xover_f2_192k", 192000)])
+@pytest.mark.parametrize("stim", ["full", "noise", "impulse", "sine"])
+def test_c2_ragged_batch_bit_exact(oracle_lib, prog, fs, stim):
+    """C2 program (8 cascades of 4/4/6/8/6/6/8/6 sections, TPDF dither on two of them, six delays), ragged sizes: 37 streams
+    at 5 per CTA (last CTA: 2), 333 frames (partial last tile).  Full-scale noise saturates sections (replayed tiles)."""
+    w = load_program(prog)
+    S, T = 37, 333
+    seeds = np.arange(S, dtype=np.int32) * 7 + 1
+    ex = _v3(w, fs, S, seeds=seeds, dither=24)
+    x = synth.pcm(stim, S, T, ex.n_in, fs)
+    ys, sts = oracle_run(oracle_lib, w, 2, fs, x, seeds, 24)
+    y = ex.process(x)
+    assert ex.last_kernel == "chain" and ex.last_chain_variant == 3, ex.trace
+    assert np.count_nonzero(y != ys) == 0, f"{np.count_nonzero(y != ys)}/{y.size} samples differ"
+    for s in (0, 1, 4, 5, 35, S - 1):
+        got, exp = ex.get_state(s), expected_state(ex, sts[s])
+        diff = np.nonzero(got != exp)[0]
+        assert diff.size == 0, f"stream {s}: state words {diff[:8]} differ"
+
+
+def test_any_split_into_periods_and_kernel_switches(oracle_lib):
+    """ALSA periods of any size (1 frame, odd sizes, around tile boundaries) and alternating with the generic and the v2
+    chain kernels mid-stream: identical output and state (one state layout for all kernels)."""
+    w = load_program("c2_testrpi_xover_f2_192k")
+    S, T = 11, 1500
+    x = synth.pcm("full", S, T, 2, 192000)
+    seeds = np.arange(S, dtype=np.int32)
+    a = Executor(w, 192000, 2, S, seeds=seeds); a.set_kernel(KERNEL_GENERIC)
+    ya = a.process(x)
+    b = _v3(w, 192000, S, seeds=seeds)
+    cuts = [0, 1, 2, 33, 65, 66, 130, 577, 1024, 1056, T]
+    yb = np.concatenate([b.process(np.ascontiguousarray(x[:, c0:c1])) for c0, c1 in zip(cuts, cuts[1:])], axis=1)
+    assert b.last_chain_variant == 3
+    assert np.array_equal(ya, yb)
+    c = Executor(w, 192000, 2, S, seeds=seeds)
+    parts = []
+    for i, (c0, c1) in enumerate(zip(cuts, cuts[1:])):
+        c.set_kernel((KERNEL_CHAIN_V3, KERNEL_GENERIC, KERNEL_CHAIN_V2)[i % 3])
+        parts.append(c.process(np.ascontiguousarray(x[:, c0:c1])))
+    assert np.array_equal(ya, np.concatenate(parts, axis=1))
+    for s in (0, 4, 5, S - 1):
+        assert np.array_equal(a.get_state(s), b.get_state(s)), s
+        assert np.array_equal(a.get_state(s), c.get_state(s)), s
+
+
+def _odd_program():
+    """Cascades of 1, 3, 5 and 7 sections; sources LOAD (no gain: the cascade sees X >> 28), LOAD_GAIN 1.0, 0.35 and -1.7;
+    SAT0DB and SAT0DB_TPDF finishes; fixed delays of 0, 7 and 40 samples; paths with two and four STOREs; output 0 is stored by
+    the first path and again by the last one (the later STORE wins, the first path still runs for its state)."""
+    from oracle import wire
+    fs = 48000
+    a = wire.Asm(fmt=2, fmin=fs, fmax=fs)
+    a.core(); a.tpdf_calc(20)
+    a.param()
+    secs = [wire.rbj_peak(fs, f, q, g) for f, q, g in ((120.0, 0.7, 2.0), (900.0, 1.2, 0.5), (2500.0, 3.0, 1.8), (5200.0, 0.9, 0.6),
+                                                         (9000.0, 2.0, 1.5), (300.0, 0.5, 1.2), (14000.0, 1.0, 0.8))]
+    hdr = {n: a.biquad_sections([[c] for c in secs[:n]]) for n in (1, 3, 5, 7)}
+    a.load(8); a.biquads(hdr[1]); a.sat0db(); a.store(0)
+    a.load_gain(9, 1.0); a.biquads(hdr[3]); a.sat0db_tpdf(); a.delay_fixed_us(150, fs); a.store(1)
+    a.core()
+    a.load_gain(8, 0.35); a.biquads(hdr[5]); a.sat0db(); a.delay_fixed_us(840, fs); a.store(2)
+    a.load_gain(9, -1.7); a.biquads(hdr[7]); a.sat0db_tpdf(); a.store(3); a.store(7)
+    a.load_gain(8, 1.0); a.biquads(hdr[3]); a.sat0db(); a.store(0); a.store(4); a.store(5); a.store(6)
+    return a.end(), fs
+
+
+@pytest.mark.parametrize("stim", ["full", "noise"])
+def test_odd_cascade_lengths_sources_and_finishes(oracle_lib, stim):
+    w, fs = _odd_program()
+    S, T = 13, 777
+    seeds = np.arange(S, dtype=np.int32) + 3
+    ex = _v3(w, fs, S, seeds=seeds, dither=24)
+    x = synth.pcm(stim, S, T, ex.n_in, fs)
+    ys, sts = oracle_run(oracle_lib, w, 2, fs, x, seeds, 24)
+    y = ex.process(x)
+    assert ex.last_chain_variant == 3, ex.trace
+    assert np.array_equal(y, ys), f"{np.count_nonzero(y != ys)}/{y.size} samples differ"
+    for s in (0, 4, 5, S - 1):
+        assert np.array_equal(ex.get_state(s), expected_state(ex, sts[s])), s
+
+
+def test_delay_times_patched_mid_stream(oracle_lib):
+    """Delay PARAMs shortened / lengthened / zeroed between calls: stale ring indices (used once, then wrapped,
+    dsp_runtime.c:769-794) -- frame 0 of such a call takes the exact path and swaps with ring[idx0] in the state block."""
+    w, dps = _delay_param_program(True)
+    fs, S, T = 48000, 7, 333
+    x = synth.pcm("full", S, 3 * T, 2, fs)
+    ex = _v3(w, fs, S, seeds=np.arange(S, dtype=np.int32))
+    orcs = [oracle_lib.Oracle(w, 2, fs, seed=s) for s in range(S)]
+    words = w.copy()
+    for part, (us0, us1) in enumerate(((1500, 400), (200, 2900), (2500, 0))):
+        for dp, us in zip(dps, (us0, us1)):
+            words[dp] = (int(words[dp]) & ~0xFFFF) | us
+        ex.reload_params(words)
+        xs = np.ascontiguousarray(x[:, part * T:(part + 1) * T])
+        y = ex.process(xs)
+        assert ex.last_chain_variant == 3, ex.trace
+        for s in range(S):
+            for dp, us in zip(dps, (us0, us1)):
+                orcs[s].code[dp] = words[dp]
+            assert np.array_equal(y[s], orcs[s].process(xs[s])), (part, s, ex.last_kernel, ex.last_chain_variant)
+    for s in (0, S - 1):
+        assert np.array_equal(ex.get_state(s)[: ex.data_size], orcs[s].data), s
+
+
+def test_foreign_state_block_with_incoherent_histories():
+    """The fast path keeps only the y histories inside a cascade (x history of section k+1 == y history of section k for every
+    state the reference can reach).  A state block that violates this (set_state with arbitrary words) must still be honoured:
+    same result as the generic interpreter started from the same block."""
+    w = load_program("c2_testrpi_xover_f2_192k")
+    S, T = 6, 200
+    rng = np.random.default_rng(5)
+    x = synth.pcm("noise", S, T, 2, 192000)
+    a = Executor(w, 192000, 2, S); a.set_kernel(KERNEL_GENERIC)
+    b = _v3(w, 192000, S)
+    blk = a.get_state(0)
+    for s in range(S):
+        st = blk.copy()
+        st[2:50] = rng.integers(-2 ** 20, 2 ** 20, 48)          # biquad words of the two core-1 cascades: incoherent on purpose
+        a.set_state(s, st); b.set_state(s, st)
+    ya, yb = a.process(x), b.process(x)
+    assert b.last_chain_variant == 3
+    assert np.array_equal(ya, yb)
+    for s in range(S):
+        assert np.array_equal(a.get_state(s), b.get_state(s)), s
+
+
+def test_v3_refuses_what_it_cannot_run():
+    """Program shapes outside v3 (float format, 16-section cascades, mixers) are refused when v3 is forced and run on the other
+    kernels under AUTO."""
+    for prog, fmt, fs in (("c3_peq16_f2_48k", 2, 48000), ("c3_peq16_f3_48k", 3, 48000)):
+        ex = Executor(load_program(prog), fs, fmt, 8)
+        x = synth.pcm("noise", 8, 64, ex.n_in, fs)
+        ex.set_kernel(KERNEL_CHAIN_V3)
+        with pytest.raises(AvdspError):
+            ex.process(x)
+        ex.set_kernel(KERNEL_AUTO)
+        ex.process(x)
+        assert ex.last_kernel == "chain" and ex.last_chain_variant == 2
