@@ -619,42 +619,62 @@ bool planChain3Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain3G
         g.postRing = R; g.postPitch = R + 1;
         g.rawPitchBytes = F3 * plan.h.nIn * 4 + 16;         // 16-byte aligned rows, 4-bank skew between streams
         g.rawStageBytes = NS * g.rawPitchBytes;
-        // warps -> sub-partitions (warp id % 4).  Cascade parts are packed first-fit-decreasing into four bins of equal section
-        // count (C2: 4+4+4 | 4+4+4 | 3+3+3+3 | 3+3+3+3); the dither and store warps take the slots that are left, the dither
-        // warp (the busier one) on the lightest bin.  Cascade warp index w (rows, tables) is independent of the hardware warp id.
+        // warps -> sub-partitions (hardware warp id % 4, tools/microbench_smsp.cu).  Every warp gets an issue cost per frame
+        // (5 MACs + shift + saturation record per section; more for a SAT0DB_TPDF finish or a LOAD_GAIN; the dither and store
+        // warps count too); longest-processing-time first, then pairwise swaps while they flatten the four sums.  C2 ends up
+        // as (4T,4,3,helper) x 2 + (4,3,3,3) x 2: 8.66 ms per step against 9.08 with equal section counts per sub-partition
+        // (both TPDF parts on one of them) -- the heaviest single warp sets the pace of its sub-partition.
+        // Cascade warp index w (rows, tables) is independent of the hardware warp id.
         {
             const int total = nParts + 1 + g.nStore;
-            int slots[4], order[kChain3MaxWarps], binOf[kChain3MaxWarps];
+            int slots[4];
             for (int q = 0; q < 4; q++) slots[q] = (total - q + 3) / 4;   // warp ids q, q+4, ... below total
-            for (int k = 0; k < nParts; k++) order[k] = k;
-            std::stable_sort(order, order + nParts, [&](int a, int b) { return parts[a].nsec > parts[b].nsec; });
-            int sum = 0;
-            for (int k = 0; k < nParts; k++) sum += parts[k].nsec;
-            int load[4], used[4];
-            for (int capLoad = (sum + 3) / 4; ; capLoad++) {
-                bool ok = true;
-                for (int q = 0; q < 4; q++) load[q] = used[q] = 0;
-                for (int k = 0; k < nParts && ok; k++) {
-                    int q = 0;
-                    // keep 1 + nStore slots for the helper warps overall
-                    for (; q < 4; q++) if (used[q] < slots[q] && load[q] + parts[order[k]].nsec <= capLoad) break;
-                    if (q == 4) { ok = false; break; }
-                    binOf[order[k]] = q; used[q]++; load[q] += parts[order[k]].nsec;
-                }
-                if (ok) break;
-                if (capLoad > sum) break;                    // cannot happen: every part fits somewhere
+            int itemCost[32], itemBin[32], order[32];
+            for (int k = 0; k < total; k++) {
+                order[k] = k;
+                if (k >= nParts) { itemCost[k] = 8; continue; }              // helper warps: k == nParts dither, then store
+                const ChainDesc& d = plan.chains[parts[k].chain];
+                itemCost[k] = 5 * parts[k].nsec + 2;
+                if (parts[k].fin && (d.satKind & 1)) itemCost[k] += 6;
+                if (parts[k].src < 0 && !(d.srcKind == SRC_LOAD_GAIN && d.srcArg == (1 << kMant))) itemCost[k] += 2;
+            }
+            std::stable_sort(order, order + total, [&](int a, int b) { return itemCost[a] > itemCost[b]; });
+            int binCost[4] = {0, 0, 0, 0}, used[4] = {0, 0, 0, 0};
+            for (int k = 0; k < total; k++) {
+                int best = -1;
+                for (int q = 0; q < 4; q++) if (used[q] < slots[q] && (best < 0 || binCost[q] < binCost[best])) best = q;
+                itemBin[order[k]] = best; used[best]++; binCost[best] += itemCost[order[k]];
+            }
+            for (int iter = 0; iter < 64; iter++) {
+                int ba = -1, bb = -1; long long bestGain = 0;
+                for (int a = 0; a < total; a++)
+                    for (int b = a + 1; b < total; b++) {
+                        const int qa = itemBin[a], qb = itemBin[b];
+                        if (qa == qb || itemCost[a] == itemCost[b]) continue;
+                        const int dlt = itemCost[a] - itemCost[b];             // a's bin loses dlt, b's bin gains it
+                        const long long before = (long long)binCost[qa] * binCost[qa] + (long long)binCost[qb] * binCost[qb];
+                        const long long after = (long long)(binCost[qa] - dlt) * (binCost[qa] - dlt) + (long long)(binCost[qb] + dlt) * (binCost[qb] + dlt);
+                        if (before - after > bestGain) { bestGain = before - after; ba = a; bb = b; }
+                    }
+                if (ba < 0) break;
+                const int qa = itemBin[ba], qb = itemBin[bb], dlt = itemCost[ba] - itemCost[bb];
+                binCost[qa] -= dlt; binCost[qb] += dlt;
+                itemBin[ba] = qb; itemBin[bb] = qa;
+            }
+            if (const char* ov = getenv("AVDSP_B200_BINS3")) {          // experiments: "b0,b1,..." = sub-partition of item k (parts, dither, stores)
+                int k = 0;
+                for (const char* q = ov; *q && k < total; q++) if (*q >= '0' && *q <= '3') itemBin[k++] = *q - '0';
+                int cnt[4] = {0, 0, 0, 0};
+                for (int kk = 0; kk < total; kk++) cnt[itemBin[kk]]++;
+                for (int q = 0; q < 4; q++) if (cnt[q] != slots[q]) return false;
             }
             int next[4] = {0, 0, 0, 0};
             for (int k = 0; k < 32; k++) g.warpRole[k] = -1;
             int slotOf[kChain3MaxWarps];
             // cascade index = part index k (rows follow the part order); hardware warp id = bin + 4 * position in the bin
-            for (int k = 0; k < nParts; k++) { slotOf[k] = k; g.warpRole[binOf[k] + 4 * next[binOf[k]]++] = k; }
-            for (int hk = 0; hk < 1 + g.nStore; hk++) {       // helpers: lightest bin with a free slot
-                int best = -1;
-                for (int q = 0; q < 4; q++) if (next[q] < slots[q] && (best < 0 || load[q] < load[best])) best = q;
-                if (best < 0) return false;
-                g.warpRole[best + 4 * next[best]++] = -1 - hk;
-                load[best] += 2;                             // spread the helpers
+            for (int k = 0; k < total; k++) {
+                const int id = itemBin[k] + 4 * next[itemBin[k]]++;
+                if (k < nParts) { slotOf[k] = k; g.warpRole[id] = k; } else g.warpRole[id] = -1 - (k - nParts);
             }
             for (int k = 0; k < nParts; k++) {
                 const int w = slotOf[k];
