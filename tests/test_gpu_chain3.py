@@ -167,3 +167,32 @@ def test_v3_refuses_what_it_cannot_run():
         ex.set_kernel(KERNEL_AUTO)
         ex.process(x)
         assert ex.last_kernel == "chain" and ex.last_chain_variant == 2
+
+
+@pytest.mark.parametrize("T", [257, 96, 1000])
+def test_planar_layout_device_buffers_and_bulk_copies(oracle_lib, T):
+    """Every way the PCM can reach the kernel: planar [stream][channel][frame] host buffers (input tiles staged with plain
+    copies, lane = frame stores), interleaved device buffers whose rows are 16-byte friendly (bulk copies of full tiles, plain
+    copy of a partial last tile) and rows that are not (T odd: plain copies only)."""
+    import torch
+    from avdsp_b200 import PLANAR
+    w = load_program("c2_testrpi_xover_f2_192k")
+    S = 33
+    seeds = np.arange(S, dtype=np.int32) + 11
+    x = synth.pcm("full", S, T, 2, 192000)
+    ys, sts = oracle_run(oracle_lib, w, 2, 192000, x, seeds, 31)
+    ex = _v3(w, 192000, S, seeds=seeds)
+    yp = ex.process(np.ascontiguousarray(x.transpose(0, 2, 1)), layout=PLANAR)
+    assert ex.last_chain_variant == 3
+    assert np.array_equal(yp.transpose(0, 2, 1), ys)
+    assert np.array_equal(ex.get_state(S - 1), expected_state(ex, sts[S - 1]))
+    ex2 = _v3(w, 192000, S, seeds=seeds)
+    yd = ex2.process(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    assert ex2.last_chain_variant == 3
+    assert np.array_equal(yd.cpu().numpy(), ys)
+    ex3 = _v3(w, 192000, S, seeds=seeds)
+    yq = ex3.process(torch.from_numpy(np.ascontiguousarray(x.transpose(0, 2, 1))).cuda(), layout=PLANAR)
+    torch.cuda.synchronize()
+    assert np.array_equal(yq.cpu().numpy().transpose(0, 2, 1), ys)
+    assert np.array_equal(ex3.get_state(0), expected_state(ex3, sts[0]))
