@@ -474,12 +474,14 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
         // v3 (a cascade part per lane, lane = stream) wants full warps and several equal warps per sub-partition: AUTO takes it at
         // batch width (>= 16 streams per SM) when the cascades could be cut into parts of <= 4 sections (measured on C2: 9.06 ms
-        // against v2's 9.50; with whole 6- and 8-section cascades per warp v3 is the slower one); everything else runs on v2
+        // against v2's 9.50; with whole 6- and 8-section cascades per warp v3 is the slower one) and the call is long enough to
+        // pay for v3's pipeline fill and drain (parts run a tile behind each other: C2 breaks even near 1500 frames per call --
+        // 128 frames: v2 0.083 ms / v3 0.117, 1024: 0.262 / 0.267, 4096: 0.864 / 0.816); everything else runs on v2
         const bool v3Ok = h->chain3Usable && use == AVDSP_B200_KERNEL_CHAIN;
         static const int envChain3 = [] { const char* v = getenv("AVDSP_B200_CHAIN3"); return (v && *v) ? atoi(v) : -1; }();
         bool v3 = v3Ok && h->kernelSel != AVDSP_B200_KERNEL_CHAIN_V2 &&
                   (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V3 || envChain3 == 1 ||
-                   (envChain3 != 0 && h->geom3.maxSec <= 4 && h->geom3.streamsPerCta >= 16 && nFrames >= 64));
+                   (envChain3 != 0 && h->geom3.maxSec <= 4 && h->geom3.streamsPerCta >= 16 && nFrames >= std::max(1536, 48 * h->geom3.gmax)));
         if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V3 && !v3)
             return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel v3 requested but the program shape does not map to it");
         if (v3) e = launchChain3(h->L.chain, h->geom3, A, stream);
