@@ -164,6 +164,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args, wl)
 
+    # rank 0 prints ONE JSON line on stdout: whatever native libraries write to file descriptor 1 (NCCL's "NCCL version ..."
+    # banner) goes to stderr instead
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import avdsp_b200
@@ -331,7 +337,7 @@ def main():
                        "kernel": kname, "frames_per_s": frames_job / (total_ms * 1e-3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": binding, "roofline_hbm": hbm, ("roofline_int" if fmt == 2 else "roofline_fp32"): pipe, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
