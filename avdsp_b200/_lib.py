@@ -18,7 +18,7 @@ SYMBOLS = [
     "dspQNM", "dspQM64", "dspQM32", "dspOpcodeText",
     "avdsp_b200_create", "avdsp_b200_destroy", "avdsp_b200_reset", "avdsp_b200_io_map",
     "avdsp_b200_process", "avdsp_b200_process_async", "avdsp_b200_process_range", "avdsp_b200_process_pcm",
-    "avdsp_b200_set_order", "avdsp_b200_set_kernel", "avdsp_b200_last_kernel", "avdsp_b200_last_chain_variant", "avdsp_b200_launch_count",
+    "avdsp_b200_set_order", "avdsp_b200_set_kernel", "avdsp_b200_last_kernel", "avdsp_b200_last_chain_variant", "avdsp_b200_describe", "avdsp_b200_launch_count",
     "avdsp_b200_reload_params", "avdsp_b200_state_words", "avdsp_b200_data_size", "avdsp_b200_aux_offset",
     "avdsp_b200_mem_offset", "avdsp_b200_num_mem", "avdsp_b200_mem_word", "avdsp_b200_get_state",
     "avdsp_b200_set_state", "avdsp_b200_num_streams", "avdsp_b200_num_cores", "avdsp_b200_trace",
@@ -63,6 +63,7 @@ def lib():
     L.avdsp_b200_set_kernel.argtypes = [vp, ci]
     L.avdsp_b200_last_kernel.argtypes = [vp]
     L.avdsp_b200_last_chain_variant.argtypes = [vp]
+    L.avdsp_b200_describe.argtypes = [vp, ci, ci, ci, ci, ci, ci, C.c_char_p, ci]
     L.avdsp_b200_launch_count.argtypes = [vp]
     L.avdsp_b200_launch_count.restype = C.c_longlong
     L.avdsp_b200_reload_params.argtypes = [vp, vp, ci]

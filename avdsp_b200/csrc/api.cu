@@ -163,47 +163,20 @@ struct avdsp_b200 {
     std::string trace;
 };
 
-static int uploadPlanData(avdsp_b200* h) {
-    cudaSetDevice(h->device);
+// Host-only half of plan preparation: which kernels can take the program, their CTA geometries, the lowering trace.
+static void planGeometries(avdsp_b200* h, std::vector<ChainLane>* lanes1, std::vector<ChainLane>* lanes2) {
     const Lowered& L = h->L;
-    // big pool (FIR taps, data tables)
-    if (h->dBig) { cudaFree(h->dBig); h->dBig = nullptr; }
-    h->bigWords = L.bigPool.size();
-    if (h->bigWords) {
-        CU(cudaMalloc(&h->dBig, h->bigWords * 4));
-        CU(cudaMemcpy(h->dBig, L.bigPool.data(), h->bigWords * 4, cudaMemcpyHostToDevice));
-    }
-    // chain geometry
     h->chainUsable = false;
-    if (L.chainOk && chainKernelSupports(L.chain)) {
-        std::vector<ChainLane> lanes(1024);
-        if (planChainGeometry(L.chain, h->nStreams, h->numSMs, &h->geom, lanes.data())) {
-            if (!h->dLanes) CU(cudaMalloc(&h->dLanes, 1024 * sizeof(ChainLane)));
-            CU(cudaMemcpy(h->dLanes, lanes.data(), 1024 * sizeof(ChainLane), cudaMemcpyHostToDevice));
-            h->chainUsable = true;
-        }
-    }
+    lanes1->assign(1024, ChainLane{});
+    if (L.chainOk && chainKernelSupports(L.chain)) h->chainUsable = planChainGeometry(L.chain, h->nStreams, h->numSMs, &h->geom, lanes1->data());
     h->chain2Usable = false;
-    if (L.chainOk && chain2Supports(L.chain)) {
-        std::vector<ChainLane> lanes(1024);
-        if (planChain2Geometry(L.chain, h->nStreams, h->numSMs, &h->geom2, lanes.data())) {
-            if (!h->dLanes2) CU(cudaMalloc(&h->dLanes2, 1024 * sizeof(ChainLane)));
-            CU(cudaMemcpy(h->dLanes2, lanes.data(), 1024 * sizeof(ChainLane), cudaMemcpyHostToDevice));
-            h->chain2Usable = true;
-        }
-    }
+    lanes2->assign(1024, ChainLane{});
+    if (L.chainOk && chain2Supports(L.chain)) h->chain2Usable = planChain2Geometry(L.chain, h->nStreams, h->numSMs, &h->geom2, lanes2->data());
     h->chain3Usable = h->chain2Usable && planChain3Geometry(L.chain, h->nStreams, h->numSMs, &h->geom3);
     h->mixUsable = false;
     if (L.chainOk) { std::string why; h->mixUsable = buildMixPlan(L.chain, &h->mix, &why); }
     h->firUsable = L.firOk;
-    if (h->dFirTaps) { cudaFree(h->dFirTaps); h->dFirTaps = nullptr; }
-    if (h->firUsable) {
-        std::vector<unsigned char> blobs;
-        firTcBuildTaps(L.fir, L.fir.aluClass == ALU_INT64 ? FIRTC_I8 : FIRTC_TF32, L.bigPool.data(), &blobs);
-        CU(cudaMalloc(&h->dFirTaps, blobs.size()));
-        CU(cudaMemcpy(h->dFirTaps, blobs.data(), blobs.size(), cudaMemcpyHostToDevice));
-    }
-    char line[320];
+    char line[512];
     h->trace = L.trace;
     if (h->firUsable) {
         snprintf(line, sizeof line, "time-parallel FIR kernel: usable (%d paths, longest impulse %d taps)\n", L.fir.nPaths, L.fir.maxLen);
@@ -223,8 +196,17 @@ static int uploadPlanData(avdsp_b200* h) {
             snprintf(line, sizeof line, " %d:%d+%d@%d", h->geom3.warpChain[w], h->geom3.warpFirstSec[w], h->geom3.warpNsec[w], h->geom3.warpBase[w]);
             h->trace += line;
         }
-        snprintf(line, sizeof line, "\n");
-        h->trace += line;
+        h->trace += "; sub-partitions (sections of the cascade warps on hardware warps q, q+4, ..; d = dither warp, s = store warp):";
+        for (int q = 0; q < 4; q++) {
+            h->trace += q ? " |" : " ";
+            for (int id = q; id < h->geom3.threads / 32; id += 4) {
+                const int role = h->geom3.warpRole[id];
+                if (role >= 0) snprintf(line, sizeof line, " %d", h->geom3.warpNsec[role]);
+                else snprintf(line, sizeof line, " %s", role == -1 ? "d" : "s");
+                h->trace += line;
+            }
+        }
+        h->trace += "\n";
     }
     if (h->chainUsable)
         snprintf(line, sizeof line, "chain kernel geometry: %d streams/CTA, %d sections/lane, %d lane threads, %d work threads, tile %d frames, depth %d, %zu B smem\n",
@@ -232,6 +214,35 @@ static int uploadPlanData(avdsp_b200* h) {
     else
         snprintf(line, sizeof line, "chain kernel not used: %s\n", L.chainOk ? "geometry does not fit" : L.chainWhyNot.c_str());
     h->trace += line;
+}
+
+static int uploadPlanData(avdsp_b200* h) {
+    cudaSetDevice(h->device);
+    const Lowered& L = h->L;
+    // big pool (FIR taps, data tables)
+    if (h->dBig) { cudaFree(h->dBig); h->dBig = nullptr; }
+    h->bigWords = L.bigPool.size();
+    if (h->bigWords) {
+        CU(cudaMalloc(&h->dBig, h->bigWords * 4));
+        CU(cudaMemcpy(h->dBig, L.bigPool.data(), h->bigWords * 4, cudaMemcpyHostToDevice));
+    }
+    std::vector<ChainLane> lanes1, lanes2;
+    planGeometries(h, &lanes1, &lanes2);
+    if (h->chainUsable) {
+        if (!h->dLanes) CU(cudaMalloc(&h->dLanes, 1024 * sizeof(ChainLane)));
+        CU(cudaMemcpy(h->dLanes, lanes1.data(), 1024 * sizeof(ChainLane), cudaMemcpyHostToDevice));
+    }
+    if (h->chain2Usable) {
+        if (!h->dLanes2) CU(cudaMalloc(&h->dLanes2, 1024 * sizeof(ChainLane)));
+        CU(cudaMemcpy(h->dLanes2, lanes2.data(), 1024 * sizeof(ChainLane), cudaMemcpyHostToDevice));
+    }
+    if (h->dFirTaps) { cudaFree(h->dFirTaps); h->dFirTaps = nullptr; }
+    if (h->firUsable) {
+        std::vector<unsigned char> blobs;
+        firTcBuildTaps(L.fir, L.fir.aluClass == ALU_INT64 ? FIRTC_I8 : FIRTC_TF32, L.bigPool.data(), &blobs);
+        CU(cudaMalloc(&h->dFirTaps, blobs.size()));
+        CU(cudaMemcpy(h->dFirTaps, blobs.data(), blobs.size(), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -325,6 +336,20 @@ int avdsp_b200_create(avdsp_b200_t** out, const int32_t* prog, int progWords, in
 }
 
 void avdsp_b200_destroy(avdsp_b200_t* h) { freeAll(h); }
+
+int avdsp_b200_describe(const int32_t* prog, int progWords, int fs, int format, int defaultDither, int nStreams, int numSMs,
+                        char* out, int outLen) {
+    if (!out || outLen < 1 || nStreams < 1 || numSMs < 1) return setErr(AVDSP_B200_ERR_ARG, "bad argument");
+    avdsp_b200 h;                                            // host-only: decode + lower + plan, nothing touches CUDA
+    std::string err;
+    const int rc = decodeProgram(prog, progWords, 0x7FFFFFFF, format, fs, defaultDither, &h.L, &err);
+    if (rc < 0) return setErr(rc, err);
+    h.nStreams = nStreams; h.numSMs = numSMs;
+    std::vector<ChainLane> lanes1, lanes2;
+    planGeometries(&h, &lanes1, &lanes2);
+    snprintf(out, (size_t)outLen, "%s", h.trace.c_str());
+    return rc;
+}
 
 int avdsp_b200_reset(avdsp_b200_t* h, int fs, const int32_t* seeds, int defaultDither) {
     if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");

@@ -163,6 +163,14 @@ class Executor:
         return y_host
 
 
+def describe(words, fs: int, fmt: int = 2, n_streams: int = 1, dither: int = 31, num_sms: int = 148) -> str:
+    """Lowering trace + kernel geometries for `n_streams` streams on a GPU with `num_sms` SMs.  Host-only (no CUDA device needed)."""
+    w = np.ascontiguousarray(words, dtype=np.int32)
+    buf = C.create_string_buffer(1 << 16)
+    _check(_lib.lib().avdsp_b200_describe(w.ctypes.data, len(w), fs, fmt, dither, n_streams, num_sms, buf, len(buf)))
+    return buf.value.decode()
+
+
 def measure_int_peak(device: int = 0, iters: int = 4096) -> float:
     """mad.wide.s32 per second the whole device sustains (denominator of the INT-pipe roofline)."""
     return float(_lib.lib().avdsp_b200_measure_int_peak(device, iters))

@@ -162,6 +162,11 @@ int  avdsp_b200_num_streams(const avdsp_b200_t *);
 int  avdsp_b200_num_cores(const avdsp_b200_t *);
 /* human-readable lowering trace (the counterpart of the reference's DSP_PRINTF>=2 opcode trace) */
 const char *avdsp_b200_trace(const avdsp_b200_t *);
+/* The same trace without an instance and without a CUDA device: validate + lower `prog` and plan the kernel geometries for
+ * nStreams streams on a GPU with numSMs SMs (148 on B200); writes at most outLen-1 characters.  Returns totalLength or the
+ * error codes of avdsp_b200_create.  Host-side inspection only: no kernel runs. */
+int  avdsp_b200_describe(const int32_t *prog, int progWords, int fs, int format, int defaultDither, int nStreams, int numSMs,
+                         char *out, int outLen);
 /* message of the last failure in this thread ("" when none) */
 const char *avdsp_b200_last_error(void);
 

@@ -1,0 +1,69 @@
+"""Host logic of the kernel planners, through the C ABI's host-only entry point avdsp_b200_describe (no CUDA device needed):
+which kernels can take a program and how k_chain3 cuts cascades into part warps and places them on the SM sub-partitions."""
+import re
+
+import pytest
+
+from conftest import load_program
+import avdsp_b200
+
+
+def _v3(trace):
+    for ln in trace.splitlines():
+        if ln.startswith("chain kernel v3 geometry"):
+            return ln
+    return None
+
+
+def test_c2_is_cut_into_fourteen_part_warps_with_flat_sub_partitions():
+    w = load_program("c2_testrpi_xover_f2_192k")
+    ln = _v3(avdsp_b200.describe(w, 192000, 2, n_streams=4096, num_sms=148))
+    assert ln is not None
+    assert "28 streams/CTA" in ln and "14 cascade warps of <= 4 sections" in ln
+    parts = [tuple(map(int, m)) for m in re.findall(r" (\d+):(\d+)\+(\d+)@(\d+)", ln.split("parts (chain:first+n@base):")[1].split(";")[0])]
+    per_chain = {}
+    for chain, first, n, base in parts:
+        per_chain.setdefault(chain, []).append((first, n, base))
+    assert {c: sum(n for _, n, _ in v) for c, v in per_chain.items()} == {0: 4, 1: 4, 2: 6, 3: 8, 4: 6, 5: 6, 6: 8, 7: 6}
+    for v in per_chain.values():
+        v.sort()
+        assert v[0][0] == 0 and v[0][2] == 0                       # a chain starts at its first section, on the frame being read
+        for (f0, n0, b0), (f1, n1, b1) in zip(v, v[1:]):
+            assert f1 == f0 + n0                                   # parts tile the cascade
+            assert b1 == b0 + n0 - 1 + 32                          # the next part runs one tile behind the previous part's tail
+    bins = ln.split("s = store warp):")[1].split("|")
+    assert len(bins) == 4
+    sums = sorted(sum(int(t) for t in b.split() if t.isdigit()) for b in bins)
+    assert sums == [11, 11, 13, 13]                                # (4T,4,3,helper) x 2 + (4,3,3,3) x 2: see DESIGN.md 4.2a
+    assert sorted(len(b.split()) for b in bins) == [4, 4, 4, 4]
+    assert sum("d" in b.split() for b in bins) == 1 and sum("s" in b.split() for b in bins) == 1
+    size = int(re.search(r"(\d+) B smem", ln).group(1))
+    assert size <= 227 * 1024
+
+
+@pytest.mark.parametrize("streams,per_cta", [(64, 1), (148 * 9, 9), (148 * 40, 32)])
+def test_streams_per_cta_follow_the_sm_count(streams, per_cta):
+    w = load_program("c2_testrpi_xover_f2_192k")
+    ln = _v3(avdsp_b200.describe(w, 192000, 2, n_streams=streams, num_sms=148))
+    assert ln is not None and f"{per_cta} streams/CTA" in ln
+
+
+def test_programs_outside_the_v3_shape_are_left_to_the_other_kernels():
+    for prog, fmt, fs in (("c3_peq16_f2_48k", 2, 48000), ("c3_peq16_f3_48k", 3, 48000)):   # 16-section cascades / float format
+        t = avdsp_b200.describe(load_program(prog), fs, fmt, n_streams=65536)
+        assert _v3(t) is None and "chain kernel v2 geometry" in t
+    t = avdsp_b200.describe(load_program("c5_mixer8x8_f2_192k"), 192000, 2, n_streams=4096)
+    assert "time-parallel mix kernel: usable" in t and _v3(t) is None
+    t = avdsp_b200.describe(load_program("c4_fir4096_f2_48k"), 48000, 2, n_streams=1024)
+    assert "time-parallel FIR kernel: usable" in t
+
+
+def test_describe_reports_the_reference_error_codes():
+    w = load_program("c2_testrpi_xover_f2_192k").copy()
+    w[3] ^= 1                                                       # checksum word
+    with pytest.raises(avdsp_b200.AvdspError) as e:
+        avdsp_b200.describe(w, 192000, 2)
+    assert e.value.code == -4
+    with pytest.raises(avdsp_b200.AvdspError) as e:
+        avdsp_b200.describe(load_program("c2_testrpi_xover_f2_192k"), 44100, 2)    # fs outside the header range
+    assert e.value.code == -2
