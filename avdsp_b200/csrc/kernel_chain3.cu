@@ -50,7 +50,7 @@ constexpr int TP3 = 4 * F3 + 1;         // tpdf ring pitch (words)
 constexpr int kBarFull3 = 1;            // +parity: inputs of tile i ready and the post ring has room (helpers arrive, cascades wait)
 constexpr int kBarDone3 = 3;            // +parity: cascade warps finished tile i (cascades arrive, helpers wait)
 #ifndef AVDSP_UNR3
-#define AVDSP_UNR3 4
+#define AVDSP_UNR3 6
 #endif
 constexpr unsigned kSatBias3  = (1u << (kMantBQ - 1)) - 2u;     // in range <=> (unsigned)(hi + bias) <= limit
 constexpr unsigned kSatLimit3 = (1u << kMantBQ) - 3u;           // (checkbiquadsat, runtime/dsp_biquadSTD.h:25-32)
@@ -263,20 +263,27 @@ __device__ __forceinline__ void cascadeWarp(const ChainPlan& P, const Chain2Args
             unsigned rj = ra;
             unsigned pj = postRow + (fin ? ((unsigned)(t0 & RM) << 2) : (unsigned)((i % 3) * F3) * 4u);
             unsigned tj = (unsigned)((t0 - LAGA) << 2);
+            // one step; jj is a compile-time offset inside the unrolled group
+            auto step = [&](int jj) {
+                const int smp = lds3(rj); rj += rstep;
+                const int x = (MODE & 1) ? smp : q59ToS31(mul32(smp, gain));
+                const long long acc = cascStep<NSEC>(L, x, w0, w1);
+                int v;
+                if (MODE & 2) v = finishTpdf3(acc, lds3(tpdfRow + ((tj + 4u * jj) & TM4)), tpdfUp, tpdfSh);
+                else v = q59ToS31(acc);        // SAT0DB of a clamped accumulator is its own >> 28 (replayed exactly if a clamp fired)
+                if (live) sts3(pj + 4u * jj, v);
+            };
+            // groups of AVDSP_UNR3 steps: 6 = lcm of the history depths (y1..y3, X1..X2), so the register rotation closes on itself
+            // and the loop needs no moves (they would be IMAD.MOVs on the very pipe the MACs saturate); the tile's last steps follow
+            constexpr int kMain = (F3 / AVDSP_UNR3) * AVDSP_UNR3;
 #pragma unroll 1
-            for (int j0 = 0; j0 < F3; j0 += AVDSP_UNR3) {
+            for (int j0 = 0; j0 < kMain; j0 += AVDSP_UNR3) {
 #pragma unroll
-                for (int jj = 0; jj < AVDSP_UNR3; jj++) {
-                    const int smp = lds3(rj); rj += rstep;
-                    const int x = (MODE & 1) ? smp : q59ToS31(mul32(smp, gain));
-                    const long long acc = cascStep<NSEC>(L, x, w0, w1);
-                    int v;
-                    if (MODE & 2) v = finishTpdf3(acc, lds3(tpdfRow + ((tj + 4u * jj) & TM4)), tpdfUp, tpdfSh);
-                    else v = q59ToS31(acc);        // SAT0DB of a clamped accumulator is its own >> 28 (replayed exactly if a clamp fired)
-                    if (live) sts3(pj + 4u * jj, v);
-                }
+                for (int jj = 0; jj < AVDSP_UNR3; jj++) step(jj);
                 pj += 4u * AVDSP_UNR3; tj += 4u * AVDSP_UNR3;
             }
+#pragma unroll
+            for (int jj = 0; jj < F3 - kMain; jj++) step(jj);
             if (__any_sync(0xffffffffu, max(w0, w1) > kSatLimit3)) {
                 if (CKREG) {
 #pragma unroll
