@@ -175,7 +175,9 @@ __device__ __forceinline__ void cascadeWarp(const ChainPlan& P, const Chain2Args
     const int srcWarp = G.warpSrc[w];                       // -1: the staged PCM tile; else the warp whose row feeds this part
     const bool fin = G.warpFinal[w] != 0;                   // last part of its chain: SAT0DB[_TPDF], delay line, post ring
     const bool live = lane < nsHere;
-    const int sl = min(lane, NS - 1);                       // idle lanes shadow the last stream's shared-memory rows (reads only)
+    // idle lanes (beyond the CTA's streams) shadow the last live stream: they read its rows and load its state, so they compute a
+    // copy of it (never garbage that could fire the saturation record and force exact replays of every tile) and store nothing
+    const int sl = min(lane, nsHere - 1);
     const int RM = G.postRing - 1;
     const unsigned RM4 = (unsigned)RM << 2, TM4 = (unsigned)(4 * F3 - 1) << 2;
     const unsigned sb = smemAddr3(smem);
@@ -191,7 +193,7 @@ __device__ __forceinline__ void cascadeWarp(const ChainPlan& P, const Chain2Args
     const bool tpdfUp = P.h.tpdfShift >= 0;
     const int tpdfSh = (tpdfUp ? P.h.tpdfShift : -P.h.tpdfShift) & 63;
     const bool wantTpdf = fin && (d.satKind & 1) != 0;
-    int* st = A.state + (size_t)(s0 + (live ? lane : 0)) * W;
+    int* st = A.state + (size_t)(s0 + sl) * W;
 
     Casc<NSEC> L;
     L.X1 = L.X2 = 0;
@@ -199,8 +201,8 @@ __device__ __forceinline__ void cascadeWarp(const ChainPlan& P, const Chain2Args
     for (int k = 0; k < NSEC; k++) {
         const int* cf = P.pool + d.coefOff + 5 * (sec0 + k);
         L.b0[k] = cf[0]; L.b1[k] = cf[1]; L.b2[k] = cf[2]; L.a1[k] = cf[3]; L.a2[k] = cf[4];
-        L.acc[k] = 0; L.y1[k] = L.y2[k] = L.y3[k] = L.rx1[k] = L.rx2[k] = 0;
-        if (live) {
+        L.y3[k] = 0;
+        {
             const int* q = st + P.pool[d.secStateOff + sec0 + k];   // [acc_lo, acc_hi, x1, x2, y1, y2] (dsp_biquadSTD.h:45)
             L.acc[k] = (long long)(((unsigned long long)(unsigned)q[1] << 32) | (unsigned)q[0]);
             L.rx1[k] = q[2]; L.rx2[k] = q[3]; L.y1[k] = q[4]; L.y2[k] = q[5];
