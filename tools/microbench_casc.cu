@@ -1,6 +1,7 @@
 // microbench_casc.cu -- the k_chain3 section step (skewed cascade of CH sections in registers) in isolation:
 // does it matter where the coefficients come from?  MODE 0: 5*CH coefficient registers per lane (what k_chain3 does: the
-// chain of a warp is only known at run time); MODE 1: constant-bank operands with compile-time offsets (c[bank][imm]
+// chain of a warp is only known at run time -- but see MODE 2: with a block-uniform address ptxas keeps them in UNIFORM registers);
+// MODE 2: 5*CH coefficient VECTOR registers (lane-dependent address), k_chain3's real situation; MODE 1: constant-bank operands with compile-time offsets (c[bank][imm]
 // operands: two register sources per IMAD.WIDE instead of three).  W warps per sub-partition, one CTA per SM.
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -22,7 +23,9 @@ __global__ void __launch_bounds__(512) k(long long* out, const int* __restrict__
 #pragma unroll
     for (int c = 0; c < CH; c++) {
         acc[c] = (long long)(threadIdx.x + c) * 0x100001ll; y1[c] = c; y2[c] = c + 1; y3[c] = c + 2;
-        const int* cf = coefG + 5 * c + (blockIdx.x & 1);
+        // MODE 2: the address depends on the lane, so ptxas cannot keep the coefficients in uniform registers (what k_chain3 gets:
+        // its chain is a function of the warp id); MODE 0: block-uniform address -> ptxas promotes them to uniform registers
+        const int* cf = coefG + 5 * c + (MODE == 2 ? (int)(threadIdx.x & 1) : (int)(blockIdx.x & 1));
         b0[c] = cf[0]; b1[c] = cf[1]; b2[c] = cf[2]; a1[c] = cf[3]; a2[c] = cf[4];
     }
     unsigned w0 = 0, w1 = 0;
@@ -31,7 +34,7 @@ __global__ void __launch_bounds__(512) k(long long* out, const int* __restrict__
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             long long a[CH];
-            if (MODE == 0) {
+            if (MODE == 0 || MODE == 2) {
 #pragma unroll
                 for (int c = 0; c < CH; c++) a[c] = mac32(acc[c], c ? y2[c - 1] : X1, b1[c]);
 #pragma unroll
@@ -84,7 +87,7 @@ template <int CH, int MODE> void run(int W, int iters, const int* dCoef) {
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);
     const double perClkSM = best / (p.multiProcessorCount * (double)clk * 1e3);
     printf("{\"sections\": %d, \"coefficients\": \"%s\", \"warps_per_subpartition\": %d, \"T_mac_per_s\": %.3f, \"mac_per_clk_per_SM\": %.2f, "
-           "\"cycles_per_warp_mac_per_subpartition\": %.2f}\n", CH, MODE ? "constant bank" : "registers", W, best / 1e12, perClkSM, 128.0 / perClkSM);
+           "\"cycles_per_warp_mac_per_subpartition\": %.2f}\n", CH, MODE == 1 ? "constant bank" : MODE == 2 ? "vector registers" : "uniform registers", W, best / 1e12, perClkSM, 128.0 / perClkSM);
     cudaFree(d);
 }
 
@@ -98,5 +101,8 @@ int main() {
     for (int W : {1, 2, 3, 4}) run<4, 1>(W, 2048, dCoef);
     for (int W : {2, 3, 4}) run<3, 0>(W, 2048, dCoef);
     for (int W : {2, 3, 4}) run<3, 1>(W, 2048, dCoef);
+    for (int W : {1, 2, 3, 4}) run<8, 2>(W, 2048, dCoef);
+    for (int W : {1, 2, 3, 4}) run<4, 2>(W, 2048, dCoef);
+    for (int W : {2, 3, 4}) run<3, 2>(W, 2048, dCoef);
     return 0;
 }
