@@ -7,21 +7,23 @@
 // 32x32+64 IMAD.WIDE issues at 1/4 rate and every other ALU instruction next to it costs real time
 // (tools/microbench_mix.cu), and k_chain2 spends 13 such instructions per 10 MACs in the section loop plus 36 % of all
 // instructions in helper warps that move samples between rings.  Here
-//   * a lane owns ONE WHOLE CASCADE of one stream: accumulators, histories and coefficients of all its sections stay
-//     in registers for the whole launch -- no shuffles, no x / accumulator rings.  Per section and frame:
-//     5 accumulating IMAD.WIDE + 1 funnel shift + 1 VIADDMNMX (sticky saturation record);
+//   * a lane owns one cascade -- or one PART of a long cascade, see below -- of one stream: accumulators, histories and
+//     coefficients of its sections stay in registers for the whole launch -- no shuffles, no x / accumulator rings.
+//     Per section and frame: 5 accumulating IMAD.WIDE + 1 funnel shift + 1 VIADDMNMX (sticky saturation record);
 //   * the sections of a lane are SKEWED IN TIME (section k works on frame t-k at step t), so the K section updates of a
-//     step are independent chains and a single warp keeps the quarter-rate pipe busy (an un-skewed cascade is one long
-//     dependent chain MAC -> shift -> MAC ...: measured 390 cycles per frame for 8 sections).  Exact, because section k
-//     of frame n only needs section k-1 of the same frame.  The input history of section k+1 is the output history of
+//     step are independent chains (an un-skewed cascade is one dependent chain MAC -> shift -> MAC ... per frame and
+//     leans on ptxas to interleave the history MACs).  Exact, because section k of frame n only needs section k-1 of
+//     the same frame.  The fast loop runs in groups of 6 steps = lcm of the history depths, so the register rotation
+//     closes on itself and the loop carries no moves.  The input history of section k+1 is the output history of
 //     section k, so a section keeps (acc, y1, y2, y3) only; the reference's separate x1/x2 words are honoured on the
 //     first two frames of a launch and rebuilt at its end.  Launch edges (pipeline fill / drain) run a predicated form;
 //   * a warp = one chain (or one PART of a chain) x up to 32 streams, so a warp's work is uniform.  One warp issues an
 //     IMAD.WIDE every ~6.7 cycles at best, two per sub-partition reach 4.8, three or more ~4.5 (tools/microbench_warps.cu),
 //     and a warp that finishes its tile early leaves its neighbour alone with the pipe -- so long cascades are cut into
-//     parts of <= 4 sections that run as separate warps (C2: 14 warps of 3 or 4 sections, 12 sections per
-//     sub-partition).  A part hands its output to the next part through a shared-memory row, one tile later (the consumer
-//     part runs F + lag frames behind and waits on a per-part tile counter), so parts never synchronise inside a tile;
+//     parts of <= 4 sections that run as separate warps (C2: 14 warps of 3 or 4 sections, placed on the sub-partitions
+//     by issue cost, planChain3Geometry).  A part hands its output to the next part through a shared-memory row (three
+//     tiles deep), one tile later (the consumer part runs F + lag frames behind and waits on a per-part tile counter),
+//     so parts never synchronise inside a tile;
 //   * the lane reads its input sample straight from the staged PCM tile (cp.async.bulk + mbarrier, issued two tiles
 //     ahead by the helper warp; plain copies when the caller's buffer is not 16-byte friendly), applies LOAD_GAIN
 //     itself, finishes SAT0DB / SAT0DB_TPDF itself and parks the s.31 value in a shared-memory post ring that doubles
@@ -29,12 +31,14 @@
 //   * helper warps: warp C runs the per-stream xoshiro128+ (lane = stream) one tile ahead and stages the input; the
 //     store warps read the post ring at frame - delay, apply the STORE mask and write 128-byte coalesced runs;
 //   * saturation (checkbiquadsat fires on the accumulator's high word): tiles run optimistically and are replayed from
-//     a shared-memory checkpoint with the exact per-section clamp when the sticky record fired (as in k_chain2).
+//     a checkpoint (registers for parts of <= 4 sections, shared memory for longer ones) with the exact per-section
+//     clamp when the sticky record fired (as in k_chain2).
 //
 // Ring bookkeeping (F = 32 frames per tile; lag of a warp = its step offset `base` + its sections - 1; gmax = largest lag):
-//   row ring  [warp][stream][R] by STEP: the tail of warp w writes at step t the value of frame t - lag_w, i.e. frame f
-//             sits at (f + lag_w) mod R; R >= 2F + gmax + longest delay (power of two).  Final parts park the finished
-//             s.31 output there (the post ring = the delay line), the other parts their last section's y for the next part
+//   row ring  [warp][stream][..] by STEP: the tail of warp w writes at step t the value of frame t - lag_w.  Final parts park the
+//             finished s.31 output there (the post ring = the delay line): frame f sits at (f + lag_w) mod R,
+//             R >= 2F + gmax + longest delay (power of two); the other parts their last section's y for the next part, in a
+//             row of three tiles (slot = tile mod 3: the producer is never more than two tiles ahead of its consumer)
 //   tpdf ring [stream][4F]       by frame (the dither warp runs one tile ahead)
 //   window i = frames [iF - gmax, (i+1)F - gmax): every chain has finished them when tile i is done.
 #include "avdsp_dev.cuh"
