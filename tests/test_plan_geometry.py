@@ -67,3 +67,30 @@ def test_describe_reports_the_reference_error_codes():
     with pytest.raises(avdsp_b200.AvdspError) as e:
         avdsp_b200.describe(load_program("c2_testrpi_xover_f2_192k"), 44100, 2)    # fs outside the header range
     assert e.value.code == -2
+
+
+def test_odd_cascade_lengths_are_cut_into_near_equal_parts():
+    """Cascades of 1, 3, 5, 7 and 3 sections: 5 -> 3 + 2, 7 -> 4 + 3, the rest stay whole (the program of tests/test_gpu_chain3.py)."""
+    from oracle import wire
+    fs = 48000
+    a = wire.Asm(fmt=2, fmin=fs, fmax=fs)
+    a.core(); a.tpdf_calc(20)
+    a.param()
+    secs = [wire.rbj_peak(fs, f, q, g) for f, q, g in ((120.0, 0.7, 2.0), (900.0, 1.2, 0.5), (2500.0, 3.0, 1.8), (5200.0, 0.9, 0.6),
+                                                         (9000.0, 2.0, 1.5), (300.0, 0.5, 1.2), (14000.0, 1.0, 0.8))]
+    hdr = {n: a.biquad_sections([[c] for c in secs[:n]]) for n in (1, 3, 5, 7)}
+    a.load(8); a.biquads(hdr[1]); a.sat0db(); a.store(0)
+    a.load_gain(9, 1.0); a.biquads(hdr[3]); a.sat0db_tpdf(); a.delay_fixed_us(150, fs); a.store(1)
+    a.core()
+    a.load_gain(8, 0.35); a.biquads(hdr[5]); a.sat0db(); a.delay_fixed_us(840, fs); a.store(2)
+    a.load_gain(9, -1.7); a.biquads(hdr[7]); a.sat0db_tpdf(); a.store(3); a.store(7)
+    a.load_gain(8, 1.0); a.biquads(hdr[3]); a.sat0db(); a.store(0); a.store(4); a.store(5); a.store(6)
+    ln = _v3(avdsp_b200.describe(a.end(), fs, 2, n_streams=148 * 20))
+    assert ln is not None and "20 streams/CTA" in ln
+    parts = [tuple(map(int, m)) for m in re.findall(r" (\d+):(\d+)\+(\d+)@(\d+)", ln.split("parts (chain:first+n@base):")[1].split(";")[0])]
+    sizes = {}
+    for chain, first, n, base in parts:
+        sizes.setdefault(chain, []).append(n)
+    assert sorted(map(tuple, sizes.values())) == [(1,), (3,), (3,), (3, 2), (4, 3)]
+    # the ring must hold two tiles, the largest lag (second part of the 7-section chain: 3 + 32 + 2) and the longest delay (40)
+    assert "largest lag 37 frames" in ln and "row ring 256 steps" in ln
