@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 
 namespace avdsp {
 
@@ -33,8 +34,8 @@ struct Ctx {
         if (idx < 0 || idx >= total) fail(ERR_MALFORMED, "opcode at word %d points outside the program (%d)", atOp, idx);
         return w[idx];
     }
-    void checkData(int off, int n, int atOp) {
-        if (off < 0 || n < 0 || off + n > L->dataSize) fail(ERR_MALFORMED, "opcode at word %d: data offset %d outside the data area", atOp, off);
+    void checkData(int off, int64_t n, int atOp) {      // 64-bit: off + n must not wrap for offsets near INT_MAX
+        if (off < 0 || n < 0 || (int64_t)off + n > (int64_t)L->dataSize) fail(ERR_MALFORMED, "opcode at word %d: data offset %d outside the data area", atOp, off);
     }
     void checkIo(int io, int atOp) {
         if (io < 0 || io >= kIoSlots) fail(ERR_MALFORMED, "opcode at word %d: io index %d out of range", atOp, io);
@@ -135,7 +136,7 @@ void lowerCore(Ctx& cx, int begin) {
                 if (n > maxSize) n = maxSize;
             }
             if (n == 0) break;                              // "sanity check ... delay=0 to bypass it"
-            cx.checkData(off, 1 + (int)n * (op == OP_DELAY_DP ? aw : 1), p);
+            cx.checkData(off, 1 + (int64_t)n * (op == OP_DELAY_DP ? aw : 1), p);
             cx.emit(op, 0, off, (int32_t)n, 0); break; }
         case OP_BIQUADS: {                                  // :827-849
             int off = arg(0), h = p + arg(1);
@@ -155,7 +156,7 @@ void lowerCore(Ctx& cx, int begin) {
             int lw = cx.code(t, p), delay = lw >> 16;
             if (delay) {
                 if (delay < 0) cx.fail(ERR_MALFORMED, "opcode at word %d: negative FIR delay", p);
-                cx.checkData(off, 1 + delay, p);
+                cx.checkData(off, 1 + (int64_t)delay, p);
                 cx.emit(OP_FIR, 0, off, delay, 0);          // n==0: plain ring delay of `delay` samples
             } else if (lw > 0) {
                 cx.checkData(off, lw, p);
@@ -167,9 +168,11 @@ void lowerCore(Ctx& cx, int begin) {
             }
             break; }
         case OP_DATA_TABLE: {                               // :900-923
-            int size = arg(2), idxOff = arg(3), t = p + arg(4);
-            if (size <= 0) cx.fail(ERR_MALFORMED, "opcode at word %d: empty data table", p);
-            cx.code(t + size - 1, p);
+            int div = arg(1), size = arg(2), idxOff = arg(3), t = p + arg(4);
+            if (size <= 0 || size > cx.total) cx.fail(ERR_MALFORMED, "opcode at word %d: data table size %d", p, size);
+            // index += div; if (index >= size) index -= size (:911-912) only stays inside the table for 0 <= div < size
+            if (div < 0 || div >= size) cx.fail(ERR_MALFORMED, "opcode at word %d: data table divider %d outside [0, size)", p, div);
+            cx.code(t, p); cx.code(t + size - 1, p);
             cx.checkData(idxOff, 1, p);
             int first = L->gen.h.nPool;
             cx.pool(arg(0)); cx.pool(arg(1)); cx.pool(size); cx.pool(idxOff); cx.pool((int)L->bigPool.size());
@@ -187,14 +190,14 @@ void lowerCore(Ctx& cx, int begin) {
         case OP_RMS: {
             int off = arg(0), delay = arg(1);
             if (delay < 0) cx.fail(ERR_MALFORMED, "opcode at word %d: negative RMS delay", p);
-            cx.checkData(off, 5 + 2 * aw + delay * aw, p);
+            cx.checkData(off, 5 + 2 * (int64_t)aw + (int64_t)delay * aw, p);
             int first = L->gen.h.nPool;
             cx.pool(arg(2 + 2 * L->fsRel)); cx.pool(arg(3 + 2 * L->fsRel));
             cx.emit(op, 0, off, delay, first); break; }
         case OP_DISTRIB:
             cx.checkIo(arg(0), p);
             if (arg(1) < 2) cx.fail(ERR_MALFORMED, "opcode at word %d: DISTRIB size < 2", p);
-            cx.checkData(arg(2), 1 + arg(1), p);
+            cx.checkData(arg(2), 1 + (int64_t)arg(1), p);
             cx.emit(op, 0, arg(0), arg(1), arg(2)); break;
         case OP_DIRAC: case OP_SQUAREWAVE:
             cx.checkData(arg(0), 1, p); cx.emit(op, 0, arg(0), arg(1), arg(2 + L->fsRel)); break;
@@ -577,6 +580,10 @@ int decodeProgram(const int32_t* prog, int progWords, int maxWords, int format, 
     }
     if (ncores < 1) return bad(ERR_NO_CORE, "no cores defined in the program");
     if (sum != (uint32_t)prog[H_CHECKSUM]) return bad(ERR_CHECKSUM, "checksum problem with the program");
+    // encoder 0x100 files (module_avdsp/rpi/*.bin, osx/mydspcode.bin: 11-word header, TPDF_CALC without its data word)
+    // decode to wild data offsets in the reference runtime itself, which does not look at the version: named error here
+    if (wordSkip(prog[0]) != H_WORDS || prog[H_VERSION] < kMinEncoderVersion)
+        return bad(ERR_ENCODER_OLD, "program was made by an encoder older than 0x102 (different header / opcode layouts)");
     const int maxOpcode = (int)((uint32_t)prog[H_FORMAT] >> 16), enc = (int)((uint32_t)prog[H_FORMAT] & 0xFFFF);
     if (maxOpcode >= OP_MAX_OPCODE) return bad(ERR_OPCODE_NEW, "program uses opcodes newer than this runtime");
     // The reference converts encodings in place (dspChangeFormat) but that path is unreliable
@@ -601,6 +608,7 @@ int decodeProgram(const int32_t* prog, int progWords, int maxWords, int format, 
         if (k > kMaxCores) return bad(ERR_PLAN_SIZE, "more DSP_CORE sections than the executor supports");
         CoreInfo ci;
         ci.coreWord = cw;
+        if (wordOpcode(prog[cw]) == OP_CORE && cw + 2 >= total) return bad(ERR_MALFORMED, "DSP_CORE in the last words of the program");
         if (wordOpcode(prog[cw]) == OP_CORE) { ci.beginWord = findCoreBeginWord(prog, cw); ci.usedIn = (uint32_t)prog[cw + 1]; ci.usedOut = (uint32_t)prog[cw + 2]; }
         else { ci.beginWord = 0; ci.usedIn = (uint32_t)prog[H_USEDIN]; ci.usedOut = (uint32_t)prog[H_USEDOUT]; }
         L->cores.push_back(ci);
@@ -621,13 +629,13 @@ int relowerProgram(const int32_t* prog, int progWords, Lowered* L, std::string* 
         if (sk == 0) break;
         p += sk;
     }
-    std::vector<int32_t> keep = L->words;
-    GenericPlan keepGen = L->gen;
-    L->words.assign(prog, prog + L->totalLength);
-    const int oldState = L->gen.h.stateWords;
-    try { lowerAll(L); }
-    catch (const Fail& f) { L->words = keep; L->gen = keepGen; if (err) *err = f.msg; return f.code; }
-    if (L->gen.h.stateWords != oldState) { L->words = keep; lowerAll(L); if (err) *err = "state layout changed"; return ERR_ARG; }
+    // lower into a copy and swap it in only on success: a failure leaves every plan, pool and MEM table as it was
+    std::unique_ptr<Lowered> tmp(new Lowered(*L));
+    tmp->words.assign(prog, prog + L->totalLength);
+    try { lowerAll(tmp.get()); }
+    catch (const Fail& f) { if (err) *err = f.msg; return f.code; }
+    if (tmp->gen.h.stateWords != L->gen.h.stateWords) { if (err) *err = "state layout changed"; return ERR_ARG; }
+    *L = std::move(*tmp);
     return L->totalLength;
 }
 

@@ -32,6 +32,7 @@ enum Err : int {
     ERR_CUDA        = -10,
     ERR_MALFORMED   = -11,  // ours: pointer/offset walks outside the program or data area
     ERR_PLAN_SIZE   = -12,  // ours: lowered plan exceeds the kernel-parameter budget
+    ERR_ENCODER_OLD = -13,  // ours: file made by an encoder older than 0x102 (11-word header, other opcode layouts)
 };
 
 enum AluClass : int { ALU_INT64 = 0, ALU_F32 = 1, ALU_F64 = 2 };

@@ -28,6 +28,7 @@ enum { H_HEAD = 0, H_TOTAL = 1, H_DATASIZE = 2, H_CHECKSUM = 3, H_NUMCORES = 4, 
        H_FORMAT = 6, H_FREQMIN = 7, H_FREQMAX = 8, H_USEDIN = 9, H_USEDOUT = 10, H_SERIAL = 11,
        H_WORDS = 12 };
 
+constexpr int kMinEncoderVersion = 0x102;   // encoder/dsp_encoder.c:12; older files have other layouts
 constexpr int kMant   = 28;   // DSP_MANT
 constexpr int kMantBQ = 28;   // DSP_MANTBQ
 constexpr int kNumFreq = 14;

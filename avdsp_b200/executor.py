@@ -129,22 +129,46 @@ class Executor:
         planar.  numpy array -> host path (copies inside the call); torch CUDA tensor -> device path.
         Returns the outputs in the same layout and memory space."""
         if isinstance(x, np.ndarray):
-            x = np.ascontiguousarray(x, dtype=np.int32)
+            x = self._as_words(x)
             n_frames = x.shape[1] if layout == INTERLEAVED else x.shape[2]
             si, so = self._shapes(n_frames, layout)
-            assert x.shape == si, (x.shape, si)
-            y = np.empty(so, dtype=np.int32) if out is None else out
+            if x.shape != si:
+                raise ValueError(f"input shape {x.shape}, expected {si}")
+            if out is None:
+                y = np.empty(so, dtype=np.int32)
+            else:       # the C call writes prod(so) words through this pointer: it has to be exactly that buffer
+                if not (isinstance(out, np.ndarray) and out.shape == so and out.dtype.itemsize == 4 and out.dtype.kind in "iuf"
+                        and out.flags.c_contiguous and out.flags.writeable):
+                    raise ValueError(f"out must be a writable C-contiguous 32-bit array of shape {so}")
+                y = out
             _check(self._L.avdsp_b200_process(self._h, x.ctypes.data, y.ctypes.data, n_frames, layout, HOST))
             return y
         import torch
-        assert x.is_cuda and x.dtype == torch.int32 and x.is_contiguous()
+        if not (x.is_cuda and x.dtype in (torch.int32, torch.float32) and x.is_contiguous()):
+            raise ValueError("device input must be a contiguous int32 (float32 for DSP_FORMAT 5/6) CUDA tensor")
         n_frames = x.shape[1] if layout == INTERLEAVED else x.shape[2]
         si, so = self._shapes(n_frames, layout)
-        assert tuple(x.shape) == si, (tuple(x.shape), si)
-        y = torch.empty(so, dtype=torch.int32, device=x.device) if out is None else out
+        if tuple(x.shape) != si:
+            raise ValueError(f"input shape {tuple(x.shape)}, expected {si}")
+        if out is None:
+            y = torch.empty(so, dtype=x.dtype, device=x.device)
+        else:
+            if not (out.is_cuda and out.device == x.device and tuple(out.shape) == so and out.is_contiguous()
+                    and out.dtype in (torch.int32, torch.float32)):
+                raise ValueError(f"out must be a contiguous 32-bit CUDA tensor of shape {so} on {x.device}")
+            y = out
         stream = torch.cuda.current_stream(x.device).cuda_stream
         _check(self._L.avdsp_b200_process_async(self._h, x.data_ptr(), y.data_ptr(), n_frames, layout, stream))
         return y
+
+    @staticmethod
+    def _as_words(x: np.ndarray) -> np.ndarray:
+        """32-bit samples as they are: int32 s.31, or float32 BIT PATTERNS for DSP_FORMAT 5/6 (never value-cast)."""
+        if x.dtype == np.float32 or x.dtype == np.uint32:
+            return np.ascontiguousarray(x).view(np.int32)
+        if x.dtype != np.int32:
+            raise ValueError(f"PCM must be int32 (or float32 for DSP_FORMAT 5/6), not {x.dtype}")
+        return np.ascontiguousarray(x)
 
     def process_pcm(self, raw: np.ndarray, pcm_format: int, n_frames: int) -> np.ndarray:
         """ALSA sample formats (linux/avdsp_plugin.c:109-121): raw = interleaved S16_LE (int16 array) or S24_3LE

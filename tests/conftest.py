@@ -90,4 +90,14 @@ CASES = [
     ("c4s_fir_f4_multifs", 4, 48000),
     ("c4s_fir_f5_multifs", 5, 48000),
     ("c4s_fir_f6_multifs", 6, 88200),
+    # every opcode of the runtime's switch, every DSP_FORMAT (oracle/progs/allops_*.c, make_golden.asm_misc_program)
+    *[(f"allops_alu_f{f}_48k", f, 48000) for f in (2, 3, 4, 5, 6)],
+    *[(f"allops_gen_f{f}_multifs", f, fs) for f, fs in ((2, 44100), (2, 192000), (3, 88200), (4, 176400), (5, 48000), (6, 96000))],
+    *[(f"allops_misc_f{f}_multifs", f, fs) for f, fs in ((2, 96000), (3, 48000), (4, 88200), (5, 44100), (6, 96000))],
+    # the remaining checked-in fixtures of the reference (X/Y crossovers, DELAY_DP, SHIFT, SAT0DB_GAIN, MEM hand-offs)
+    ("ref_dacfabriceo", 2, 96000),
+    ("ref_dacfabriceo_oppo", 2, 44100),
+    ("ref_lxmini_lr2", 2, 96000),
+    ("ref_lxmini_lv8", 2, 192000),
+    ("ref_win_mydspcode", 2, 88200),
 ]

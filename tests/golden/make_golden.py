@@ -46,9 +46,56 @@ PROGRAMS = {
     "ref_dsptest1":                ("testfunction", "bin", "-dspformat 3 -fsmax 96000 -test1 -dither 26"),
     "ref_dac8prodsp":              ("oktodac", "hex", "-dspformat 2 -dac8prodsp -dither 24"),
 }
+# our own all-opcode programs (oracle/progs/allops_*.c) on the unchanged encoder: every `case` of the runtime's switch
+# (runtime/dsp_runtime.c:319-1305) executes at least once in every DSP_FORMAT
+for _f in (2, 3, 4, 5, 6):
+    PROGRAMS[f"allops_alu_f{_f}_48k"] = ("allops_alu", "bin", f"-dspformat {_f} -fsmin 48000 -fsmax 48000" + (" -int" if _f == 2 else ""))
+    PROGRAMS[f"allops_gen_f{_f}_multifs"] = ("allops_gen", "bin", f"-dspformat {_f} -fsmin 44100 -fsmax 192000")
 MUST_MATCH = {"ref_crossoverLV6": "crossoverLV6.bin", "ref_dacdiy1": "dacdiy1.bin",
               "ref_dsptest1": "dsptest1.bin", "ref_dac8prodsp": "dac8prodsp.h"}
 
+# checked-in fixtures of the reference that its current sources no longer regenerate byte for byte (uninitialised MEM words
+# in dacfabriceo*.bin; the LXmini sources moved on): taken as they are, as test vectors.
+# name -> path under /root/reference/module_avdsp
+COPIED = {
+    "ref_dacfabriceo":      "osx/dacfabriceo.bin",
+    "ref_dacfabriceo_oppo": "osx/dacfabriceo_oppo.bin",
+    "ref_lxmini_lr2":       "osx/dacfabriceo_LXmini_LR2.bin",
+    "ref_lxmini_lv8":       "osx/dacfabriceo_LXmini_LV8.bin",
+    "ref_win_mydspcode":    "windows/mydspcode.bin",
+    # encoder 0x100 files: 11-word header, other opcode layouts (the reference runtime crashes on the first): decoder must reject
+    "old_rpi_dacfabriceo":  "rpi/dacfabriceo.bin",
+    "old_rpi_testrew":      "rpi/testrew.bin",
+    "old_osx_mydspcode":    "osx/mydspcode.bin",
+}
+
+
+def asm_misc_program(fmt):
+    """Opcodes the encoder has no emitter for (LOAD_MEM_DATA, runtime/dsp_runtime.c:1277-1281) or only WIP ones, in the layout
+    the runtime decodes; plus the 32-bit DELAY_1 / DELAY forms next to their 64-bit twins."""
+    a = wire.Asm(fmt=fmt, fmin=44100, fmax=96000)
+    a.core()
+    tp = a.tpdf_calc(24)
+    a.store(0)
+    a.load_mem_data(tp)                 # X = the 64-bit TPDF value TPDF_CALC left in the data area
+    a.store(1)
+    a.load_gain(8, 0.5)
+    a.delay_1()
+    a.load_mem_data(a.data - 2)         # reads back what DELAY_1 just stored
+    a.sat0db()
+    a.store(2)
+    a.core()
+    a.load_gain(9, 0.5)
+    a.delay_fixed_us(250, 96000, dp=True)
+    a.delay_fixed_us(100, 96000, dp=False)
+    a.sat0db()
+    a.store(3)
+    a.load_gain(8, 0.25)
+    a.dcblock([-0.003, -0.0025, -0.0015, -0.00125])
+    a.clip(0.1)
+    a.sat0db_tpdf()
+    a.store(4)
+    return a.end()
 
 
 def fir_taps(n, seed):
@@ -99,6 +146,8 @@ ASM_PROGRAMS = {}
 for _f in (2, 3):
     ASM_PROGRAMS[f"c4_fir4096_f{_f}_48k"] = (_f, lambda f=_f: fir_program(f, [[4096], [4096]]))
 for _f in (2, 3, 4, 5, 6):
+    ASM_PROGRAMS[f"allops_misc_f{_f}_multifs"] = (_f, lambda f=_f: asm_misc_program(f))
+for _f in (2, 3, 4, 5, 6):
     # two sampling rates: 48k convolution (ragged lengths), 96k: channel 0 plain delay, channel 1 skipped
     ASM_PROGRAMS[f"c4s_fir_f{_f}_multifs"] = (_f, lambda f=_f: fir_program(
         f, [[100, None, ("delay", 37)], [33, None, None]], fmin=48000, fmax=96000, variants=["gain", "satgain"]))
@@ -127,10 +176,28 @@ for fmt in (3, 4, 5, 6):
     VECTORS[f"c4s_f{fmt}_96k_full"] = (f"c4s_fir_f{fmt}_multifs", fmt, 96000, 0, 24, "full", 256)
 VECTORS["c4_f3_noise"] = ("c4_fir4096_f3_48k", 3, 48000, 0, 31, "noise", 640)
 VECTORS["dac8prodsp_96k"] = ("ref_dac8prodsp", 2, 96000, 0, 24, "noise", 1024)
+# every opcode, every DSP_FORMAT
+for fmt in (2, 3, 4, 5, 6):
+    VECTORS[f"allops_alu_f{fmt}_noise"] = (f"allops_alu_f{fmt}_48k", fmt, 48000, 0, 31, "noise", 512)
+    VECTORS[f"allops_alu_f{fmt}_full"] = (f"allops_alu_f{fmt}_48k", fmt, 48000, 5, 24, "full", 512)
+    VECTORS[f"allops_gen_f{fmt}_48k"] = (f"allops_gen_f{fmt}_multifs", fmt, 48000, 0, 31, "noise", 1536)
+    VECTORS[f"allops_gen_f{fmt}_96k"] = (f"allops_gen_f{fmt}_multifs", fmt, 96000, 9, 24, "full", 1536)
+    VECTORS[f"allops_misc_f{fmt}_44k"] = (f"allops_misc_f{fmt}_multifs", fmt, 44100, 2, 24, "noise", 512)
+VECTORS["allops_gen_f2_192k_sine"] = ("allops_gen_f2_multifs", 2, 192000, 0, 20, "sine", 2048)
+# the remaining fixtures of the reference (osx/*.bin, windows/mydspcode.bin): DELAY_DP, SHIFT, SAT0DB_GAIN, X/Y crossovers
+VECTORS["dacfabriceo_48k"] = ("ref_dacfabriceo", 2, 48000, 0, 24, "noise", 1024)
+VECTORS["dacfabriceo_96k"] = ("ref_dacfabriceo", 2, 96000, 3, 31, "full", 1024)
+VECTORS["dacfabriceo_oppo_88k"] = ("ref_dacfabriceo_oppo", 2, 88200, 0, 24, "noise", 1024)
+VECTORS["lxmini_lr2_192k"] = ("ref_lxmini_lr2", 2, 192000, 0, 23, "noise", 1024)
+VECTORS["lxmini_lr2_44k"] = ("ref_lxmini_lr2", 2, 44100, 1, 31, "full", 1024)
+VECTORS["lxmini_lv8_96k"] = ("ref_lxmini_lv8", 2, 96000, 0, 23, "noise", 1024)
+VECTORS["lxmini_lv8_176k"] = ("ref_lxmini_lv8", 2, 176400, 4, 24, "sine", 1024)
+VECTORS["win_mydspcode_48k"] = ("ref_win_mydspcode", 2, 48000, 0, 24, "noise", 1024)
+VECTORS["win_mydspcode_192k"] = ("ref_win_mydspcode", 2, 192000, 8, 31, "full", 1024)
 
 
 def prog_path(name):
-    if name in ASM_PROGRAMS:
+    if name in ASM_PROGRAMS or name in COPIED:
         return os.path.join(PROGDIR, name + ".bin")
     kind = PROGRAMS[name][1]
     return os.path.join(PROGDIR, name + (".bin" if kind == "bin" else ".h"))
@@ -157,6 +224,13 @@ def make_programs():
             assert a == b, f"{name}: regenerated file differs from the reference's checked-in {MUST_MATCH[name]}"
             print(f"  {name}: byte-identical to osx/{MUST_MATCH[name]}")
         print(f"  wrote {os.path.relpath(out, ROOT)} ({os.path.getsize(out)} bytes)")
+
+
+def copy_fixtures():
+    for name, rel in COPIED.items():
+        raw = open(os.path.join("/root/reference/module_avdsp", rel), "rb").read()
+        open(prog_path(name), "wb").write(raw)
+        print(f"  copied {rel} -> {os.path.relpath(prog_path(name), ROOT)} ({len(raw)} bytes)")
 
 
 def make_asm_programs():
@@ -191,5 +265,6 @@ if __name__ == "__main__":
         raise SystemExit("oracle/_ref is not built: run `make -C oracle` where /root/reference exists")
     if not sys.argv[1:]:
         make_programs()
+        copy_fixtures()
     make_asm_programs()
     make_vectors()

@@ -369,6 +369,29 @@ def test_full_width_batch_properties(oracle_lib, prog, fs, S, T):
         assert np.array_equal(ys[s], o.process(xs[s])), s
 
 
+@pytest.mark.parametrize("stim", ["noise", "full"])
+def test_chain3_full_width_distinct_streams(oracle_lib, stim):
+    """The geometry the benchmark runs (4096 streams -> 28 per CTA, k_chain3) on 4096 DISTINCT streams: every lane class of a
+    CTA (first, last live lane 27, first lane of the next CTA 28, middle, last stream) bit for bit against the oracle,
+    outputs and state; 2048 frames so that AUTO takes k_chain3 (>= 1536)."""
+    prog, fs, S, T = "c2_testrpi_xover_f2_192k", 192000, 4096, 2048
+    w = load_program(prog)
+    seeds = np.arange(S, dtype=np.int32) * 7 + 1
+    ex = Executor(w, fs, 2, S, seeds=seeds)
+    xs = synth.pcm(stim, S, T, ex.n_in, fs)
+    ys = ex.process(xs)
+    assert ex.last_kernel == "chain" and ex.last_chain_variant == 3
+    for s in (0, 1, 5, 13, 26, 27, 28, 29, 55, 56, 2000, 2001, 4067, 4068, S - 1):
+        o = oracle_lib.Oracle(w, 2, fs, seed=int(seeds[s]))
+        assert np.array_equal(ys[s], o.process(xs[s])), s
+        st = ex.get_state(s)
+        assert np.array_equal(st[: ex.data_size], o.data), s
+        assert np.array_equal(st[ex.aux_offset: ex.aux_offset + 7], o.aux()[:7]), s
+    # no two distinct streams may produce the same output (a lane shadowing another would)
+    sig = ys.reshape(S, -1)[:, 64 * 8: 64 * 8 + 64]
+    assert len({row.tobytes() for row in sig}) == S
+
+
 @pytest.mark.parametrize("prog,fmt", [("c4_fir4096_f3_48k", 3), ("c4s_fir_f3_multifs", 3), ("c4_fir4096_f2_48k", 2)])
 def test_fir_kernel_periods_and_kernel_switches(oracle_lib, prog, fmt):
     """DSP_FIR through the time-parallel kernel: ALSA-period sized calls, calls shorter than the impulse, a switch to the
