@@ -23,6 +23,8 @@ SYMBOLS = [
     "avdsp_b200_mem_offset", "avdsp_b200_num_mem", "avdsp_b200_mem_word", "avdsp_b200_get_state",
     "avdsp_b200_set_state", "avdsp_b200_num_streams", "avdsp_b200_num_cores", "avdsp_b200_trace",
     "avdsp_b200_last_error", "avdsp_b200_measure_int_peak", "avdsp_b200_measure_f32_peak",
+    "avdsp_b200_create_multi", "avdsp_b200_num_devices", "avdsp_b200_shard_info", "avdsp_b200_host_alloc", "avdsp_b200_host_free",
+    "avdsp_b200_copy_only",
 ]
 
 _lib = None
@@ -51,6 +53,15 @@ def lib():
     vp, ci, pi = C.c_void_p, C.c_int, C.POINTER(C.c_int)
     L.avdsp_b200_create.argtypes = [C.POINTER(vp), vp, ci, ci, ci, ci, vp, ci, ci]
     L.avdsp_b200_create.restype = ci
+    L.avdsp_b200_create_multi.argtypes = [C.POINTER(vp), vp, ci, ci, ci, ci, vp, ci, C.c_uint]
+    L.avdsp_b200_create_multi.restype = ci
+    L.avdsp_b200_num_devices.argtypes = [vp]
+    L.avdsp_b200_shard_info.argtypes = [vp, ci, pi, pi, pi, pi]
+    L.avdsp_b200_host_alloc.argtypes = [vp, C.c_size_t]
+    L.avdsp_b200_host_alloc.restype = vp
+    L.avdsp_b200_host_free.argtypes = [vp, vp]
+    L.avdsp_b200_host_free.restype = None
+    L.avdsp_b200_copy_only.argtypes = [vp, vp, vp, ci, ci]
     L.avdsp_b200_destroy.argtypes = [vp]
     L.avdsp_b200_destroy.restype = None
     L.avdsp_b200_reset.argtypes = [vp, ci, vp, ci]

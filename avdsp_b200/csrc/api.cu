@@ -10,13 +10,17 @@
 #include "../../include/avdsp_b200.h"
 #include "decoder.h"
 #include "kernels.h"
+#include "host_numa.h"
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace avdsp;
@@ -26,6 +30,7 @@ static int setErr(int code, const std::string& msg) { g_lastError = msg; return 
 static int cudaErr(cudaError_t e, const char* what) {
     return setErr(AVDSP_B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
+#define NO_MULTI(h, what) do { if (!(h)->shards.empty()) return setErr(AVDSP_B200_ERR_UNSUPPORTED, what " takes a single-device instance (device buffers belong to one GPU)"); } while (0)
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cudaErr(e_, #call); } while (0)
 
 // ---------------------------------------------------------------------------------------------
@@ -124,51 +129,14 @@ __global__ void k_widen_pcm(const unsigned char* __restrict__ src, int fmt, int*
     dst[i] = v;
 }
 
-struct avdsp_b200 {
-    int device = 0, numSMs = 148;
-    int nStreams = 0;
-    Lowered L;
-    std::vector<int32_t> seeds;
-    int* dState = nullptr;
-    int* dBig = nullptr; size_t bigWords = 0;
-    int* dMemInit = nullptr;
-    int* dSeeds = nullptr;
-    ChainLane* dLanes = nullptr;
-    ChainGeom geom{};
-    bool chainUsable = false;       // kernel_chain.cu  (v1: tile-synchronous)
-    ChainLane* dLanes2 = nullptr;
-    Chain2Geom geom2{};
-    bool chain2Usable = false;      // kernel_chain2.cu (v2: warp-specialised, the default)
-    Chain3Geom geom3{};
-    bool chain3Usable = false;      // kernel_chain3.cu (v3: one cascade per lane; the common crossover / EQ shape at batch width)
-    int lastChainVariant = 0;       // 2 / 3: which chain kernel the last AVDSP_B200_KERNEL_CHAIN launch used
-    MixPlan mix{};
-    bool mixUsable = false;         // kernel_mix.cu (time-parallel: programs without biquads)
-    bool firUsable = false;         // kernel_fir.cu (time-parallel FIR paths)
-    unsigned char* dFirTaps = nullptr;              // kernel_fir_tc.cu: pre-swizzled Toeplitz taps blobs
-    unsigned char* dFirWs = nullptr; size_t firWsBytes = 0;     // ... and the packed-sample workspace
-    unsigned* dJump = nullptr; int jumpL = -1;      // PRNG jump matrix for segments of jumpL draws
-    int* dTpdf = nullptr; size_t tpdfWords = 0;     // scratch dither values of a launch
-    int period = 0, kernelSel = AVDSP_B200_KERNEL_AUTO, lastKernel = 0;
-    long long launches = 0;
-    cudaStream_t stream = nullptr;          // for the synchronous calls
-    // host-memspace staging: a few slots of device buffers + copy streams
-    static constexpr int kSlots = 3;
-    cudaStream_t slotStream[kSlots] = {nullptr, nullptr, nullptr};
-    int* slotIn[kSlots] = {nullptr, nullptr, nullptr};
-    int* slotOut[kSlots] = {nullptr, nullptr, nullptr};
-    size_t slotInWords = 0, slotOutWords = 0;
-    cudaEvent_t evIn[kSlots] = {nullptr, nullptr, nullptr}, evKernel[kSlots] = {nullptr, nullptr, nullptr}, evOut[kSlots] = {nullptr, nullptr, nullptr};
-    void* pcmRaw = nullptr; int* pcmIn = nullptr; int* pcmOut = nullptr; size_t pcmRawBytes = 0, pcmInWords = 0, pcmOutWords = 0;
-    std::string trace;
-};
+#include "instance.h"
+
+static int quiesce(avdsp_b200* h);
+static int resetShards(avdsp_b200* h, int fs, const int32_t* seeds, int defaultDither);
 
 // Host-only half of plan preparation: which kernels can take the program, their CTA geometries, the lowering trace.
-static void planGeometries(avdsp_b200* h, std::vector<ChainLane>* lanes1, std::vector<ChainLane>* lanes2) {
+static void planGeometries(avdsp_b200* h, std::vector<ChainLane>* lanes2) {
     const Lowered& L = h->L;
-    h->chainUsable = false;
-    lanes1->assign(1024, ChainLane{});
-    if (L.chainOk && chainKernelSupports(L.chain)) h->chainUsable = planChainGeometry(L.chain, h->nStreams, h->numSMs, &h->geom, lanes1->data());
     h->chain2Usable = false;
     lanes2->assign(1024, ChainLane{});
     if (L.chainOk && chain2Supports(L.chain)) h->chain2Usable = planChain2Geometry(L.chain, h->nStreams, h->numSMs, &h->geom2, lanes2->data());
@@ -208,12 +176,10 @@ static void planGeometries(avdsp_b200* h, std::vector<ChainLane>* lanes1, std::v
         }
         h->trace += "\n";
     }
-    if (h->chainUsable)
-        snprintf(line, sizeof line, "chain kernel geometry: %d streams/CTA, %d sections/lane, %d lane threads, %d work threads, tile %d frames, depth %d, %zu B smem\n",
-                 h->geom.streamsPerCta, h->geom.secPerLane, h->geom.laneThreads, h->geom.workThreads, h->geom.tileFrames, h->geom.maxDepth, h->geom.smemBytes);
-    else
-        snprintf(line, sizeof line, "chain kernel not used: %s\n", L.chainOk ? "geometry does not fit" : L.chainWhyNot.c_str());
-    h->trace += line;
+    if (!h->chain2Usable && !h->mixUsable) {
+        snprintf(line, sizeof line, "chain kernels not used: %s\n", L.chainOk ? "geometry does not fit" : L.chainWhyNot.c_str());
+        h->trace += line;
+    }
 }
 
 static int uploadPlanData(avdsp_b200* h) {
@@ -226,12 +192,8 @@ static int uploadPlanData(avdsp_b200* h) {
         CU(cudaMalloc(&h->dBig, h->bigWords * 4));
         CU(cudaMemcpy(h->dBig, L.bigPool.data(), h->bigWords * 4, cudaMemcpyHostToDevice));
     }
-    std::vector<ChainLane> lanes1, lanes2;
-    planGeometries(h, &lanes1, &lanes2);
-    if (h->chainUsable) {
-        if (!h->dLanes) CU(cudaMalloc(&h->dLanes, 1024 * sizeof(ChainLane)));
-        CU(cudaMemcpy(h->dLanes, lanes1.data(), 1024 * sizeof(ChainLane), cudaMemcpyHostToDevice));
-    }
+    std::vector<ChainLane> lanes2;
+    planGeometries(h, &lanes2);
     if (h->chain2Usable) {
         if (!h->dLanes2) CU(cudaMalloc(&h->dLanes2, 1024 * sizeof(ChainLane)));
         CU(cudaMemcpy(h->dLanes2, lanes2.data(), 1024 * sizeof(ChainLane), cudaMemcpyHostToDevice));
@@ -273,12 +235,18 @@ static int initState(avdsp_b200* h) {
 
 static void freeAll(avdsp_b200* h) {
     if (!h) return;
+    for (auto& kv : h->hostAllocs) { cudaHostUnregister(kv.first); hostFreePlaced(kv.first, kv.second); }
+    h->hostAllocs.clear();
+    if (!h->shards.empty()) {
+        for (avdsp_b200* sh : h->shards) freeAll(sh);
+        delete h;
+        return;
+    }
     cudaSetDevice(h->device);
     if (h->dState) cudaFree(h->dState);
     if (h->dBig) cudaFree(h->dBig);
     if (h->dMemInit) cudaFree(h->dMemInit);
     if (h->dSeeds) cudaFree(h->dSeeds);
-    if (h->dLanes) cudaFree(h->dLanes);
     if (h->dLanes2) cudaFree(h->dLanes2);
     if (h->dJump) cudaFree(h->dJump);
     if (h->dTpdf) cudaFree(h->dTpdf);
@@ -295,6 +263,7 @@ static void freeAll(avdsp_b200* h) {
         if (h->evKernel[k]) cudaEventDestroy(h->evKernel[k]);
         if (h->evOut[k]) cudaEventDestroy(h->evOut[k]);
     }
+    if (h->evLast) { cudaEventSynchronize(h->evLast); cudaEventDestroy(h->evLast); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -324,8 +293,10 @@ int avdsp_b200_create(avdsp_b200_t** out, const int32_t* prog, int progWords, in
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     h->numSMs = prop.multiProcessorCount;
+    { char bus[64] = {0}; if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) == cudaSuccess) h->numaNode = numaNodeOfPci(bus); }
     if (seeds) h->seeds.assign(seeds, seeds + nStreams);
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->evLast, cudaEventDisableTiming));
     const size_t words = (size_t)nStreams * h->L.gen.h.stateWords;
     CU(cudaMalloc(&h->dState, std::max<size_t>(words, 1) * 4));
     int r = uploadPlanData(h.get()); if (r < 0) return r;
@@ -345,14 +316,16 @@ int avdsp_b200_describe(const int32_t* prog, int progWords, int fs, int format, 
     const int rc = decodeProgram(prog, progWords, 0x7FFFFFFF, format, fs, defaultDither, &h.L, &err);
     if (rc < 0) return setErr(rc, err);
     h.nStreams = nStreams; h.numSMs = numSMs;
-    std::vector<ChainLane> lanes1, lanes2;
-    planGeometries(&h, &lanes1, &lanes2);
+    std::vector<ChainLane> lanes2;
+    planGeometries(&h, &lanes2);
     snprintf(out, (size_t)outLen, "%s", h.trace.c_str());
     return rc;
 }
 
 int avdsp_b200_reset(avdsp_b200_t* h, int fs, const int32_t* seeds, int defaultDither) {
     if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
+    if (!h->shards.empty()) return resetShards(h, fs, seeds, defaultDither);
+    { const int q = quiesce(h); if (q < 0) return q; }
     if (fs != h->L.fs || defaultDither != h->L.defaultDither) {
         Lowered nl;
         std::string err;
@@ -379,15 +352,25 @@ int avdsp_b200_io_map(const avdsp_b200_t* h, int* nIn, int* inIdx, int* nOut, in
 
 int avdsp_b200_set_order(avdsp_b200_t* h, int period) {
     if (!h || period < 0) return setErr(AVDSP_B200_ERR_ARG, "bad period");
+    for (avdsp_b200* sh : h->shards) sh->period = period;
     h->period = period; return 0;
 }
 int avdsp_b200_set_kernel(avdsp_b200_t* h, int which) {
     if (!h || which < 0 || which > AVDSP_B200_KERNEL_CHAIN_V3) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
+    for (avdsp_b200* sh : h->shards) sh->kernelSel = which;
     h->kernelSel = which; return 0;
 }
-int avdsp_b200_last_kernel(const avdsp_b200_t* h) { return h ? h->lastKernel : 0; }
-int avdsp_b200_last_chain_variant(const avdsp_b200_t* h) { return (h && h->lastKernel == AVDSP_B200_KERNEL_CHAIN) ? h->lastChainVariant : 0; }
-long long avdsp_b200_launch_count(const avdsp_b200_t* h) { return h ? h->launches : 0; }
+int avdsp_b200_last_kernel(const avdsp_b200_t* h) { return !h ? 0 : h->shards.empty() ? h->lastKernel : h->shards[0]->lastKernel; }
+int avdsp_b200_last_chain_variant(const avdsp_b200_t* h) {
+    if (h && !h->shards.empty()) h = h->shards[0];
+    return (h && h->lastKernel == AVDSP_B200_KERNEL_CHAIN) ? h->lastChainVariant : 0;
+}
+long long avdsp_b200_launch_count(const avdsp_b200_t* h) {
+    if (!h) return 0;
+    long long n = h->launches;
+    for (const avdsp_b200* sh : h->shards) n += sh->launches;
+    return n;
+}
 int avdsp_b200_state_words(const avdsp_b200_t* h) { return h ? h->L.gen.h.stateWords : 0; }
 int avdsp_b200_data_size(const avdsp_b200_t* h) { return h ? h->L.gen.h.dataSize : 0; }
 int avdsp_b200_aux_offset(const avdsp_b200_t* h) { return h ? h->L.gen.h.auxOff : 0; }
@@ -418,12 +401,13 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         outSS = (long long)cap * nOut; outFS = 1; outCS = cap;
     } else return setErr(AVDSP_B200_ERR_ARG, "unknown layout");
     int* st = h->dState + (size_t)first * P.stateWords;
+    CU(cudaStreamWaitEvent(stream, h->evLast, 0));          // stream-ordered after the instance's previous launch (see evLast)
     const bool chainOrder = h->period == 0 && coreSel < 0 && !planOverride;
     int use = AVDSP_B200_KERNEL_GENERIC;
     if (chainOrder && h->kernelSel != AVDSP_B200_KERNEL_GENERIC) {
-        if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1) { if (h->chainUsable) use = AVDSP_B200_KERNEL_CHAIN_V1; }
-        else if (h->chain2Usable) use = AVDSP_B200_KERNEL_CHAIN;
-        else if (h->chainUsable) use = AVDSP_B200_KERNEL_CHAIN_V1;
+        if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1)
+            return setErr(AVDSP_B200_ERR_UNSUPPORTED, "the first, tile-synchronous chain kernel was removed; use AVDSP_B200_KERNEL_CHAIN");
+        if (h->chain2Usable) use = AVDSP_B200_KERNEL_CHAIN;
     }
     if (chainOrder && h->mixUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_MIX)) use = AVDSP_B200_KERNEL_MIX;
     if (chainOrder && h->firUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_FIR)) use = AVDSP_B200_KERNEL_FIR;
@@ -513,14 +497,6 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         else e = launchChain2(h->L.chain, h->geom2, A, stream);
         h->lastChainVariant = v3 ? 3 : 2;
         h->lastKernel = AVDSP_B200_KERNEL_CHAIN;
-    } else if (use == AVDSP_B200_KERNEL_CHAIN_V1) {
-        ChainArgs A{};
-        A.in = in; A.out = out; A.state = st; A.lanes = h->dLanes;
-        A.nStreams = n; A.nFrames = nFrames;
-        A.inStreamStride = inSS; A.outStreamStride = outSS;
-        A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
-        e = launchChain(h->L.chain, h->geom, A, stream);
-        h->lastKernel = AVDSP_B200_KERNEL_CHAIN_V1;
     } else {
         GenericArgs A{};
         A.in = in; A.out = out; A.state = st; A.bigPool = h->dBig;
@@ -533,7 +509,16 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         h->lastKernel = AVDSP_B200_KERNEL_GENERIC;
     }
     if (e != cudaSuccess) return cudaErr(e, "kernel launch");
+    CU(cudaEventRecord(h->evLast, stream));
     h->launches++;
+    return 0;
+}
+
+// host-side access to an instance's device data: after everything that was launched on it, on any stream
+static int quiesce(avdsp_b200* h) {
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventSynchronize(h->evLast));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -563,6 +548,7 @@ extern "C" {
 int avdsp_b200_process_range(avdsp_b200_t* h, const void* in, void* out, int nFrames, int layout,
                              int firstStream, int nStreams, void* cudaStream) {
     if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
+    NO_MULTI(h, "avdsp_b200_process_range / _async");
     if (nFrames < 0 || firstStream < 0 || nStreams < 0 || firstStream + nStreams > h->nStreams) return setErr(AVDSP_B200_ERR_ARG, "bad frame/stream range");
     if ((!in && h->L.gen.h.nIn) || (!out && h->L.gen.h.nOut)) return setErr(AVDSP_B200_ERR_ARG, "NULL buffer");
     CU(cudaSetDevice(h->device));
@@ -574,18 +560,11 @@ int avdsp_b200_process_async(avdsp_b200_t* h, const void* in, void* out, int nFr
     return avdsp_b200_process_range(h, in, out, nFrames, layout, 0, h->nStreams, cudaStream);
 }
 
-int avdsp_b200_process(avdsp_b200_t* h, const void* in, void* out, int nFrames, int layout, int memspace) {
-    if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
-    if (nFrames < 0) return setErr(AVDSP_B200_ERR_ARG, "negative frame count");
-    if (nFrames == 0) return 0;
+} // extern "C"
+
+// host buffers of a single-device instance; copyOnly: the same DMA schedule without the launches (the copy roofline of the host path)
+static int processHost(avdsp_b200* h, const void* in, void* out, int nFrames, int layout, bool copyOnly) {
     CU(cudaSetDevice(h->device));
-    if (memspace == AVDSP_B200_DEVICE) {
-        const int r = avdsp_b200_process_range(h, in, out, nFrames, layout, 0, h->nStreams, h->stream);
-        if (r < 0) return r;
-        CU(cudaStreamSynchronize(h->stream));
-        return 0;
-    }
-    if (memspace != AVDSP_B200_HOST) return setErr(AVDSP_B200_ERR_ARG, "unknown memspace");
     // Host buffers.  The time loop of a launch is sequential, so cutting the batch by streams would only shrink
     // the grid; the batch is cut in TIME instead: chunk c of every stream is copied in (one strided 2-D DMA),
     // processed by one launch over all streams, and copied out, through kSlots staging buffers.  Three CUDA
@@ -620,8 +599,10 @@ int avdsp_b200_process(avdsp_b200_t* h, const void* in, void* out, int nFrames, 
         CU(cudaEventRecord(h->evIn[slot], sIn));
         CU(cudaStreamWaitEvent(sK, h->evIn[slot], 0));
         CU(cudaStreamWaitEvent(sK, h->evOut[slot], 0));
-        const int r = launchRange(h, h->slotIn[slot], h->slotOut[slot], nf, layout, 0, h->nStreams, sK, -1, nullptr, (int)chunk);
-        if (r < 0) return r;
+        if (!copyOnly) {
+            const int r = launchRange(h, h->slotIn[slot], h->slotOut[slot], nf, layout, 0, h->nStreams, sK, -1, nullptr, (int)chunk);
+            if (r < 0) return r;
+        }
         CU(cudaEventRecord(h->evKernel[slot], sK));
         CU(cudaStreamWaitEvent(sOut, h->evKernel[slot], 0));
         if (P.nOut)
@@ -635,12 +616,183 @@ int avdsp_b200_process(avdsp_b200_t* h, const void* in, void* out, int nFrames, 
     return 0;
 }
 
+
+// ---- multi-device instances: fan a call out over the shards, one host thread per GPU running next to it ----
+template <typename Fn>
+static int forShards(avdsp_b200* h, Fn fn) {
+    const size_t n = h->shards.size();
+    std::vector<int> rc(n, 0);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> th;
+    th.reserve(n);
+    for (size_t k = 0; k < n; k++)
+        th.emplace_back([&, k] {
+            bindThreadToNode(h->shards[k]->numaNode);        // staging thread next to its GPU (no-op when the topology is unknown)
+            rc[k] = fn((int)k, h->shards[k]);
+            if (rc[k] < 0) msg[k] = g_lastError;             // thread-local: carry it over to the caller's thread
+        });
+    for (auto& t : th) t.join();
+    for (size_t k = 0; k < n; k++) if (rc[k] < 0) return setErr(rc[k], "device " + std::to_string(h->shards[k]->device) + ": " + msg[k]);
+    return 0;
+}
+static int shardOf(const avdsp_b200* h, int stream) {
+    int k = 0;
+    while (k + 1 < (int)h->shards.size() && stream >= h->shardFirst[k + 1]) k++;
+    return k;
+}
+static int resetShards(avdsp_b200* h, int fs, const int32_t* seeds, int defaultDither) {
+    if (fs != h->L.fs || defaultDither != h->L.defaultDither) {
+        Lowered nl; std::string err;
+        const std::vector<int32_t> words = h->L.words;
+        const int rc = decodeProgram(words.data(), (int)words.size(), 0x7FFFFFFF, h->L.format, fs, defaultDither, &nl, &err);
+        if (rc < 0) return setErr(rc, err);
+        h->L = nl;
+    }
+    if (seeds) h->seeds.assign(seeds, seeds + h->nStreams); else h->seeds.clear();
+    return forShards(h, [&](int k, avdsp_b200* sh) { return avdsp_b200_reset(sh, fs, seeds ? seeds + h->shardFirst[k] : nullptr, defaultDither); });
+}
+
+extern "C" {
+
+int avdsp_b200_process(avdsp_b200_t* h, const void* in, void* out, int nFrames, int layout, int memspace) {
+    if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
+    if (nFrames < 0) return setErr(AVDSP_B200_ERR_ARG, "negative frame count");
+    if (nFrames == 0) return 0;
+    if (!h->shards.empty()) {
+        if (memspace != AVDSP_B200_HOST) return setErr(AVDSP_B200_ERR_UNSUPPORTED, "a multi-device instance processes HOST buffers (device buffers belong to one GPU)");
+        if (layout != AVDSP_B200_INTERLEAVED && layout != AVDSP_B200_PLANAR) return setErr(AVDSP_B200_ERR_ARG, "unknown layout");
+        const PlanHeader& P = h->L.gen.h;
+        // both layouts are stream-major: shard k's streams are one contiguous slice of either buffer
+        return forShards(h, [&](int k, avdsp_b200* sh) {
+            const size_t f = (size_t)h->shardFirst[k] * (size_t)nFrames;
+            return avdsp_b200_process(sh, (const int32_t*)in + f * P.nIn, (int32_t*)out + f * P.nOut, nFrames, layout, AVDSP_B200_HOST);
+        });
+    }
+    CU(cudaSetDevice(h->device));
+    if (memspace == AVDSP_B200_DEVICE) {
+        const int r = avdsp_b200_process_range(h, in, out, nFrames, layout, 0, h->nStreams, h->stream);
+        if (r < 0) return r;
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (memspace != AVDSP_B200_HOST) return setErr(AVDSP_B200_ERR_ARG, "unknown memspace");
+    return processHost(h, in, out, nFrames, layout, false);
+}
+
+int avdsp_b200_copy_only(avdsp_b200_t* h, const void* in, void* out, int nFrames, int layout) {
+    if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
+    if (nFrames <= 0) return nFrames < 0 ? setErr(AVDSP_B200_ERR_ARG, "negative frame count") : 0;
+    if (!h->shards.empty()) {
+        const PlanHeader& P = h->L.gen.h;
+        return forShards(h, [&](int k, avdsp_b200* sh) {
+            const size_t f = (size_t)h->shardFirst[k] * (size_t)nFrames;
+            return avdsp_b200_copy_only(sh, (const int32_t*)in + f * P.nIn, (int32_t*)out + f * P.nOut, nFrames, layout);
+        });
+    }
+    return processHost(h, in, out, nFrames, layout, true);
+}
+
+int avdsp_b200_create_multi(avdsp_b200_t** out, const int32_t* prog, int progWords, int fs, int format,
+                            int nStreams, const int32_t* seeds, int defaultDither, unsigned deviceMask) {
+    if (!out) return setErr(AVDSP_B200_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (nStreams < 1) return setErr(AVDSP_B200_ERR_ARG, "nStreams must be >= 1");
+    std::unique_ptr<avdsp_b200, void (*)(avdsp_b200*)> h(new avdsp_b200, freeAll);
+    std::string err;
+    const int rc = decodeProgram(prog, progWords, 0x7FFFFFFF, format, fs, defaultDither, &h->L, &err);
+    if (rc < 0) return setErr(rc, err);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return setErr(AVDSP_B200_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                               " (avdsp_b200 has no CPU fallback)");
+    std::vector<int> devs;
+    for (int d = 0; d < 32; d++) if ((deviceMask >> d) & 1u) { if (d >= ndev) return setErr(AVDSP_B200_ERR_ARG, "deviceMask names a device that does not exist"); devs.push_back(d); }
+    if (devs.empty()) return setErr(AVDSP_B200_ERR_ARG, "deviceMask is empty");
+    if (const char* rp = getenv("AVDSP_B200_MULTI_REPLICATE")) {       // tests on a one-GPU box: every device of the mask carries k shards
+        const int k = atoi(rp);
+        if (k > 1 && k <= 16) { const std::vector<int> base = devs; for (int i = 1; i < k; i++) devs.insert(devs.end(), base.begin(), base.end()); }
+    }
+    if ((int)devs.size() > nStreams) devs.resize(nStreams);
+    h->device = -1; h->nStreams = nStreams;
+    if (seeds) h->seeds.assign(seeds, seeds + nStreams);
+    // contiguous balanced ranges, the first (nStreams mod n) shards one stream longer (avdsp_b200/sharding.py: same partition)
+    const int n = (int)devs.size(), q = nStreams / n, r = nStreams % n;
+    h->shardFirst.assign(1, 0);
+    for (int k = 0; k < n; k++) h->shardFirst.push_back(h->shardFirst.back() + q + (k < r ? 1 : 0));
+    h->shards.assign(n, nullptr);
+    const int frc = forShards(h.get(), [&](int k, avdsp_b200* /*null*/) {
+        const int first = h->shardFirst[k], cnt = h->shardFirst[k + 1] - first;
+        return std::min(0, avdsp_b200_create(&h->shards[k], prog, progWords, fs, format, cnt, seeds ? seeds + first : nullptr, defaultDither, devs[k]));
+    });
+    if (frc < 0) { for (auto& sh : h->shards) { if (sh) freeAll(sh); } h->shards.clear(); return frc; }
+    h->trace = h->shards[0]->trace;
+    h->numSMs = h->shards[0]->numSMs;
+    g_lastError.clear();
+    *out = h.release();
+    return rc;
+}
+
+int avdsp_b200_num_devices(const avdsp_b200_t* h) { return !h ? 0 : h->shards.empty() ? 1 : (int)h->shards.size(); }
+int avdsp_b200_shard_info(const avdsp_b200_t* h, int k, int* device, int* firstStream, int* nStreams, int* numaNode) {
+    if (!h || k < 0 || k >= avdsp_b200_num_devices(h)) return setErr(AVDSP_B200_ERR_ARG, "bad shard index");
+    const avdsp_b200* sh = h->shards.empty() ? h : h->shards[k];
+    if (device) *device = sh->device;
+    if (firstStream) *firstStream = h->shards.empty() ? 0 : h->shardFirst[k];
+    if (nStreams) *nStreams = sh->nStreams;
+    if (numaNode) *numaNode = sh->numaNode;
+    return 0;
+}
+
+// PCM buffers placed for the instance: page-locked, and every shard's slice ([stream][...] layouts: contiguous) on the host
+// NUMA node next to the GPU that will DMA it.  bytesPerStream = nFrames * channels * 4 for the buffer in question.
+void* avdsp_b200_host_alloc(avdsp_b200_t* h, size_t bytesPerStream) {
+    if (!h || bytesPerStream == 0) { setErr(AVDSP_B200_ERR_ARG, "bad argument"); return nullptr; }
+    const int n = avdsp_b200_num_devices(h);
+    std::vector<size_t> off(1, 0);
+    std::vector<int> nodes;
+    for (int k = 0; k < n; k++) {
+        int first = 0, cnt = 0, node = -1;
+        avdsp_b200_shard_info(h, k, nullptr, &first, &cnt, &node);
+        off.push_back((size_t)(first + cnt) * bytesPerStream);
+        nodes.push_back(node);
+    }
+    const size_t bytes = (size_t)h->nStreams * bytesPerStream;
+    void* p = hostAllocPlaced(bytes, off, nodes);
+    if (!p) { setErr(AVDSP_B200_ERR_ARG, "host allocation failed"); return nullptr; }
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { hostFreePlaced(p, bytes); cudaErr(e, "cudaHostRegister"); return nullptr; }
+    h->hostAllocs[p] = bytes;
+    return p;
+}
+void avdsp_b200_host_free(avdsp_b200_t* h, void* p) {
+    if (!h || !p) return;
+    auto it = h->hostAllocs.find(p);
+    if (it == h->hostAllocs.end()) return;
+    cudaHostUnregister(p);
+    hostFreePlaced(p, it->second);
+    h->hostAllocs.erase(it);
+}
+
+} // extern "C"
+
+extern "C" {
+
 int avdsp_b200_process_pcm(avdsp_b200_t* h, const void* in, int pcmFormat, void* out, int nFrames, int memspace) {
     if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
     if (pcmFormat == AVDSP_B200_PCM_S32) return avdsp_b200_process(h, in, out, nFrames, AVDSP_B200_INTERLEAVED, memspace);
     if (pcmFormat != AVDSP_B200_PCM_S16 && pcmFormat != AVDSP_B200_PCM_S24_3LE) return setErr(AVDSP_B200_ERR_ARG, "unknown PCM format");
     if (nFrames < 0) return setErr(AVDSP_B200_ERR_ARG, "negative frame count");
     if (nFrames == 0) return 0;
+    if (!h->shards.empty()) {
+        if (memspace != AVDSP_B200_HOST) return setErr(AVDSP_B200_ERR_UNSUPPORTED, "a multi-device instance processes HOST buffers");
+        const PlanHeader& PP = h->L.gen.h;
+        const size_t bps = pcmFormat == AVDSP_B200_PCM_S16 ? 2 : 3;
+        return forShards(h, [&](int k, avdsp_b200* sh) {
+            const size_t f = (size_t)h->shardFirst[k] * (size_t)nFrames;
+            return avdsp_b200_process_pcm(sh, (const unsigned char*)in + f * PP.nIn * bps, pcmFormat, (int32_t*)out + f * PP.nOut, nFrames, memspace);
+        });
+    }
     CU(cudaSetDevice(h->device));
     const PlanHeader& P = h->L.gen.h;
     const size_t nIn = (size_t)h->nStreams * nFrames * P.nIn, nOut = (size_t)h->nStreams * nFrames * P.nOut;
@@ -671,22 +823,27 @@ int avdsp_b200_reload_params(avdsp_b200_t* h, const int32_t* prog, int progWords
     std::string err;
     const int rc = relowerProgram(prog, progWords, &h->L, &err);
     if (rc < 0) return setErr(rc, err);
-    CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(h->stream));
+    if (!h->shards.empty()) {
+        const int r = forShards(h, [&](int, avdsp_b200* sh) { return std::min(0, avdsp_b200_reload_params(sh, prog, progWords)); });
+        return r < 0 ? r : rc;
+    }
+    { const int q = quiesce(h); if (q < 0) return q; }
     const int r = uploadPlanData(h);
     return r < 0 ? r : rc;
 }
 
 int avdsp_b200_get_state(avdsp_b200_t* h, int stream, int32_t* words) {
     if (!h || !words || stream < 0 || stream >= h->nStreams) return setErr(AVDSP_B200_ERR_ARG, "bad stream index");
-    CU(cudaSetDevice(h->device));
+    if (!h->shards.empty()) { const int k = shardOf(h, stream); return avdsp_b200_get_state(h->shards[k], stream - h->shardFirst[k], words); }
+    { const int q = quiesce(h); if (q < 0) return q; }
     const int W = h->L.gen.h.stateWords;
     CU(cudaMemcpy(words, h->dState + (size_t)stream * W, (size_t)W * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 int avdsp_b200_set_state(avdsp_b200_t* h, int stream, const int32_t* words) {
     if (!h || !words || stream < 0 || stream >= h->nStreams) return setErr(AVDSP_B200_ERR_ARG, "bad stream index");
-    CU(cudaSetDevice(h->device));
+    if (!h->shards.empty()) { const int k = shardOf(h, stream); return avdsp_b200_set_state(h->shards[k], stream - h->shardFirst[k], words); }
+    { const int q = quiesce(h); if (q < 0) return q; }
     const int W = h->L.gen.h.stateWords;
     CU(cudaMemcpy(h->dState + (size_t)stream * W, words, (size_t)W * 4, cudaMemcpyHostToDevice));
     return 0;

@@ -7,7 +7,7 @@
 // kernel parameter: micro-op fetches are warp-uniform constant loads); (2) one warp runs 32
 // independent streams in lock step, so dispatch is never divergent; (3) all state the reference
 // keeps in process globals is per stream.  Programs that consist of independent signal paths take
-// the faster systolic kernel (kernel_chain.cu) instead; this one is the always-correct path.
+// the faster systolic kernel (kernel_chain2.cu, kernel_chain3.cu) instead; this one is the always-correct path.
 #include "avdsp_dev.cuh"
 #include "kernels.h"
 #include <algorithm>
@@ -53,12 +53,49 @@ template <int CLS, typename Ptr> __device__ __forceinline__ void stSP(Ptr p, typ
 template <int CLS> __device__ __forceinline__ auto par(int bits) {
     if constexpr (CLS == ALU_INT64) return bits; else return __int_as_float(bits);
 }
+// Plain C arithmetic of the reference's ALU type as its host executes it.  int64: wrapping.  double: the device's binary64 NaN
+// rules are the host's (default NaN 0xFFF8000000000000, payloads propagate).  float: the device returns the canonical NaN
+// 0x7FFFFFFF for every invalid operation and every NaN input, the x86 host the reference (and the goldens) run on returns the
+// "real indefinite" 0xFFC00000 for an invalid operation and the first NaN operand, quieted, otherwise.  That is visible:
+// DSP_DITHER in the float formats turns its zero-initialised error word into -inf on the very first frame (dspShiftFloat on
+// 0.0, dsp_ieee754.h:297-314), the next frames compute inf - inf, and the saturation (an exponent test on the raw bits,
+// :170-184) sends a negative NaN to -1.0 and a positive one to +1.0.
+__device__ __forceinline__ float nanX86(float r, float a, float b) {
+    if (__builtin_expect(r == r, 1)) return r;
+    const unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
+    if ((ua & 0x7FFFFFFFu) > 0x7F800000u) return __uint_as_float(ua | 0x00400000u);
+    if ((ub & 0x7FFFFFFFu) > 0x7F800000u) return __uint_as_float(ub | 0x00400000u);
+    return __uint_as_float(0xFFC00000u);
+}
+__device__ __forceinline__ long long aAdd(long long a, long long b) { return (long long)((unsigned long long)a + (unsigned long long)b); }
+__device__ __forceinline__ long long aSub(long long a, long long b) { return (long long)((unsigned long long)a - (unsigned long long)b); }
+__device__ __forceinline__ long long aMul(long long a, long long b) { return (long long)((unsigned long long)a * (unsigned long long)b); }
+__device__ __forceinline__ long long aNeg(long long a) { return (long long)(0ull - (unsigned long long)a); }
+__device__ __forceinline__ double aAdd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double aSub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double aMul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double aDiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double aNeg(double a) { return __longlong_as_double(__double_as_longlong(a) ^ (long long)0x8000000000000000ull); }
+__device__ __forceinline__ float aAdd(float a, float b) { return nanX86(__fadd_rn(a, b), a, b); }
+__device__ __forceinline__ float aSub(float a, float b) { return nanX86(__fsub_rn(a, b), a, b); }
+__device__ __forceinline__ float aMul(float a, float b) { return nanX86(__fmul_rn(a, b), a, b); }
+__device__ __forceinline__ float aDiv(float a, float b) { return nanX86(__fdiv_rn(a, b), a, b); }
+__device__ __forceinline__ float aNeg(float a) { return __uint_as_float(__float_as_uint(a) ^ 0x80000000u); }      // xorps: flips NaN signs too
+__device__ __forceinline__ float aSqrt(float a) {          // sqrt() of the promoted value, rounded back (double rounding is exact for sqrt)
+    if (a != a) return __uint_as_float(__float_as_uint(a) | 0x00400000u);
+    if (a < 0.0f) return __uint_as_float(0xFFC00000u);
+    return __fsqrt_rn(a);
+}
+__device__ __forceinline__ double aSqrt(double a) { return sqrt(a); }
+// cvttss2si: NaN and out-of-range give the "integer indefinite" 0x80000000 (the device would give 0 / saturate)
+__device__ __forceinline__ int f2iX86(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000; }
+
 // acc += a*b in the reference's arithmetic (dspmacs64_32_32 / dspMaccFloatFloat)
 template <int CLS, typename A, typename B>
 __device__ __forceinline__ void macc(typename AluT<CLS>::T& acc, A a, B b) {
     if constexpr (CLS == ALU_INT64) acc = mac32(acc, a, b);
-    else if constexpr (CLS == ALU_F32) acc = __fadd_rn(acc, mulFF(a, b));
-    else acc = __dadd_rn(acc, mulFD(a, b));
+    else if constexpr (CLS == ALU_F32) acc = aAdd(acc, mulFF(a, b));
+    else acc = aAdd(acc, mulFD(a, b));
 }
 template <int CLS> __device__ __forceinline__ typename AluT<CLS>::T i2a(int v, int shift) {
     if constexpr (CLS == ALU_F32) return i2fScaled(v, shift);
@@ -72,8 +109,8 @@ __device__ __forceinline__ TpdfTab makeTab(int d) { TpdfTab t; t.dither = d; t.m
 template <int CLS>
 __device__ __forceinline__ void tpdfApply(typename AluT<CLS>::T& X, const TpdfTab& t, int tpdfValue) {
     if constexpr (CLS == ALU_INT64) X += tpdfScaledI(tpdfValue, t.shift);
-    else if constexpr (CLS == ALU_F32) X = __fadd_rn(X, i2fScaled(tpdfValue, 31 + t.dither - 1));
-    else X = __dadd_rn(X, i2dScaled(tpdfValue, 31 + t.dither - 1));
+    else if constexpr (CLS == ALU_F32) X = aAdd(X, i2fScaled(tpdfValue, 31 + t.dither - 1));
+    else X = aAdd(X, i2dScaled(tpdfValue, 31 + t.dither - 1));
 }
 template <int CLS>
 __device__ __forceinline__ void tpdfTruncate(typename AluT<CLS>::T& X, const TpdfTab& t) {
@@ -110,21 +147,21 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
         case OP_COPYXY: Y = X; break;
         case OP_COPYYX: X = Y; break;
         case OP_CLRXY:  X = 0; Y = 0; break;
-        case OP_ADDXY: X = X + Y; break;
-        case OP_ADDYX: Y = Y + X; break;
-        case OP_SUBXY: X = X - Y; break;
-        case OP_SUBYX: Y = Y - X; break;
-        case OP_NEGX:  X = -X; break;
-        case OP_NEGY:  Y = -Y; break;
-        case OP_MULXY: X = X * Y; break;
+        case OP_ADDXY: X = aAdd(X, Y); break;
+        case OP_ADDYX: Y = aAdd(Y, X); break;
+        case OP_SUBXY: X = aSub(X, Y); break;
+        case OP_SUBYX: Y = aSub(Y, X); break;
+        case OP_NEGX:  X = aNeg(X); break;
+        case OP_NEGY:  Y = aNeg(Y); break;
+        case OP_MULXY: X = aMul(X, Y); break;
         case OP_DIVXY:
-            if constexpr (CLS == ALU_INT64) X = (Y == 0 || (X == LLONG_MIN && Y == -1)) ? 0 : X / Y; else X = X / Y;
+            if constexpr (CLS == ALU_INT64) X = (Y == 0 || (X == LLONG_MIN && Y == -1)) ? 0 : X / Y; else X = aDiv(X, Y);
             break;
         case OP_DIVYX:
-            if constexpr (CLS == ALU_INT64) Y = (X == 0 || (Y == LLONG_MIN && X == -1)) ? 0 : Y / X; else Y = Y / X;
+            if constexpr (CLS == ALU_INT64) Y = (X == 0 || (Y == LLONG_MIN && X == -1)) ? 0 : Y / X; else Y = aDiv(Y, X);
             break;
-        case OP_AVGXY: X = X / 2 + Y / 2; break;
-        case OP_AVGYX: Y = X / 2 + Y / 2; break;
+        case OP_AVGXY: if constexpr (CLS == ALU_INT64) X = X / 2 + Y / 2; else X = aAdd(aDiv(X, (ALU)2), aDiv(Y, (ALU)2)); break;
+        case OP_AVGYX: if constexpr (CLS == ALU_INT64) Y = X / 2 + Y / 2; else Y = aAdd(aDiv(X, (ALU)2), aDiv(Y, (ALU)2)); break;
         case OP_SHIFT:
             if constexpr (CLS == ALU_INT64) {
                 const int n = m.a;
@@ -142,8 +179,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
                     for (unsigned bit = 1u << 15; bit; bit >>= 1) { unsigned t = res | bit; t *= t; if (X >= (long long)t) res = t; }
                 }
                 X = res;
-            } else if constexpr (CLS == ALU_F32) X = (float)sqrt((double)X);
-            else X = sqrt(X);
+            } else X = aSqrt(X);
             break;
         case OP_SAT0DB: X = saturate<CLS>(X); break;
         case OP_SAT0DB_TPDF: tpdfApply<CLS>(X, tp, R.tpdfValue); X = saturate<CLS>(X); break;
@@ -182,7 +218,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             else if (sampleInt) {
                 const float t = i2fScaled(IO(m.a), 31);
                 if constexpr (CLS == ALU_F32) X = mulFF(t, __int_as_float(m.b)); else X = mulFD(t, __int_as_float(m.b));
-            } else { X = (ALU)__int_as_float(IO(m.a)); X = X * (ALU)__int_as_float(m.b); }
+            } else { X = (ALU)__int_as_float(IO(m.a)); X = aMul(X, (ALU)__int_as_float(m.b)); }
             break;
         case OP_LOAD_MUX: {
             X = 0;
@@ -205,16 +241,16 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
         case OP_STORE_MEM:     stA<CLS>(st + m.a, X); break;
         case OP_LOAD_MEM_DATA: X = ldA<CLS>(st + m.a); break;
         case OP_GAIN: case OP_MUL_VALUE:
-            if constexpr (CLS == ALU_INT64) X = X * (long long)m.a; else X = X * (ALU)__int_as_float(m.a);
+            if constexpr (CLS == ALU_INT64) X = X * (long long)m.a; else X = aMul(X, (ALU)__int_as_float(m.a));
             break;
         case OP_VALUE: Y = X; if constexpr (CLS == ALU_INT64) X = m.a; else X = (ALU)__int_as_float(m.a); break;
         case OP_VALUE_INT: Y = X; X = (ALU)m.a; break;
-        case OP_MUL_VALUE_INT: X = X * (ALU)m.a; break;
+        case OP_MUL_VALUE_INT: X = aMul(X, (ALU)m.a); break;
         case OP_DIV_VALUE:
-            if constexpr (CLS == ALU_INT64) X = (m.a == 0) ? 0 : X / m.a; else X = X / (ALU)__int_as_float(m.a);
+            if constexpr (CLS == ALU_INT64) X = (m.a == 0) ? 0 : X / m.a; else X = aDiv(X, (ALU)__int_as_float(m.a));
             break;
         case OP_DIV_VALUE_INT:
-            if constexpr (CLS == ALU_INT64) X = (m.a == 0) ? 0 : X / m.a; else X = X / (ALU)m.a;
+            if constexpr (CLS == ALU_INT64) X = (m.a == 0) ? 0 : X / m.a; else X = aDiv(X, (ALU)m.a);
             break;
         case OP_AND_VALUE_INT:
             if constexpr (CLS == ALU_INT64) X &= (long long)m.a;
@@ -329,10 +365,10 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             } else {
                 float xn = (float)X;
                 const float prevX = __int_as_float(sp[0]); sp[0] = __float_as_int(xn);
-                xn = __fsub_rn(xn, prevX);
+                xn = aSub(xn, prevX);
                 X = ldA<CLS>(ap);
                 const float prevY = (float)X;
-                X = X + (ALU)xn;
+                X = aAdd(X, (ALU)xn);
                 macc<CLS>(X, prevY, __int_as_float(m.b));
                 stA<CLS>(ap, X);
             }
@@ -340,13 +376,13 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
         case OP_DITHER: {
             SPi e = st + m.a;
             ALU t0 = ldA<CLS>(e); const ALU t1 = ldA<CLS>(e + AW), t2 = ldA<CLS>(e + 2 * AW);
-            X = X + t0;
+            X = aAdd(X, t0);
             if constexpr (CLS == ALU_INT64) t0 >>= 1; else if constexpr (CLS == ALU_F32) t0 = shiftF(t0, -1); else t0 = shiftD(t0, -1);
-            X = X - t1; X = X + t2;
+            X = aSub(X, t1); X = aAdd(X, t2);
             stA<CLS>(e + AW, t0); stA<CLS>(e + 2 * AW, t1);
             const ALU s0 = X;
             tpdfApply<CLS>(X, tp, R.tpdfValue); tpdfTruncate<CLS>(X, tp);
-            stA<CLS>(e, s0 - X);
+            stA<CLS>(e, aSub(s0, X));
             break; }
         case OP_DITHER_NS2: {
             SPi e = st + m.a;
@@ -357,7 +393,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             stSP<CLS>(e + 1, e0); stSP<CLS>(e + 2, e1);
             ALU s0 = X;
             tpdfApply<CLS>(X, tp, R.tpdfValue); tpdfTruncate<CLS>(X, tp);
-            s0 = s0 - X;
+            s0 = aSub(s0, X);
             if constexpr (CLS == ALU_INT64) e[0] = (int)(s0 >> kMant); else stSP<CLS>(e, (SPT)s0);
             break; }
         case OP_RMS: {
@@ -371,14 +407,14 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
                 if (factor > 0) { const int sv = (int)(((long long)(int)X * factor) >> 32); X = ldA<CLS>(sumsq); X = mac32(X, sv, sv); }
                 else { const int sx = (int)(((long long)(int)X * factor) >> 32), sy = (int)(((long long)(int)Y * factor) >> 32);
                        X = ldA<CLS>(sumsq); X = mac32(X, sx, sy); }
-            } else { if (factor > 0) X = X * X; else X = X * Y; X = X + ldA<CLS>(sumsq); }
+            } else { if (factor > 0) X = aMul(X, X); else X = aMul(X, Y); X = aAdd(X, ldA<CLS>(sumsq)); }
             if (counter >= maxCounter) {
                 if (delay) {
                     unsigned idx = d[1];
                     SPi line = sumsq + (2 * AW + (int)idx * AW);
                     const ALU old = ldA<CLS>(line);
                     stA<CLS>(line, X);
-                    X = X - old; X = X + ldA<CLS>(avg);
+                    X = aSub(X, old); X = aAdd(X, ldA<CLS>(avg));
                     idx++; if (idx >= delay) idx = 0;
                     d[1] = idx;
                 }
@@ -400,7 +436,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
                             X = (long long)d[2];
                         } else { X = (long long)d[3]; d[2] = (unsigned)X; }
                     }
-                } else X = (ALU)sqrt((double)ldA<CLS>(avg));
+                } else X = aSqrt(ldA<CLS>(avg));
             }
             break; }
         case OP_DISTRIB: {
@@ -411,7 +447,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             const SPT sv = (SPT)X;
             if (sv != 0) {
                 int pos;
-                if constexpr (CLS == ALU_INT64) pos = (int)(((long long)sv * size) >> 32); else pos = (int)(sv * (float)middle);
+                if constexpr (CLS == ALU_INT64) pos = (int)(((long long)sv * size) >> 32); else pos = f2iX86(aMul(sv, (float)middle));
                 pos += middle;
                 if (pos >= 0 && pos < size) tab[pos]++;
             }
@@ -440,7 +476,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             ALU th;
             if constexpr (CLS == ALU_INT64) th = (long long)((unsigned long long)0x80000000u * (unsigned long long)(unsigned)m.a);
             else th = (ALU)__int_as_float(m.a);
-            if (X > th) X = th; else if (X < -th) X = -th;
+            if (X > th) X = th; else if (X < aNeg(th)) X = aNeg(th);
             break; }
         default: break;
         }

@@ -33,28 +33,6 @@ struct ChainLane {
     int flags;       // bit0 head, bit1 tail
     int firstSec;    // index of the lane's first section inside the chain
 };
-struct ChainGeom {
-    int streamsPerCta;     // NS
-    int secPerLane;        // K
-    int laneThreads;       // threads that own sections (multiple of 32, may be 0)
-    int workThreads;       // threads taking part in the element-wise phases (>= laneThreads, multiple of 32)
-    int tileFrames;        // F
-    int maxDepth;          // pipeline depth in lanes
-    size_t smemBytes;
-};
-struct ChainArgs {
-    const int* in;  int* out;
-    int* state;
-    const ChainLane* lanes;     // [laneThreads]
-    int nStreams, nFrames;
-    long long inStreamStride, outStreamStride;
-    int inFrameStride, inChStride, outFrameStride, outChStride;
-};
-// choose CTA geometry for a plan and a stream count; fills the lane table (host memory)
-bool planChainGeometry(const ChainPlan& plan, int nStreams, int numSMs, ChainGeom* geom, ChainLane* lanesOut /*[1024]*/);
-cudaError_t launchChain(const ChainPlan& plan, const ChainGeom& geom, const ChainArgs& args, cudaStream_t stream);
-bool chainKernelSupports(const ChainPlan& plan);
-
 // ---- warp-specialised systolic chain kernel (kernel_chain2.cu) -----------------------------------
 struct Chain2Geom {
     int streamsPerCta;     // NS

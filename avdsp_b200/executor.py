@@ -36,7 +36,9 @@ def _check(rc: int) -> int:
 class Executor:
     """n_streams independent instances of one encoded DSP program on one GPU."""
 
-    def __init__(self, words, fs: int, fmt: int = 2, n_streams: int = 1, seeds=None, dither: int = 31, device: int = 0):
+    def __init__(self, words, fs: int, fmt: int = 2, n_streams: int = 1, seeds=None, dither: int = 31, device: int = 0, devices=None):
+        """devices: list of CUDA ordinals -> one multi-device instance (avdsp_b200_create_multi): the streams are cut into
+        contiguous ranges, one per GPU; such an instance takes host (numpy) buffers only."""
         L = _lib.lib()
         self._L = L
         self.words = np.ascontiguousarray(words, dtype=np.int32)
@@ -47,8 +49,16 @@ class Executor:
             self._seeds = np.ascontiguousarray(seeds, dtype=np.int32)
             assert self._seeds.shape == (n_streams,)
             sp = self._seeds.ctypes.data
-        self.total_length = _check(L.avdsp_b200_create(C.byref(self._h), self.words.ctypes.data, len(self.words), fs, fmt,
-                                                       n_streams, sp, dither, device))
+        if devices is None:
+            self.total_length = _check(L.avdsp_b200_create(C.byref(self._h), self.words.ctypes.data, len(self.words), fs, fmt,
+                                                           n_streams, sp, dither, device))
+        else:
+            mask = 0
+            for d in devices:
+                mask |= 1 << int(d)
+            self.total_length = _check(L.avdsp_b200_create_multi(C.byref(self._h), self.words.ctypes.data, len(self.words), fs, fmt,
+                                                                 n_streams, sp, dither, mask))
+        self.n_devices = L.avdsp_b200_num_devices(self._h)
         n_in, n_out = C.c_int(), C.c_int()
         a, b = (C.c_int * 32)(), (C.c_int * 32)()
         L.avdsp_b200_io_map(self._h, C.byref(n_in), a, C.byref(n_out), b)
@@ -61,6 +71,30 @@ class Executor:
         self.num_mem = L.avdsp_b200_num_mem(self._h)
         self.mem_words = [L.avdsp_b200_mem_word(self._h, k) for k in range(self.num_mem)]
         self.num_cores = L.avdsp_b200_num_cores(self._h)
+
+    def shards(self):
+        """[(device, first_stream, n_streams, numa_node)] per GPU of the instance"""
+        out = []
+        for k in range(self.n_devices):
+            v = [C.c_int() for _ in range(4)]
+            _check(self._L.avdsp_b200_shard_info(self._h, k, *[C.byref(q) for q in v]))
+            out.append(tuple(q.value for q in v))
+        return out
+
+    def alloc_pcm(self, n_frames: int, channels: int) -> np.ndarray:
+        """Page-locked int32 [n_streams, n_frames, channels] buffer placed for this instance (avdsp_b200_host_alloc: each GPU's
+        slice on the host NUMA node next to it).  Freed with the Executor."""
+        per = n_frames * channels * 4
+        p = self._L.avdsp_b200_host_alloc(self._h, per)
+        if not p:
+            raise AvdspError(-9, _lib.last_error())
+        buf = (C.c_int32 * (self.n_streams * n_frames * channels)).from_address(p)
+        return np.ctypeslib.as_array(buf).reshape(self.n_streams, n_frames, channels)
+
+    def copy_only(self, x_host: np.ndarray, y_host: np.ndarray, layout: int = INTERLEAVED):
+        """The DMA schedule of the host path without the kernel (avdsp_b200_copy_only): the copy roofline of process()."""
+        n_frames = x_host.shape[1] if layout == INTERLEAVED else x_host.shape[2]
+        _check(self._L.avdsp_b200_copy_only(self._h, x_host.ctypes.data, y_host.ctypes.data, n_frames, layout))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -159,6 +193,22 @@ class Executor:
             y = out
         stream = torch.cuda.current_stream(x.device).cuda_stream
         _check(self._L.avdsp_b200_process_async(self._h, x.data_ptr(), y.data_ptr(), n_frames, layout, stream))
+        return y
+
+    def process_range(self, x, first: int, out=None, layout: int = INTERLEAVED, stream=None):
+        """Streams [first, first + x.shape[0]) only, device tensors, enqueued on `stream` (a torch.cuda.Stream; default: the
+        current one).  Calls on one Executor are ordered by the library whatever stream they are given."""
+        import torch
+        n = int(x.shape[0])
+        n_frames = x.shape[1] if layout == INTERLEAVED else x.shape[2]
+        if not (x.is_cuda and x.dtype in (torch.int32, torch.float32) and x.is_contiguous()):
+            raise ValueError("device input must be a contiguous 32-bit CUDA tensor")
+        so = (n, n_frames, self.n_out) if layout == INTERLEAVED else (n, self.n_out, n_frames)
+        y = torch.empty(so, dtype=x.dtype, device=x.device) if out is None else out
+        if tuple(y.shape) != so or not y.is_contiguous():
+            raise ValueError(f"out must be contiguous with shape {so}")
+        st = (stream or torch.cuda.current_stream(x.device)).cuda_stream
+        _check(self._L.avdsp_b200_process_range(self._h, x.data_ptr(), y.data_ptr(), n_frames, layout, first, n, st))
         return y
 
     @staticmethod

@@ -47,6 +47,12 @@ WORKLOADS = {
 }
 
 
+def workload_config(desc, prog, S, T, fs, n_in, n_out):
+    """`config` of the JSON line: the same keys and values in both arms (ours / reference)"""
+    return {"workload": desc, "program": prog, "streams_per_gpu": S, "frames_per_step": T, "fs": fs, "n_in": n_in, "n_out": n_out,
+            "layout": "interleaved [stream][frame][channel] int32"}
+
+
 def prog_file(name):
     return os.path.join(ROOT, "tests", "golden", "programs", name + ".bin")
 
@@ -128,17 +134,17 @@ def run_reference(args, wl):
     fr = max(1500000 * 240 // wl[5] // 1000 * 1000, 1000) if args.frames is None else args.frames   # bounded sample: ~0.6 s per host thread per step
     for _ in range(args.warmup):
         cpu_reference_rate(prog, fmt, fs, max(1000, fr // 20), cores)
-    tot_frames, tot_s, kind, n_out = 0.0, 0.0, "reference", 8
+    tot_frames, tot_s, kind, n_out, n_in = 0.0, 0.0, "reference", 8, 2
     for _ in range(args.steps):
         r = cpu_reference_rate(prog, fmt, fs, fr, cores)
-        tot_frames += r["frames"]; tot_s += r["seconds"]; kind = r["kind"]; n_out = r["n_out"]; used = r["cores"]
+        tot_frames += r["frames"]; tot_s += r["seconds"]; kind = r["kind"]; n_out = r["n_out"]; n_in = r.get("n_in", n_in); used = r["cores"]
     val = tot_frames * n_out / tot_s / 1e6
     sample = f"{used} streams x {fr} frames per step (one stream per host thread), stream-major, canonical core order"
     line = {"impl": "reference", "metric": "channel-samples/sec", "value": val, "unit": "Msps", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64" if fmt == 2 else "f32",
             "data": "synthetic",
-            "config": {"workload": desc, "program": prog, "streams": S, "frames_per_step": T, "fs": fs},
+            "config": workload_config(desc, prog, S if args.streams is None else args.streams, T, fs, n_in, n_out),
             "cpu_baseline": {"value": val, "unit": "Msps", "cores": used, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -154,7 +160,11 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=None)
     ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank owns --streams streams of its own (default); strong: --streams is the whole job, sharded over the ranks "
+                         "(BASELINE configs[2]: 65536 float streams sharded across 2/4/8)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-multi", action="store_true", help="skip the one-call multi-device arm (avdsp_b200_create_multi) at N > 1")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "chain", "chain_v2", "chain_v3", "mix", "fir", "fir_tc"],
                     help="force a kernel (diagnostics; the default is what the product picks)")
@@ -196,7 +206,11 @@ def main():
         torch.cuda.synchronize()
 
     words = avdsp_b200.load_bin(prog_file(prog))
-    first = rank * S                                   # weak scaling: rank r owns streams [r*S, (r+1)*S)
+    S_job = S * world if args.scaling == "weak" else S
+    if args.scaling == "strong":                       # the job's streams sharded over the ranks (contiguous balanced ranges)
+        first, S = avdsp_b200.shard_range(S_job, rank, world)
+    else:
+        first = rank * S                               # weak scaling: rank r owns streams [r*S, (r+1)*S)
     seeds = np.arange(first, first + S, dtype=np.int32)
     ex = avdsp_b200.Executor(words, fs, fmt, S, seeds=seeds, dither=31, device=local)
     if args.kernel != "auto":
@@ -235,30 +249,66 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    frames_job = float(S) * T * world * args.steps
+    frames_job = float(S_job) * T * args.steps
     value = frames_job * n_out / (total_ms * 1e-3) / 1e6
 
     # ---- end to end through the host-facing C-ABI call: pinned host PCM in, pinned host PCM out
     e2e = None
     if not args.no_e2e:
-        xh = torch.empty((S, T, n_in), dtype=torch.int32).pin_memory()
-        yh = torch.empty((S, T, n_out), dtype=torch.int32).pin_memory()
-        xh.copy_(x)
+        # page-locked host PCM placed on the NUMA node next to this rank's GPU (avdsp_b200_host_alloc)
+        xh = ex.alloc_pcm(T, n_in)
+        yh = ex.alloc_pcm(T, n_out)
+        xh[:] = x.cpu().numpy()
         torch.cuda.synchronize()
+
+        def timed(fn, reps):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()                               # synchronous: returns when the outputs are in host memory
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt.item())
+
         for _ in range(2):
             ex.process_pinned(xh, yh)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            ex.process_pinned(xh, yh)          # synchronous: returns when the outputs are in host memory
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": frames_job * n_out / float(dt.item()) / 1e6, "unit": "Msps",
+        dt = timed(lambda: ex.process_pinned(xh, yh), args.steps)
+        chk = int(yh[0, :64].astype(np.int64).sum())
+        # the same DMA schedule without the kernel: what PCIe + host memory allow for this call on this box
+        ex.copy_only(xh, yh)
+        dtc = timed(lambda: ex.copy_only(xh, yh), max(2, args.steps // 2)) / max(2, args.steps // 2) * args.steps
+        e2e = {"value": frames_job * n_out / dt / 1e6, "unit": "Msps",
                "h2d_bytes_per_step": S * T * n_in * 4, "d2h_bytes_per_step": S * T * n_out * 4,
-               "ms_per_step": 1e3 * float(dt.item()) / args.steps,
-               "checksum": int(yh[0, :64].to(torch.int64).sum().item())}
+               "ms_per_step": 1e3 * dt / args.steps, "checksum": chk,
+               "host_buffers": "avdsp_b200_host_alloc: page-locked, on the NUMA node next to the GPU",
+               "numa_node": ex.shards()[0][3],
+               "roofline": {"bound": "pcie+host memory (copy-only run of the same call: same buffers, same 2-D chunked DMA schedule, no kernel)",
+                            "achieved": (S * T * (n_in + n_out) * 4) * world / (dt / args.steps) / 1e9,
+                            "peak": (S * T * (n_in + n_out) * 4) * world / (dtc / args.steps) / 1e9, "unit": "GB/s (both directions, whole job)",
+                            "frac": dtc / dt}}
+        # one C call over all GPUs of the box (avdsp_b200_create_multi), timed on rank 0 while the other ranks idle
+        if world > 1 and not args.no_multi:
+            ex_m = None
+            barrier()
+            if rank == 0:
+                ex_m = avdsp_b200.Executor(words, fs, fmt, S_job, seeds=np.arange(S_job, dtype=np.int32), dither=31, devices=list(range(world)))
+                xm = ex_m.alloc_pcm(T, n_in)
+                ym = ex_m.alloc_pcm(T, n_out)
+                for a0 in range(0, S_job, S):            # synthetic PCM: rank 0's block repeated
+                    nn = min(S, S_job - a0)
+                    xm[a0:a0 + nn] = xh[:nn]
+                ex_m.process(xm, out=ym)
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    ex_m.process(xm, out=ym)
+                dtm = time.perf_counter() - t0
+                e2e["multi_device_call"] = {"value": frames_job * n_out / dtm / 1e6, "unit": "Msps", "ms_per_step": 1e3 * dtm / args.steps,
+                                            "api": "avdsp_b200_create_multi + avdsp_b200_process(HOST): one process, one call, one staging thread per GPU",
+                                            "devices": world, "shards": ex_m.shards()}
+                ex_m.close()
+            barrier()
         del xh, yh
 
     if rank != 0:
@@ -281,7 +331,11 @@ def main():
             if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
         traffic = tot or None
-    common = {"traffic": traffic, "kernel": f"k_{kname}", "kernel_ms": kernel_ms, "launches_per_step": launches_per_step}
+    # `traffic` (DRAM bytes per launch) cannot be measured inside an un-profiled run: null here, and the figure of the committed
+    # ncu capture of this workload + kernel is quoted beside it with its source (it does not follow code changes by itself)
+    traffic_ncu = {"value": traffic, "source": f"profiles/{prof_name}_ncu_summary.txt (committed `ncu --set full` capture, not this run)"} if traffic else None
+    traffic = None
+    common = {"traffic": traffic, "traffic_ncu": traffic_ncu, "kernel": f"k_{kname}", "kernel_ms": kernel_ms, "launches_per_step": launches_per_step}
     hbm = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
            "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, **common}
     hbm["frac"] = hbm["achieved"] / hbm["peak"]
@@ -329,12 +383,11 @@ def main():
                          f"{r['seconds']:.2f} s"}
 
     line = {"metric": "channel-samples/sec", "value": value, "unit": "Msps", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "int64" if fmt == 2 else "f32", "data": "synthetic",
-            "config": {"workload": desc, "program": prog, "streams_per_gpu": S, "frames_per_step": T, "fs": fs,
-                       "n_in": n_in, "n_out": n_out, "layout": "interleaved [stream][frame][channel] int32",
-                       "l2": f"inputs+outputs {alg_bytes / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)",
-                       "kernel": kname, "frames_per_s": frames_job / (total_ms * 1e-3)},
+            "config": workload_config(desc, prog, S if args.scaling == "weak" else S_job, T, fs, n_in, n_out),
+            "run": {"l2": f"inputs+outputs {alg_bytes / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)",
+                    "kernel": kname, "frames_per_s": frames_job / (total_ms * 1e-3), "streams_job": S_job, "streams_this_rank": S},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": binding, "roofline_hbm": hbm, ("roofline_int" if fmt == 2 else "roofline_fp32"): pipe, "cpu_baseline": cpu}
     print(json.dumps(line), file=json_out, flush=True)

@@ -20,6 +20,7 @@
 #ifndef AVDSP_B200_H_
 #define AVDSP_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -91,7 +92,7 @@ enum { AVDSP_B200_INTERLEAVED = 0,     /* [stream][frame][channel]  (what ALSA h
 enum { AVDSP_B200_HOST = 0, AVDSP_B200_DEVICE = 1 };
 /* kernel selection (diagnostics and tests; AUTO is the product behaviour) */
 enum { AVDSP_B200_KERNEL_AUTO = 0, AVDSP_B200_KERNEL_GENERIC = 1, AVDSP_B200_KERNEL_CHAIN = 2,
-       AVDSP_B200_KERNEL_CHAIN_V1 = 3 /* the earlier tile-synchronous chain kernel, kept for A/B runs */,
+       AVDSP_B200_KERNEL_CHAIN_V1 = 3 /* removed (the first, tile-synchronous chain kernel): selecting it returns ERR_UNSUPPORTED */,
        AVDSP_B200_KERNEL_MIX = 4      /* time-parallel kernel for programs without biquads (mixers, delays, dither) */,
        AVDSP_B200_KERNEL_FIR = 5      /* time-parallel tiled DSP_FIR kernels (runtime/dsp_firSTD.h, dsp_runtime.c:928-969) */,
        AVDSP_B200_KERNEL_FIR_TC = 6   /* DSP_FIR as a Toeplitz GEMM on tcgen05 tensor cores: DSP_FORMAT 2 bit-exact (8-bit limbs, the
@@ -107,6 +108,23 @@ enum { AVDSP_B200_KERNEL_AUTO = 0, AVDSP_B200_KERNEL_GENERIC = 1, AVDSP_B200_KER
  * returns totalLength (>0) or a negative error code. */
 int  avdsp_b200_create(avdsp_b200_t **out, const int32_t *prog, int progWords, int fs, int format,
                        int nStreams, const int32_t *seeds, int defaultDither, int device);
+/* The same over several GPUs of one box (SURVEY.md 8b `deviceMask`): bit d of deviceMask = CUDA device d takes part.  The
+ * streams are cut into contiguous balanced ranges, one per device (the first nStreams mod n ranges one stream longer); each
+ * range is an independent single-device instance, no collective on the data path.  A multi-device instance takes HOST
+ * buffers only (avdsp_b200_process / _process_pcm / _copy_only with AVDSP_B200_HOST): one call fans the buffer out, one
+ * staging thread per GPU running on the host NUMA node next to it.  Everything else (reset, reload_params, set_order,
+ * get/set_state by global stream index, io_map, ...) works as on a single-device instance; avdsp_b200_process_async /
+ * _process_range return AVDSP_B200_ERR_UNSUPPORTED. */
+int  avdsp_b200_create_multi(avdsp_b200_t **out, const int32_t *prog, int progWords, int fs, int format,
+                             int nStreams, const int32_t *seeds, int defaultDither, unsigned deviceMask);
+int  avdsp_b200_num_devices(const avdsp_b200_t *);
+/* shard k of the instance: its CUDA device, stream range and the host NUMA node next to that device (-1: unknown) */
+int  avdsp_b200_shard_info(const avdsp_b200_t *, int k, int *device, int *firstStream, int *nStreams, int *numaNode);
+/* Page-locked PCM buffer of nStreams * bytesPerStream bytes placed for this instance: every shard's slice (both layouts are
+ * stream-major, so a shard's streams are one contiguous slice) lies on the host NUMA node next to the GPU that will DMA
+ * it.  The host path works with any host memory; buffers from here are what makes it scale over the GPUs of a box. */
+void *avdsp_b200_host_alloc(avdsp_b200_t *, size_t bytesPerStream);
+void avdsp_b200_host_free(avdsp_b200_t *, void *p);
 void avdsp_b200_destroy(avdsp_b200_t *);
 /* dspRuntimeReset for every stream: zero the data area, re-seed the PRNG, MEM words back to the
  * program's initial values.  fs may change (must stay inside the program's range). */
@@ -121,7 +139,13 @@ int  avdsp_b200_io_map(const avdsp_b200_t *, int *nIn, int *inIdx, int *nOut, in
  * order (frame-major, cores ascending, one io[] per frame) unless avdsp_b200_set_order chose the
  * plugin's.  Any split of a frame range into successive calls gives identical output. Synchronous. */
 int  avdsp_b200_process(avdsp_b200_t *, const void *in, void *out, int nFrames, int layout, int memspace);
-/* Same with device buffers, enqueued on the caller's CUDA stream (cudaStream_t as void*), no sync. */
+/* The DMA schedule of avdsp_b200_process(HOST) without the kernel launches: what the box's PCIe / host memory can do for
+ * exactly this call.  bench.py reports e2e against it. */
+int  avdsp_b200_copy_only(avdsp_b200_t *, const void *in, void *out, int nFrames, int layout);
+/* Same with device buffers, enqueued on the caller's CUDA stream (cudaStream_t as void*), no sync.
+ * Calls on ONE instance are stream-ordered by the library whatever stream they are given (each launch waits for the
+ * instance's previous launch: launches continue each other's state and share per-instance scratch); instances are
+ * independent of each other.  reload_params / reset / get_state / set_state wait for everything launched before. */
 int  avdsp_b200_process_async(avdsp_b200_t *, const void *in, void *out, int nFrames, int layout, void *cudaStream);
 /* Process a sub-range of the streams: [firstStream, firstStream+nStreams) (buffers hold only those). */
 int  avdsp_b200_process_range(avdsp_b200_t *, const void *in, void *out, int nFrames, int layout,

@@ -639,3 +639,70 @@ def test_delay_first_paths_with_patched_delays(oracle_lib):
                 assert np.array_equal(y[s], orcs[s].process(xs[s])), (part, s, ex.last_kernel)
         for s in (0, S - 1):
             assert np.array_equal(ex.get_state(s)[: ex.data_size], orcs[s].data), (s, ex.last_kernel)
+
+
+@pytest.mark.parametrize("prog,fs", [("c5_mixer8x8_f2_192k", 192000), ("c2_testrpi_xover_f2_192k", 192000), ("c4_fir4096_f2_48k", 48000)])
+def test_ranges_on_two_cuda_streams_equal_one_call(prog, fs):
+    """avdsp_b200_process_range with firstStream != 0 on two CUDA streams at once: launches of one instance share scratch
+    (dither rows, FIR workspace, PRNG jump matrices), the library orders them itself (include/avdsp_b200.h)."""
+    import torch
+    w = load_program(prog)
+    S, T = 96, 1024
+    seeds = np.arange(S, dtype=np.int32) + 3
+    a = Executor(w, fs, 2, S, seeds=seeds)
+    b = Executor(w, fs, 2, S, seeds=seeds)
+    x = torch.from_numpy(synth.pcm("full", S, T, a.n_in, fs)).cuda()
+    ref = a.process(x)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    cut = 40
+    for rep in range(2):                        # second round: continues the state, other split
+        lo, hi = (cut, S - cut) if rep == 0 else (S - cut, cut)
+        if rep == 1:
+            ref = a.process(x)
+            torch.cuda.synchronize()
+        with torch.cuda.stream(s1):
+            y1 = b.process_range(x[:lo].contiguous(), 0, stream=s1)
+        with torch.cuda.stream(s2):
+            y2 = b.process_range(x[lo:].contiguous(), lo, stream=s2)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat([y1, y2]), ref), rep
+    for s in (0, cut - 1, cut, S - 1):
+        assert np.array_equal(a.get_state(s), b.get_state(s))
+
+
+@pytest.mark.parametrize("replicate", [1, 3])
+def test_multi_device_instance_fans_host_buffers_out(oracle_lib, monkeypatch, replicate):
+    """avdsp_b200_create_multi (SURVEY.md 8b deviceMask): one C call over every GPU of the box.  On a one-GPU box the shards
+    are replicated on device 0 (AVDSP_B200_MULTI_REPLICATE) so that the range arithmetic is exercised all the same."""
+    import torch
+    ndev = torch.cuda.device_count()
+    monkeypatch.setenv("AVDSP_B200_MULTI_REPLICATE", str(replicate))
+    w = load_program("c2_testrpi_xover_f2_192k")
+    fs, S, T = 192000, 37, 700
+    seeds = np.arange(S, dtype=np.int32) * 5 + 2
+    ex = Executor(w, fs, 2, S, seeds=seeds, dither=24, devices=list(range(ndev)))
+    sh = ex.shards()
+    assert len(sh) == ndev * replicate and sh[0][1] == 0 and sum(n for _, _, n, _ in sh) == S
+    assert all(a[1] + a[2] == b[1] for a, b in zip(sh, sh[1:]))                  # contiguous ranges
+    assert max(n for _, _, n, _ in sh) - min(n for _, _, n, _ in sh) <= 1         # balanced
+    x = ex.alloc_pcm(T, ex.n_in)
+    y = ex.alloc_pcm(T, ex.n_out)
+    x[:] = synth.pcm("full", S, T, ex.n_in, fs)
+    ys, sts = oracle_run(oracle_lib, w, 2, fs, x, seeds, 24)
+    ex.process(x[:, :300].copy(), out=None)                                         # plain (unplaced) memory works too
+    ex.reset(seeds=seeds, dither=24)
+    ex.process(x, out=y)
+    assert np.array_equal(y, ys)
+    for s in (0, sh[-1][1], S - 1):
+        assert np.array_equal(ex.get_state(s), expected_state(ex, sts[s])), s
+    z = np.zeros_like(y)
+    ex.copy_only(x, z)                                                              # same DMA schedule, no kernel: state untouched
+    assert np.array_equal(ex.get_state(S - 1), expected_state(ex, sts[S - 1]))
+    with pytest.raises(AvdspError):
+        ex.process(torch.zeros((S, 8, ex.n_in), dtype=torch.int32, device="cuda"))  # device buffers belong to one GPU
+    # S16 periods through the multi instance
+    raw = (x[:, :64] >> 16).astype(np.int16)
+    ex.reset(seeds=seeds, dither=24)
+    one = Executor(w, fs, 2, S, seeds=seeds, dither=24)
+    assert np.array_equal(ex.process_pcm(raw, 1, 64), one.process_pcm(raw, 1, 64))
