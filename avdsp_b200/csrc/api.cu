@@ -627,7 +627,7 @@ static int forShards(avdsp_b200* h, Fn fn) {
     th.reserve(n);
     for (size_t k = 0; k < n; k++)
         th.emplace_back([&, k] {
-            bindThreadToNode(h->shards[k]->numaNode);        // staging thread next to its GPU (no-op when the topology is unknown)
+            if (h->shards[k]) bindThreadToNode(h->shards[k]->numaNode);      // staging thread next to its GPU (no-op when the topology is unknown)
             rc[k] = fn((int)k, h->shards[k]);
             if (rc[k] < 0) msg[k] = g_lastError;             // thread-local: carry it over to the caller's thread
         });
@@ -721,8 +721,10 @@ int avdsp_b200_create_multi(avdsp_b200_t** out, const int32_t* prog, int progWor
     h->shardFirst.assign(1, 0);
     for (int k = 0; k < n; k++) h->shardFirst.push_back(h->shardFirst.back() + q + (k < r ? 1 : 0));
     h->shards.assign(n, nullptr);
-    const int frc = forShards(h.get(), [&](int k, avdsp_b200* /*null*/) {
+    const int frc = forShards(h.get(), [&](int k, avdsp_b200* /*not created yet*/) {
         const int first = h->shardFirst[k], cnt = h->shardFirst[k + 1] - first;
+        char bus[64] = {0};
+        if (cudaDeviceGetPCIBusId(bus, sizeof bus, devs[k]) == cudaSuccess) bindThreadToNode(numaNodeOfPci(bus));   // state and staging allocations next to the GPU
         return std::min(0, avdsp_b200_create(&h->shards[k], prog, progWords, fs, format, cnt, seeds ? seeds + first : nullptr, defaultDither, devs[k]));
     });
     if (frc < 0) { for (auto& sh : h->shards) { if (sh) freeAll(sh); } h->shards.clear(); return frc; }
