@@ -402,7 +402,8 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
     } else return setErr(AVDSP_B200_ERR_ARG, "unknown layout");
     int* st = h->dState + (size_t)first * P.stateWords;
     CU(cudaStreamWaitEvent(stream, h->evLast, 0));          // stream-ordered after the instance's previous launch (see evLast)
-    const bool chainOrder = h->period == 0 && coreSel < 0 && !planOverride;
+    // the fused kernels run the canonical order; a plugin-order request may use them when the two orders provably agree
+    const bool chainOrder = (h->period == 0 || h->L.orderIndependent) && coreSel < 0 && !planOverride;
     int use = AVDSP_B200_KERNEL_GENERIC;
     if (chainOrder && h->kernelSel != AVDSP_B200_KERNEL_GENERIC) {
         if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1)

@@ -486,6 +486,62 @@ void buildFirPlan(Lowered* L) {
     for (int k = 0; k < g.h.nOut; k++) if (owner[k] < 0) f.unwritten[f.nUnwritten++] = k;
 }
 
+// Do the two loop orders agree?  Inside one core the op sequence is the same in both; what differs is WHEN a core sees what
+// another core left behind.  So: no MEM word, io slot or dither state may cross a core boundary, and what the plugin copies
+// in and out per core (its DSP_CORE bitmaps, fresh io[] per core and frame) must cover what the core reads and writes.
+void analyseOrder(Lowered* L) {
+    const GenericPlan& g = L->gen;
+    auto no = [&](const char* why) { L->orderIndependent = false; L->orderWhy = why; };
+    L->orderIndependent = true; L->orderWhy.clear();
+    if (g.h.nCores <= 1) return;
+    int tpdfCore = -1;
+    std::map<int, int> memCore;                       // MEM state offset -> the one core that touches it
+    int writer[kIoSlots], reader[kIoSlots];
+    for (int k = 0; k < kIoSlots; k++) writer[k] = reader[k] = -1;
+    uint32_t hostIn = 0;
+    for (int k = 0; k < g.h.nIn; k++) hostIn |= 1u << g.h.inIdx[k];
+    for (int c = 0; c < g.h.nCores; c++) {
+        const uint32_t cin = L->cores[c].usedIn, cout = L->cores[c].usedOut;
+        auto rd = [&](int slot) { if (reader[slot] >= 0 && reader[slot] != c) reader[slot] = -2; else if (reader[slot] != -2) reader[slot] = c;
+                                  return !((hostIn >> slot) & 1u) || ((cin >> slot) & 1u); };
+        auto wr = [&](int slot) { if (writer[slot] >= 0 && writer[slot] != c) writer[slot] = -2; else if (writer[slot] != -2) writer[slot] = c;
+                                  return ((cout >> slot) & 1u) != 0; };
+        for (int i = g.h.coreStart[c]; i < g.h.coreStart[c + 1]; i++) {
+            const MicroOp& m = g.ops[i];
+            bool ok = true;
+            switch (m.op) {
+            case OP_TPDF_CALC:
+                if (tpdfCore >= 0 && tpdfCore != c) return no("DSP_TPDF_CALC in more than one core");
+                tpdfCore = c;
+                if (m.a != g.h.defaultDither && c != 0) return no("DSP_TPDF_CALC switches the dither table in a core other than the first");
+                break;
+            case OP_LOAD: case OP_LOAD_GAIN: ok = rd(m.a); break;
+            case OP_LOAD_MUX: for (int k = 0; k < m.n; k++) ok = rd(g.pool[m.a + 2 * k]) && ok; break;
+            case OP_STORE: case OP_DISTRIB: ok = wr(m.a); break;
+            case OP_LOAD_STORE: for (int k = 0; k < m.n; k++) { ok = rd(g.pool[m.a + 2 * k]) && ok; ok = wr(g.pool[m.a + 2 * k + 1]) && ok; } break;
+            case OP_LOAD_MEM: case OP_STORE_MEM: {
+                auto it = memCore.find(m.a);
+                if (it == memCore.end()) memCore[m.a] = c; else if (it->second != c) return no("a MEM word is shared between cores");
+                break; }
+            case OP_LOAD_MEM_DATA: return no("DSP_LOAD_MEM_DATA reads another opcode's data words");
+            default: break;
+            }
+            if (!ok) return no("a core reads or writes an io slot its DSP_CORE bitmaps do not list (the plugin would not copy it)");
+        }
+    }
+    for (int k = 0; k < kIoSlots; k++)
+        if (reader[k] != -1 && writer[k] != -1 && (reader[k] == -2 || writer[k] == -2 || reader[k] != writer[k])) return no("an io slot is handed from one core to another");
+    if (tpdfCore >= 0)
+        for (int c = 0; c < g.h.nCores; c++) {
+            if (c == tpdfCore) continue;
+            for (int i = g.h.coreStart[c]; i < g.h.coreStart[c + 1]; i++) {
+                const int op = g.ops[i].op;
+                if (op == OP_SAT0DB_TPDF || op == OP_SAT0DB_TPDF_GAIN || op == OP_DITHER || op == OP_DITHER_NS2 || op == OP_TPDF || op == OP_WHITE)
+                    return no("a core uses the dither value another core computes");
+            }
+        }
+}
+
 void lowerAll(Lowered* L) {
     Ctx cx; cx.L = L; cx.w = L->words.data(); cx.total = L->totalLength;
     cx.delayFactor = (uint32_t)(4294.967296 * (double)L->fs);      // dsp_runtime.c:81-90
@@ -518,6 +574,7 @@ void lowerAll(Lowered* L) {
     for (int i = 0; i < g.h.nOps; i++)
         if (g.ops[i].op == OP_LOAD_MEM || g.ops[i].op == OP_STORE_MEM) g.ops[i].a = g.h.memOff + 2 * g.ops[i].a;
 
+    analyseOrder(L);
     try { buildChainPlan(L); L->chainOk = true; L->chainWhyNot.clear(); }
     catch (const ChainFail& f) { L->chainOk = false; L->chainWhyNot = f.why; }
     try { buildFirPlan(L); L->firOk = true; L->firWhyNot.clear(); }
@@ -533,6 +590,7 @@ void lowerAll(Lowered* L) {
             snprintf(line, sizeof line, "  %3d op=%2d n=%d a=%d b=%d c=%d\n", i, m.op, m.n, m.a, m.b, m.c); L->trace += line;
         }
     }
+    L->trace += std::string("loop order: ") + (L->orderIndependent ? "plugin order == canonical order (no data crosses a core boundary)" : ("order-dependent: " + L->orderWhy)) + "\n";
     snprintf(line, sizeof line, "state: data=%d aux@%d mem@%d x%d words/stream=%d; chain kernel: %s%s\n",
              g.h.dataSize, g.h.auxOff, g.h.memOff, g.h.nMem, g.h.stateWords, L->chainOk ? "yes" : "no: ", L->chainWhyNot.c_str());
     L->trace += line;

@@ -31,6 +31,11 @@ struct Lowered {
     bool firOk = false;                  // program maps to the time-parallel FIR kernels (kernel_fir.cu)
     std::string firWhyNot;
     FirPlan fir{};
+    // true when no data flows from one core to another (MEM words, io slots, the TPDF value / dither table): then the ALSA
+    // plugin's core-major loop nest (linux/avdsp_plugin.c:95-142) and the canonical frame-major order give identical results
+    // for every period size, and a plugin-order request can run on the fused kernels
+    bool orderIndependent = false;
+    std::string orderWhy;
     // MEM words (LOAD_MEM / STORE_MEM targets inside the code area)
     std::vector<int> memWord;            // code word index of each slot
     // human readable trace of the lowering (replaces the reference's DSP_PRINTF=2 opcode trace)

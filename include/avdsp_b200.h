@@ -82,7 +82,7 @@ enum {
     AVDSP_B200_ERR_CUDA        = -10,
     AVDSP_B200_ERR_MALFORMED   = -11,  /* a pointer/offset in the program leaves the program or its data area */
     AVDSP_B200_ERR_PLAN_SIZE   = -12,  /* lowered plan exceeds the kernel-parameter budget */
-    AVDSP_B200_ERR_ENCODER_OLD = -13   /* file made by an encoder older than 0x102 (module_avdsp/rpi/*.bin: 11-word header, TPDF_CALC
+    AVDSP_B200_ERR_ENCODER_OLD = -13   /* file made by an encoder older than 0x102 (the .bin files under module_avdsp/rpi: 11-word header, TPDF_CALC
                                           without its data word): the reference runtime does not check and walks into wild offsets */
 };
 

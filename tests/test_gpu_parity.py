@@ -213,7 +213,8 @@ def test_plugin_order_mode(oracle_lib):
         canon = Executor(w, fs, 2, S, seeds=[0, 1, 2], dither=24).process(x)
         ex.set_order(period)
         y = ex.process(x)
-        assert ex.last_kernel == "generic"
+        # C2's cores do not talk to each other: the decoder proves both orders equal and keeps the fused kernel
+        assert ex.last_kernel == ("chain" if int(w[8]) == 9 else "generic")
         nin, nout = max(ex.in_idx) - 8 + 1, max(ex.out_idx) + 1
         for s in range(S):
             o = oracle_lib.Oracle(w, 2, fs, seed=s, dither=24)

@@ -94,3 +94,23 @@ def test_odd_cascade_lengths_are_cut_into_near_equal_parts():
     assert sorted(map(tuple, sizes.values())) == [(1,), (3,), (3,), (3, 2), (4, 3)]
     # the ring must hold two tiles, the largest lag (second part of the 7-section chain: 3 + 32 + 2) and the longest delay (40)
     assert "largest lag 37 frames" in ln and "row ring 256 steps" in ln
+
+
+def test_loop_order_analysis():
+    """The decoder proves when the ALSA plugin's core-major loop nest equals the canonical order (no MEM word, io slot or
+    dither value crosses a core boundary); only then does a plugin-order request keep the fused kernels."""
+    def order(prog, fs, fmt=2):
+        return [ln for ln in avdsp_b200.describe(load_program(prog), fs, fmt).splitlines() if ln.startswith("loop order")][0]
+    for prog, fs in (("c2_testrpi_xover_f2_192k", 192000), ("c3_peq16_f2_48k", 48000), ("c5_mixer8x8_f2_192k", 192000)):
+        assert "plugin order == canonical order" in order(prog, fs), prog
+    assert "MEM word is shared" in order("ref_dacdiy1", 192000)
+    assert "dither value another core computes" in order("ref_crossoverLV6", 48000)
+    from oracle import wire
+    a = wire.Asm(fmt=2)
+    a.core(); a.load(8); a.store(0)
+    a.core(); a.load(0); a.store(1)                      # io hand-off: core 2 reads what core 1 stored
+    assert "handed from one core to another" in [ln for ln in avdsp_b200.describe(a.end(), 48000, 2).splitlines() if ln.startswith("loop order")][0]
+    a = wire.Asm(fmt=2)
+    a.core(); a.load(8); a.store(0)
+    a.core(); a.tpdf_calc(20); a.load(9); a.store(1)     # the dither table (STORE mask) changes in core 2: core 1's first period differs
+    assert "switches the dither table" in [ln for ln in avdsp_b200.describe(a.end(), 48000, 2).splitlines() if ln.startswith("loop order")][0]
