@@ -10,3 +10,4 @@ from .executor import (AvdspError, Executor, describe, measure_int_peak, measure
                        KERNEL_CHAIN_V2, KERNEL_CHAIN_V3)
 from .program import load, load_bin, load_hex, header  # noqa: F401
 from .sharding import shard_range  # noqa: F401
+from . import params  # noqa: F401

@@ -24,7 +24,7 @@ SYMBOLS = [
     "avdsp_b200_set_state", "avdsp_b200_num_streams", "avdsp_b200_num_cores", "avdsp_b200_trace",
     "avdsp_b200_last_error", "avdsp_b200_measure_int_peak", "avdsp_b200_measure_f32_peak",
     "avdsp_b200_create_multi", "avdsp_b200_num_devices", "avdsp_b200_shard_info", "avdsp_b200_host_alloc", "avdsp_b200_host_free",
-    "avdsp_b200_copy_only",
+    "avdsp_b200_copy_only", "avdsp_b200_param_index", "avdsp_b200_set_param", "avdsp_b200_num_variants",
 ]
 
 _lib = None
@@ -62,6 +62,9 @@ def lib():
     L.avdsp_b200_host_free.argtypes = [vp, vp]
     L.avdsp_b200_host_free.restype = None
     L.avdsp_b200_copy_only.argtypes = [vp, vp, vp, ci, ci]
+    L.avdsp_b200_param_index.argtypes = [vp, ci, ci]
+    L.avdsp_b200_set_param.argtypes = [vp, ci, ci, ci, vp, ci]
+    L.avdsp_b200_num_variants.argtypes = [vp]
     L.avdsp_b200_destroy.argtypes = [vp]
     L.avdsp_b200_destroy.restype = None
     L.avdsp_b200_reset.argtypes = [vp, ci, vp, ci]

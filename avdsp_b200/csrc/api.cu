@@ -242,6 +242,9 @@ static void freeAll(avdsp_b200* h) {
         delete h;
         return;
     }
+    if (h->evLast) cudaEventSynchronize(h->evLast);
+    for (avdsp_b200* v : h->variants) freeAll(v);
+    h->variants.clear();
     cudaSetDevice(h->device);
     if (h->dState) cudaFree(h->dState);
     if (h->dBig) cudaFree(h->dBig);
@@ -335,6 +338,14 @@ int avdsp_b200_reset(avdsp_b200_t* h, int fs, const int32_t* seeds, int defaultD
         if (nl.gen.h.stateWords != h->L.gen.h.stateWords) return setErr(AVDSP_B200_ERR_ARG, "state layout changed on reset");
         h->L = nl;
         const int r = uploadPlanData(h); if (r < 0) return r;
+        for (avdsp_b200* v : h->variants) {                   // the overrides stay; their plans follow the new rate / dither
+            Lowered vl;
+            const std::vector<int32_t> vw = v->L.words;
+            const int vr = decodeProgram(vw.data(), (int)vw.size(), 0x7FFFFFFF, h->L.format, fs, defaultDither, &vl, &err);
+            if (vr < 0) return setErr(vr, err);
+            v->L = vl;
+            const int ur = uploadPlanData(v); if (ur < 0) return ur;
+        }
     }
     if (seeds) h->seeds.assign(seeds, seeds + h->nStreams); else h->seeds.clear();
     return initState(h);
@@ -385,10 +396,12 @@ const char* avdsp_b200_trace(const avdsp_b200_t* h) { return h ? h->trace.c_str(
 
 // One launch over streams [first, first+n) with device buffers.  coreSel/plan override serve the
 // dspRuntime_<fmt> compatibility path.
-static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int layout, int first, int n,
-                       cudaStream_t stream, int coreSel = -1, const GenericPlan* planOverride = nullptr, int cap = 0) {
+// `pl` carries the plans (the instance itself, or the variant a per-stream parameter override created, see avdsp_b200_set_param);
+// state, scratch and bookkeeping are the instance's.
+static int launchRun(avdsp_b200* h, avdsp_b200* pl, const int* in, int* out, int nFrames, int layout, int first, int n,
+                     cudaStream_t stream, int coreSel, const GenericPlan* planOverride, int cap) {
     if (nFrames == 0 || n == 0) return 0;
-    const GenericPlan& G = planOverride ? *planOverride : h->L.gen;
+    const GenericPlan& G = planOverride ? *planOverride : pl->L.gen;
     const PlanHeader& P = G.h;
     const int nIn = P.nIn, nOut = P.nOut;
     if (cap <= 0) cap = nFrames;            // frames the buffers are laid out for (>= nFrames: staging slots are reused for a shorter last chunk)
@@ -403,40 +416,40 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
     int* st = h->dState + (size_t)first * P.stateWords;
     CU(cudaStreamWaitEvent(stream, h->evLast, 0));          // stream-ordered after the instance's previous launch (see evLast)
     // the fused kernels run the canonical order; a plugin-order request may use them when the two orders provably agree
-    const bool chainOrder = (h->period == 0 || h->L.orderIndependent) && coreSel < 0 && !planOverride;
+    const bool chainOrder = (h->period == 0 || pl->L.orderIndependent) && coreSel < 0 && !planOverride;
     int use = AVDSP_B200_KERNEL_GENERIC;
     if (chainOrder && h->kernelSel != AVDSP_B200_KERNEL_GENERIC) {
         if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1)
             return setErr(AVDSP_B200_ERR_UNSUPPORTED, "the first, tile-synchronous chain kernel was removed; use AVDSP_B200_KERNEL_CHAIN");
-        if (h->chain2Usable) use = AVDSP_B200_KERNEL_CHAIN;
+        if (pl->chain2Usable) use = AVDSP_B200_KERNEL_CHAIN;
     }
-    if (chainOrder && h->mixUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_MIX)) use = AVDSP_B200_KERNEL_MIX;
-    if (chainOrder && h->firUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_FIR)) use = AVDSP_B200_KERNEL_FIR;
+    if (chainOrder && pl->mixUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_MIX)) use = AVDSP_B200_KERNEL_MIX;
+    if (chainOrder && pl->firUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_FIR)) use = AVDSP_B200_KERNEL_FIR;
     // tensor-core Toeplitz GEMM: the bit-exact int8-limb form is the default for fixed-point batches that fill a tile;
     // the 3xTF32 form (stated tolerance) only on request
-    if (chainOrder && h->firUsable && (h->kernelSel == AVDSP_B200_KERNEL_FIR_TC ||
-        (h->kernelSel == AVDSP_B200_KERNEL_AUTO && h->L.fir.aluClass == ALU_INT64 && n >= 32 && nFrames >= 128 && h->L.fir.maxLen >= 256)))
+    if (chainOrder && pl->firUsable && (h->kernelSel == AVDSP_B200_KERNEL_FIR_TC ||
+        (h->kernelSel == AVDSP_B200_KERNEL_AUTO && pl->L.fir.aluClass == ALU_INT64 && n >= 32 && nFrames >= 128 && pl->L.fir.maxLen >= 256)))
         use = AVDSP_B200_KERNEL_FIR_TC;
     if (h->kernelSel == AVDSP_B200_KERNEL_FIR_TC && use != AVDSP_B200_KERNEL_FIR_TC)
-        return setErr(AVDSP_B200_ERR_UNSUPPORTED, "tensor-core FIR kernel requested but this program/order does not map to it: " + h->L.firWhyNot);
+        return setErr(AVDSP_B200_ERR_UNSUPPORTED, "tensor-core FIR kernel requested but this program/order does not map to it: " + pl->L.firWhyNot);
     if (h->kernelSel == AVDSP_B200_KERNEL_FIR && use != AVDSP_B200_KERNEL_FIR)
-        return setErr(AVDSP_B200_ERR_UNSUPPORTED, "FIR kernel requested but this program/order does not map to it: " + h->L.firWhyNot);
+        return setErr(AVDSP_B200_ERR_UNSUPPORTED, "FIR kernel requested but this program/order does not map to it: " + pl->L.firWhyNot);
     if (h->kernelSel == AVDSP_B200_KERNEL_MIX && use != AVDSP_B200_KERNEL_MIX)
         return setErr(AVDSP_B200_ERR_UNSUPPORTED, "mix kernel requested but the program has biquads or does not map to independent paths");
     if ((h->kernelSel == AVDSP_B200_KERNEL_CHAIN || h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V1 || h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V2 ||
          h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V3) && use == AVDSP_B200_KERNEL_GENERIC)
-        return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel requested but this program/order does not map to it: " + h->L.chainWhyNot);
+        return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel requested but this program/order does not map to it: " + pl->L.chainWhyNot);
     cudaError_t e;
     if (use == AVDSP_B200_KERNEL_FIR || use == AVDSP_B200_KERNEL_FIR_TC) {
         FirArgs A{};
-        A.in = in; A.out = out; A.state = st; A.bigPool = h->dBig;
+        A.in = in; A.out = out; A.state = st; A.bigPool = pl->dBig;
         A.nStreams = n; A.nFrames = nFrames;
         A.inStreamStride = inSS; A.outStreamStride = outSS;
         A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
         int nl = 0;
         if (use == AVDSP_B200_KERNEL_FIR_TC) {
-            const int kind = h->L.fir.aluClass == ALU_INT64 ? FIRTC_I8 : FIRTC_TF32;
-            const size_t need = firTcWorkspaceBytes(h->L.fir, kind, n, nFrames);
+            const int kind = pl->L.fir.aluClass == ALU_INT64 ? FIRTC_I8 : FIRTC_TF32;
+            const size_t need = firTcWorkspaceBytes(pl->L.fir, kind, n, nFrames);
             if (need > h->firWsBytes) {
                 CU(cudaStreamSynchronize(stream));
                 if (h->dFirWs) cudaFree(h->dFirWs);
@@ -444,8 +457,8 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
                 CU(cudaMalloc(&h->dFirWs, need));
                 h->firWsBytes = need;
             }
-            e = launchFirTc(h->L.fir, kind, A, h->dFirTaps, h->dFirWs, stream, &nl);
-        } else e = launchFir(h->L.fir, A, h->numSMs, stream, &nl);
+            e = launchFirTc(pl->L.fir, kind, A, pl->dFirTaps, h->dFirWs, stream, &nl);
+        } else e = launchFir(pl->L.fir, A, h->numSMs, stream, &nl);
         h->lastKernel = use;
         h->launches += nl - 1;
     } else if (use == AVDSP_B200_KERNEL_MIX) {
@@ -457,8 +470,8 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         A.vecIn = inCS == 1 && inFS == nIn && (inSS & 3) == 0 && ((size_t)in & 15) == 0;
         A.vecOut = outCS == 1 && (nOut & 3) == 0 && (outFS & 3) == 0 && (outSS & 3) == 0 && ((size_t)out & 15) == 0;
         int J = 1, Lseg = nFrames;
-        mixPrngSegments(h->mix, A, h->numSMs, &J, &Lseg);
-        if (h->mix.hasCalc || h->mix.anyTpdf) {
+        mixPrngSegments(pl->mix, A, h->numSMs, &J, &Lseg);
+        if (pl->mix.hasCalc || pl->mix.anyTpdf) {
             const size_t need = (size_t)n * nFrames;
             if (need > h->tpdfWords) { if (h->dTpdf) cudaFree(h->dTpdf); h->dTpdf = nullptr; CU(cudaMalloc(&h->dTpdf, need * 4)); h->tpdfWords = need; }
             constexpr int kJumpLevels = kMixJumpLevels;       // thread j applies M^(2L * 2^b) for the bits b set in j
@@ -473,12 +486,12 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         }
         A.tpdfBuf = h->dTpdf;
         int nl = 1;
-        e = launchMix(h->mix, A, h->dJump, J, Lseg, h->numSMs, stream, &nl);
+        e = launchMix(pl->mix, A, h->dJump, J, Lseg, h->numSMs, stream, &nl);
         h->lastKernel = AVDSP_B200_KERNEL_MIX;
         h->launches += nl - 1;                               // one is counted below
     } else if (use == AVDSP_B200_KERNEL_CHAIN) {
         Chain2Args A{};
-        A.in = in; A.out = out; A.state = st; A.lanes = h->dLanes2;
+        A.in = in; A.out = out; A.state = st; A.lanes = pl->dLanes2;
         A.nStreams = n; A.nFrames = nFrames;
         A.inStreamStride = inSS; A.outStreamStride = outSS;
         A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
@@ -487,31 +500,51 @@ static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int 
         // against v2's 9.50; with whole 6- and 8-section cascades per warp v3 is the slower one) and the call is long enough to
         // pay for v3's pipeline fill and drain (parts run a tile behind each other: C2 breaks even near 1500 frames per call --
         // 128 frames: v2 0.083 ms / v3 0.117, 1024: 0.262 / 0.267, 4096: 0.864 / 0.816); everything else runs on v2
-        const bool v3Ok = h->chain3Usable && use == AVDSP_B200_KERNEL_CHAIN;
+        const bool v3Ok = pl->chain3Usable && use == AVDSP_B200_KERNEL_CHAIN;
         static const int envChain3 = [] { const char* v = getenv("AVDSP_B200_CHAIN3"); return (v && *v) ? atoi(v) : -1; }();
         bool v3 = v3Ok && h->kernelSel != AVDSP_B200_KERNEL_CHAIN_V2 &&
                   (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V3 || envChain3 == 1 ||
-                   (envChain3 != 0 && h->geom3.maxSec <= 4 && h->geom3.streamsPerCta >= 16 && nFrames >= std::max(1536, 48 * h->geom3.gmax)));
+                   (envChain3 != 0 && pl->geom3.maxSec <= 4 && pl->geom3.streamsPerCta >= 16 && nFrames >= std::max(1536, 48 * pl->geom3.gmax)));
         if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V3 && !v3)
             return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel v3 requested but the program shape does not map to it");
-        if (v3) e = launchChain3(h->L.chain, h->geom3, A, stream);
-        else e = launchChain2(h->L.chain, h->geom2, A, stream);
+        if (v3) e = launchChain3(pl->L.chain, pl->geom3, A, stream);
+        else e = launchChain2(pl->L.chain, pl->geom2, A, stream);
         h->lastChainVariant = v3 ? 3 : 2;
         h->lastKernel = AVDSP_B200_KERNEL_CHAIN;
     } else {
         GenericArgs A{};
-        A.in = in; A.out = out; A.state = st; A.bigPool = h->dBig;
+        A.in = in; A.out = out; A.state = st; A.bigPool = pl->dBig;
         A.nStreams = n; A.nFrames = nFrames;
         A.inStreamStride = inSS; A.outStreamStride = outSS;
         A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
         A.coreSel = coreSel; A.period = coreSel >= 0 ? 0 : h->period;
-        for (int c = 0; c < P.nCores && c < kMaxCores; c++) { A.coreInMask[c] = h->L.cores[c].usedIn; A.coreOutMask[c] = h->L.cores[c].usedOut; }
+        for (int c = 0; c < P.nCores && c < kMaxCores; c++) { A.coreInMask[c] = pl->L.cores[c].usedIn; A.coreOutMask[c] = pl->L.cores[c].usedOut; }
         e = launchGeneric(G, A, stream);
         h->lastKernel = AVDSP_B200_KERNEL_GENERIC;
     }
     if (e != cudaSuccess) return cudaErr(e, "kernel launch");
     CU(cudaEventRecord(h->evLast, stream));
     h->launches++;
+    return 0;
+}
+
+
+// Streams [first, first+n): one launch, or one per run of streams that share a parameter variant.
+static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int layout, int first, int n,
+                       cudaStream_t stream, int coreSel = -1, const GenericPlan* planOverride = nullptr, int cap = 0) {
+    if (h->variantOf.empty() || planOverride) return launchRun(h, h, in, out, nFrames, layout, first, n, stream, coreSel, planOverride, cap);
+    const PlanHeader& P = h->L.gen.h;
+    const size_t c = (size_t)(cap > 0 ? cap : nFrames);
+    for (int a = first; a < first + n;) {
+        const int v = h->variantOf[a];
+        int b = a + 1;
+        while (b < first + n && h->variantOf[b] == v) b++;
+        const size_t off = (size_t)(a - first) * c;                // both layouts are stream-major
+        const int r = launchRun(h, v ? h->variants[v - 1] : h, in ? in + off * P.nIn : in, out ? out + off * P.nOut : out, nFrames, layout,
+                                a, b - a, stream, coreSel, nullptr, cap);
+        if (r < 0) return r;
+        a = b;
+    }
     return 0;
 }
 
@@ -821,6 +854,105 @@ int avdsp_b200_process_pcm(avdsp_b200_t* h, const void* in, int pcmFormat, void*
     return 0;
 }
 
+} // extern "C"
+
+// ---- per-stream parameter overrides (the dump-file workflow per stream) -------------------------------
+static void dropVariants(avdsp_b200* h) {
+    for (avdsp_b200* v : h->variants) freeAll(v);
+    h->variants.clear();
+    h->variantOf.clear();
+}
+// plans for `words` (the loaded program with some PARAM words replaced): an existing variant with exactly these words, or a new one
+static int variantFor(avdsp_b200* h, const std::vector<int32_t>& words, int* id) {
+    if (words == h->L.words) { *id = 0; return 0; }
+    for (size_t k = 0; k < h->variants.size(); k++) if (h->variants[k]->L.words == words) { *id = (int)k + 1; return 0; }
+    std::unique_ptr<avdsp_b200, void (*)(avdsp_b200*)> v(new avdsp_b200, freeAll);
+    v->device = h->device; v->numSMs = h->numSMs; v->nStreams = h->nStreams;
+    v->L = h->L;
+    std::string err;
+    const int rc = relowerProgram(words.data(), (int)words.size(), &v->L, &err);       // same opcode structure, same state layout, else an error
+    if (rc < 0) return setErr(rc, err);
+    const int r = uploadPlanData(v.get());
+    if (r < 0) return r;
+    h->variants.push_back(v.release());
+    *id = (int)h->variants.size();
+    return 0;
+}
+
+extern "C" {
+
+int avdsp_b200_param_index(const avdsp_b200_t* h, int offset, int paramNum) {
+    if (!h) return setErr(AVDSP_B200_ERR_ARG, "NULL instance");
+    const std::vector<int32_t>& w = h->L.words;
+    const int total = h->L.totalLength;
+    if (paramNum == 0) return (offset >= 0 && offset < total) ? offset : setErr(AVDSP_B200_ERR_ARG, "parameter offset outside the program");
+    // encoder/dsp_encoder.c:380-412 (findInParamSpace): relative to the first data word of the DSP_PARAM_NUM section with this number
+    for (int p = 0; p < total;) {
+        const int op = wordOpcode(w[p]), sk = wordSkip(w[p]);
+        if (sk == 0) break;
+        if (op == OP_PARAM_NUM && p + 1 < total && w[p + 1] == paramNum) {
+            const int idx = p + 2 + offset;
+            return (offset >= 0 && idx < p + sk) ? idx : setErr(AVDSP_B200_ERR_ARG, "parameter offset outside its DSP_PARAM_NUM section");
+        }
+        p += sk;
+    }
+    return setErr(AVDSP_B200_ERR_ARG, "no DSP_PARAM_NUM section with this number");
+}
+
+int avdsp_b200_set_param(avdsp_b200_t* h, int firstStream, int nStreams, int wordIndex, const int32_t* values, int nWords) {
+    if (!h || !values) return setErr(AVDSP_B200_ERR_ARG, "NULL argument");
+    if (firstStream < 0 || nStreams < 0 || firstStream + nStreams > h->nStreams) return setErr(AVDSP_B200_ERR_ARG, "bad stream range");
+    if (wordIndex < 0 || nWords < 0 || wordIndex + nWords > h->L.totalLength) return setErr(AVDSP_B200_ERR_ARG, "parameter words outside the program");
+    if (nStreams == 0 || nWords == 0) return 0;
+    if (!h->shards.empty()) {
+        for (size_t k = 0; k < h->shards.size(); k++) {
+            const int a = std::max(firstStream, h->shardFirst[k]), b = std::min(firstStream + nStreams, h->shardFirst[k + 1]);
+            if (b <= a) continue;
+            const int r = avdsp_b200_set_param(h->shards[k], a - h->shardFirst[k], b - a, wordIndex, values, nWords);
+            if (r < 0) return r;
+        }
+        return 0;
+    }
+    { const int q = quiesce(h); if (q < 0) return q; }
+    if (h->variantOf.empty()) h->variantOf.assign(h->nStreams, 0);
+    // streams of the range may sit on different variants already: patch each of those once
+    std::map<int, int> moved;                 // old variant -> new variant
+    for (int s = firstStream; s < firstStream + nStreams; s++) {
+        const int old = h->variantOf[s];
+        auto it = moved.find(old);
+        if (it == moved.end()) {
+            std::vector<int32_t> words = old ? h->variants[old - 1]->L.words : h->L.words;
+            for (int k = 0; k < nWords; k++) words[wordIndex + k] = values[k];
+            int id = 0;
+            const int r = variantFor(h, words, &id);
+            if (r < 0) return r;
+            it = moved.emplace(old, id).first;
+        }
+        h->variantOf[s] = it->second;
+    }
+    // variants nobody runs any more are released (ids above shift down)
+    std::vector<int> used(h->variants.size() + 1, 0);
+    for (int v : h->variantOf) used[v] = 1;
+    std::vector<int> remap(h->variants.size() + 1, 0);
+    std::vector<avdsp_b200*> keep;
+    for (size_t k = 0; k < h->variants.size(); k++) {
+        if (used[k + 1]) { keep.push_back(h->variants[k]); remap[k + 1] = (int)keep.size(); }
+        else freeAll(h->variants[k]);
+    }
+    h->variants.swap(keep);
+    bool any = false;
+    for (int& v : h->variantOf) { v = remap[v]; any = any || v != 0; }
+    if (!any) h->variantOf.clear();
+    return 0;
+}
+
+int avdsp_b200_num_variants(const avdsp_b200_t* h) {
+    if (!h) return 0;
+    int n = h->shards.empty() ? 1 + (int)h->variants.size() : 0;
+    for (const avdsp_b200* sh : h->shards) n += 1 + (int)sh->variants.size();
+    return n;
+}
+
 int avdsp_b200_reload_params(avdsp_b200_t* h, const int32_t* prog, int progWords) {
     if (!h || !prog) return setErr(AVDSP_B200_ERR_ARG, "NULL argument");
     std::string err;
@@ -831,6 +963,7 @@ int avdsp_b200_reload_params(avdsp_b200_t* h, const int32_t* prog, int progWords
         return r < 0 ? r : rc;
     }
     { const int q = quiesce(h); if (q < 0) return q; }
+    dropVariants(h);                                          // a new program for everybody: per-stream overrides start over
     const int r = uploadPlanData(h);
     return r < 0 ? r : rc;
 }

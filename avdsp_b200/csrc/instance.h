@@ -50,6 +50,11 @@ struct avdsp_b200 {
     // one single-device instance per GPU, contiguous balanced ranges (stream s of the whole = stream s - shardFirst[k] of shard k)
     std::vector<avdsp_b200*> shards;
     std::vector<int> shardFirst;       // [nShards + 1]
+    // per-stream parameter overrides (avdsp_b200_set_param): variantOf[s] == 0: the program as loaded, v > 0: variants[v - 1],
+    // an object of this type that only carries plans (own L, dBig, dLanes2, dFirTaps, geometries) for the patched words.
+    // Empty variantOf: no override anywhere.  Streams keep their state blocks whatever variant they run.
+    std::vector<int> variantOf;
+    std::vector<avdsp_b200*> variants;
     int numaNode = -1;                 // host NUMA node next to `device` (-1: unknown)
     std::map<void*, size_t> hostAllocs;   // avdsp_b200_host_alloc: pointer -> bytes
 };

@@ -124,6 +124,19 @@ class Executor:
         _check(self._L.avdsp_b200_reload_params(self._h, w.ctypes.data, len(w)))
         self.words = w
 
+    def param_index(self, offset: int, param_num: int = 0) -> int:
+        """dump-file entry (offset, PARAM_NUM number) -> word index in the program (avdsp_b200_param_index)"""
+        return _check(self._L.avdsp_b200_param_index(self._h, offset, param_num))
+
+    def set_param(self, first_stream: int, n_streams: int, word_index: int, values):
+        """streams [first_stream, first_stream + n_streams) run with program words [word_index, ...) replaced by `values`"""
+        v = np.ascontiguousarray(values, dtype=np.int32).reshape(-1)
+        _check(self._L.avdsp_b200_set_param(self._h, first_stream, n_streams, word_index, v.ctypes.data, len(v)))
+
+    @property
+    def num_variants(self) -> int:
+        return int(self._L.avdsp_b200_num_variants(self._h))
+
     @property
     def last_kernel(self) -> str:
         return KERNEL_NAMES[self._L.avdsp_b200_last_kernel(self._h)]

@@ -171,6 +171,18 @@ long long avdsp_b200_launch_count(const avdsp_b200_t *);
  * program -- the dump-file workflow, encoder/dsp_encoder.c:476-503.  Opcode structure must be unchanged. */
 int  avdsp_b200_reload_params(avdsp_b200_t *, const int32_t *prog, int progWords);
 
+/* Per-stream parameters (the dump-file workflow per stream: a different crossover / EQ / delay / gain per room).
+ * From now on the streams [firstStream, firstStream + nStreams) run with the program words [wordIndex, wordIndex + nWords)
+ * replaced by `values` (PARAM data: gains, biquad coefficients, delay words, bypass flags ...).  Cumulative per stream;
+ * opcode words and the state layout must stay as they are (same rule as avdsp_b200_reload_params, which also clears every
+ * override).  Streams keep their state.  Cost model: streams that share one parameter set AND are neighbours run in one
+ * launch -- give each room a contiguous stream range.  avdsp_b200_param_index turns a dump-file entry `name offset num size`
+ * (encoder/dsp_encoder.c:476-503: offset relative to the data of DSP_PARAM_NUM section `num`, absolute when num == 0) into
+ * the word index to pass here. */
+int  avdsp_b200_param_index(const avdsp_b200_t *, int offset, int paramNum);
+int  avdsp_b200_set_param(avdsp_b200_t *, int firstStream, int nStreams, int wordIndex, const int32_t *values, int nWords);
+int  avdsp_b200_num_variants(const avdsp_b200_t *);      /* distinct parameter sets alive (1 = no override) */
+
 /* Per-stream state block, int32 words:  [0,dataSize) = the reference data area, same word offsets
  * (runtime/dsp_runtime.c:137-141);  then 8 aux words (xoshiro s0..s3, tpdfValue, tpdfRandom, current
  * global dither, pad -- the reference's process globals, runtime/dsp_tpdf.h:11-33);  then the 64-bit

@@ -29,9 +29,10 @@ PROGDIR = os.path.join(ROOT, "tests", "golden", "programs")
 VECDIR = os.path.join(ROOT, "tests", "golden", "vectors")
 REF_OSX = "/root/reference/module_avdsp/osx"
 
+PROGDIR_EARLY = os.path.join(ROOT, "tests", "golden", "programs")   # the symbol table dspcreate -dumpfile writes for C1 is a fixture too
 # name -> (program .so, output kind, dspcreate arguments)
 PROGRAMS = {
-    "c1_crossover2x2lfe_f2_48k":   ("crossover2x2lfe", "bin", "-dspformat 2 -fsmin 48000 -fsmax 48000 -dumpfile /tmp/avdsp_dump.txt"),
+    "c1_crossover2x2lfe_f2_48k":   ("crossover2x2lfe", "bin", "-dspformat 2 -fsmin 48000 -fsmax 48000 -dumpfile " + os.path.join(PROGDIR_EARLY, "c1_crossover2x2lfe_f2_48k.dump")),
     "c2_testrpi_xover_f2_192k":    ("testrpi", "bin", "-dspformat 2 -fsmin 192000 -fsmax 192000 -crossover"),
     "c2_testrpi_xover_f2_multifs": ("testrpi", "bin", "-dspformat 2 -fsmax 192000 -crossover"),
     "c3_peq16_f3_48k":             ("c3_peq16", "bin", "-dspformat 3 -fsmin 48000 -fsmax 48000"),

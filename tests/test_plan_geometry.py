@@ -114,3 +114,19 @@ def test_loop_order_analysis():
     a.core(); a.load(8); a.store(0)
     a.core(); a.tpdf_calc(20); a.load(9); a.store(1)     # the dither table (STORE mask) changes in core 2: core 1's first period differs
     assert "switches the dither table" in [ln for ln in avdsp_b200.describe(a.end(), 48000, 2).splitlines() if ln.startswith("loop order")][0]
+
+
+def test_dump_file_symbol_table_resolves_to_program_words():
+    """`dspcreate -dumpfile` (encoder/dsp_encoder.c:476-503): name, offset, PARAM_NUM number, size"""
+    import os
+    from conftest import GOLDEN
+    from avdsp_b200 import params
+    from oracle import wire
+    w = load_program("c1_crossover2x2lfe_f2_48k")
+    t = params.load_dump(os.path.join(GOLDEN, "programs", "c1_crossover2x2lfe_f2_48k.dump"))
+    assert t["BQ2_LOWPASS_1"] == params.Symbol("BQ2_LOWPASS_1", 0, 1, 28)
+    for name in ("BQ2_LOWPASS_1", "BQ2_HIGHPASS_3", "BQ4_EQ_LFE_-1", "BQ6_PRE_FILTER"):
+        i = params.word_index(w, t[name])
+        assert (int(w[i]) >> 16) & 0xFFFF == wire.OP["BIQUADS"], name      # the section header the BIQUADS opcode points to
+    i = params.word_index(w, t["DELAY_HIGH_LOW_1"])
+    assert int(w[i]) & 0xFFFF == 294 and int(w[i]) >> 16 == 71             # microseconds | max samples << 16 (encoder :1111-1118)
