@@ -144,6 +144,7 @@ static void planGeometries(avdsp_b200* h, std::vector<ChainLane>* lanes2) {
     h->mixUsable = false;
     if (L.chainOk) { std::string why; h->mixUsable = buildMixPlan(L.chain, &h->mix, &why); }
     h->firUsable = L.firOk;
+    h->dagUsable = L.dagOk && L.dag && planDagGeometry(*L.dag, h->nStreams, h->numSMs, &h->geomDag);
     char line[512];
     h->trace = L.trace;
     if (h->firUsable) {
@@ -176,6 +177,12 @@ static void planGeometries(avdsp_b200* h, std::vector<ChainLane>* lanes2) {
         }
         h->trace += "\n";
     }
+    if (h->dagUsable) {
+        snprintf(line, sizeof line, "DAG kernel geometry: %d nodes (depth %d, longest cascade %d sections), %d streams/CTA, %d threads, input rows of %d frames, %d words/stream, %zu B smem%s\n",
+                 L.dag->nNodes, L.dag->maxDepth, L.dag->maxSec, h->geomDag.streamsPerCta, h->geomDag.threads, h->geomDag.rawMask + 1, h->geomDag.perStreamWords,
+                 h->geomDag.smemBytes, (h->chain2Usable || h->mixUsable || h->firUsable) ? " (another fused kernel takes this program first)" : "");
+        h->trace += line;
+    } else if (!L.dagOk && !h->chain2Usable && !h->mixUsable && !h->firUsable) h->trace += "DAG kernel not used: " + L.dagWhyNot + "\n";
     if (!h->chain2Usable && !h->mixUsable) {
         snprintf(line, sizeof line, "chain kernels not used: %s\n", L.chainOk ? "geometry does not fit" : L.chainWhyNot.c_str());
         h->trace += line;
@@ -367,7 +374,7 @@ int avdsp_b200_set_order(avdsp_b200_t* h, int period) {
     h->period = period; return 0;
 }
 int avdsp_b200_set_kernel(avdsp_b200_t* h, int which) {
-    if (!h || which < 0 || which > AVDSP_B200_KERNEL_CHAIN_V3) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
+    if (!h || which < 0 || which > AVDSP_B200_KERNEL_DAG) return setErr(AVDSP_B200_ERR_ARG, "bad kernel selector");
     for (avdsp_b200* sh : h->shards) sh->kernelSel = which;
     h->kernelSel = which; return 0;
 }
@@ -423,6 +430,11 @@ static int launchRun(avdsp_b200* h, avdsp_b200* pl, const int* in, int* out, int
             return setErr(AVDSP_B200_ERR_UNSUPPORTED, "the first, tile-synchronous chain kernel was removed; use AVDSP_B200_KERNEL_CHAIN");
         if (pl->chain2Usable) use = AVDSP_B200_KERNEL_CHAIN;
     }
+    // X/Y dataflow programs: the DAG kernel when no other fused kernel takes the program (or on request)
+    if (chainOrder && pl->dagUsable && ((h->kernelSel == AVDSP_B200_KERNEL_AUTO && use == AVDSP_B200_KERNEL_GENERIC && !pl->mixUsable && !pl->firUsable) ||
+                                        h->kernelSel == AVDSP_B200_KERNEL_DAG)) use = AVDSP_B200_KERNEL_DAG;
+    if (h->kernelSel == AVDSP_B200_KERNEL_DAG && use != AVDSP_B200_KERNEL_DAG)
+        return setErr(AVDSP_B200_ERR_UNSUPPORTED, "DAG kernel requested but this program/order does not map to it: " + pl->L.dagWhyNot);
     if (chainOrder && pl->mixUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_MIX)) use = AVDSP_B200_KERNEL_MIX;
     if (chainOrder && pl->firUsable && (h->kernelSel == AVDSP_B200_KERNEL_AUTO || h->kernelSel == AVDSP_B200_KERNEL_FIR)) use = AVDSP_B200_KERNEL_FIR;
     // tensor-core Toeplitz GEMM: the bit-exact int8-limb form is the default for fixed-point batches that fill a tile;
@@ -489,6 +501,14 @@ static int launchRun(avdsp_b200* h, avdsp_b200* pl, const int* in, int* out, int
         e = launchMix(pl->mix, A, h->dJump, J, Lseg, h->numSMs, stream, &nl);
         h->lastKernel = AVDSP_B200_KERNEL_MIX;
         h->launches += nl - 1;                               // one is counted below
+    } else if (use == AVDSP_B200_KERNEL_DAG) {
+        Chain2Args A{};
+        A.in = in; A.out = out; A.state = st; A.lanes = nullptr;
+        A.nStreams = n; A.nFrames = nFrames;
+        A.inStreamStride = inSS; A.outStreamStride = outSS;
+        A.inFrameStride = inFS; A.inChStride = inCS; A.outFrameStride = outFS; A.outChStride = outCS;
+        e = launchDag(*pl->L.dag, pl->geomDag, A, stream);
+        h->lastKernel = AVDSP_B200_KERNEL_DAG;
     } else if (use == AVDSP_B200_KERNEL_CHAIN) {
         Chain2Args A{};
         A.in = in; A.out = out; A.state = st; A.lanes = pl->dLanes2;

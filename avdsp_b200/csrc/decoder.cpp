@@ -9,6 +9,7 @@
 #include "decoder.h"
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <memory>
 
@@ -423,6 +424,237 @@ void buildChainPlan(Lowered* L) {
     }
 }
 
+
+// ---- DAG recognition (kernel_dag.cu): symbolic execution of the X/Y register pair ------------------------------
+namespace {
+struct SymVal {
+    enum Type { UNDEF = 0, EXPR, FINISHED } type = UNDEF;
+    DagOperand a{}, b{};
+    int comb = 0, postShift = 0, hasPostGain = 0, postGain = 0;
+    int fresh = -1;          // EXPR that is exactly the 64-bit value of this node, nothing applied since
+    int node = -1;           // FINISHED: the node whose s.31 output this is
+    bool plainOperand() const { return type == EXPR && comb == 0 && postShift == 0 && !hasPostGain; }
+};
+DagOperand opdNone() { DagOperand o{}; o.kind = OPD_NONE; o.muxStateOff = -1; return o; }
+int dagPool(DagPlan& d, int32_t v) {
+    if (d.nPool >= kMaxDagPool) throw ChainFail{"DAG pool full"};
+    d.pool[d.nPool] = v; return d.nPool++;
+}
+} // namespace
+
+void buildDagPlan(Lowered* L) {
+    const GenericPlan& g = L->gen;
+    if (g.h.aluClass != ALU_INT64 || !g.h.sampleInt) throw ChainFail{"the DAG kernel is fixed point (DSP_FORMAT 2)"};
+    std::shared_ptr<DagPlan> dp(new DagPlan);
+    DagPlan& d = *dp;
+    memset(&d, 0, sizeof d);
+    d.nIn = g.h.nIn; d.nOut = g.h.nOut;
+    d.dataSize = g.h.dataSize; d.stateWords = g.h.stateWords; d.auxOff = g.h.auxOff;
+    d.storeDither = g.h.defaultDither;
+    for (int k = 0; k < kIoSlots; k++) { d.outNode[k] = -1; d.outDelayed[k] = 0; d.outRaw[k] = -1; }
+    int inChOfSlot[kIoSlots], outChOfSlot[kIoSlots];
+    for (int k = 0; k < kIoSlots; k++) inChOfSlot[k] = outChOfSlot[k] = -1;
+    for (int k = 0; k < g.h.nIn; k++)  inChOfSlot[g.h.inIdx[k]] = k;
+    for (int k = 0; k < g.h.nOut; k++) outChOfSlot[g.h.outIdx[k]] = k;
+    uint32_t written = 0;
+    for (int i = 0; i < g.h.nOps; i++) {
+        const MicroOp& m = g.ops[i];
+        if (m.op == OP_STORE || m.op == OP_DISTRIB) written |= 1u << m.a;
+        if (m.op == OP_LOAD_STORE) for (int k = 0; k < m.n; k++) written |= 1u << g.pool[m.a + 2 * k + 1];
+    }
+    auto inputCh = [&](int slot) -> int {
+        if ((written >> slot) & 1u) throw ChainFail{"an input slot is also written by the program (io hand-off between paths)"};
+        return inChOfSlot[slot];             // -1: never fed by the host, reads 0
+    };
+    std::vector<bool> sealed(kMaxDagNodes, false);     // no more sections may be appended (somebody holds the node's value)
+    std::map<int, int> memNode;                        // MEM state offset -> the node stored there last
+    auto newNode = [&](const SymVal& in) -> int {
+        if (d.nNodes >= kMaxDagNodes) throw ChainFail{"more DAG nodes than kMaxDagNodes"};
+        DagNode& n = d.nodes[d.nNodes];
+        memset(&n, 0, sizeof n);
+        n.a = in.a; n.b = in.comb ? in.b : opdNone();
+        n.comb = in.comb; n.postShift = in.postShift; n.hasPostGain = in.hasPostGain; n.postGain = in.postGain;
+        n.memOff = -1; n.finKind = FIN_NONE;
+        int depth = 0;
+        for (const DagOperand* o : {&n.a, &n.b})
+            if (o->kind == OPD_NODE) { d.nodes[o->arg].exportAcc = 1; sealed[o->arg] = true; depth = std::max(depth, d.nodes[o->arg].depth + 1); }
+        n.depth = depth;
+        d.maxDepth = std::max(d.maxDepth, depth);
+        return d.nNodes++;
+    };
+    auto exprOfNode = [&](int id) { SymVal v; v.type = SymVal::EXPR; v.a = opdNone(); v.a.kind = OPD_NODE; v.a.arg = id; v.b = opdNone(); v.fresh = id; return v; };
+    auto claimOutput = [&](int ch, int node, int delayed) {
+        const int prev = d.outNode[ch];
+        if (prev >= 0) {                                // a later STORE of the frame wins: the earlier one is dead
+            DagNode& o = d.nodes[prev];
+            int w = 0;
+            for (int k = 0; k < o.nStores; k++) if (o.storeCh[k] != ch) { o.storeCh[w] = o.storeCh[k]; o.storeDelayed[w] = o.storeDelayed[k]; w++; }
+            o.nStores = w;
+        }
+        d.outNode[ch] = node; d.outDelayed[ch] = delayed; d.outRaw[ch] = -1;
+        if (node >= 0) {
+            DagNode& n = d.nodes[node];
+            if (n.nStores >= kMaxDagStores) throw ChainFail{"too many STOREs on one path"};
+            n.storeCh[n.nStores] = ch; n.storeDelayed[n.nStores] = delayed; n.nStores++;
+        }
+    };
+    bool anyXY = false;
+    for (int core = 0; core < g.h.nCores; core++) {
+        SymVal X, Y;                                     // every core call starts with X = Y = 0 (dsp_runtime.c:308-309)
+        X.type = Y.type = SymVal::EXPR; X.a = Y.a = opdNone(); X.b = Y.b = opdNone();
+        for (int i = g.h.coreStart[core]; i < g.h.coreStart[core + 1]; i++) {
+            const MicroOp& m = g.ops[i];
+            switch (m.op) {
+            case OP_TPDF_CALC:
+                if (core != 0 || d.hasTpdfCalc || d.nNodes) throw ChainFail{"TPDF_CALC not at the very start of core 1"};
+                for (int k = 0; k < d.nOut; k++) if (d.outNode[k] != -1) { /* raw copies in front are fine: they use neither the value nor the mask */ }
+                d.hasTpdfCalc = 1; d.tpdfDither = m.a; d.tpdfDataOff = m.b; d.storeDither = m.a;
+                X = SymVal(); X.type = SymVal::UNDEF;     // X = the dither value: nobody may use it
+                break;
+            case OP_LOAD_STORE:
+                for (int k = 0; k < m.n; k++) {
+                    const int ch = outChOfSlot[g.pool[m.a + 2 * k + 1]];
+                    if (ch < 0) throw ChainFail{"LOAD_STORE to a slot outside the declared outputs"};
+                    claimOutput(ch, -2, 0);
+                    d.outNode[ch] = -2; d.outRaw[ch] = inputCh(g.pool[m.a + 2 * k]);
+                }
+                break;
+            case OP_LOAD: case OP_LOAD_GAIN: case OP_LOAD_MUX: {
+                Y = X;
+                if (Y.fresh >= 0) sealed[Y.fresh] = true;
+                X = SymVal(); X.type = SymVal::EXPR; X.a = opdNone(); X.b = opdNone();
+                if (m.op == OP_LOAD_MUX) {
+                    X.a.kind = OPD_MUX; X.a.n = m.n; X.a.muxStateOff = m.b; X.a.arg = d.nPool;
+                    for (int k = 0; k < m.n; k++) { dagPool(d, inputCh(g.pool[m.a + 2 * k])); dagPool(d, g.pool[m.a + 2 * k + 1]); }
+                } else {
+                    X.a.kind = OPD_RAW; X.a.arg = inputCh(m.a);
+                    if (m.op == OP_LOAD_GAIN) { X.a.hasGain = 1; X.a.gain = m.b; }
+                }
+                break; }
+            case OP_LOAD_MEM: {
+                Y = X;
+                if (Y.fresh >= 0) sealed[Y.fresh] = true;
+                auto it = memNode.find(m.a);
+                if (it == memNode.end()) throw ChainFail{"LOAD_MEM of a word no earlier path of the frame stored"};
+                X = exprOfNode(it->second); X.fresh = -1;           // a copy of the node's value, not the running accumulator
+                sealed[it->second] = true;
+                break; }
+            case OP_STORE_MEM:
+                if (X.type != SymVal::EXPR || X.fresh < 0 || !X.plainOperand()) throw ChainFail{"STORE_MEM of something that is not a cascade's accumulator"};
+                if (d.nodes[X.fresh].memOff >= 0 && d.nodes[X.fresh].memOff != m.a) throw ChainFail{"one accumulator stored to two MEM words"};
+                d.nodes[X.fresh].memOff = m.a; d.nodes[X.fresh].exportAcc = 1; sealed[X.fresh] = true;
+                memNode[m.a] = X.fresh;
+                break;
+            case OP_COPYXY: Y = X; if (X.fresh >= 0) sealed[X.fresh] = true; anyXY = true; break;
+            case OP_COPYYX: X = Y; if (Y.fresh >= 0) sealed[Y.fresh] = true; anyXY = true; break;
+            case OP_SWAPXY: std::swap(X, Y); anyXY = true; break;
+            case OP_CLRXY:  X = SymVal(); X.type = SymVal::EXPR; X.a = opdNone(); X.b = opdNone(); Y = X; break;
+            case OP_ADDXY: case OP_SUBXY: case OP_ADDYX: case OP_SUBYX: {
+                anyXY = true;
+                SymVal& dst = (m.op == OP_ADDXY || m.op == OP_SUBXY) ? X : Y;
+                SymVal& src = (m.op == OP_ADDXY || m.op == OP_SUBXY) ? Y : X;
+                if (!dst.plainOperand() || !src.plainOperand()) throw ChainFail{"X/Y arithmetic on values the DAG kernel cannot combine"};
+                if (dst.a.kind == OPD_NONE && (m.op == OP_ADDXY || m.op == OP_ADDYX)) { const int f = src.fresh; dst = src; dst.fresh = -1; if (f >= 0) sealed[f] = true; break; }
+                SymVal r; r.type = SymVal::EXPR; r.a = dst.a; r.b = src.a; r.comb = (m.op == OP_ADDXY || m.op == OP_ADDYX) ? 1 : -1;
+                for (const DagOperand* o : {&r.a, &r.b}) if (o->kind == OPD_NODE) sealed[o->arg] = true;
+                if (r.b.kind == OPD_NONE) { r.comb = 0; }
+                dst = r;
+                break; }
+            case OP_GAIN:
+                if (X.type != SymVal::EXPR) throw ChainFail{"GAIN on a value that is not in the ALU as an expression"};
+                if (X.plainOperand() && X.a.kind == OPD_RAW && !X.a.hasGain) { X.a.hasGain = 1; X.a.gain = m.a; }
+                else if (!X.hasPostGain && X.a.kind != OPD_NONE) { X.hasPostGain = 1; X.postGain = m.a; }
+                else throw ChainFail{"two gains in a row on one value"};
+                break;
+            case OP_SHIFT: {
+                const int sh = m.a <= -100 ? kMant : -m.a;
+                if (X.type != SymVal::EXPR || m.a >= 0 || sh > 63 || X.hasPostGain || X.postShift || X.a.kind == OPD_NONE) throw ChainFail{"SHIFT form the DAG kernel does not fuse"};
+                if (X.fresh >= 0) sealed[X.fresh] = true;
+                X.postShift = sh; X.fresh = -1;
+                break; }
+            case OP_DELAY:
+                if (X.type == SymVal::FINISHED) {
+                    DagNode& n = d.nodes[X.node];
+                    if (n.delayN) throw ChainFail{"two delays behind one saturation"};
+                    n.delayN = m.b; n.delayOff = m.a;
+                } else if (X.plainOperand() && X.a.kind == OPD_RAW && !X.a.hasGain && !X.a.delayKind) {
+                    X.a.delayKind = 1; X.a.delayN = m.b; X.a.delayOff = m.a;
+                } else throw ChainFail{"DELAY on a value the DAG kernel cannot delay (only raw samples and saturated outputs)"};
+                break;
+            case OP_DELAY_DP:
+                if (X.plainOperand() && X.a.kind == OPD_NODE && !X.a.delayKind) {
+                    sealed[X.a.arg] = true;
+                    X.a.delayKind = 2; X.a.delayN = m.b; X.a.delayOff = m.a; X.fresh = -1;
+                } else throw ChainFail{"DELAY_DP on a value the DAG kernel cannot delay (only cascade accumulators)"};
+                break;
+            case OP_BIQUADS: {
+                if (X.type != SymVal::EXPR) throw ChainFail{"BIQUADS on a value that is not in the ALU as an expression"};
+                // a lane holds at most 8 sections: longer cascades continue in another node (x = the previous node's value >> 28,
+                // which is the previous section's y: exactly what consecutive sections hand to each other)
+                for (int first = 0; first < m.n;) {
+                    int id;
+                    if (X.fresh >= 0 && X.plainOperand() && !sealed[X.fresh] && d.nodes[X.fresh].finKind == FIN_NONE && d.nodes[X.fresh].nsec < 8) id = X.fresh;
+                    else { id = newNode(X); d.nodes[id].coefOff = d.nPool; d.nodes[id].secStateOff = -1; }
+                    DagNode& n = d.nodes[id];
+                    const int take = std::min(m.n - first, 8 - n.nsec);
+                    // coefficients and state offsets of a node are contiguous in the pool: re-pack when sections are appended
+                    std::vector<int32_t> coefs, offs;
+                    for (int k = 0; k < n.nsec; k++) { for (int q = 0; q < 5; q++) coefs.push_back(d.pool[n.coefOff + 5 * k + q]); offs.push_back(d.pool[n.secStateOff + k]); }
+                    for (int k = first; k < first + take; k++) { for (int q = 0; q < 5; q++) coefs.push_back(g.pool[m.b + 5 * k + q]); offs.push_back(m.a + 6 * k); }
+                    n.nsec = (int)offs.size();
+                    n.coefOff = d.nPool; for (int32_t v : coefs) dagPool(d, v);
+                    n.secStateOff = d.nPool; for (int32_t v : offs) dagPool(d, v);
+                    d.maxSec = std::max(d.maxSec, n.nsec);
+                    X = exprOfNode(id);
+                    first += take;
+                }
+                break; }
+            case OP_SAT0DB: case OP_SAT0DB_TPDF: case OP_SAT0DB_GAIN: case OP_SAT0DB_TPDF_GAIN: {
+                if (X.type != SymVal::EXPR) throw ChainFail{"saturation of a value that is not in the ALU as an expression"};
+                int id;
+                if (X.fresh >= 0 && X.comb == 0 && X.postShift == 0 && d.nodes[X.fresh].finKind == FIN_NONE) {
+                    id = X.fresh;                        // [GAIN] behind the cascade belongs to the finish
+                    d.nodes[id].finHasGain = X.hasPostGain; d.nodes[id].finGain = X.postGain;
+                } else { SymVal in = X; id = newNode(in); d.nodes[id].nsec = 0; }
+                DagNode& n = d.nodes[id];
+                n.finKind = FIN_SAT;
+                n.satKind = m.op == OP_SAT0DB ? SAT_PLAIN : m.op == OP_SAT0DB_TPDF ? SAT_TPDF : m.op == OP_SAT0DB_GAIN ? SAT_GAIN : SAT_TPDF_GAIN;
+                n.satGain = m.a;
+                sealed[id] = true;
+                X = SymVal(); X.type = SymVal::FINISHED; X.node = id;
+                break; }
+            case OP_STORE: {
+                const int ch = outChOfSlot[m.a];
+                if (ch < 0) throw ChainFail{"STORE to a slot outside the declared outputs"};
+                if (X.type == SymVal::EXPR) {            // DSP_STORE of an unsaturated value: its low word, masked
+                    if (X.a.kind == OPD_NONE && X.comb == 0) throw ChainFail{"STORE of a cleared ALU"};
+                    SymVal in = X;
+                    const int id = newNode(in);
+                    d.nodes[id].nsec = 0; d.nodes[id].finKind = FIN_TRUNC; sealed[id] = true;
+                    if (X.fresh >= 0) sealed[X.fresh] = true;
+                    X = SymVal(); X.type = SymVal::FINISHED; X.node = id;
+                }
+                if (X.type != SymVal::FINISHED) throw ChainFail{"STORE of an undefined value"};
+                claimOutput(ch, X.node, d.nodes[X.node].delayN > 0 ? 1 : 0);
+                break; }
+            default:
+                throw ChainFail{"an opcode the DAG kernel does not fuse"};
+            }
+        }
+    }
+    if (d.nNodes == 0) throw ChainFail{"no signal path"};
+    int finals = 0;
+    for (int k = 0; k < d.nNodes; k++) {
+        const DagNode& n = d.nodes[k];
+        if (n.finKind == FIN_NONE && !n.exportAcc) throw ChainFail{"a cascade whose result nobody uses"};
+        if (n.finKind != FIN_NONE) finals++;
+        for (const DagOperand* o : {&n.a, &n.b}) if (o->kind == OPD_RAW && o->arg >= d.nIn) throw ChainFail{"bad input channel"};
+    }
+    (void)finals; (void)anyXY;
+    d.tpdfShift = kMant - d.storeDither + 1;
+    L->dag = dp;
+}
+
 // ---- FIR path recognition (kernel_fir.cu) ---------------------------------------------------------
 // LOAD|LOAD_GAIN -> FIR(convolution) -> [GAIN] -> SAT0DB|SAT0DB_GAIN -> STORE+ , any number of such paths per core.
 void buildFirPlan(Lowered* L) {
@@ -577,6 +809,9 @@ void lowerAll(Lowered* L) {
     analyseOrder(L);
     try { buildChainPlan(L); L->chainOk = true; L->chainWhyNot.clear(); }
     catch (const ChainFail& f) { L->chainOk = false; L->chainWhyNot = f.why; }
+    L->dag.reset();
+    try { buildDagPlan(L); L->dagOk = true; L->dagWhyNot.clear(); }
+    catch (const ChainFail& f) { L->dagOk = false; L->dagWhyNot = f.why; L->dag.reset(); }
     try { buildFirPlan(L); L->firOk = true; L->firWhyNot.clear(); }
     catch (const ChainFail& f) { L->firOk = false; L->firWhyNot = f.why; }
 

@@ -3,6 +3,7 @@
 // (runtime/dsp_runtime.c:302-1314 is the semantics being lowered) into plans (plan.h).
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 #include "plan.h"
@@ -26,6 +27,9 @@ struct Lowered {
     bool chainOk = false;
     std::string chainWhyNot;
     ChainPlan chain{};
+    bool dagOk = false;                  // X/Y dataflow program that maps to a DAG of cascades (kernel_dag.cu)
+    std::string dagWhyNot;
+    std::shared_ptr<DagPlan> dag;      // re-lowering allocates a new one (copies of a Lowered may share the old)
     std::vector<int32_t> bigPool;        // FIR taps / data tables (device: HBM)
     std::vector<FirDesc> firs;
     bool firOk = false;                  // program maps to the time-parallel FIR kernels (kernel_fir.cu)

@@ -22,6 +22,8 @@ struct avdsp_b200 {
     bool chain2Usable = false;      // kernel_chain2.cu (v2: warp-specialised, the default)
     avdsp::Chain3Geom geom3{};
     bool chain3Usable = false;      // kernel_chain3.cu (v3: one cascade per lane; the common crossover / EQ shape at batch width)
+    avdsp::DagGeom geomDag{};
+    bool dagUsable = false;         // kernel_dag.cu (X/Y dataflow programs: a DAG of cascades, node per warp)
     int lastChainVariant = 0;       // 2 / 3: which chain kernel the last AVDSP_B200_KERNEL_CHAIN launch used
     avdsp::MixPlan mix{};
     bool mixUsable = false;         // kernel_mix.cu (time-parallel: programs without biquads)

@@ -71,6 +71,27 @@ bool chain2Supports(const ChainPlan& plan);
 bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2Geom* geom, ChainLane* lanesOut /*[1024]*/);
 cudaError_t launchChain2(const ChainPlan& plan, const Chain2Geom& geom, const Chain2Args& args, cudaStream_t stream);
 
+// ---- DAG kernel (kernel_dag.cu): programs that route signals through the X/Y registers -------------------------------
+constexpr int kDagMaxThreads = 384;         // up to 12 warps of 168 registers: whole cascades (<= 8 sections) per lane
+struct DagGeom {
+    int streamsPerCta;     // NS (<= 32): lane = stream, warp = node
+    int threads, nStore;
+    int perStreamWords;    // one stream's block of rows in shared memory (odd)
+    int rawOff, rawMask;   // staged input PCM, one row per channel: word offset inside a stream's block, frames - 1 (power of two)
+    int tpdfOff, tpdfMask; // dither values
+    int nRawOut;           // output channels that are DSP_LOAD_STORE copies (written by the staging warp)
+    int accMask[kMaxDagNodes];
+    int staleOff;          // word offset (from the start of shared memory) of the stale-index notes for the store warps
+    int accLoOff[kMaxDagNodes], accHiOff[kMaxDagNodes];       // 64-bit node values, two planes
+    int postOff[kMaxDagNodes], postMask[kMaxDagNodes];        // finished s.31 outputs (the delay line behind the saturation)
+    int aDlyOff[kMaxDagNodes], aDlyMask[kMaxDagNodes];        // private delay rows of the operands (DSP_DELAY on a sample, DSP_DELAY_DP)
+    int bDlyOff[kMaxDagNodes], bDlyMask[kMaxDagNodes];
+    size_t smemBytes;
+};
+struct Chain2Args;
+bool planDagGeometry(const DagPlan& plan, int nStreams, int numSMs, DagGeom* geom);
+cudaError_t launchDag(const DagPlan& plan, const DagGeom& geom, const Chain2Args& args, cudaStream_t stream);
+
 // ---- register-resident cascade kernel (kernel_chain3.cu): lane = one whole cascade of one stream ------------------
 constexpr int kChain3MaxChains = 10;        // chains of a program the kernel takes
 constexpr int kChain3MaxWarps = 16;         // cascade warps of a CTA (chains, or parts of chains)

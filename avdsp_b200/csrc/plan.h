@@ -144,6 +144,57 @@ struct ChainPlan {
     int32_t     pool[kMaxChainPool];
 };
 
+// ---------------------------------------------------------------- DAG plan (kernel_dag.cu) ----
+// Programs that route signals through the X/Y register pair -- subtractive crossovers (`COPYXY ... SWAPXY ... SUBYX`:
+// dspprogs/crossoverLV6.c, oktodac_fabriceo.c), forks (`COPYXY ... SWAPXY`: crossover2x2lfe.c), sums of MEM words
+// (`LOAD_MEM; LOAD_MEM; ADDXY`) -- are not sets of independent chains: a path may start from a combination of what other
+// paths computed in the same frame.  The decoder executes X/Y symbolically and turns such a program into a small DAG:
+// every NODE is  input expression -> [biquad cascade] -> [finish: gain / saturate / dither -> post-saturation delay -> stores],
+// the expression being  V = A [+|- B]  [>> shift] [* gain]  over OPERANDS (an input sample, optionally delayed (DSP_DELAY)
+// and scaled; the 64-bit value of an earlier node, optionally delayed (DSP_DELAY_DP); a LOAD_MUX sum).
+constexpr int kMaxDagNodes  = 10;
+constexpr int kMaxDagStores = 6;
+constexpr int kMaxDagPool   = 1536;
+enum DagOpdKind : int { OPD_NONE = 0 /* the value 0 */, OPD_RAW = 1, OPD_NODE = 2, OPD_MUX = 3 };
+enum DagFinish  : int { FIN_NONE = 0 /* no output of its own */, FIN_SAT = 1 /* [GAIN] -> SAT0DB[_TPDF][_GAIN] */,
+                        FIN_TRUNC = 2 /* DSP_STORE of an unsaturated value: its low word (dsp_runtime.c:610-633) */ };
+struct DagOperand {
+    int32_t kind;                // DagOpdKind
+    int32_t arg;                 // RAW: input CHANNEL (-1: slot nobody feeds, reads 0); NODE: node index; MUX: pool offset of (channel, gain) pairs
+    int32_t n;                   // MUX: pair count
+    int32_t hasGain, gain;       // RAW: X = sample * gain (LOAD_GAIN, or LOAD [DELAY] GAIN);  NODE: unused
+    int32_t delayKind;           // 0 none; 1 DSP_DELAY on the raw sample, before the gain (ring of int32); 2 DSP_DELAY_DP on a node value (ring of int64)
+    int32_t delayN, delayOff;    // samples; data-area offset of the ring ([index | line], dsp_runtime.c:769-824)
+    int32_t muxStateOff;         // MUX: data offset of the stored 64-bit sum, else -1
+};
+struct DagNode {
+    DagOperand a, b;
+    int32_t comb;                // 0: V = A;  +1: V = A + B;  -1: V = A - B
+    int32_t postShift;           // > 0: V >>= postShift (DSP_SHIFT with a negative count) after the combination
+    int32_t hasPostGain, postGain;   // then V *= gain (DSP_GAIN, 64 x 32 wrapping)
+    int32_t nsec, coefOff, secStateOff;      // cascade: x = V >> 28 (dsp_runtime.c:831); pool offsets as in ChainDesc
+    int32_t exportAcc;           // a later node (or a MEM word) takes this node's 64-bit value
+    int32_t memOff;              // DSP_STORE_MEM target (state offset) or -1
+    int32_t finKind;             // DagFinish
+    int32_t finHasGain, finGain; // DSP_GAIN between the cascade and the saturation
+    int32_t satKind, satGain;    // ChainSat
+    int32_t delayN, delayOff;    // DSP_DELAY behind the saturation (ring of s.31 values), 0: none
+    int32_t depth;               // tiles behind the input: 1 + deepest NODE operand
+    int32_t nStores;
+    int32_t storeCh[kMaxDagStores], storeDelayed[kMaxDagStores];   // OUTPUT CHANNEL; 1: the STORE sits behind the DELAY
+};
+struct DagPlan {
+    int32_t nNodes, nIn, nOut, nPool;
+    int32_t dataSize, stateWords, auxOff;
+    int32_t hasTpdfCalc, tpdfDither, tpdfDataOff, storeDither, tpdfShift;
+    int32_t maxDepth, maxSec;
+    // output channel -> where its samples come from: node >= 0 (its post row, `delayed`: read behind the node's DELAY),
+    // -1: nobody stores it (reads 0), -2: DSP_LOAD_STORE copy of input channel outRaw[ch] (no saturation, no STORE mask)
+    int32_t outNode[kIoSlots], outDelayed[kIoSlots], outRaw[kIoSlots];
+    DagNode nodes[kMaxDagNodes];
+    int32_t pool[kMaxDagPool];
+};
+
 // ---------------------------------------------------------------- FIR plan -------------------
 // DSP_FIR taps live in HBM ("big pool"); one entry per FIR micro-op.
 struct FirDesc {

@@ -17,8 +17,9 @@ INTERLEAVED, PLANAR = 0, 1
 HOST, DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CHAIN, KERNEL_CHAIN_V1, KERNEL_MIX, KERNEL_FIR, KERNEL_FIR_TC = 0, 1, 2, 3, 4, 5, 6
 KERNEL_CHAIN_V2, KERNEL_CHAIN_V3 = 7, 8        # force k_chain2 / k_chain3 (KERNEL_CHAIN and AUTO choose between them)
+KERNEL_DAG = 9                                 # X/Y dataflow programs (kernel_dag.cu)
 PCM_S32, PCM_S16, PCM_S24_3LE = 0, 1, 2
-KERNEL_NAMES = {0: "none", 1: "generic", 2: "chain", 3: "chain_v1", 4: "mix", 5: "fir", 6: "fir_tc"}
+KERNEL_NAMES = {0: "none", 1: "generic", 2: "chain", 3: "chain_v1", 4: "mix", 5: "fir", 6: "fir_tc", 9: "dag"}
 
 
 class AvdspError(RuntimeError):

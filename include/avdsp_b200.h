@@ -99,7 +99,10 @@ enum { AVDSP_B200_KERNEL_AUTO = 0, AVDSP_B200_KERNEL_GENERIC = 1, AVDSP_B200_KER
                                          AUTO choice for batches), DSP_FORMAT 3 as 3xTF32 under a stated tolerance (only on request) */,
        AVDSP_B200_KERNEL_CHAIN_V2 = 7 /* force the section-lane chain kernel (kernel_chain2.cu) */,
        AVDSP_B200_KERNEL_CHAIN_V3 = 8 /* force the cascade-per-lane chain kernel (kernel_chain3.cu); KERNEL_CHAIN / AUTO pick between
-                                         v2 and v3 themselves (v3: common crossover / EQ shapes at batch width) */ };
+                                         v2 and v3 themselves (v3: common crossover / EQ shapes at batch width) */,
+       AVDSP_B200_KERNEL_DAG = 9      /* programs that route signals through the X/Y registers (subtractive crossovers, forks, sums of MEM
+                                         words): a DAG of cascades, one node per warp (kernel_dag.cu); AUTO takes it when no other fused
+                                         kernel can run the program */ };
 
 /* Load + validate + lower a program (dspRuntimeInit + dspRuntimeReset for nStreams independent
  * instances).  prog: progWords little-endian 32-bit words exactly as written by dspcreate (.bin).
