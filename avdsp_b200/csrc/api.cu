@@ -178,8 +178,8 @@ static void planGeometries(avdsp_b200* h, std::vector<ChainLane>* lanes2) {
         h->trace += "\n";
     }
     if (h->dagUsable) {
-        snprintf(line, sizeof line, "DAG kernel geometry: %d nodes (depth %d, longest cascade %d sections), %d streams/CTA, %d threads, input rows of %d frames, %d words/stream, %zu B smem%s\n",
-                 L.dag->nNodes, L.dag->maxDepth, L.dag->maxSec, h->geomDag.streamsPerCta, h->geomDag.threads, h->geomDag.rawMask + 1, h->geomDag.perStreamWords,
+        snprintf(line, sizeof line, "DAG kernel geometry: %d nodes (depth %d, longest cascade %d sections), %d streams/CTA, %d threads, tiles of %d frames, input rows of %d frames, %d words/stream, %zu B smem%s\n",
+                 L.dag->nNodes, L.dag->maxDepth, L.dag->maxSec, h->geomDag.streamsPerCta, h->geomDag.threads, h->geomDag.tileFrames, h->geomDag.rawMask + 1, h->geomDag.perStreamWords,
                  h->geomDag.smemBytes, (h->chain2Usable || h->mixUsable || h->firUsable) ? " (another fused kernel takes this program first)" : "");
         h->trace += line;
     } else if (!L.dagOk && !h->chain2Usable && !h->mixUsable && !h->firUsable) h->trace += "DAG kernel not used: " + L.dagWhyNot + "\n";

@@ -23,11 +23,11 @@
 #include "kernels.h"
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace avdsp {
 namespace {
 
-constexpr int FD = 32;                     // frames per tile
 
 // one reference delay ring (dsp_runtime.c:769-824: [index | line of n elements]) mapped onto a frame-indexed row:
 // frame f's value sits at f & mask, the n elements the reference ring holds at launch start are "virtual frames" -n..-1
@@ -121,20 +121,26 @@ __device__ __forceinline__ void dagNodeWarp(const DagPlan& P, const Chain2Args& 
     const int NS = G.streamsPerCta, T = A.nFrames, W = P.stateWords;
     const int s0 = blockIdx.x * NS, nsHere = min(NS, A.nStreams - s0);
     const bool live = lane < nsHere;
+    const int FD = G.tileFrames;
     const int nTiles = (T + FD - 1) / FD, nIter = nTiles + P.maxDepth + 2;
     DagLaneCtx C;
     C.blk = smem + (live ? lane : 0) * G.perStreamWords;
     C.st = A.state + (size_t)(s0 + (live ? lane : 0)) * W;
-    BqStateI s[NSEC > 0 ? NSEC : 1];
-    int cf[NSEC > 0 ? NSEC : 1][5];
+    // cascade state in registers.  The two history words of a section swap roles every frame (even frames: x1 = xa, x2 = xb and
+    // the new x lands in xb; odd frames the other way round), so the frame loop, unrolled by two, carries no register moves
+    // (ptxas emits them as IMAD.MOVs, on the very pipe the MACs run on)
+    constexpr int NS_ = NSEC > 0 ? NSEC : 1;
+    long long sAcc[NS_];
+    int xa[NS_], xb[NS_], ya[NS_], yb[NS_];
+    int cf[NS_][5];
     DagDelay da, db, dp;
     const int postMask = G.postMask[w], postOff = G.postOff[w];
     if (live) {
 #pragma unroll
         for (int k = 0; k < NSEC; k++) {
             const int* q = C.st + P.pool[n.secStateOff + k];          // [acc_lo, acc_hi, x1, x2, y1, y2] (dsp_biquadSTD.h:45)
-            s[k].acc = (long long)(((unsigned long long)(unsigned)q[1] << 32) | (unsigned)q[0]);
-            s[k].x1 = q[2]; s[k].x2 = q[3]; s[k].y1 = q[4]; s[k].y2 = q[5];
+            sAcc[k] = (long long)(((unsigned long long)(unsigned)q[1] << 32) | (unsigned)q[0]);
+            xa[k] = q[2]; xb[k] = q[3]; ya[k] = q[4]; yb[k] = q[5];
 #pragma unroll
             for (int c = 0; c < 5; c++) cf[k][c] = P.pool[n.coefOff + 5 * k + c];
         }
@@ -149,51 +155,100 @@ __device__ __forceinline__ void dagNodeWarp(const DagPlan& P, const Chain2Args& 
             smem[G.staleOff + (w * 32 + lane) * 2 + 1] = dp.ovLo;
         } else if (n.finKind != FIN_NONE) smem[G.staleOff + (w * 32 + lane) * 2] = 0;
     }
+    // the node's description in registers (the plan sits in the constant bank, but the frame loop should not re-read it)
+    const DagOperand oa = n.a, ob = n.b;
+    const int comb = n.comb, postShift = n.postShift, hasPostGain = n.hasPostGain, postGain = n.postGain;
+    const int exportAcc = n.exportAcc, finKind = n.finKind, finHasGain = n.finHasGain, finGain = n.finGain, satKind = n.satKind, satGain = n.satGain;
+    const int aDlyOff = G.aDlyOff[w], aDlyMask = G.aDlyMask[w], bDlyOff = G.bDlyOff[w], bDlyMask = G.bDlyMask[w];
+    const int accLo = G.accLoOff[w], accHi = G.accHiOff[w], accMask = G.accMask[w];
+    const int tpdfOff = G.tpdfOff, tpdfMask = G.tpdfMask, tpdfShift = P.tpdfShift;
+    // the common source: one input sample, LOAD or LOAD_GAIN, nothing else in front of the cascade
+    const bool simpleIn = oa.kind == OPD_RAW && oa.arg >= 0 && !oa.delayKind && !comb && !postShift && !hasPostGain;
+    const int* rawRow = C.blk + G.rawOff + (oa.kind == OPD_RAW && oa.arg >= 0 ? oa.arg : 0) * (G.rawMask + 1);
+    const int rawMask = G.rawMask;
     long long muxLast = 0, lastAcc = 0;
+
+    // one frame; PAR selects which of the two history register sets plays "1" this frame
+    auto frame = [&](int f, auto parTag) {
+        constexpr bool PAR = decltype(parTag)::value;
+        long long V;
+        if (simpleIn) {
+            const int smp = rawRow[f & rawMask];
+            V = oa.hasGain ? mul32(smp, oa.gain) : (long long)smp;
+        } else {
+            V = dagOperand(P, G, oa, da, aDlyOff, aDlyMask, C, f, muxLast);
+            if (comb) {
+                const long long B = dagOperand(P, G, ob, db, bDlyOff, bDlyMask, C, f, muxLast);
+                V = comb > 0 ? (long long)((unsigned long long)V + (unsigned long long)B) : (long long)((unsigned long long)V - (unsigned long long)B);
+            }
+            if (postShift) V >>= postShift;
+            if (hasPostGain) V = V * (long long)postGain;
+        }
+        long long acc = V;
+        if constexpr (NSEC > 0) {
+            // dsp_calc_biquads_int (dsp_biquadSTD.h:34-77).  Four of a section's five products only involve last frame's
+            // state: they are issued for ALL sections first (independent chains, wrapping adds commute), so the path through
+            // the cascade is one MAC + clamp + shift per section
+            long long part[NS_];
+#pragma unroll
+            for (int k = 0; k < NSEC; k++) part[k] = mac32(sAcc[k], PAR ? xb[k] : xa[k], cf[k][1]);
+#pragma unroll
+            for (int k = 0; k < NSEC; k++) part[k] = mac32(part[k], PAR ? xa[k] : xb[k], cf[k][2]);
+#pragma unroll
+            for (int k = 0; k < NSEC; k++) part[k] = mac32(part[k], PAR ? yb[k] : ya[k], cf[k][3]);
+#pragma unroll
+            for (int k = 0; k < NSEC; k++) part[k] = mac32(part[k], PAR ? ya[k] : yb[k], cf[k][4]);
+            int x = q59ToS31(V);                               // the cascade takes X >> 28 (dsp_runtime.c:831)
+#pragma unroll
+            for (int k = 0; k < NSEC; k++) {
+                long long a = mac32(part[k], x, cf[k][0]);
+                // checkbiquadsat (dsp_biquadSTD.h:25-32) without a branch: in range <=> -2^27 + 2 <= hi <= 2^27 - 1
+                const int hi = hi32(a);
+                const long long top = ((long long)(1 << (kMantBQ - 1)) << 32) - 1, bot = -((long long)(1 << (kMantBQ - 1)) << 32);
+                a = hi >= (1 << (kMantBQ - 1)) ? top : a;
+                a = hi <= 1 - (1 << (kMantBQ - 1)) ? bot : a;
+                sAcc[k] = a;
+                if (PAR) xa[k] = x; else xb[k] = x;            // the older history word is overwritten: it is next frame's "1"
+                x = q59ToS31(a);
+                if (PAR) ya[k] = x; else yb[k] = x;
+            }
+            acc = sAcc[NSEC - 1];
+        }
+        lastAcc = acc;
+        if (exportAcc) { C.blk[accLo + (f & accMask)] = lo32(acc); C.blk[accHi + (f & accMask)] = hi32(acc); }
+        if (finKind != FIN_NONE) {
+            int v;
+            if (finKind == FIN_TRUNC) v = lo32(acc);
+            else {
+                long long Y = acc;
+                if (finHasGain) Y = Y * (long long)finGain;                                        // dsp_runtime.c:636-640
+                if (satKind >= SAT_GAIN) { Y >>= kMant; Y = Y * (long long)satGain; }              // :494-534
+                if (satKind & 1) Y += tpdfScaledI(C.blk[tpdfOff + (f & tpdfMask)], tpdfShift);     // dspTpdfApply, dsp_tpdf.h:141-145
+                v = sat64_031_s32(Y);
+            }
+            if (dp.staleIdx >= 0 && f == 0) C.st[dp.off + 1 + dp.staleIdx] = v;    // the reference's swap with line[idx0]
+            C.blk[postOff + (f & postMask)] = v;
+        }
+    };
+    // Frames alternate parity from the start of the LAUNCH (frame 0 is even), whatever the tile boundaries
     for (int it = 0; it < nIter; it++) {
         __syncthreads();
         const int j = it - 1 - n.depth;
         if (!live || j < 0 || j >= nTiles) continue;
-        const int f1 = min(T, j * FD + FD);
+        int f = j * FD;
+        const int f1 = min(T, f + FD);                         // FD is even: a tile starts on an even frame
 #pragma unroll 1
-        for (int f = j * FD; f < f1; f++) {
-            long long V = dagOperand(P, G, n.a, da, G.aDlyOff[w], G.aDlyMask[w], C, f, muxLast);
-            if (n.comb) {
-                const long long B = dagOperand(P, G, n.b, db, G.bDlyOff[w], G.bDlyMask[w], C, f, muxLast);
-                V = n.comb > 0 ? (long long)((unsigned long long)V + (unsigned long long)B) : (long long)((unsigned long long)V - (unsigned long long)B);
-            }
-            if (n.postShift) V >>= n.postShift;
-            if (n.hasPostGain) V = V * (long long)n.postGain;
-            long long acc = V;
-            if (NSEC > 0) {
-                int x = q59ToS31(V);                               // the cascade takes X >> 28 (dsp_runtime.c:831)
-#pragma unroll
-                for (int k = 0; k < NSEC; k++) x = biquadStepI(s[k], x, cf[k][0], cf[k][1], cf[k][2], cf[k][3], cf[k][4]);
-                acc = s[NSEC - 1].acc;
-            }
-            lastAcc = acc;
-            if (n.exportAcc) { C.blk[G.accLoOff[w] + (f & G.accMask[w])] = lo32(acc); C.blk[G.accHiOff[w] + (f & G.accMask[w])] = hi32(acc); }
-            if (n.finKind != FIN_NONE) {
-                int v;
-                if (n.finKind == FIN_TRUNC) v = lo32(acc);
-                else {
-                    long long Y = acc;
-                    if (n.finHasGain) Y = Y * (long long)n.finGain;                                        // dsp_runtime.c:636-640
-                    if (n.satKind >= SAT_GAIN) { Y >>= kMant; Y = Y * (long long)n.satGain; }              // :494-534
-                    if (n.satKind & 1) Y += tpdfScaledI(C.blk[G.tpdfOff + (f & G.tpdfMask)], P.tpdfShift);             // dspTpdfApply, dsp_tpdf.h:141-145
-                    v = sat64_031_s32(Y);
-                }
-                if (dp.staleIdx >= 0 && f == 0) C.st[dp.off + 1 + dp.staleIdx] = v;    // the reference's swap with line[idx0]
-                C.blk[postOff + (f & postMask)] = v;
-            }
-        }
+        for (; f + 1 < f1; f += 2) { frame(f, std::false_type{}); frame(f + 1, std::true_type{}); }
+        if (f < f1) frame(f, std::false_type{});                // odd frame count: only the launch's last frame (T odd)
     }
     if (!live) return;
-    // back to the reference layout
+    // back to the reference layout: after an odd number of frames the two history sets have swapped roles
+    const bool swapped = (T & 1) != 0;
 #pragma unroll
     for (int k = 0; k < NSEC; k++) {
         int* q = C.st + P.pool[n.secStateOff + k];
-        q[0] = lo32(s[k].acc); q[1] = hi32(s[k].acc); q[2] = s[k].x1; q[3] = s[k].x2; q[4] = s[k].y1; q[5] = s[k].y2;
+        q[0] = lo32(sAcc[k]); q[1] = hi32(sAcc[k]);
+        q[2] = swapped ? xb[k] : xa[k]; q[3] = swapped ? xa[k] : xb[k]; q[4] = swapped ? yb[k] : ya[k]; q[5] = swapped ? ya[k] : yb[k];
     }
     if (n.a.delayKind == 1) delayWriteBack<1>(da, T, C.st, C.blk + G.aDlyOff[w], nullptr, G.aDlyMask[w]);
     if (n.a.delayKind == 2) delayWriteBack<2>(da, T, C.st, C.blk + G.aDlyOff[w], C.blk + G.aDlyOff[w] + G.aDlyMask[w] + 1, G.aDlyMask[w]);
@@ -229,6 +284,7 @@ k_dag(const __grid_constant__ DagPlan P, const Chain2Args A, const __grid_consta
     }
     const int NS = G.streamsPerCta, T = A.nFrames, W = P.stateWords;
     const int s0 = blockIdx.x * NS, nsHere = min(NS, A.nStreams - s0);
+    const int FD = G.tileFrames;
     const int nTiles = (T + FD - 1) / FD, nIter = nTiles + P.maxDepth + 2;
     if (warp == P.nNodes) {
         // ---- input staging (tile `it` at iteration `it`) and the per-stream dither PRNG (lane = stream; DSP_TPDF_CALC,
@@ -242,30 +298,39 @@ k_dag(const __grid_constant__ DagPlan P, const Chain2Args A, const __grid_consta
             g.s0 = auxp[AUX_S0]; g.s1 = auxp[AUX_S1]; g.s2 = auxp[AUX_S2]; g.s3 = auxp[AUX_S3];
             tpdfValue = auxp[AUX_TPDF_VALUE]; tpdfRandom = auxp[AUX_TPDF_RANDOM]; dith = auxp[AUX_DITHER];
         }
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_dag);
+        // frame of element e of a stream's tile (e = frame * nIn + channel): a small table instead of a division per element
+        int* stageFr = smem_dag + G.tabOff + 4 * FD * P.nOut;
+        for (int e = lane; e < FD * nIn; e += 32) stageFr[e] = e / nIn;
+        __syncwarp();
         for (int it = 0; it < nIter; it++) {
             __syncthreads();
             if (it >= nTiles) continue;
             const int f0 = it * FD, nf = min(FD, T - f0);
-            // lane = word inside a stream's interleaved run: consecutive lanes read consecutive words
+            // lane = word inside a stream's interleaved run: consecutive lanes read consecutive words.  Asynchronous copies
+            // (LDGSTS): all of the tile's loads are in flight at once instead of one round trip to HBM per stream
             for (int s = 0; s < nsHere; s++) {
                 const int* src = A.in + (size_t)(s0 + s) * A.inStreamStride + (size_t)f0 * A.inFrameStride;
-                int* blk = smem_dag + s * G.perStreamWords + G.rawOff;
+                const unsigned blk = sbase + (unsigned)(s * G.perStreamWords + G.rawOff) * 4u;
                 for (int e = lane; e < nf * nIn; e += 32) {
-                    const int fr = e / nIn, ch = e - fr * nIn;
-                    blk[ch * (G.rawMask + 1) + ((f0 + fr) & G.rawMask)] = src[(size_t)fr * A.inFrameStride + (size_t)ch * A.inChStride];
+                    const int fr = stageFr[e], ch = e - fr * nIn;
+                    const unsigned dst = blk + (unsigned)(ch * (G.rawMask + 1) + ((f0 + fr) & G.rawMask)) * 4u;
+                    const int* p = src + (size_t)fr * A.inFrameStride + (size_t)ch * A.inChStride;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(p) : "memory");
                 }
             }
-            // DSP_LOAD_STORE copies (dsp_runtime.c:738-747: no saturation, no STORE mask) leave straight from here
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            // DSP_LOAD_STORE copies (dsp_runtime.c:738-747: no saturation, no STORE mask) leave straight from here:
+            // lane = (stream, frame) pair, one pass per copied channel
             if (G.nRawOut) {
+                asm volatile("cp.async.wait_all;" ::: "memory");
                 __syncwarp();
-                for (int s = 0; s < nsHere; s++) {
-                    const int* blk = smem_dag + s * G.perStreamWords + G.rawOff;
-                    int* dst = A.out + (size_t)(s0 + s) * A.outStreamStride + (size_t)f0 * A.outFrameStride;
-                    for (int ch = 0; ch < P.nOut; ch++) {
-                        if (P.outNode[ch] != -2) continue;
-                        const int src = P.outRaw[ch];
-                        for (int fr = lane; fr < nf; fr += 32)
-                            dst[(size_t)fr * A.outFrameStride + (size_t)ch * A.outChStride] = src >= 0 ? blk[src * (G.rawMask + 1) + ((f0 + fr) & G.rawMask)] : 0;
+                for (int k = 0; k < G.nRawOut; k++) {
+                    const int ch = G.rawOutCh[k], src = G.rawOutSrc[k];
+                    for (int e = lane; e < nsHere * nf; e += 32) {
+                        const int s = e / nf, fr = e - s * nf;
+                        const int v = src >= 0 ? smem_dag[s * G.perStreamWords + G.rawOff + src * (G.rawMask + 1) + ((f0 + fr) & G.rawMask)] : 0;
+                        A.out[(size_t)(s0 + s) * A.outStreamStride + (size_t)(f0 + fr) * A.outFrameStride + (size_t)ch * A.outChStride] = v;
                     }
                 }
             }
@@ -281,6 +346,7 @@ k_dag(const __grid_constant__ DagPlan P, const Chain2Args A, const __grid_consta
                     for (; jf < nf; jf++) row[(f0 + jf) & G.tpdfMask] = tpdfValue;
                 }
             }
+            asm volatile("cp.async.wait_all;" ::: "memory");       // the tile is in shared memory before the next barrier
         }
         if (auxp) {
             auxp[AUX_S0] = g.s0; auxp[AUX_S1] = g.s1; auxp[AUX_S2] = g.s2; auxp[AUX_S3] = g.s3;
@@ -289,10 +355,28 @@ k_dag(const __grid_constant__ DagPlan P, const Chain2Args A, const __grid_consta
         }
         return;
     }
-    // ---- store warps: tile it - 2 - maxDepth; lane = word inside a stream's output run (interleaved: 128-byte stores)
+    // ---- store warps: tile it - 2 - maxDepth; lane = word inside a stream's output run (interleaved: 128-byte stores).
+    // What element e = frame * nOut + channel of a tile reads is the same for every tile and stream: a table built once
+    // (row of the channel's node, frame offset behind its DELAY, ring mask, position in the caller's layout)
     const int sw = warp - P.nNodes - 1, nSW = G.nStore;
     const int nOut = P.nOut;
     const int storeMask = ditherMask(P.storeDither);
+    int* tabRow = smem_dag + G.tabOff;                  // >= 0: word offset of the post row in a stream's block; -1: reads 0; -2: written elsewhere
+    int* tabFr = tabRow + FD * nOut;                     // frame inside the tile minus the delay
+    int* tabMask = tabFr + FD * nOut;
+    int* tabDst = tabMask + FD * nOut;
+    int* tabNode = smem_dag + G.tabOff + 4 * FD * nOut + FD * P.nIn;
+    if (sw == 0) {
+        for (int e = lane; e < FD * nOut; e += 32) {
+            const int fr = e / nOut, ch = e - fr * nOut, node = P.outNode[ch];
+            const int dn = (node >= 0 && P.outDelayed[ch]) ? P.nodes[node].delayN : 0;
+            tabRow[e] = node >= 0 ? G.postOff[node] : node;
+            tabFr[e] = fr - dn;
+            tabMask[e] = node >= 0 ? G.postMask[node] : 0;
+            tabDst[e] = fr * A.outFrameStride + ch * A.outChStride;
+            tabNode[e] = (node >= 0 && dn > 0) ? node : -1;
+        }
+    }
     for (int it = 0; it < nIter; it++) {
         __syncthreads();
         const int j = it - 2 - P.maxDepth;
@@ -301,17 +385,19 @@ k_dag(const __grid_constant__ DagPlan P, const Chain2Args A, const __grid_consta
         for (int s = sw; s < nsHere; s += nSW) {
             const int* blk = smem_dag + s * G.perStreamWords;
             int* dst = A.out + (size_t)(s0 + s) * A.outStreamStride + (size_t)f0 * A.outFrameStride;
+#pragma unroll 4
             for (int e = lane; e < nf * nOut; e += 32) {
-                const int fr = e / nOut, ch = e - fr * nOut, f = f0 + fr;
-                const int node = P.outNode[ch];
+                const int row = tabRow[e];
+                if (row == -2) continue;                           // DSP_LOAD_STORE copy: the staging warp wrote it
                 int v = 0;
-                if (node >= 0) {
-                    const int dn = P.outDelayed[ch] ? P.nodes[node].delayN : 0;
-                    if (dn > 0 && f == dn && smem_dag[G.staleOff + (node * 32 + s) * 2]) v = smem_dag[G.staleOff + (node * 32 + s) * 2 + 1];
-                    else v = blk[G.postOff[node] + ((f - dn) & G.postMask[node])];
+                if (row >= 0) {
+                    const int fd = f0 + tabFr[e];
+                    v = blk[row + (fd & tabMask[e])];
+                    // a stale ring index: the delayed read of frame 0 returns the old line[n-1] (see DagDelay)
+                    if (fd == 0 && tabNode[e] >= 0 && smem_dag[G.staleOff + (tabNode[e] * 32 + s) * 2]) v = smem_dag[G.staleOff + (tabNode[e] * 32 + s) * 2 + 1];
                     v &= storeMask;                                // DSP_STORE masks with the current dither table (:610-633)
-                } else if (node == -2) continue;                   // DSP_LOAD_STORE copy: the staging warp wrote it
-                dst[(size_t)fr * A.outFrameStride + (size_t)ch * A.outChStride] = v;
+                }
+                dst[tabDst[e]] = v;
             }
         }
     }
@@ -320,8 +406,9 @@ k_dag(const __grid_constant__ DagPlan P, const Chain2Args A, const __grid_consta
 // ------------------------------------------------------------------------------------------------ host side
 static int pow2AtLeast(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-bool planDagGeometry(const DagPlan& P, int nStreams, int numSMs, DagGeom* geom) {
+static bool planDagGeometryTile(const DagPlan& P, int nStreams, int numSMs, int FD, DagGeom* geom) {
     DagGeom g{};
+    g.tileFrames = FD;
     if (P.nNodes < 1 || P.nNodes > kMaxDagNodes) return false;
     const int maxWarps = kDagMaxThreads / 32;
     if (P.nNodes + 2 > maxWarps) return false;
@@ -333,7 +420,7 @@ bool planDagGeometry(const DagPlan& P, int nStreams, int numSMs, DagGeom* geom) 
     int rawLag = 1, tpdfLag = 1, accLag[kMaxDagNodes];
     for (int w = 0; w < P.nNodes; w++) accLag[w] = 1;
     g.nRawOut = 0;
-    for (int ch = 0; ch < P.nOut; ch++) if (P.outNode[ch] == -2) g.nRawOut++;
+    for (int ch = 0; ch < P.nOut; ch++) if (P.outNode[ch] == -2) { g.rawOutCh[g.nRawOut] = ch; g.rawOutSrc[g.nRawOut] = P.outRaw[ch]; g.nRawOut++; }
     for (int w = 0; w < P.nNodes; w++) {
         const DagNode& n = P.nodes[w];
         for (const DagOperand* o : {&n.a, &n.b}) {
@@ -371,7 +458,8 @@ bool planDagGeometry(const DagPlan& P, int nStreams, int numSMs, DagGeom* geom) 
         }
     }
     g.perStreamWords = words | 1;                                  // odd pitch: lane = stream walks the banks
-    const size_t fixedWords = (size_t)kMaxDagNodes * 32 * 2;         // stale-index notes for the store warps
+    // stale-index notes for the store warps + their per-element table (5 words per output element of a tile) + the staging table
+    const size_t fixedWords = (size_t)kMaxDagNodes * 32 * 2 + (size_t)FD * (5 * std::max(P.nOut, 1) + std::max(P.nIn, 1));
     int NS = (nStreams + numSMs - 1) / numSMs;
     if (const char* v = getenv("AVDSP_B200_NS_DAG")) { const int e = atoi(v); if (e > 0) NS = e; }
     NS = std::max(1, std::min(NS, 32));
@@ -380,9 +468,25 @@ bool planDagGeometry(const DagPlan& P, int nStreams, int numSMs, DagGeom* geom) 
     NS = (int)std::min<size_t>((size_t)NS, budget / (size_t)g.perStreamWords);
     g.streamsPerCta = NS;
     g.staleOff = NS * g.perStreamWords;
+    g.tabOff = g.staleOff + kMaxDagNodes * 32 * 2;
     g.smemBytes = ((size_t)g.staleOff + fixedWords) * 4;
     *geom = g;
     return true;
+}
+
+// 32-frame tiles when a CTA can then hold its share of the streams (one wave), else 16-frame tiles: rows shrink with the tile, and a
+// second wave of CTAs costs more than twice as many barriers
+bool planDagGeometry(const DagPlan& P, int nStreams, int numSMs, DagGeom* geom) {
+    const int want = std::max(1, std::min(32, (nStreams + numSMs - 1) / numSMs));
+    DagGeom best{}; bool have = false;
+    for (int fd : {32, 16}) {
+        DagGeom g{};
+        if (!planDagGeometryTile(P, nStreams, numSMs, fd, &g)) continue;
+        if (!have || g.streamsPerCta > best.streamsPerCta) { best = g; have = true; }
+        if (g.streamsPerCta >= want) break;
+    }
+    if (have) *geom = best;
+    return have;
 }
 
 cudaError_t launchDag(const DagPlan& plan, const DagGeom& geom, const Chain2Args& args, cudaStream_t stream) {

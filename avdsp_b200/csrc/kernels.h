@@ -76,12 +76,15 @@ constexpr int kDagMaxThreads = 384;         // up to 12 warps of 168 registers: 
 struct DagGeom {
     int streamsPerCta;     // NS (<= 32): lane = stream, warp = node
     int threads, nStore;
+    int tileFrames;        // frames per iteration (32, or 16 when that lets a CTA hold its share of the streams)
     int perStreamWords;    // one stream's block of rows in shared memory (odd)
     int rawOff, rawMask;   // staged input PCM, one row per channel: word offset inside a stream's block, frames - 1 (power of two)
     int tpdfOff, tpdfMask; // dither values
     int nRawOut;           // output channels that are DSP_LOAD_STORE copies (written by the staging warp)
+    int rawOutCh[kIoSlots], rawOutSrc[kIoSlots];           // ... which ones, and the input channel each copies (-1: reads 0)
     int accMask[kMaxDagNodes];
     int staleOff;          // word offset (from the start of shared memory) of the stale-index notes for the store warps
+    int tabOff;            // ... of the store warps' per-element table and the staging warp's frame table
     int accLoOff[kMaxDagNodes], accHiOff[kMaxDagNodes];       // 64-bit node values, two planes
     int postOff[kMaxDagNodes], postMask[kMaxDagNodes];        // finished s.31 outputs (the delay line behind the saturation)
     int aDlyOff[kMaxDagNodes], aDlyMask[kMaxDagNodes];        // private delay rows of the operands (DSP_DELAY on a sample, DSP_DELAY_DP)

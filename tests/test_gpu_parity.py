@@ -140,7 +140,7 @@ def test_chain_kernel_is_selected_for_the_benchmark_programs():
         assert ex.last_kernel == kern, ex.trace
     ex = Executor(load_program("c1_crossover2x2lfe_f2_48k"), 48000, 2, 4)   # MEM hand-off, X/Y dataflow
     ex.process(synth.pcm("noise", 4, 64, ex.n_in, 48000))
-    assert ex.last_kernel == "generic"
+    assert ex.last_kernel == "dag"                       # not a set of independent chains: a DAG of cascades (kernel_dag.cu)
     with pytest.raises(AvdspError):
         ex.set_kernel(KERNEL_CHAIN); ex.process(synth.pcm("noise", 4, 8, ex.n_in, 48000))
 

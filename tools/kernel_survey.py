@@ -3,7 +3,12 @@ sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 import numpy as np, torch
 from conftest import CASES, load_program
 from avdsp_b200 import Executor, synth
+# which kernel AUTO picks for every test program at batch width (4096 streams), and what it sustains (device-resident PCM)
+seen = set()
 for prog, fmt, fs in CASES:
+    if (prog, fmt) in seen or "allops" in prog:
+        continue
+    seen.add((prog, fmt))
     w = load_program(prog)
     S, T = 4096, 4800
     ex = Executor(w, fs, fmt, S)
