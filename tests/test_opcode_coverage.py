@@ -16,6 +16,17 @@ from oracle import wire                                          # noqa: E402
 STRUCTURAL = {"END_OF_CODE", "HEADER", "NOP", "CORE", "PARAM", "PARAM_NUM"}
 
 
+# first line of each opcode's `case` in /root/reference/module_avdsp/runtime/dsp_runtime.c
+RT_LINE = {"SWAPXY": 337, "COPYXY": 344, "COPYYX": 349, "CLRXY": 354, "ADDXY": 360, "ADDYX": 365, "SUBXY": 370, "SUBYX": 375, "NEGX": 380,
+           "NEGY": 385, "SHIFT": 390, "MULXY": 408, "DIVXY": 414, "DIVYX": 420, "AVGXY": 426, "AVGYX": 432, "SQRTX": 438, "SAT0DB": 464,
+           "SAT0DB_TPDF": 478, "SAT0DB_GAIN": 494, "SAT0DB_TPDF_GAIN": 514, "TPDF_CALC": 537, "TPDF": 547, "LOAD": 565, "LOAD_GAIN": 586,
+           "STORE": 610, "GAIN": 636, "VALUE": 643, "VALUE_INT": 651, "WHITE": 664, "MUL_VALUE": 678, "DIV_VALUE": 685, "MUL_VALUE_INT": 692,
+           "DIV_VALUE_INT": 703, "AND_VALUE_INT": 714, "DELAY_1": 726, "LOAD_STORE": 738, "LOAD_MEM": 750, "STORE_MEM": 760, "DELAY": 769,
+           "DELAY_DP": 798, "BIQUADS": 827, "SERIAL": 863, "LOAD_MUX": 871, "DATA_TABLE": 900, "FIR": 928, "FIR(delay)": 940, "RMS": 972,
+           "DCBLOCK": 1063, "DITHER": 1112, "DITHER_NS2": 1138, "DISTRIB": 1175, "DIRAC": 1213, "SQUAREWAVE": 1234, "CLIP": 1264,
+           "LOAD_MEM_DATA": 1277, "SINE": 1284}
+
+
 def executed_opcodes(words, fs):
     """Opcode names inside the cores of the program (what dspRuntime walks), minus forms that are skipped at this fs."""
     w = np.asarray(words).view(np.uint32)
@@ -68,14 +79,14 @@ def test_every_opcode_is_executed_by_a_reference_made_golden():
 
 
 if __name__ == "__main__":
+    import re
     t = coverage()
-    print("| opcode | runtime/dsp_runtime.c | formats pinned | golden vectors (tests/golden/vectors) |")
+    print("| opcode | `dsp_runtime.c` | formats pinned | golden vectors that execute it (families; `tests/golden/vectors/*.npz`) |")
     print("|---|---|---|---|")
     for n in wire.OPCODES + ["FIR(delay)"]:
         if n in STRUCTURAL:
             continue
         vs = t.get(n, [])
         fm = ",".join(str(f) for f in sorted({f for _, f in vs}))
-        names = sorted({v for v, _ in vs})
-        shown = ", ".join(names[:4]) + (f", … (+{len(names) - 4})" if len(names) > 4 else "")
-        print(f"| {n} | | {fm} | {shown} |")
+        fam = sorted({re.sub(r"_f\d.*$|_\d+k.*$|_(noise|full|sine|impulse)$", "", v) for v, _ in vs})
+        print(f"| {n} | :{RT_LINE.get(n, '')} | {fm} | {', '.join(fam)} ({len(vs)} vectors) |")
