@@ -524,7 +524,7 @@ static int launchRun(avdsp_b200* h, avdsp_b200* pl, const int* in, int* out, int
         static const int envChain3 = [] { const char* v = getenv("AVDSP_B200_CHAIN3"); return (v && *v) ? atoi(v) : -1; }();
         bool v3 = v3Ok && h->kernelSel != AVDSP_B200_KERNEL_CHAIN_V2 &&
                   (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V3 || envChain3 == 1 ||
-                   (envChain3 != 0 && pl->geom3.maxSec <= 4 && pl->geom3.streamsPerCta >= 16 && nFrames >= std::max(1536, 48 * pl->geom3.gmax)));
+                   (envChain3 != 0 && pl->geom3.maxSec <= 4 && pl->geom3.streamsPerCta >= 16 && nFrames >= std::max(1536, 32 * pl->geom3.gmax)));
         if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V3 && !v3)
             return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel v3 requested but the program shape does not map to it");
         if (v3) e = launchChain3(pl->L.chain, pl->geom3, A, stream);

@@ -603,7 +603,9 @@ bool planChain3Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain3G
         Chain3Geom g{};
         for (int c = 0; c < C && fits; c++) {
             const int nsec = plan.chains[c].nsec, np = (nsec + partMax - 1) / partMax;
-            if (np > 2) { fits = false; break; }            // lags beyond F + 2 * partMax would outrun the dither ring (4 tiles)
+            // a SAT0DB_TPDF finish reads the dither ring (4 tiles) at the part's lag: at most two parts there; plain chains may be
+            // cut further (C3: 16 sections = four parts of four), their lag only lengthens the row ring
+            if (np > ((plan.chains[c].satKind & 1) ? 2 : 4)) { fits = false; break; }
             int first = 0, base = 0, prev = -1;
             for (int p = 0; p < np; p++) {
                 if (nParts >= kChain3MaxWarps) { fits = false; break; }
