@@ -358,6 +358,296 @@ __device__ __forceinline__ void cascadeWarp(const ChainPlan& P, const Chain2Args
     }
 }
 
+// ------------------------------------------------------------------------------------------------ float class (DSP_FORMAT 3)
+// dsp_calc_biquads_float (runtime/dsp_biquadSTD.h:84-119): acc += x*b0; += x1*b1; += x2*b2; += y1*(a1-1); += y2*a2 in THIS order,
+// every product truncated (dspMulFloatFloat, dsp_ieee754.h:336-375 == mul.rz.ftz.f32 outside the underflow range, see
+// kernel_chain2.cu), every sum rounded to nearest; y = the accumulator itself.  No saturation inside a float cascade, so no
+// checkpoint / replay.  Same skew, same rows, same helper warps as the fixed-point form; the lane converts its input sample
+// (dspIntToFloatScaled + LOAD_GAIN) and finishes with dspSaturateFloat0db + dsps31Float0DB itself.
+template <int NSEC>
+struct CascF {
+    float acc[NSEC], y1[NSEC], y2[NSEC], y3[NSEC];
+    float X1, X2, rx1[NSEC], rx2[NSEC];
+    float b0[NSEC], b1[NSEC], b2[NSEC], a1[NSEC], a2[NSEC];
+};
+__device__ __forceinline__ float maccF3(float acc, float a, float b) { return __fadd_rn(acc, mulFF_fast(a, b)); }
+
+template <int NSEC>
+__device__ __forceinline__ float cascStepF(CascF<NSEC>& L, float xin) {
+    float acc[NSEC];
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) acc[k] = maccF3(L.acc[k], k ? L.y1[k - 1] : xin, L.b0[k]);
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) acc[k] = maccF3(acc[k], k ? L.y2[k - 1] : L.X1, L.b1[k]);
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) acc[k] = maccF3(acc[k], k ? L.y3[k - 1] : L.X2, L.b2[k]);
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) acc[k] = maccF3(acc[k], L.y1[k], L.a1[k]);
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) acc[k] = maccF3(acc[k], L.y2[k], L.a2[k]);
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) { L.acc[k] = acc[k]; L.y3[k] = L.y2[k]; L.y2[k] = L.y1[k]; L.y1[k] = acc[k]; }
+    L.X2 = L.X1; L.X1 = xin;
+    return acc[NSEC - 1];
+}
+// any step of the launch: section k commits only when its frame t-k lies in [0,T); the reference's own x1/x2 words stand in for
+// outputs older than the launch on its first two frames
+template <int NSEC>
+__device__ __forceinline__ float cascStepExactF(CascF<NSEC>& L, float xin, int t, int T) {
+    float in[NSEC], x1[NSEC], x2[NSEC];
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) {
+        const int f = t - k;
+        in[k] = k ? L.y1[k - 1] : xin;
+        x1[k] = k ? (f == 0 ? L.rx1[k] : L.y2[k - 1]) : L.X1;
+        x2[k] = k ? (f == 0 ? L.rx2[k] : (f == 1 ? L.rx1[k] : L.y3[k - 1])) : L.X2;
+    }
+    float last = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) {
+        if ((unsigned)(t - k) < (unsigned)T) {
+            float acc = L.acc[k];
+            acc = maccF3(acc, in[k], L.b0[k]);
+            acc = maccF3(acc, x1[k], L.b1[k]);
+            acc = maccF3(acc, x2[k], L.b2[k]);
+            acc = maccF3(acc, L.y1[k], L.a1[k]);
+            acc = maccF3(acc, L.y2[k], L.a2[k]);
+            L.acc[k] = acc;
+            L.y3[k] = L.y2[k]; L.y2[k] = L.y1[k]; L.y1[k] = acc;
+            if (k == NSEC - 1) last = acc;
+        }
+    }
+    if ((unsigned)t < (unsigned)T) { L.X2 = L.X1; L.X1 = xin; }
+    return last;
+}
+
+// Interior tiles run two sections per instruction: f32x2 operands (sm_100a FMUL2.FTZ.RZ / FADD2), the same per-element arithmetic
+// in half the issue slots (the float step is issue-bound, not FP32-pipe-bound).  Pair p holds sections 2p (low half) and 2p+1.
+__device__ __forceinline__ unsigned long long packF3(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float loF3(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); (void)hi; return lo; }
+__device__ __forceinline__ float hiF3(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); (void)lo; return hi; }
+__device__ __forceinline__ unsigned long long macF3x2(unsigned long long acc, unsigned long long a, unsigned long long b) {
+    unsigned long long p;
+    asm("mul.rz.ftz.f32x2 %0, %1, %2;" : "=l"(p) : "l"(a), "l"(b));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(acc), "l"(p));
+    return acc;
+}
+template <int NP>
+struct CascP { unsigned long long acc[NP], x1[NP], x2[NP], y1[NP], y2[NP], b0[NP], b1[NP], b2[NP], a1[NP], a2[NP]; };
+template <int NP>
+__device__ __forceinline__ float cascStepP(CascP<NP>& Q, float xin) {
+    unsigned long long in[NP], acc[NP];
+    in[0] = packF3(xin, loF3(Q.y1[0]));                            // the odd section works on what the even one produced one step ago
+#pragma unroll
+    for (int p = 1; p < NP; p++) in[p] = packF3(hiF3(Q.y1[p - 1]), loF3(Q.y1[p]));
+#pragma unroll
+    for (int p = 0; p < NP; p++) acc[p] = macF3x2(Q.acc[p], in[p], Q.b0[p]);
+#pragma unroll
+    for (int p = 0; p < NP; p++) acc[p] = macF3x2(acc[p], Q.x1[p], Q.b1[p]);
+#pragma unroll
+    for (int p = 0; p < NP; p++) acc[p] = macF3x2(acc[p], Q.x2[p], Q.b2[p]);
+#pragma unroll
+    for (int p = 0; p < NP; p++) acc[p] = macF3x2(acc[p], Q.y1[p], Q.a1[p]);
+#pragma unroll
+    for (int p = 0; p < NP; p++) acc[p] = macF3x2(acc[p], Q.y2[p], Q.a2[p]);
+#pragma unroll
+    for (int p = 0; p < NP; p++) { Q.acc[p] = acc[p]; Q.x2[p] = Q.x1[p]; Q.x1[p] = in[p]; Q.y2[p] = Q.y1[p]; Q.y1[p] = acc[p]; }
+    return hiF3(acc[NP - 1]);
+}
+
+// FINM 0: the part hands its float on to the next part; 1: final part, SAT0DB; 2: final part, SAT0DB_TPDF
+template <int NSEC, int FINM>
+__device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Args& A, const Chain3Geom& G, unsigned char* smem, int w, int lane) {
+    constexpr int LAG = NSEC - 1;
+    constexpr bool fin = FINM != 0;
+    constexpr bool PACKED = (NSEC % 2) == 0;
+    constexpr int NP = PACKED ? NSEC / 2 : 1;
+    const int NS = G.streamsPerCta, W = P.h.stateWords, T = A.nFrames;
+    const int s0 = blockIdx.x * NS, nsHere = min(NS, A.nStreams - s0);
+    const int c = G.warpChain[w];
+    const ChainDesc& d = P.chains[c];
+    const int sec0 = G.warpFirstSec[w], base = G.warpBase[w], LAGA = base + LAG, srcWarp = G.warpSrc[w];
+    const bool live = lane < nsHere;
+    const int sl = min(lane, nsHere - 1);
+    const int RM = G.postRing - 1;
+    const unsigned RM4 = (unsigned)RM << 2, TM4 = (unsigned)(4 * F3 - 1) << 2;
+    const unsigned sb = smemAddr3(smem);
+    const unsigned postRow = sb + (unsigned)G.warpRowOff[w] + (unsigned)(sl * G.warpPitch[w]) * 4u;
+    const unsigned srcRow = sb + (unsigned)G.warpRowOff[max(srcWarp, 0)] + (unsigned)(sl * G.warpPitch[max(srcWarp, 0)]) * 4u;
+    volatile int* tileDone = reinterpret_cast<volatile int*>(smem + G.doneOff);
+    const unsigned tpdfRow = sb + G.tpdfOff + (unsigned)(sl * TP3) * 4u;
+    const unsigned rawRow = sb + G.rawOff + (unsigned)(sl * G.rawPitchBytes) + (unsigned)d.srcCh * 4u;
+    const unsigned fb = (unsigned)P.h.nIn * 4u;
+    const unsigned mbar = sb + G.mbarOff;
+    const bool fromPrev = srcWarp >= 0;
+    const bool hasSrcGain = !fromPrev && d.srcKind == SRC_LOAD_GAIN;
+    const float gain = hasSrcGain ? __int_as_float(d.srcArg) : 1.0f;     // mul.rz by 1.0 is exact: LOAD and LOAD_GAIN share the fast form
+    const int dither = P.h.storeDither;
+    int* st = A.state + (size_t)(s0 + sl) * W;
+
+    CascF<NSEC> L;
+    L.X1 = L.X2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NSEC; k++) {
+        const int* cf = P.pool + d.coefOff + 5 * (sec0 + k);
+        L.b0[k] = __int_as_float(cf[0]); L.b1[k] = __int_as_float(cf[1]); L.b2[k] = __int_as_float(cf[2]);
+        L.a1[k] = __int_as_float(cf[3]); L.a2[k] = __int_as_float(cf[4]);
+        L.y3[k] = 0.0f;
+        const int* q = st + P.pool[d.secStateOff + sec0 + k];       // [acc, -, x1, x2, y1, y2] as floats (dsp_biquadSTD.h:84-119)
+        L.acc[k] = __int_as_float(q[0]);
+        L.rx1[k] = __int_as_float(q[2]); L.rx2[k] = __int_as_float(q[3]); L.y1[k] = __int_as_float(q[4]); L.y2[k] = __int_as_float(q[5]);
+        if (k == 0) { L.X1 = L.rx1[0]; L.X2 = L.rx2[0]; }
+    }
+    // the post ring is the delay line (ring of s.31 values behind the saturation), exactly as in the fixed-point form
+    const int n = fin ? d.delayN : 0;
+    int idx0 = 0, staleIdx = -1;
+    if (live && n > 0) {
+        const int* ring = st + d.delayOff + 1;
+        idx0 = st[d.delayOff];
+        const bool stale = idx0 >= n || idx0 < 0;
+        for (int k = 0; k < n; k++) {
+            const int v = !stale ? ring[(idx0 + k) % n] : (k == 0 ? ring[idx0] : ring[k - 1]);
+            sts3(postRow + ((unsigned)((k - n + LAGA) & RM) << 2), v);
+        }
+        if (stale) { sts3(postRow + ((unsigned)(LAGA & RM) << 2), ring[n - 1]); staleIdx = idx0; idx0 = n - 1; }
+    }
+    const bool anyStale = __any_sync(0xffffffffu, staleIdx >= 0);
+    const int nTiles = (T + G.gmax + F3 - 1) / F3;
+    // input word -> the cascade's x.  Fast form (the host checked the gains, G.floatFast): hardware convert, exact scale, mul.rz.ftz;
+    // no branches -- the previous part's float and the converted sample are both formed, one is selected
+    auto sourceFast = [&](int smp) -> float {
+        float x = mulFF_fast(i2f31Fast(smp), gain);
+        x = smp == 0 ? 0.0f : x;                                   // the reference's product of a zero is +0, never -0
+        return fromPrev ? __int_as_float(smp) : x;
+    };
+    auto sourceExact = [&](int smp) -> float {
+        if (fromPrev) return __int_as_float(smp);
+        float x = i2fScaled(smp, 31);
+        if (hasSrcGain) { x = mulFF(x, gain); if (smp == 0) x = 0.0f; }
+        return x;
+    };
+    // accumulator -> what goes into the row: the float itself (hand-over) or the finished s.31 sample
+    auto emit = [&](float acc, int f) -> int {
+        if (FINM == 0) return __float_as_int(acc);
+        if (FINM == 2) acc = __fadd_rn(acc, i2fScaled(lds3(tpdfRow + ((unsigned)(f << 2) & TM4)), 31 + dither - 1));
+        // the saturated FLOAT goes into the post ring: a DSP_DELAY behind the saturation keeps floats in this format
+        // (dspALU_SP_t, dsp_runtime.c:769-794); the store warps convert to s.31 (dsps31Float0DB) like DSP_STORE does
+        return __float_as_int(satF(acc));
+    };
+
+    for (int i = 0; i < nTiles; i++) {
+        barSync3(kBarFull3 + (i & 1), G.threads);
+        const int t0 = i * F3;
+        unsigned ra, rstep;
+        if (srcWarp < 0) {
+            if (G.tma && t0 + F3 <= T) mbarWait3(mbar + 8u * (unsigned)(i & 1), (unsigned)((i >> 1) & 1));
+            ra = rawRow + (unsigned)(i & 1) * (unsigned)G.rawStageBytes; rstep = fb;
+        } else {
+            if (i > 0) { while (tileDone[srcWarp] < i) { } __threadfence_block(); __syncwarp(); }
+            ra = srcRow + (unsigned)(((i + 2) % 3) * F3) * 4u; rstep = 4u;
+        }
+        const int tl0 = t0 - base;
+        const bool interior = G.floatFast && tl0 >= LAG + 2 && tl0 + F3 <= T && !(anyStale && tl0 <= LAG);
+        if (interior) {
+            unsigned rj = ra;
+            unsigned pj = postRow + (fin ? ((unsigned)(t0 & RM) << 2) : (unsigned)((i % 3) * F3) * 4u);
+            int fj = t0 - LAGA;
+            CascP<NP> Q;
+            if constexpr (PACKED) {
+                // explicit x1/x2 per section: section k's input history is section k-1's output history
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    const int e = 2 * p, o = 2 * p + 1;
+                    Q.acc[p] = packF3(L.acc[e], L.acc[o]);
+                    Q.x1[p] = packF3(e ? L.y2[e - 1] : L.X1, L.y2[o - 1]);
+                    Q.x2[p] = packF3(e ? L.y3[e - 1] : L.X2, L.y3[o - 1]);
+                    Q.y1[p] = packF3(L.y1[e], L.y1[o]); Q.y2[p] = packF3(L.y2[e], L.y2[o]);
+                    Q.b0[p] = packF3(L.b0[e], L.b0[o]); Q.b1[p] = packF3(L.b1[e], L.b1[o]); Q.b2[p] = packF3(L.b2[e], L.b2[o]);
+                    Q.a1[p] = packF3(L.a1[e], L.a1[o]); Q.a2[p] = packF3(L.a2[e], L.a2[o]);
+                }
+            }
+            auto step = [&](int jj) {
+                const int smp = lds3(rj); rj += rstep;
+                float acc;
+                if constexpr (PACKED) acc = cascStepP<NP>(Q, sourceFast(smp)); else acc = cascStepF<NSEC>(L, sourceFast(smp));
+                const int v = emit(acc, fj + jj);
+                if (live) sts3(pj + 4u * jj, v);
+            };
+            constexpr int kMain = (F3 / AVDSP_UNR3) * AVDSP_UNR3;
+#pragma unroll 1
+            for (int j0 = 0; j0 < kMain; j0 += AVDSP_UNR3) {
+#pragma unroll
+                for (int jj = 0; jj < AVDSP_UNR3; jj++) step(jj);
+                pj += 4u * AVDSP_UNR3; fj += AVDSP_UNR3;
+            }
+#pragma unroll
+            for (int jj = 0; jj < F3 - kMain; jj++) step(jj);
+            if constexpr (PACKED) {
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    const int e = 2 * p, o = 2 * p + 1;
+                    L.acc[e] = loF3(Q.acc[p]); L.acc[o] = hiF3(Q.acc[p]);
+                    L.y1[e] = loF3(Q.y1[p]); L.y1[o] = hiF3(Q.y1[p]); L.y2[e] = loF3(Q.y2[p]); L.y2[o] = hiF3(Q.y2[p]);
+                    // y3 of a section = x2 of the next one (the last section's y3 feeds nobody in this lane)
+                    if (e) L.y3[e - 1] = loF3(Q.x2[p]); else { L.X1 = loF3(Q.x1[0]); L.X2 = loF3(Q.x2[0]); }
+                    L.y3[o - 1] = hiF3(Q.x2[p]);
+                }
+                L.y3[NSEC - 1] = 0.0f;
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < F3; j++) {
+                const int t = t0 + j, tl = t - base;
+                if (tl >= T + LAG) break;
+                if (tl < 0) continue;
+                const int smp = tl < T ? lds3(ra + (unsigned)j * rstep) : 0;
+                const float acc = cascStepExactF<NSEC>(L, G.floatFast ? sourceFast(smp) : sourceExact(smp), tl, T);
+                const int f = tl - LAG;
+                if (f >= 0) {
+                    const int v = emit(acc, f);
+                    if (live) {
+                        if (f == 0 && staleIdx >= 0) st[d.delayOff + 1 + staleIdx] = v;
+                        else sts3(postRow + (fin ? ((unsigned)(t << 2) & RM4) : (unsigned)((i % 3) * F3 + j) * 4u), v);
+                    }
+                }
+            }
+        }
+        if (!fin) {
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); tileDone[w] = i + 1; }
+        }
+        barArrive3(kBarDone3 + (i & 1), G.threads);
+    }
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < NSEC; k++) {
+            int* q = st + P.pool[d.secStateOff + sec0 + k];
+            q[0] = __float_as_int(L.acc[k]);
+            if (k == 0) { q[2] = __float_as_int(L.X1); q[3] = __float_as_int(L.X2); }
+            else if (T >= 2) { q[2] = __float_as_int(L.y1[k - 1]); q[3] = __float_as_int(L.y2[k - 1]); }
+            else if (T == 1) { q[2] = __float_as_int(L.y1[k - 1]); q[3] = __float_as_int(L.rx1[k]); }
+            q[4] = __float_as_int(L.y1[k]); q[5] = __float_as_int(L.y2[k]);
+        }
+        if (n > 0 && T > 0) {
+            int* ring = st + d.delayOff + 1;
+            for (int k = 0; k < n; k++) {
+                const long long j = (long long)T - n + k;
+                ring[(int)(((long long)idx0 + j + n) % n)] = lds3(postRow + ((unsigned)(((int)j + LAGA) & RM) << 2));
+            }
+            st[d.delayOff] = (int)(((long long)idx0 + T) % n);
+        }
+    }
+}
+template <int NSEC>
+__device__ __forceinline__ void cascadeWarpFin(const ChainPlan& P, const Chain2Args& A, const Chain3Geom& G, unsigned char* smem, int w, int lane) {
+    const int finm = !G.warpFinal[w] ? 0 : (P.chains[G.warpChain[w]].satKind & 1) ? 2 : 1;
+    switch (finm) {
+    case 0:  cascadeWarpF<NSEC, 0>(P, A, G, smem, w, lane); break;
+    case 1:  cascadeWarpF<NSEC, 1>(P, A, G, smem, w, lane); break;
+    default: cascadeWarpF<NSEC, 2>(P, A, G, smem, w, lane); break;
+    }
+}
+
 template <int NSEC, bool CKREG>
 __device__ __forceinline__ void cascadeWarpMode(const ChainPlan& P, const Chain2Args& A, const Chain3Geom& G, unsigned char* smem,
                                                 int w, int lane, int mode) {
@@ -371,41 +661,55 @@ __device__ __forceinline__ void cascadeWarpMode(const ChainPlan& P, const Chain2
 
 // store pass of one stream's window, interleaved output with NOUT (power of two) channels: 32/NOUT frames per pass, one
 // 128-byte run per pass; per-lane constants (row, lag - delay, mask) in registers
-template <int NOUT>
+// post-ring word -> s.31 sample: the fixed-point form parks it as such, the float form parks the saturated float
+template <bool FLT> __device__ __forceinline__ int post3(int v) { if (FLT) return f2s31SatFast(v); return v; }
+
+template <int NOUT, bool FLT>
 __device__ __forceinline__ void storeTile3(int* __restrict__ out, unsigned rowA, unsigned p4, unsigned RM4, int mask, bool clean,
                                            int f0, int fs, int T) {
     constexpr int FPP = 32 / NOUT, NPASS = F3 / FPP;
     if (clean) {
 #pragma unroll
-        for (int p = 0; p < NPASS; p++) out[p * 32] = lds3(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4)) & mask;
+        for (int p = 0; p < NPASS; p++) out[p * 32] = post3<FLT>(lds3(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
     } else {
 #pragma unroll 1
         for (int p = 0; p < NPASS; p++) {
             const int f = f0 + p * FPP + fs;
-            if (f >= 0 && f < T) out[p * 32] = lds3(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4)) & mask;
+            if (f >= 0 && f < T) out[p * 32] = post3<FLT>(lds3(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
         }
     }
 }
 
 // all streams of one store warp for one window: the channel-count dispatch sits outside the stream loop, the loop itself is
 // pointer bumps + the passes
-template <int NOUT>
+template <int NOUT, bool FLT>
 __device__ __forceinline__ void storeStreams3(int* __restrict__ out, size_t outStep, unsigned rowA, unsigned rowStep, int cnt, unsigned p4,
                                               unsigned RM4, int mask, bool clean, int f0, int fs, int T) {
 #pragma unroll 1
-    for (int s = 0; s < cnt; s++, out += outStep, rowA += rowStep) storeTile3<NOUT>(out, rowA, p4, RM4, mask, clean, f0, fs, T);
+    for (int s = 0; s < cnt; s++, out += outStep, rowA += rowStep) storeTile3<NOUT, FLT>(out, rowA, p4, RM4, mask, clean, f0, fs, T);
 }
 
 } // namespace
 
 // MAXSEC = 8: whole cascades, up to 12 warps of 168 registers;  MAXSEC = 4: cascades cut into parts, up to 16 warps of 128
-template <int MAXSEC>
+// FLT: the float class (DSP_FORMAT 3) as its own instance, so that the fixed-point kernel's code (instruction-cache sensitive) is unchanged
+template <int MAXSEC, bool FLT = false>
 __global__ void __launch_bounds__(MAXSEC > 4 ? kChain3MaxThreads : kChain3MaxThreadsParts, 1)
 k_chain3(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_constant__ Chain3Geom G) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int role = G.warpRole[threadIdx.x >> 5];          // >= 0: cascade warp (index); -1: dither warp; <= -2: store warp -2-k
-    if (role >= 0) {
+    if constexpr (FLT) {
+        if (role >= 0) {
+            switch (G.warpNsec[role]) {
+            case 1: cascadeWarpFin<1>(P, A, G, smem_raw, role, lane); break;
+            case 2: cascadeWarpFin<2>(P, A, G, smem_raw, role, lane); break;
+            case 3: cascadeWarpFin<3>(P, A, G, smem_raw, role, lane); break;
+            default: cascadeWarpFin<4>(P, A, G, smem_raw, role, lane); break;
+            }
+            return;
+        }
+    } else if (role >= 0) {
         const int warp = role;
         const ChainDesc& d = P.chains[G.warpChain[warp]];
         const bool unity = G.warpSrc[warp] >= 0 || (d.srcKind == SRC_LOAD_GAIN && d.srcArg == (1 << kMant));
@@ -510,7 +814,8 @@ k_chain3(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
             auxp[AUX_TPDF_VALUE] = tpdfValue; auxp[AUX_TPDF_RANDOM] = tpdfRandom; auxp[AUX_DITHER] = dith;
             if (drew) {   // TPDF_CALC leaves its last value (as an ALU word) in the data area (dsp_runtime.c:541-543)
                 int* q = A.state + (size_t)(s0 + lane) * W + P.h.tpdfDataOff;
-                q[0] = tpdfValue; q[1] = tpdfValue >> 31;
+                if (FLT) q[0] = __float_as_int(i2fScaled(tpdfValue, 31));          // the ALU word is a float in DSP_FORMAT 3
+                else { q[0] = tpdfValue; q[1] = tpdfValue >> 31; }
             }
         }
         return;
@@ -539,12 +844,12 @@ k_chain3(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
             const size_t outStep = (size_t)nSW * (size_t)A.outStreamStride;
             const unsigned rowA = sb + bRow + (unsigned)(sw * G.postPitch) * 4u, rowStep = (unsigned)(nSW * G.postPitch) * 4u;
             switch (nOut) {
-            case 1:  storeStreams3<1>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
-            case 2:  storeStreams3<2>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
-            case 4:  storeStreams3<4>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
-            case 8:  storeStreams3<8>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
-            case 16: storeStreams3<16>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
-            default: storeStreams3<32>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            case 1:  storeStreams3<1, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            case 2:  storeStreams3<2, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            case 4:  storeStreams3<4, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            case 8:  storeStreams3<8, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            case 16: storeStreams3<16, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            default: storeStreams3<32, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
             }
         } else {
             // any other layout (planar): lane = frame, channels in a loop; consecutive lanes store consecutive frames
@@ -556,7 +861,7 @@ k_chain3(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         int v = 0;
                         if (oc >= 0) {
                             const int off = G.chainLag[oc] - P.chains[oc].delayN;
-                            v = lds3(sb + (unsigned)G.warpRowOff[G.chainRow[oc]] + (unsigned)(sl * G.postPitch) * 4u + ((unsigned)((f + off) << 2) & RM4)) & storeMask;
+                            v = post3<FLT>(lds3(sb + (unsigned)G.warpRowOff[G.chainRow[oc]] + (unsigned)(sl * G.postPitch) * 4u + ((unsigned)((f + off) << 2) & RM4))) & storeMask;
                         }
                         A.out[(size_t)(s0 + sl) * A.outStreamStride + (size_t)f * A.outFrameStride + (size_t)ch * A.outChStride] = v;
                     }
@@ -569,13 +874,13 @@ static int envInt3(const char* name, int dflt) { const char* v = getenv(name); r
 
 bool chain3Supports(const ChainPlan& plan) {
     const ChainHeader& h = plan.h;
-    if (h.aluClass != ALU_INT64 || !h.sampleInt) return false;
+    if ((h.aluClass != ALU_INT64 && h.aluClass != ALU_F32) || !h.sampleInt) return false;      // DSP_FORMAT 2 and 3
     if (h.nChains <= 0 || h.nChains > kChain3MaxChains || h.nIn <= 0) return false;
     if (h.nOut <= 0 || h.nOut > 32 || (h.nOut & (h.nOut - 1)) != 0) return false;
     if (h.nRaw || h.nDelayFirst || h.nMemCopy) return false;
     for (int c = 0; c < h.nChains; c++) {
         const ChainDesc& d = plan.chains[c];
-        if (d.nsec < 1 || d.nsec > 8) return false;
+        if (d.nsec < 1 || d.nsec > 16) return false;        // up to four parts of four sections (plain finish), see planChain3Geometry
         if (d.srcKind != SRC_LOAD && d.srcKind != SRC_LOAD_GAIN) return false;
         if (d.srcCh < 0 || d.srcCh >= h.nIn) return false;
         if (d.hasGain || d.delayFirst) return false;
@@ -596,6 +901,7 @@ bool planChain3Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain3G
     // Two shapes: cascades cut into parts of <= 4 sections (more, equal warps: the faster shape when it fits), else whole cascades
     for (int partMax : {envInt3("AVDSP_B200_PART3", 4), 8}) {
         if (partMax < 1 || partMax > 8) continue;
+        if (plan.h.aluClass == ALU_F32 && partMax > 4) continue;      // the float form exists for parts of <= 4 sections
         struct Part { int chain, first, nsec, base, src, fin; };
         Part parts[kChain3MaxWarps];
         int nParts = 0, gmax = 0, maxSec = 0;
@@ -622,6 +928,13 @@ bool planChain3Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain3G
         if (!fits) continue;
         const int maxThreads = maxSec > 4 ? kChain3MaxThreads : kChain3MaxThreadsParts;
         g.streamsPerCta = NS;
+        g.floatFast = 1;          // float class: hardware convert + mul.rz.ftz on the source when every LOAD_GAIN gain is within [2^-30, 2^30]
+        for (int c = 0; c < C; c++)
+            if (plan.chains[c].srcKind == SRC_LOAD_GAIN) {
+                const int ex = (int)(((uint32_t)plan.chains[c].srcArg >> 23) & 255u);
+                if (ex != 0 && (ex < 127 - 30 || ex > 127 + 30)) g.floatFast = 0;
+            }
+        if (envInt3("AVDSP_B200_FLOAT_EXACT_HELPERS", 0)) g.floatFast = 0;
         g.nCascade = nParts;
         g.gmax = gmax;
         g.maxSec = maxSec;
@@ -730,7 +1043,11 @@ cudaError_t launchChain3(const ChainPlan& plan, const Chain3Geom& geom, const Ch
     g.tma = chain3TmaOk(plan, args) ? 1 : 0;
     const int blocks = (args.nStreams + g.streamsPerCta - 1) / g.streamsPerCta;
     cudaError_t e;
-    if (g.maxSec > 4) {
+    if (plan.h.aluClass == ALU_F32) {
+        e = cudaFuncSetAttribute(k_chain3<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes);
+        if (e != cudaSuccess) return e;
+        k_chain3<4, true><<<blocks, g.threads, g.smemBytes, stream>>>(plan, args, g);
+    } else if (g.maxSec > 4) {
         e = cudaFuncSetAttribute(k_chain3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes);
         if (e != cudaSuccess) return e;
         k_chain3<8><<<blocks, g.threads, g.smemBytes, stream>>>(plan, args, g);

@@ -112,6 +112,7 @@ struct Chain3Geom {
     int rawPitchBytes, rawStageBytes;     // staged input tiles: bytes per stream row / per stage (2 stages)
     int postOff, tpdfOff, ckOff, doneOff, mbarOff, rawOff;   // shared-memory map (bytes)
     int tma;               // filled per launch: the caller's input buffer allows bulk copies (else plain staged copies)
+    int floatFast;         // float class: the source may use the hardware convert + mul.rz.ftz (gains checked on the host)
     // cascade warp -> what it runs (dealt so that the four sub-partitions carry equal section counts)
     int warpChain[kChain3MaxWarps], warpFirstSec[kChain3MaxWarps], warpNsec[kChain3MaxWarps];
     int warpBase[kChain3MaxWarps];        // step offset of the part: its section k works on frame t - base - k at step t

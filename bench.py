@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-multi", action="store_true", help="skip the one-call multi-device arm (avdsp_b200_create_multi) at N > 1")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "chain", "chain_v2", "chain_v3", "mix", "fir", "fir_tc"],
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "chain", "chain_v2", "chain_v3", "mix", "fir", "fir_tc", "dag"],
                     help="force a kernel (diagnostics; the default is what the product picks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -216,7 +216,7 @@ def main():
     if args.kernel != "auto":
         ex.set_kernel({"generic": avdsp_b200.KERNEL_GENERIC, "chain": avdsp_b200.KERNEL_CHAIN, "mix": avdsp_b200.KERNEL_MIX,
                        "fir": avdsp_b200.KERNEL_FIR, "fir_tc": avdsp_b200.KERNEL_FIR_TC,
-                       "chain_v2": avdsp_b200.KERNEL_CHAIN_V2, "chain_v3": avdsp_b200.KERNEL_CHAIN_V3}[args.kernel])
+                       "chain_v2": avdsp_b200.KERNEL_CHAIN_V2, "chain_v3": avdsp_b200.KERNEL_CHAIN_V3, "dag": avdsp_b200.KERNEL_DAG}[args.kernel])
     n_in, n_out = ex.n_in, ex.n_out
     x = synth.pcm_torch("noise", S, T, n_in, dev, first_stream=first)       # synthetic PCM, resident in HBM
     y = torch.empty((S, T, n_out), dtype=torch.int32, device=dev)

@@ -28,6 +28,70 @@ def _v3(w, fs, S, **kw):
     return ex
 
 
+@pytest.mark.parametrize("stim", ["full", "noise", "impulse"])
+def test_c3_sixteen_section_cascades_in_four_parts(oracle_lib, stim):
+    """C3 (16-section PEQ per channel, plain SAT0DB): the cascade runs as four part warps, each a tile behind the previous one
+    (lag 108 frames); where the test fixture asks for whole cascades or parts of two the geometry does not fit and v3 declines."""
+    w, fs = load_program("c3_peq16_f2_48k"), 48000
+    S, T = 23, 777
+    seeds = np.arange(S, dtype=np.int32)
+    ex = Executor(w, fs, 2, S, seeds=seeds, dither=31)
+    ex.set_kernel(KERNEL_CHAIN_V3)
+    x = synth.pcm(stim, S, T, ex.n_in, fs)
+    try:
+        a = ex.process(x[:, :300])
+    except AvdspError:
+        assert "chain kernel v3 geometry" not in ex.trace          # parts of 2 (8 per chain) or whole 16-section cascades: no v3 shape
+        return
+    b = ex.process(x[:, 300:])                                     # a second call: fill / drain of the four-deep part pipeline
+    assert ex.last_chain_variant == 3
+    ys, sts = oracle_run(oracle_lib, w, 2, fs, x, seeds, 31)
+    assert np.array_equal(np.concatenate([a, b], axis=1), ys)
+    for s in (0, 4, 5, S - 1):
+        assert np.array_equal(ex.get_state(s), expected_state(ex, sts[s])), s
+
+
+def _float_state_close(got, exp):
+    """float class of the chain kernels: products are mul.rz.ftz.f32; the reference flushes products next to 2^-126 one binade
+    earlier (dsp_ieee754.h:336-375).  Stated tolerance on float state words: 2^-100 absolute; s.31 outputs identical."""
+    d = np.nonzero(got != exp)[0]
+    return d.size == 0 or np.abs(got[d].view(np.float32).astype(np.float64) - exp[d].view(np.float32).astype(np.float64)).max() <= 2.0 ** -100
+
+
+@pytest.mark.parametrize("stim", ["noise", "impulse", "sine"])
+def test_float_class_dsp_format_3(oracle_lib, stim):
+    """DSP_FORMAT 3 (float ALU, int32 samples) on k_chain3: C3's 16-section cascades as four part warps, and a shorter program
+    with TPDF finish, LOAD without gain and a delay line; s.31 outputs identical to the reference's float arithmetic."""
+    from oracle import wire
+    fs = 48000
+    a = wire.Asm(fmt=3, fmin=fs, fmax=fs)
+    a.core(); a.tpdf_calc(24); a.param()
+    e1 = a.biquad_sections([[wire.rbj_peak(fs, 300 * (k + 1), 1.0 + 0.3 * k, 1.4 if k & 1 else 0.7)] for k in range(5)])
+    e2 = a.biquad_sections([[wire.rbj_peak(fs, 900 * (k + 1), 2.0, 0.8)] for k in range(3)])
+    dl = a.delay_param(2000, 700, fs)
+    a.load_gain(8, 0.8); a.biquads(e1); a.sat0db_tpdf(); a.delay(dl); a.store(0)
+    a.load(9); a.biquads(e2); a.sat0db(); a.store(1)
+    own = a.end()
+    for w, S, T in ((load_program("c3_peq16_f3_48k"), 23, 777), (own, 11, 500)):
+        seeds = np.arange(S, dtype=np.int32) + 5
+        ex = Executor(w, fs, 3, S, seeds=seeds, dither=24)
+        ex.set_kernel(KERNEL_CHAIN_V3)
+        x = synth.pcm(stim, S, T, ex.n_in, fs)
+        try:
+            y1 = ex.process(x[:, :260])
+        except AvdspError:
+            assert "chain kernel v3 geometry" not in ex.trace      # fixture shapes the float form does not have (parts > 4 sections)
+            continue
+        y2 = ex.process(x[:, 260:])
+        assert ex.last_chain_variant == 3
+        ys, sts = oracle_run(oracle_lib, w, 3, fs, x, seeds, 24)
+        assert np.array_equal(np.concatenate([y1, y2], axis=1), ys)
+        for s in (0, 4, 5, S - 1):
+            got, exp = ex.get_state(s), expected_state(ex, sts[s])
+            dd = np.nonzero(got != exp)[0]
+            assert _float_state_close(got, exp), (s, dd[:10], got[dd[:10]].view(np.float32), exp[dd[:10]].view(np.float32), got[dd[:10]], exp[dd[:10]])
+
+
 @pytest.mark.parametrize("prog,fs", [("c2_testrpi_xover_f2_192k", 192000)])
 @pytest.mark.parametrize("stim", ["full", "noise", "impulse", "sine"])
 def test_c2_ragged_batch_bit_exact(oracle_lib, prog, fs, stim):
@@ -156,16 +220,20 @@ def test_foreign_state_block_with_incoherent_histories():
 
 
 def test_v3_refuses_what_it_cannot_run():
-    """Program shapes outside v3 (float format, 16-section cascades, mixers) are refused when v3 is forced and run on the other
-    kernels under AUTO."""
-    for prog, fmt, fs in (("c3_peq16_f2_48k", 2, 48000), ("c3_peq16_f3_48k", 3, 48000)):
+    """Program shapes outside v3 (mixers, gains behind the cascade, the double-ALU format 4) are refused when v3 is forced and
+    run on the other kernels under AUTO; short calls stay on v2 under AUTO even where v3 could run them."""
+    for prog, fmt, fs, kern in (("c5_mixer8x8_f2_192k", 2, 192000, "mix"), ("c1_crossover2x2lfe_f2_48k", 2, 48000, "dag"), ("c3_peq16_f4_48k", 4, 48000, "generic")):
         ex = Executor(load_program(prog), fs, fmt, 8)
-        x = synth.pcm("noise", 8, 64, ex.n_in, fs)
+        x = (synth.pcm_float if fmt >= 5 else synth.pcm)("noise", 8, 64, ex.n_in, fs)
         ex.set_kernel(KERNEL_CHAIN_V3)
         with pytest.raises(AvdspError):
             ex.process(x)
         ex.set_kernel(KERNEL_AUTO)
         ex.process(x)
+        assert ex.last_kernel == kern
+    for prog, fmt, fs in (("c3_peq16_f2_48k", 2, 48000), ("c3_peq16_f3_48k", 3, 48000)):
+        ex = Executor(load_program(prog), fs, fmt, 8)
+        ex.process(synth.pcm("noise", 8, 64, ex.n_in, fs))
         assert ex.last_kernel == "chain" and ex.last_chain_variant == 2
 
 

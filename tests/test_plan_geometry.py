@@ -49,9 +49,11 @@ def test_streams_per_cta_follow_the_sm_count(streams, per_cta):
 
 
 def test_programs_outside_the_v3_shape_are_left_to_the_other_kernels():
-    for prog, fmt, fs in (("c3_peq16_f2_48k", 2, 48000), ("c3_peq16_f3_48k", 3, 48000)):   # 16-section cascades / float format
-        t = avdsp_b200.describe(load_program(prog), fs, fmt, n_streams=65536)
-        assert _v3(t) is None and "chain kernel v2 geometry" in t
+    for prog, fmt in (("c3_peq16_f2_48k", 2), ("c3_peq16_f3_48k", 3)):          # 16 sections, plain finish: four parts of four (fmt 2 and 3)
+        t = avdsp_b200.describe(load_program(prog), 48000, fmt, n_streams=65536)
+        assert "8 cascade warps of <= 4 sections" in _v3(t) and "0:12+4@105" in _v3(t) and "chain kernel v2 geometry" in t
+    t = avdsp_b200.describe(load_program("c3_peq16_f4_48k"), 48000, 4, n_streams=65536)                # double ALU: no chain kernel
+    assert _v3(t) is None
     t = avdsp_b200.describe(load_program("c5_mixer8x8_f2_192k"), 192000, 2, n_streams=4096)
     assert "time-parallel mix kernel: usable" in t and _v3(t) is None
     t = avdsp_b200.describe(load_program("c4_fir4096_f2_48k"), 48000, 2, n_streams=1024)
