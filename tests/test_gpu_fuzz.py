@@ -1,0 +1,127 @@
+"""Randomised X/Y-dataflow programs (wire assembler) through whatever kernel AUTO picks -- k_dag where the decoder's symbolic
+X/Y execution recognises the program, the interpreter otherwise -- against the oracle, outputs and state, bit for bit.
+The generator only emits sequences that are meaningful in the reference (no division, no store of an undefined ALU), but
+it does not know what the DAG recognition accepts: both outcomes are checked, and the test requires that a fair share of
+the programs does land on k_dag."""
+import numpy as np
+import pytest
+
+from avdsp_b200 import Executor, synth, KERNEL_GENERIC
+from oracle import wire
+
+pytestmark = pytest.mark.gpu
+
+
+def random_program(rng, fs=48000):
+    a = wire.Asm(fmt=2, fmin=fs, fmax=fs)
+    n_cores = int(rng.integers(1, 4))
+    out_slots = list(range(0, 8))
+    rng.shuffle(out_slots)
+    mems = []                                           # (address, defined)
+    first = True
+    for c in range(n_cores):
+        a.core()
+        if first and rng.random() < 0.7:
+            a.tpdf_calc(int(rng.choice([20, 24, 31])))
+        first = False
+        a.param()
+        secs = [a.biquad_sections([[wire.rbj_peak(fs, float(rng.uniform(60, 15000)), float(rng.uniform(0.5, 4)), float(rng.uniform(0.5, 1.8)))]
+                                   for _ in range(int(rng.integers(1, 6)))]) for _ in range(3)]
+        dls = [a.delay_param(3000, int(rng.integers(20, 2800)), fs) for _ in range(3)]
+        new_mems = [a.mem_location() for _ in range(2)]
+        x_def = y_def = False                            # X / Y hold an expression the reference computes meaningfully
+        x_fin = False                                    # X is a saturated sample
+        for _path in range(int(rng.integers(1, 4))):
+            # a source
+            r = rng.random()
+            if r < 0.35:
+                a.load(int(rng.choice([8, 9])))
+            elif r < 0.8 or not any(d for _, d in mems):
+                a.load_gain(int(rng.choice([8, 9])), float(rng.uniform(0.2, 1.0)))
+            else:
+                a.load_mem(rng.choice([m for m, d in mems if d]))
+            y_def, x_def, x_fin = x_def and not x_fin, True, False
+            fresh = False
+            for _step in range(int(rng.integers(1, 8))):
+                r = rng.random()
+                if r < 0.12:
+                    a.simple("COPYXY"); y_def = x_def
+                elif r < 0.22 and y_def:
+                    a.simple("SWAPXY"); fresh = False
+                elif r < 0.30 and y_def and x_def:
+                    a.simple(str(rng.choice(["ADDXY", "SUBXY", "SUBYX", "ADDYX"]))); fresh = False
+                elif r < 0.55:
+                    a.biquads(secs[int(rng.integers(0, 3))]); fresh = True
+                elif r < 0.63:
+                    a.gain(float(rng.uniform(0.3, 1.2)))
+                elif r < 0.68:
+                    a.shift(int(rng.choice([-100, -28, -3])))
+                elif r < 0.74:
+                    a.delay(dls[int(rng.integers(0, 3))], dp=bool(rng.random() < 0.5))
+                elif r < 0.80 and fresh and new_mems:
+                    m = new_mems.pop(); a.store_mem(m); mems.append((m, True))
+                elif r < 0.84:
+                    a.simple("CLRXY"); y_def = False; fresh = False
+                    a.load_gain(int(rng.choice([8, 9])), 0.5)
+            # a finish and one or two stores
+            r = rng.random()
+            if r < 0.3:
+                a.sat0db()
+            elif r < 0.55:
+                a.sat0db_tpdf()
+            elif r < 0.75:
+                a.sat0db_gain(float(rng.uniform(0.4, 1.0)))
+            elif r < 0.9:
+                a.sat0db_tpdf_gain(float(rng.uniform(0.4, 1.0)))
+            # else: DSP_STORE of the unsaturated value
+            x_fin = True
+            if out_slots:
+                a.store(out_slots.pop())
+            if rng.random() < 0.4 and out_slots:
+                a.delay(dls[int(rng.integers(0, 3))])
+                a.store(out_slots.pop())
+            if rng.random() < 0.5 and y_def:
+                a.simple("SWAPXY"); x_fin = False; x_def = True; y_def = False
+                if rng.random() < 0.5:
+                    a.biquads(secs[int(rng.integers(0, 3))])
+                a.sat0db()
+                if out_slots:
+                    a.store(out_slots.pop())
+                x_fin = True
+        if not out_slots:
+            break
+    return a.end()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_xy_programs(oracle_lib, seed):
+    rng = np.random.default_rng(1000 + seed)
+    fs = 48000
+    hits = 0
+    for k in range(6):
+        w = random_program(rng, fs)
+        S, T = 5, 210
+        seeds = np.arange(S, dtype=np.int32) + seed
+        try:
+            ex = Executor(w, fs, 2, S, seeds=seeds, dither=24)
+        except Exception:
+            continue                                      # (a generated program the decoder refuses: not this test's subject)
+        x = synth.pcm("full" if k & 1 else "noise", S, T, ex.n_in, fs) if ex.n_in else np.zeros((S, T, 0), np.int32)
+        ys, sts = oracle_lib.run_streams(w, 2, fs, x, seeds=seeds, dither=24)
+        ya = ex.process(x[:, :77])
+        yb = ex.process(x[:, 77:])
+        kern = ex.last_kernel
+        hits += kern == "dag"
+        y = np.concatenate([ya, yb], axis=1)
+        assert np.array_equal(y, ys), f"seed {seed}/{k} [{kern}]: {np.count_nonzero(y != ys)} samples differ\n" + "\n".join(wire.disassemble(w))
+        for s in (0, S - 1):
+            data, aux, code = sts[s]
+            st = ex.get_state(s)
+            assert np.array_equal(st[: ex.data_size], data), f"seed {seed}/{k} [{kern}]: data area differs at {np.nonzero(st[:ex.data_size] != data)[0][:8]}\n" + "\n".join(wire.disassemble(w))
+            for q, wd in enumerate(ex.mem_words):
+                assert np.array_equal(st[ex.mem_offset + 2 * q: ex.mem_offset + 2 * q + 2], code[wd: wd + 2]), f"seed {seed}/{k} [{kern}]: MEM word {q}"
+    test_random_xy_programs.hits = getattr(test_random_xy_programs, "hits", 0) + hits
+
+
+def test_fuzz_reaches_the_dag_kernel():
+    assert getattr(test_random_xy_programs, "hits", 0) >= 20, "the random programs hardly ever map to k_dag: the generator drifted"

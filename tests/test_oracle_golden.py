@@ -101,3 +101,23 @@ def test_oracle_chunking_is_invisible(oracle_lib):
     o = oracle_lib.Oracle(w, 2, 48000)
     b = np.concatenate([o.process(x[:1]), o.process(x[1:333]), o.process(x[333:])])
     assert np.array_equal(a, b)
+
+
+def test_oracle_matches_compiled_reference_on_random_xy_programs(oracle_lib):
+    """144 randomised X/Y-dataflow programs (the generator of tests/test_gpu_fuzz.py): the restatement against the compiled
+    reference, outputs and data area.  Needs oracle/_ref (built where /root/reference exists)."""
+    from oracle import refdriver, wire
+    if not refdriver.available(2):
+        pytest.skip("oracle/_ref not built here (it needs /root/reference)")
+    from test_gpu_fuzz import random_program
+    for seed in range(24):
+        rng = np.random.default_rng(1000 + seed)
+        for k in range(6):
+            w = random_program(rng)
+            ins, _ = wire.io_maps(w)
+            x = synth.pcm("full" if k & 1 else "noise", 1, 150, len(ins), 48000)[0]
+            r = refdriver.RefProgram(w, 2, 48000, seed=seed, dither=24)
+            o = oracle_lib.Oracle(w, 2, 48000, seed=seed, dither=24)
+            assert r.rc == o.rc > 0
+            assert np.array_equal(r.process(x), o.process(x)), (seed, k)
+            assert np.array_equal(r.data, o.data), (seed, k)
