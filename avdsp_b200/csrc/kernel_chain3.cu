@@ -422,7 +422,10 @@ __device__ __forceinline__ float cascStepExactF(CascF<NSEC>& L, float xin, int t
 }
 
 // Interior tiles run two sections per instruction: f32x2 operands (sm_100a FMUL2.FTZ.RZ / FADD2), the same per-element arithmetic
-// in half the issue slots (the float step is issue-bound, not FP32-pipe-bound).  Pair p holds sections 2p (low half) and 2p+1.
+// in half the issue slots.  Pair j holds sections j (low half) and j + NP: the input pair of pair j >= 1 is then the y1 pair of
+// pair j-1 as it stands, and its x1/x2 are that pair's y2/y3 -- no half moves between registers except one per step: pair 0
+// takes (xin, y1 of section NP-1).  (The first version paired neighbouring sections and spent 0.8 register moves per packed
+// multiply on re-pairing, profiles/r2_chain3_c3f_ncu_summary.txt: 45 instructions per step and warp, now 27.)
 __device__ __forceinline__ unsigned long long packF3(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ float loF3(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); (void)hi; return lo; }
 __device__ __forceinline__ float hiF3(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); (void)lo; return hi; }
@@ -433,30 +436,30 @@ __device__ __forceinline__ unsigned long long macF3x2(unsigned long long acc, un
     return acc;
 }
 template <int NP>
-struct CascP { unsigned long long acc[NP], x1[NP], x2[NP], y1[NP], y2[NP], b0[NP], b1[NP], b2[NP], a1[NP], a2[NP]; };
+struct CascP { unsigned long long acc[NP], y1[NP], y2[NP], y3[NP], X1, X2, b0[NP], b1[NP], b2[NP], a1[NP], a2[NP]; };
 template <int NP>
 __device__ __forceinline__ float cascStepP(CascP<NP>& Q, float xin) {
-    unsigned long long in[NP], acc[NP];
-    in[0] = packF3(xin, loF3(Q.y1[0]));                            // the odd section works on what the even one produced one step ago
+    unsigned long long acc[NP];
+    const unsigned long long in0 = packF3(xin, loF3(Q.y1[NP - 1]));     // section NP works on what section NP-1 produced one step ago
 #pragma unroll
-    for (int p = 1; p < NP; p++) in[p] = packF3(hiF3(Q.y1[p - 1]), loF3(Q.y1[p]));
+    for (int j = 0; j < NP; j++) acc[j] = macF3x2(Q.acc[j], j ? Q.y1[j - 1] : in0, Q.b0[j]);
 #pragma unroll
-    for (int p = 0; p < NP; p++) acc[p] = macF3x2(Q.acc[p], in[p], Q.b0[p]);
+    for (int j = 0; j < NP; j++) acc[j] = macF3x2(acc[j], j ? Q.y2[j - 1] : Q.X1, Q.b1[j]);
 #pragma unroll
-    for (int p = 0; p < NP; p++) acc[p] = macF3x2(acc[p], Q.x1[p], Q.b1[p]);
+    for (int j = 0; j < NP; j++) acc[j] = macF3x2(acc[j], j ? Q.y3[j - 1] : Q.X2, Q.b2[j]);
 #pragma unroll
-    for (int p = 0; p < NP; p++) acc[p] = macF3x2(acc[p], Q.x2[p], Q.b2[p]);
+    for (int j = 0; j < NP; j++) acc[j] = macF3x2(acc[j], Q.y1[j], Q.a1[j]);
 #pragma unroll
-    for (int p = 0; p < NP; p++) acc[p] = macF3x2(acc[p], Q.y1[p], Q.a1[p]);
+    for (int j = 0; j < NP; j++) acc[j] = macF3x2(acc[j], Q.y2[j], Q.a2[j]);
 #pragma unroll
-    for (int p = 0; p < NP; p++) acc[p] = macF3x2(acc[p], Q.y2[p], Q.a2[p]);
-#pragma unroll
-    for (int p = 0; p < NP; p++) { Q.acc[p] = acc[p]; Q.x2[p] = Q.x1[p]; Q.x1[p] = in[p]; Q.y2[p] = Q.y1[p]; Q.y1[p] = acc[p]; }
+    for (int j = 0; j < NP; j++) { Q.acc[j] = acc[j]; Q.y3[j] = Q.y2[j]; Q.y2[j] = Q.y1[j]; Q.y1[j] = acc[j]; }
+    Q.X2 = Q.X1; Q.X1 = in0;
     return hiF3(acc[NP - 1]);
 }
 
 // FINM 0: the part hands its float on to the next part; 1: final part, SAT0DB; 2: final part, SAT0DB_TPDF
-template <int NSEC, int FINM>
+// FROMPREV: the part reads the previous part's row (floats) instead of the PCM tile
+template <int NSEC, int FINM, bool FROMPREV>
 __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Args& A, const Chain3Geom& G, unsigned char* smem, int w, int lane) {
     constexpr int LAG = NSEC - 1;
     constexpr bool fin = FINM != 0;
@@ -479,7 +482,7 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
     const unsigned rawRow = sb + G.rawOff + (unsigned)(sl * G.rawPitchBytes) + (unsigned)d.srcCh * 4u;
     const unsigned fb = (unsigned)P.h.nIn * 4u;
     const unsigned mbar = sb + G.mbarOff;
-    const bool fromPrev = srcWarp >= 0;
+    constexpr bool fromPrev = FROMPREV;
     const bool hasSrcGain = !fromPrev && d.srcKind == SRC_LOAD_GAIN;
     const float gain = hasSrcGain ? __int_as_float(d.srcArg) : 1.0f;     // mul.rz by 1.0 is exact: LOAD and LOAD_GAIN share the fast form
     const int dither = P.h.storeDither;
@@ -516,9 +519,9 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
     // input word -> the cascade's x.  Fast form (the host checked the gains, G.floatFast): hardware convert, exact scale, mul.rz.ftz;
     // no branches -- the previous part's float and the converted sample are both formed, one is selected
     auto sourceFast = [&](int smp) -> float {
-        float x = mulFF_fast(i2f31Fast(smp), gain);
-        x = smp == 0 ? 0.0f : x;                                   // the reference's product of a zero is +0, never -0
-        return fromPrev ? __int_as_float(smp) : x;
+        if (fromPrev) return __int_as_float(smp);
+        const float x = mulFF_fast(i2f31Fast(smp), gain);
+        return smp == 0 ? 0.0f : x;                                // the reference's product of a zero is +0, never -0
     };
     auto sourceExact = [&](int smp) -> float {
         if (fromPrev) return __int_as_float(smp);
@@ -534,12 +537,18 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
         // (dspALU_SP_t, dsp_runtime.c:769-794); the store warps convert to s.31 (dsps31Float0DB) like DSP_STORE does
         return __float_as_int(satF(acc));
     };
+    // interior tiles park the value BEFORE dspSaturateFloat0db: every reader of the post ring saturates anyway (the store
+    // warps' f2s31SatFast is f2s31(satF(.)), the drain below writes satF(.) into the delay line's state words) and satF is idempotent
+    auto emitLazy = [&](float acc, int f) -> int {
+        if (FINM == 2) acc = __fadd_rn(acc, i2fScaled(lds3(tpdfRow + ((unsigned)(f << 2) & TM4)), 31 + dither - 1));
+        return __float_as_int(acc);
+    };
 
     for (int i = 0; i < nTiles; i++) {
         barSync3(kBarFull3 + (i & 1), G.threads);
         const int t0 = i * F3;
         unsigned ra, rstep;
-        if (srcWarp < 0) {
+        if (!FROMPREV) {
             if (G.tma && t0 + F3 <= T) mbarWait3(mbar + 8u * (unsigned)(i & 1), (unsigned)((i >> 1) & 1));
             ra = rawRow + (unsigned)(i & 1) * (unsigned)G.rawStageBytes; rstep = fb;
         } else {
@@ -554,23 +563,21 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
             int fj = t0 - LAGA;
             CascP<NP> Q;
             if constexpr (PACKED) {
-                // explicit x1/x2 per section: section k's input history is section k-1's output history
+                Q.X1 = packF3(L.X1, L.y2[NP - 1]); Q.X2 = packF3(L.X2, L.y3[NP - 1]);
 #pragma unroll
-                for (int p = 0; p < NP; p++) {
-                    const int e = 2 * p, o = 2 * p + 1;
-                    Q.acc[p] = packF3(L.acc[e], L.acc[o]);
-                    Q.x1[p] = packF3(e ? L.y2[e - 1] : L.X1, L.y2[o - 1]);
-                    Q.x2[p] = packF3(e ? L.y3[e - 1] : L.X2, L.y3[o - 1]);
-                    Q.y1[p] = packF3(L.y1[e], L.y1[o]); Q.y2[p] = packF3(L.y2[e], L.y2[o]);
-                    Q.b0[p] = packF3(L.b0[e], L.b0[o]); Q.b1[p] = packF3(L.b1[e], L.b1[o]); Q.b2[p] = packF3(L.b2[e], L.b2[o]);
-                    Q.a1[p] = packF3(L.a1[e], L.a1[o]); Q.a2[p] = packF3(L.a2[e], L.a2[o]);
+                for (int j = 0; j < NP; j++) {
+                    const int e = j, o = j + NP;
+                    Q.acc[j] = packF3(L.acc[e], L.acc[o]);
+                    Q.y1[j] = packF3(L.y1[e], L.y1[o]); Q.y2[j] = packF3(L.y2[e], L.y2[o]); Q.y3[j] = packF3(L.y3[e], L.y3[o]);
+                    Q.b0[j] = packF3(L.b0[e], L.b0[o]); Q.b1[j] = packF3(L.b1[e], L.b1[o]); Q.b2[j] = packF3(L.b2[e], L.b2[o]);
+                    Q.a1[j] = packF3(L.a1[e], L.a1[o]); Q.a2[j] = packF3(L.a2[e], L.a2[o]);
                 }
             }
             auto step = [&](int jj) {
                 const int smp = lds3(rj); rj += rstep;
                 float acc;
                 if constexpr (PACKED) acc = cascStepP<NP>(Q, sourceFast(smp)); else acc = cascStepF<NSEC>(L, sourceFast(smp));
-                const int v = emit(acc, fj + jj);
+                const int v = emitLazy(acc, fj + jj);
                 if (live) sts3(pj + 4u * jj, v);
             };
             constexpr int kMain = (F3 / AVDSP_UNR3) * AVDSP_UNR3;
@@ -583,16 +590,14 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
 #pragma unroll
             for (int jj = 0; jj < F3 - kMain; jj++) step(jj);
             if constexpr (PACKED) {
+                L.X1 = loF3(Q.X1); L.X2 = loF3(Q.X2);
 #pragma unroll
-                for (int p = 0; p < NP; p++) {
-                    const int e = 2 * p, o = 2 * p + 1;
-                    L.acc[e] = loF3(Q.acc[p]); L.acc[o] = hiF3(Q.acc[p]);
-                    L.y1[e] = loF3(Q.y1[p]); L.y1[o] = hiF3(Q.y1[p]); L.y2[e] = loF3(Q.y2[p]); L.y2[o] = hiF3(Q.y2[p]);
-                    // y3 of a section = x2 of the next one (the last section's y3 feeds nobody in this lane)
-                    if (e) L.y3[e - 1] = loF3(Q.x2[p]); else { L.X1 = loF3(Q.x1[0]); L.X2 = loF3(Q.x2[0]); }
-                    L.y3[o - 1] = hiF3(Q.x2[p]);
+                for (int j = 0; j < NP; j++) {
+                    const int e = j, o = j + NP;
+                    L.acc[e] = loF3(Q.acc[j]); L.acc[o] = hiF3(Q.acc[j]);
+                    L.y1[e] = loF3(Q.y1[j]); L.y1[o] = hiF3(Q.y1[j]); L.y2[e] = loF3(Q.y2[j]); L.y2[o] = hiF3(Q.y2[j]);
+                    L.y3[e] = loF3(Q.y3[j]); L.y3[o] = hiF3(Q.y3[j]);
                 }
-                L.y3[NSEC - 1] = 0.0f;
             }
         } else {
 #pragma unroll 1
@@ -632,7 +637,7 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
             int* ring = st + d.delayOff + 1;
             for (int k = 0; k < n; k++) {
                 const long long j = (long long)T - n + k;
-                ring[(int)(((long long)idx0 + j + n) % n)] = lds3(postRow + ((unsigned)(((int)j + LAGA) & RM) << 2));
+                ring[(int)(((long long)idx0 + j + n) % n)] = __float_as_int(satF(__int_as_float(lds3(postRow + ((unsigned)(((int)j + LAGA) & RM) << 2)))));
             }
             st[d.delayOff] = (int)(((long long)idx0 + T) % n);
         }
@@ -641,10 +646,13 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
 template <int NSEC>
 __device__ __forceinline__ void cascadeWarpFin(const ChainPlan& P, const Chain2Args& A, const Chain3Geom& G, unsigned char* smem, int w, int lane) {
     const int finm = !G.warpFinal[w] ? 0 : (P.chains[G.warpChain[w]].satKind & 1) ? 2 : 1;
-    switch (finm) {
-    case 0:  cascadeWarpF<NSEC, 0>(P, A, G, smem, w, lane); break;
-    case 1:  cascadeWarpF<NSEC, 1>(P, A, G, smem, w, lane); break;
-    default: cascadeWarpF<NSEC, 2>(P, A, G, smem, w, lane); break;
+    switch (finm * 2 + (G.warpSrc[w] >= 0 ? 1 : 0)) {
+    case 0:  cascadeWarpF<NSEC, 0, false>(P, A, G, smem, w, lane); break;
+    case 1:  cascadeWarpF<NSEC, 0, true>(P, A, G, smem, w, lane); break;
+    case 2:  cascadeWarpF<NSEC, 1, false>(P, A, G, smem, w, lane); break;
+    case 3:  cascadeWarpF<NSEC, 1, true>(P, A, G, smem, w, lane); break;
+    case 4:  cascadeWarpF<NSEC, 2, false>(P, A, G, smem, w, lane); break;
+    default: cascadeWarpF<NSEC, 2, true>(P, A, G, smem, w, lane); break;
     }
 }
 

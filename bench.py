@@ -244,6 +244,7 @@ def main():
     launches = ex.launch_count - l0
     launches_per_step = max(launches // max(args.steps, 1), 1)
     kernel_ms = sum(a.elapsed_time(b) for a, b in evs) / max(args.steps, 1)      # all launches of one step (1 for the chain kernel, 3 for the mix path)
+    timed_kernel, timed_variant = ex.last_kernel, ex.last_chain_variant            # of the device-resident step (the e2e leg runs other sizes)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -320,9 +321,9 @@ def main():
     alg_bytes = float(S) * T * (n_in + n_out) * 4               # read every input once + write every output once
     # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of this exact workload + kernel
     traffic = None
-    kname = ex.last_kernel + (str(ex.last_chain_variant) if ex.last_kernel == "chain" else "")       # chain2 / chain3
+    kname = timed_kernel + (str(timed_variant) if timed_kernel == "chain" else "")       # chain2 / chain3
     prof_name = {("c2", "chain2"): "r1_chain2_c2", ("c2", "chain3"): "r1_chain3_c2", ("c5", "mix"): "r1_mix_c5", ("c4", "fir_tc"): "r1_firtc_i8_c4",
-                 ("c4f", "fir_tc"): "r1_firtc_tf32_c4f", ("c4f", "fir"): "r1_fir_f32_c4f"}.get((args.workload, kname if ex.last_kernel == "chain" else ex.last_kernel))
+                 ("c4f", "fir_tc"): "r1_firtc_tf32_c4f", ("c4f", "fir"): "r1_fir_f32_c4f"}.get((args.workload, kname))
     prof = os.path.join(ROOT, "profiles", f"{prof_name}_ncu_summary.txt") if prof_name else None
     if prof and S == wl[3] and T == wl[4] and os.path.exists(prof):
         tot = 0.0
@@ -354,7 +355,7 @@ def main():
                 "peak_packed_f32x2": packed / 1e12, "algorithmic_macs_per_launch": alg_macs, **common}
     pipe["frac"] = pipe["achieved"] / pipe["peak"] if int_peak else None
     tensor = None
-    if ex.last_kernel == "fir_tc":
+    if timed_kernel == "fir_tc":
         # Toeplitz GEMM on tcgen05: dense MMA operations issued per launch (kernel_fir_tc.cu geometry: 128-output blocks,
         # Hc + 128 samples of K per block; int8: 16 limb products per MAC, TF32: 3 passes)
         taps, paths = 4096, n_out

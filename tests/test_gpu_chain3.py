@@ -58,10 +58,12 @@ def _float_state_close(got, exp):
     return d.size == 0 or np.abs(got[d].view(np.float32).astype(np.float64) - exp[d].view(np.float32).astype(np.float64)).max() <= 2.0 ** -100
 
 
-@pytest.mark.parametrize("stim", ["noise", "impulse", "sine"])
+@pytest.mark.parametrize("stim", ["noise", "impulse", "sine", "full"])
 def test_float_class_dsp_format_3(oracle_lib, stim):
     """DSP_FORMAT 3 (float ALU, int32 samples) on k_chain3: C3's 16-section cascades as four part warps, and a shorter program
-    with TPDF finish, LOAD without gain and a delay line; s.31 outputs identical to the reference's float arithmetic."""
+    with TPDF finish, LOAD without gain and a delay line; s.31 outputs identical to the reference's float arithmetic.
+    "full" drives the cascades past 0 dB: interior tiles park unsaturated floats in the post ring, the store warps and the
+    delay line's write-back saturate (dspSaturateFloat0db is idempotent)."""
     from oracle import wire
     fs = 48000
     a = wire.Asm(fmt=3, fmin=fs, fmax=fs)
