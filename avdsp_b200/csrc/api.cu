@@ -274,6 +274,11 @@ static void freeAll(avdsp_b200* h) {
         if (h->evOut[k]) cudaEventDestroy(h->evOut[k]);
     }
     if (h->evLast) { cudaEventSynchronize(h->evLast); cudaEventDestroy(h->evLast); }
+    for (int k = 0; k < avdsp_b200::kVarStreams; k++) {
+        if (h->varStream[k]) { cudaStreamSynchronize(h->varStream[k]); cudaStreamDestroy(h->varStream[k]); }
+        if (h->varEv[k]) cudaEventDestroy(h->varEv[k]);
+    }
+    if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -405,8 +410,9 @@ const char* avdsp_b200_trace(const avdsp_b200_t* h) { return h ? h->trace.c_str(
 // dspRuntime_<fmt> compatibility path.
 // `pl` carries the plans (the instance itself, or the variant a per-stream parameter override created, see avdsp_b200_set_param);
 // state, scratch and bookkeeping are the instance's.
+// ordered = false: the caller (launchRange, runs of variants on forked streams) has done the instance's stream ordering itself.
 static int launchRun(avdsp_b200* h, avdsp_b200* pl, const int* in, int* out, int nFrames, int layout, int first, int n,
-                     cudaStream_t stream, int coreSel, const GenericPlan* planOverride, int cap) {
+                     cudaStream_t stream, int coreSel, const GenericPlan* planOverride, int cap, bool ordered = true) {
     if (nFrames == 0 || n == 0) return 0;
     const GenericPlan& G = planOverride ? *planOverride : pl->L.gen;
     const PlanHeader& P = G.h;
@@ -421,7 +427,7 @@ static int launchRun(avdsp_b200* h, avdsp_b200* pl, const int* in, int* out, int
         outSS = (long long)cap * nOut; outFS = 1; outCS = cap;
     } else return setErr(AVDSP_B200_ERR_ARG, "unknown layout");
     int* st = h->dState + (size_t)first * P.stateWords;
-    CU(cudaStreamWaitEvent(stream, h->evLast, 0));          // stream-ordered after the instance's previous launch (see evLast)
+    if (ordered) CU(cudaStreamWaitEvent(stream, h->evLast, 0));          // stream-ordered after the instance's previous launch (see evLast)
     // the fused kernels run the canonical order; a plugin-order request may use them when the two orders provably agree
     const bool chainOrder = (h->period == 0 || pl->L.orderIndependent) && coreSel < 0 && !planOverride;
     int use = AVDSP_B200_KERNEL_GENERIC;
@@ -543,27 +549,59 @@ static int launchRun(avdsp_b200* h, avdsp_b200* pl, const int* in, int* out, int
         h->lastKernel = AVDSP_B200_KERNEL_GENERIC;
     }
     if (e != cudaSuccess) return cudaErr(e, "kernel launch");
-    CU(cudaEventRecord(h->evLast, stream));
+    if (ordered) CU(cudaEventRecord(h->evLast, stream));
     h->launches++;
     return 0;
 }
 
 
-// Streams [first, first+n): one launch, or one per run of streams that share a parameter variant.
+// Streams [first, first+n): one launch, or one per run of streams that share a parameter variant.  The runs touch disjoint
+// streams (state blocks, PCM rows), so they are launched on forked streams and joined: the kernels size a CTA for the whole
+// batch, a run of a few streams is a few CTAs whatever it holds, and back to back on one stream every run would cost a whole
+// launch's time.  Variants whose kernels share per-instance scratch (dither rows of the mix kernel, FIR workspace) stay in order.
 static int launchRange(avdsp_b200* h, const int* in, int* out, int nFrames, int layout, int first, int n,
                        cudaStream_t stream, int coreSel = -1, const GenericPlan* planOverride = nullptr, int cap = 0) {
     if (h->variantOf.empty() || planOverride) return launchRun(h, h, in, out, nFrames, layout, first, n, stream, coreSel, planOverride, cap);
     const PlanHeader& P = h->L.gen.h;
     const size_t c = (size_t)(cap > 0 ? cap : nFrames);
-    for (int a = first; a < first + n;) {
+    bool fork = !(h->mixUsable || h->firUsable);
+    for (const avdsp_b200* v : h->variants) fork = fork && !(v->mixUsable || v->firUsable);
+    int nRuns = 0;
+    for (int a = first; a < first + n; nRuns++) { const int v = h->variantOf[a]; while (a < first + n && h->variantOf[a] == v) a++; }
+    fork = fork && nRuns > 1;
+    if (fork) {
+        if (!h->evFork) {
+            CU(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+            for (int k = 0; k < avdsp_b200::kVarStreams; k++) {
+                CU(cudaStreamCreateWithFlags(&h->varStream[k], cudaStreamNonBlocking));
+                CU(cudaEventCreateWithFlags(&h->varEv[k], cudaEventDisableTiming));
+            }
+        }
+        CU(cudaStreamWaitEvent(stream, h->evLast, 0));
+        CU(cudaEventRecord(h->evFork, stream));
+    }
+    int run = 0;
+    for (int a = first; a < first + n; run++) {
         const int v = h->variantOf[a];
         int b = a + 1;
         while (b < first + n && h->variantOf[b] == v) b++;
         const size_t off = (size_t)(a - first) * c;                // both layouts are stream-major
+        cudaStream_t s = stream;
+        if (fork) {
+            s = h->varStream[run % avdsp_b200::kVarStreams];
+            if (run < avdsp_b200::kVarStreams) CU(cudaStreamWaitEvent(s, h->evFork, 0));
+        }
         const int r = launchRun(h, v ? h->variants[v - 1] : h, in ? in + off * P.nIn : in, out ? out + off * P.nOut : out, nFrames, layout,
-                                a, b - a, stream, coreSel, nullptr, cap);
+                                a, b - a, s, coreSel, nullptr, cap, !fork);
         if (r < 0) return r;
         a = b;
+    }
+    if (fork) {
+        for (int k = 0; k < std::min(run, (int)avdsp_b200::kVarStreams); k++) {
+            CU(cudaEventRecord(h->varEv[k], h->varStream[k]));
+            CU(cudaStreamWaitEvent(stream, h->varEv[k], 0));
+        }
+        CU(cudaEventRecord(h->evLast, stream));
     }
     return 0;
 }

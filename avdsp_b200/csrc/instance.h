@@ -57,6 +57,11 @@ struct avdsp_b200 {
     // Empty variantOf: no override anywhere.  Streams keep their state blocks whatever variant they run.
     std::vector<int> variantOf;
     std::vector<avdsp_b200*> variants;
+    // runs of streams on different variants are independent launches: they go out on a few forked streams and join the caller's
+    static constexpr int kVarStreams = 32;
+    cudaStream_t varStream[kVarStreams] = {};
+    cudaEvent_t varEv[kVarStreams] = {};
+    cudaEvent_t evFork = nullptr;
     int numaNode = -1;                 // host NUMA node next to `device` (-1: unknown)
     std::map<void*, size_t> hostAllocs;   // avdsp_b200_host_alloc: pointer -> bytes
 };
