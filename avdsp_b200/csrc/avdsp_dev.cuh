@@ -120,11 +120,40 @@ __device__ __forceinline__ float mulFF(float a, float b) {
 __device__ __forceinline__ float mulFF_fast(float a, float b) {
     float r; asm("mul.rz.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
 }
+// binary32 <-> binary64 conversions and binary64 arithmetic with the x86 host's NaN rules (cvtss2sd / cvtsd2ss keep the sign and the
+// top payload bits and set the quiet bit; addsd & co. return the first NaN operand, quieted, and the negative "real indefinite"
+// for an invalid operation).  The device's converters return canonical NaNs; a cascade that has blown up to NaN then leaves
+// the reference with -1.0 where the device would say +1.0 (the saturation tests the raw sign bit).
+__device__ __forceinline__ double f2dX86(float f) {
+    if (__builtin_expect(f == f, 1)) return (double)f;
+    const unsigned long long u = __float_as_uint(f);
+    return __longlong_as_double((long long)(((u & 0x80000000ull) << 32) | 0x7FF8000000000000ull | ((u & 0x003FFFFFull) << 29)));
+}
+__device__ __forceinline__ float d2fX86(double d) {
+    if (__builtin_expect(d == d, 1)) return (float)d;
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return __uint_as_float((unsigned)((u >> 32) & 0x80000000u) | 0x7FC00000u | (unsigned)((u >> 29) & 0x003FFFFFu));
+}
+__device__ __forceinline__ double nanX86d(double r, double a, double b) {
+    if (__builtin_expect(r == r, 1)) return r;
+    const unsigned long long ua = (unsigned long long)__double_as_longlong(a), ub = (unsigned long long)__double_as_longlong(b);
+    if ((ua & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return __longlong_as_double((long long)(ua | 0x0008000000000000ull));
+    if ((ub & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return __longlong_as_double((long long)(ub | 0x0008000000000000ull));
+    return __longlong_as_double((long long)0xFFF8000000000000ull);
+}
 // dspMulFloatDouble (:377-410): exact float x float product as a double (zero/denormal inputs -> +0)
 __device__ __forceinline__ double mulFD(float a, float b) {
     const unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
-    if (((ua >> 23) & 255) == 0 || ((ub >> 23) & 255) == 0) return 0.0;
-    return __dmul_rn((double)a, (double)b);       // 48-bit product: exact in binary64
+    const int ea = (ua >> 23) & 255, eb = (ub >> 23) & 255;
+    if (ea == 0 || eb == 0) return 0.0;
+    if (__builtin_expect(ea != 255 && eb != 255, 1)) return __dmul_rn((double)a, (double)b);      // 48-bit product: exact in binary64
+    // an infinity or NaN operand (a cascade that blew up): the reference's integer code knows no special values, it adds the
+    // exponents, multiplies the mantissas and XORs the signs -- a finite double comes out
+    int e = 1023 + ea + eb - 254;
+    if ((ua ^ ub) & 0x80000000u) e |= 2048;
+    unsigned long long p = (unsigned long long)((ua & 0x7FFFFFu) | 0x800000u) * ((ub & 0x7FFFFFu) | 0x800000u);
+    if (p & 0x800000000000ull) { e++; p <<= 5; } else p <<= 6;
+    return __longlong_as_double((long long)((p & ((1ull << 52) - 1)) | ((unsigned long long)(long long)e << 52)));
 }
 // dspIntToFloatScaled (:204-250): truncating conversion, at most 7 right shifts (INT_MIN quirk kept)
 __device__ __forceinline__ float i2fScaled(int x, int shift) {

@@ -53,8 +53,8 @@ template <int CLS, typename Ptr> __device__ __forceinline__ void stSP(Ptr p, typ
 template <int CLS> __device__ __forceinline__ auto par(int bits) {
     if constexpr (CLS == ALU_INT64) return bits; else return __int_as_float(bits);
 }
-// Plain C arithmetic of the reference's ALU type as its host executes it.  int64: wrapping.  double: the device's binary64 NaN
-// rules are the host's (default NaN 0xFFF8000000000000, payloads propagate).  float: the device returns the canonical NaN
+// Plain C arithmetic of the reference's ALU type as its host executes it.  int64: wrapping.  double: the device's binary64 arithmetic
+// keeps payloads like the host, its CONVERTERS to and from binary32 do not (avdsp_dev.cuh f2dX86 / d2fX86).  float: the device returns the canonical NaN
 // 0x7FFFFFFF for every invalid operation and every NaN input, the x86 host the reference (and the goldens) run on returns the
 // "real indefinite" 0xFFC00000 for an invalid operation and the first NaN operand, quieted, otherwise.  That is visible:
 // DSP_DITHER in the float formats turns its zero-initialised error word into -inf on the very first frame (dspShiftFloat on
@@ -71,10 +71,16 @@ __device__ __forceinline__ long long aAdd(long long a, long long b) { return (lo
 __device__ __forceinline__ long long aSub(long long a, long long b) { return (long long)((unsigned long long)a - (unsigned long long)b); }
 __device__ __forceinline__ long long aMul(long long a, long long b) { return (long long)((unsigned long long)a * (unsigned long long)b); }
 __device__ __forceinline__ long long aNeg(long long a) { return (long long)(0ull - (unsigned long long)a); }
-__device__ __forceinline__ double aAdd(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double aSub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double aMul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double aDiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double aAdd(double a, double b) { return nanX86d(__dadd_rn(a, b), a, b); }
+__device__ __forceinline__ double aSub(double a, double b) { return nanX86d(__dsub_rn(a, b), a, b); }
+__device__ __forceinline__ double aMul(double a, double b) { return nanX86d(__dmul_rn(a, b), a, b); }
+__device__ __forceinline__ double aDiv(double a, double b) { return nanX86d(__ddiv_rn(a, b), a, b); }
+// ALU value -> float / float -> ALU value as the host converts them
+__device__ __forceinline__ float toF(float a) { return a; }
+__device__ __forceinline__ float toF(double a) { return d2fX86(a); }
+__device__ __forceinline__ float toF(long long a) { return (float)a; }
+template <typename T> __device__ __forceinline__ T fromF(float f) { return (T)f; }
+template <> __device__ __forceinline__ double fromF<double>(float f) { return f2dX86(f); }
 __device__ __forceinline__ double aNeg(double a) { return __longlong_as_double(__double_as_longlong(a) ^ (long long)0x8000000000000000ull); }
 __device__ __forceinline__ float aAdd(float a, float b) { return nanX86(__fadd_rn(a, b), a, b); }
 __device__ __forceinline__ float aSub(float a, float b) { return nanX86(__fsub_rn(a, b), a, b); }
@@ -186,7 +192,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
         case OP_SAT0DB_GAIN: case OP_SAT0DB_TPDF_GAIN: {
             if constexpr (CLS == ALU_INT64) { X >>= kMant; X = X * (long long)m.a; }
             else if constexpr (CLS == ALU_F32) X = mulFF(X, __int_as_float(m.a));
-            else X = mulFD((float)X, __int_as_float(m.a));
+            else X = mulFD(toF(X), __int_as_float(m.a));
             if (m.op == OP_SAT0DB_TPDF_GAIN) tpdfApply<CLS>(X, tp, R.tpdfValue);
             X = saturate<CLS>(X);
             break; }
@@ -210,7 +216,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
         case OP_LOAD:
             Y = X;
             if constexpr (CLS == ALU_INT64) X = IO(m.a);
-            else X = sampleInt ? i2a<CLS>(IO(m.a), 31) : (ALU)__int_as_float(IO(m.a));
+            else X = sampleInt ? i2a<CLS>(IO(m.a), 31) : fromF<ALU>(__int_as_float(IO(m.a)));
             break;
         case OP_LOAD_GAIN:
             Y = X;
@@ -218,7 +224,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             else if (sampleInt) {
                 const float t = i2fScaled(IO(m.a), 31);
                 if constexpr (CLS == ALU_F32) X = mulFF(t, __int_as_float(m.b)); else X = mulFD(t, __int_as_float(m.b));
-            } else { X = (ALU)__int_as_float(IO(m.a)); X = aMul(X, (ALU)__int_as_float(m.b)); }
+            } else { X = fromF<ALU>(__int_as_float(IO(m.a))); X = aMul(X, (ALU)__int_as_float(m.b)); }
             break;
         case OP_LOAD_MUX: {
             X = 0;
@@ -232,7 +238,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
         case OP_STORE:
             if constexpr (CLS == ALU_INT64) IO(m.a) = (int)X & tp.mask;
             else if (sampleInt) { if constexpr (CLS == ALU_F32) IO(m.a) = f2s31(X) & tp.mask; else IO(m.a) = d2s31(X) & tp.mask; }
-            else IO(m.a) = __float_as_int((float)X);
+            else IO(m.a) = __float_as_int(toF(X));
             break;
         case OP_LOAD_STORE:
             for (int k = 0; k < m.n; k++) IO(P.pool[m.a + 2 * k + 1]) = IO(P.pool[m.a + 2 * k]);
@@ -260,7 +266,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             SPi d = st + m.a;
             int idx = d[0];
             const SPT old = ldSP<CLS>(d + 1 + idx);
-            stSP<CLS>(d + 1 + idx, (SPT)X);
+            if constexpr (CLS == ALU_INT64) stSP<CLS>(d + 1 + idx, (SPT)X); else stSP<CLS>(d + 1 + idx, toF(X));
             X = old;
             idx++; if ((unsigned)idx >= (unsigned)m.b) idx = 0;
             d[0] = idx;
@@ -288,7 +294,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
                 }
                 X = acc;
             } else {
-                float xn = (float)X;
+                float xn = toF(X);
                 ALU acc = 0;
                 for (int k = 0; k < m.n; k++, s += 6, cf += 5) {
                     acc = ldA<CLS>(s);
@@ -301,7 +307,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
                     macc<CLS>(acc, y2, __int_as_float(cf[4]));
                     stA<CLS>(s, acc);
                     s[2] = __float_as_int(xn); s[3] = __float_as_int(x1); s[5] = __float_as_int(y1);
-                    xn = (float)acc;
+                    xn = toF(acc);
                     s[4] = __float_as_int(xn);
                 }
                 X = acc;
@@ -314,7 +320,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
                 int idx;
                 if constexpr (CLS == ALU_INT64) idx = s[0]; else idx = (int)__int_as_float(s[0]);
                 const SPT old = ldSP<CLS>(s + 1 + idx);
-                if constexpr (CLS == ALU_INT64) s[1 + idx] = (int)(X >> kMant); else stSP<CLS>(s + 1 + idx, (SPT)X);
+                if constexpr (CLS == ALU_INT64) s[1 + idx] = (int)(X >> kMant); else stSP<CLS>(s + 1 + idx, toF(X));
                 X = old;
                 idx++; if (idx >= m.b) idx = 0;
                 if constexpr (CLS == ALU_INT64) s[0] = idx; else s[0] = __float_as_int((float)idx);
@@ -326,7 +332,7 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
                     for (int k = 0; k < m.c; k++) { const int prev = s[k]; s[k] = xn; acc = mac32(acc, xn, taps[k]); xn = prev; }
                     X = acc;
                 } else {                                     // dsp_calc_fir_float (dsp_firSTD.h:38-52)
-                    float xn = (float)X;
+                    float xn = toF(X);
                     ALU acc = 0;
                     for (int k = 0; k < m.c; k++) {
                         const float prev = __int_as_float(s[k]); s[k] = __float_as_int(xn);
@@ -363,12 +369,12 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
                 stA<CLS>(ap, X);
                 sp[1] = (int)(X >> kMant);
             } else {
-                float xn = (float)X;
+                float xn = toF(X);
                 const float prevX = __int_as_float(sp[0]); sp[0] = __float_as_int(xn);
                 xn = aSub(xn, prevX);
                 X = ldA<CLS>(ap);
-                const float prevY = (float)X;
-                X = aAdd(X, (ALU)xn);
+                const float prevY = toF(X);
+                X = aAdd(X, fromF<ALU>(xn));
                 macc<CLS>(X, prevY, __int_as_float(m.b));
                 stA<CLS>(ap, X);
             }
@@ -444,7 +450,8 @@ __device__ __forceinline__ void runCore(const GenericPlan& P, int i0, int i1, in
             SPi d = st + m.c; SPi tab = d + 1;
             int idx = d[0];
             const int middle = size >> 1;
-            const SPT sv = (SPT)X;
+            SPT sv;
+            if constexpr (CLS == ALU_INT64) sv = (SPT)X; else sv = toF(X);
             if (sv != 0) {
                 int pos;
                 if constexpr (CLS == ALU_INT64) pos = (int)(((long long)sv * size) >> 32); else pos = f2iX86(aMul(sv, (float)middle));

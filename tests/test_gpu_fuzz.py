@@ -12,8 +12,8 @@ from oracle import wire
 pytestmark = pytest.mark.gpu
 
 
-def random_program(rng, fs=48000):
-    a = wire.Asm(fmt=2, fmin=fs, fmax=fs)
+def random_program(rng, fs=48000, fmt=2):
+    a = wire.Asm(fmt=fmt, fmin=fs, fmax=fs)
     n_cores = int(rng.integers(1, 4))
     out_slots = list(range(0, 8))
     rng.shuffle(out_slots)
@@ -121,6 +121,46 @@ def test_random_xy_programs(oracle_lib, seed):
             for q, wd in enumerate(ex.mem_words):
                 assert np.array_equal(st[ex.mem_offset + 2 * q: ex.mem_offset + 2 * q + 2], code[wd: wd + 2]), f"seed {seed}/{k} [{kern}]: MEM word {q}"
     test_random_xy_programs.hits = getattr(test_random_xy_programs, "hits", 0) + hits
+
+
+def nan_aware_equal(a, b, float_words=True):
+    """bit-for-bit, except that two float NaNs are equal whatever their payload: an unstable random cascade ends in inf - inf,
+    and which operand's payload an x86 addss keeps is the reference compiler's choice of operand order, not the reference's"""
+    a, b = np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32)
+    d = a != b
+    if not d.any():
+        return True
+    if not float_words:
+        return False
+    isnan = lambda u: ((u & 0x7F800000) == 0x7F800000) & ((u & 0x007FFFFF) != 0)
+    return bool(np.all(isnan(a[d]) & isnan(b[d])))
+
+
+@pytest.mark.parametrize("fmt", [3, 4, 5, 6])
+@pytest.mark.parametrize("seed", range(6))
+def test_random_xy_programs_float_formats(oracle_lib, seed, fmt):
+    """The same generator encoded for the float ALUs (DSP_FORMAT 3..6; 5/6 with float samples): the interpreter is the bit-exact
+    path for those (outputs AND data area), AUTO's choice must produce the same outputs."""
+    rng = np.random.default_rng(2000 + seed)
+    fs = 48000
+    gen = synth.pcm_float if fmt >= 5 else synth.pcm
+    for k in range(6):
+        w = random_program(rng, fs, fmt)
+        S, T = 4, 150
+        seeds = np.arange(S, dtype=np.int32) + seed
+        ex = Executor(w, fs, fmt, S, seeds=seeds, dither=24)
+        ex.set_kernel(KERNEL_GENERIC)
+        x = gen("full" if k & 1 else "noise", S, T, ex.n_in, fs)
+        ys, sts = oracle_lib.run_streams(w, fmt, fs, x, seeds=seeds, dither=24)
+        y = np.concatenate([ex.process(x[:, :61]), ex.process(x[:, 61:])], axis=1)
+        assert nan_aware_equal(y, ys, fmt >= 5), f"fmt {fmt} seed {seed}/{k}: {np.count_nonzero(y != ys)} samples differ\n" + "\n".join(wire.disassemble(w))
+        for s_ in (0, S - 1):
+            data = sts[s_][0]
+            st = ex.get_state(s_)
+            assert nan_aware_equal(st[: ex.data_size], data), f"fmt {fmt} seed {seed}/{k}: data area differs at {np.nonzero(st[:ex.data_size] != data)[0][:8]}"
+        ex2 = Executor(w, fs, fmt, S, seeds=seeds, dither=24)
+        y2 = np.concatenate([ex2.process(x[:, :61]), ex2.process(x[:, 61:])], axis=1)
+        assert nan_aware_equal(y2, ys, fmt >= 5), f"fmt {fmt} seed {seed}/{k} [AUTO: {ex2.last_kernel}]: {np.count_nonzero(y2 != ys)} samples differ"
 
 
 def test_fuzz_reaches_the_dag_kernel():

@@ -121,3 +121,25 @@ def test_oracle_matches_compiled_reference_on_random_xy_programs(oracle_lib):
             assert r.rc == o.rc > 0
             assert np.array_equal(r.process(x), o.process(x)), (seed, k)
             assert np.array_equal(r.data, o.data), (seed, k)
+
+
+@pytest.mark.parametrize("fmt", [3, 4, 5, 6])
+def test_oracle_matches_compiled_reference_on_random_xy_programs_float_formats(oracle_lib, fmt):
+    """72 programs of the same generator per float format (5/6: float samples): outputs and data area bit for bit, two NaNs
+    equal whatever their payload (see tests/test_gpu_fuzz.nan_aware_equal)."""
+    from oracle import refdriver, wire
+    if not refdriver.available(fmt):
+        pytest.skip("oracle/_ref not built here (it needs /root/reference)")
+    from test_gpu_fuzz import random_program, nan_aware_equal
+    gen = synth.pcm_float if fmt >= 5 else synth.pcm
+    for seed in range(12):
+        rng = np.random.default_rng(2000 + seed)
+        for k in range(6):
+            w = random_program(rng, 48000, fmt)
+            ins, _ = wire.io_maps(w)
+            x = gen("full" if k & 1 else "noise", 1, 150, len(ins), 48000)[0]
+            r = refdriver.RefProgram(w, fmt, 48000, seed=seed, dither=24)
+            o = oracle_lib.Oracle(w, fmt, 48000, seed=seed, dither=24)
+            assert r.rc == o.rc > 0
+            assert nan_aware_equal(r.process(x), o.process(x), fmt >= 5), (fmt, seed, k)
+            assert nan_aware_equal(r.data, o.data), (fmt, seed, k)
