@@ -93,6 +93,87 @@ def random_program(rng, fs=48000, fmt=2):
     return a.end()
 
 
+def random_misc_program(rng, fs=48000, fmt=2):
+    """The opcodes the X/Y generator above never emits: immediates, products and quotients of the registers, LOAD_MUX, LOAD_STORE,
+    core-local TPDF tables, WHITE, DITHER, DITHER_NS2, DCBLOCK, CLIP, DIRAC / SQUAREWAVE, DELAY_1 and the fixed delays.
+    Divisors are non-zero constants (the reference divides by whatever Y holds)."""
+    a = wire.Asm(fmt=fmt, fmin=fs, fmax=fs)
+    outs = list(range(8))
+    rng.shuffle(outs)
+    for c in range(int(rng.integers(1, 4))):
+        a.core()
+        if c == 0:
+            a.tpdf_calc(int(rng.choice([16, 20, 24])))
+        elif rng.random() < 0.5:
+            a.tpdf(int(rng.choice([0, 16, 20, 24])))                 # core-local table: also changes this core's STORE mask
+        a.param()
+        sec = a.biquad_sections([[wire.rbj_peak(fs, float(rng.uniform(80, 12000)), float(rng.uniform(0.5, 3)), float(rng.uniform(0.5, 1.5)))]
+                                 for _ in range(int(rng.integers(1, 4)))])
+        mux = a.mux_table([(8, float(rng.uniform(-0.6, 0.6))), (9, float(rng.uniform(-0.6, 0.6)))])
+        ns2 = a.num(float(rng.uniform(1.2, 2.2))); a.num(float(rng.uniform(-1.6, -0.6))); a.num(float(rng.uniform(0.1, 0.5)))
+        for _path in range(int(rng.integers(1, 4))):
+            if not outs:
+                break
+            r = rng.random()
+            if r < 0.25:
+                a.load(int(rng.choice([8, 9])))
+            elif r < 0.55:
+                a.load_gain(int(rng.choice([8, 9])), float(rng.uniform(0.2, 1.0)))
+            elif r < 0.7:
+                a.load_mux(mux)
+            elif r < 0.8:
+                a.simple("CLRXY"); a.dirac(float(rng.uniform(0.2, 0.9)), [int(rng.integers(3, 40))], square=bool(rng.random() < 0.5))
+            elif r < 0.9:
+                a.simple("WHITE")
+            else:
+                a.value(float(rng.uniform(-0.5, 0.5)))
+            for _step in range(int(rng.integers(0, 6))):
+                r = rng.random()
+                if r < 0.10:
+                    a.gain(float(rng.uniform(0.3, 1.2)))
+                elif r < 0.18:
+                    a.imm("MUL_VALUE", float(rng.uniform(0.3, 1.5)))
+                elif r < 0.26:
+                    a.imm("DIV_VALUE", float(rng.choice([-2.0, 0.75, 1.5, 3.0])))
+                elif r < 0.32:
+                    a.imm("MUL_VALUE_INT", int(rng.choice([2, 3, -2])), as_int=True)
+                elif r < 0.38:
+                    a.imm("DIV_VALUE_INT", int(rng.choice([2, 3, -5])), as_int=True)
+                elif r < 0.44:
+                    a.value_int(int(rng.choice([2, 3, 5]))); a.simple("SWAPXY"); a.simple(str(rng.choice(["DIVXY", "MULXY"])))
+                elif r < 0.50:
+                    a.simple("COPYXY"); a.simple(str(rng.choice(["AVGXY", "AVGYX", "NEGX", "NEGY", "ADDXY"])))
+                elif r < 0.56:
+                    a.shift(int(rng.choice([-2, -1, 1])))
+                elif r < 0.62:
+                    a.delay_1()
+                elif r < 0.70:
+                    a.delay_fixed_us(int(rng.integers(50, 900)), fs, dp=bool(rng.random() < 0.5))
+                elif r < 0.78:
+                    a.dcblock([float(rng.choice([-0.003, -0.0015, -0.0008]))])
+                elif r < 0.84:
+                    a.clip(float(rng.uniform(0.05, 0.6)))
+                elif r < 0.94:
+                    a.biquads(sec)
+            r = rng.random()
+            if r < 0.15:
+                a.dither(); a.sat0db()
+            elif r < 0.30:
+                a.dither_ns2(ns2); a.sat0db()
+            elif r < 0.45:
+                a.sat0db()
+            elif r < 0.6:
+                a.sat0db_tpdf()
+            elif r < 0.75:
+                a.sat0db_gain(float(rng.uniform(0.4, 1.0)))
+            elif r < 0.9:
+                a.sat0db_tpdf_gain(float(rng.uniform(0.4, 1.0)))
+            a.store(outs.pop())
+        if outs and rng.random() < 0.5:
+            a.load_store([(int(rng.choice([8, 9])), outs.pop())])
+    return a.end()
+
+
 @pytest.mark.parametrize("seed", range(24))
 def test_random_xy_programs(oracle_lib, seed):
     rng = np.random.default_rng(1000 + seed)
@@ -161,6 +242,32 @@ def test_random_xy_programs_float_formats(oracle_lib, seed, fmt):
         ex2 = Executor(w, fs, fmt, S, seeds=seeds, dither=24)
         y2 = np.concatenate([ex2.process(x[:, :61]), ex2.process(x[:, 61:])], axis=1)
         assert nan_aware_equal(y2, ys, fmt >= 5), f"fmt {fmt} seed {seed}/{k} [AUTO: {ex2.last_kernel}]: {np.count_nonzero(y2 != ys)} samples differ"
+
+
+@pytest.mark.parametrize("fmt", [2, 3, 4, 5, 6])
+@pytest.mark.parametrize("seed", range(6))
+def test_random_misc_programs(oracle_lib, seed, fmt):
+    """random_misc_program in every format: interpreter bit-exact (outputs and data area), AUTO's choice the same outputs."""
+    rng = np.random.default_rng(3000 + seed)
+    fs = 48000
+    gen = synth.pcm_float if fmt >= 5 else synth.pcm
+    for k in range(6):
+        w = random_misc_program(rng, fs, fmt)
+        S, T = 4, 150
+        seeds = np.arange(S, dtype=np.int32) + seed
+        ex = Executor(w, fs, fmt, S, seeds=seeds, dither=24)
+        ex.set_kernel(KERNEL_GENERIC)
+        x = gen("full" if k & 1 else "noise", S, T, max(ex.n_in, 1), fs)[:, :, : ex.n_in]
+        ys, sts = oracle_lib.run_streams(w, fmt, fs, x, seeds=seeds, dither=24)
+        y = np.concatenate([ex.process(x[:, :61]), ex.process(x[:, 61:])], axis=1)
+        assert nan_aware_equal(y, ys, fmt >= 5), f"fmt {fmt} seed {seed}/{k}: {np.count_nonzero(y != ys)} samples differ, channels {sorted(set(np.nonzero(y != ys)[2]))}\n" + "\n".join(wire.disassemble(w))
+        for s_ in (0, S - 1):
+            data = sts[s_][0]
+            st = ex.get_state(s_)
+            assert nan_aware_equal(st[: ex.data_size], data, fmt != 2), f"fmt {fmt} seed {seed}/{k}: data area differs at {np.nonzero(st[:ex.data_size] != data)[0][:8]}\n" + "\n".join(wire.disassemble(w))
+        ex2 = Executor(w, fs, fmt, S, seeds=seeds, dither=24)
+        y2 = np.concatenate([ex2.process(x[:, :61]), ex2.process(x[:, 61:])], axis=1)
+        assert nan_aware_equal(y2, ys, fmt >= 5), f"fmt {fmt} seed {seed}/{k} [AUTO: {ex2.last_kernel}]: {np.count_nonzero(y2 != ys)} samples differ\n" + "\n".join(wire.disassemble(w))
 
 
 def test_fuzz_reaches_the_dag_kernel():

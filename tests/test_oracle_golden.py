@@ -143,3 +143,25 @@ def test_oracle_matches_compiled_reference_on_random_xy_programs_float_formats(o
             assert r.rc == o.rc > 0
             assert nan_aware_equal(r.process(x), o.process(x), fmt >= 5), (fmt, seed, k)
             assert nan_aware_equal(r.data, o.data), (fmt, seed, k)
+
+
+@pytest.mark.parametrize("fmt", [2, 3, 4, 5, 6])
+def test_oracle_matches_compiled_reference_on_random_misc_programs(oracle_lib, fmt):
+    """60 programs per format of tests/test_gpu_fuzz.random_misc_program (immediates, register products and quotients, LOAD_MUX,
+    LOAD_STORE, core-local TPDF, WHITE, DITHER, DITHER_NS2, DCBLOCK, CLIP, DIRAC / SQUAREWAVE, DELAY_1, fixed delays)."""
+    from oracle import refdriver, wire
+    if not refdriver.available(fmt):
+        pytest.skip("oracle/_ref not built here (it needs /root/reference)")
+    from test_gpu_fuzz import random_misc_program, nan_aware_equal
+    gen = synth.pcm_float if fmt >= 5 else synth.pcm
+    for seed in range(10):
+        rng = np.random.default_rng(3000 + seed)
+        for k in range(6):
+            w = random_misc_program(rng, 48000, fmt)
+            ins, _ = wire.io_maps(w)
+            x = gen("full" if k & 1 else "noise", 1, 150, max(len(ins), 1), 48000)[0][:, : len(ins)]
+            r = refdriver.RefProgram(w, fmt, 48000, seed=seed, dither=24)
+            o = oracle_lib.Oracle(w, fmt, 48000, seed=seed, dither=24)
+            assert r.rc == o.rc > 0
+            assert nan_aware_equal(r.process(x), o.process(x), fmt >= 5), (fmt, seed, k)
+            assert nan_aware_equal(r.data, o.data, fmt != 2), (fmt, seed, k)
