@@ -260,6 +260,8 @@ static void freeAll(avdsp_b200* h) {
     if (h->dLanes2) cudaFree(h->dLanes2);
     if (h->dJump) cudaFree(h->dJump);
     if (h->dTpdf) cudaFree(h->dTpdf);
+    if (h->dRedo) cudaFree(h->dRedo);
+    if (h->dSnap) cudaFree(h->dSnap);
     if (h->dFirTaps) cudaFree(h->dFirTaps);
     if (h->dFirWs) cudaFree(h->dFirWs);
     if (h->pcmRaw) cudaFree(h->pcmRaw);
@@ -533,8 +535,32 @@ static int launchRun(avdsp_b200* h, avdsp_b200* pl, const int* in, int* out, int
                    (envChain3 != 0 && pl->geom3.maxSec <= 4 && pl->geom3.streamsPerCta >= 16 && nFrames >= std::max(1536, 32 * pl->geom3.gmax)));
         if (h->kernelSel == AVDSP_B200_KERNEL_CHAIN_V3 && !v3)
             return setErr(AVDSP_B200_ERR_UNSUPPORTED, "chain kernel v3 requested but the program shape does not map to it");
+        const bool flt = pl->L.chain.h.aluClass == ALU_F32;
+        if (flt) {
+            // the float class is the reference's arithmetic except next to the underflow threshold and beyond the binary32 range
+            // (avdsp_dev.cuh, fltGuard): snapshot the state, let the cascades flag the streams that came near either, and have the
+            // interpreter re-execute exactly those from the snapshot.  Costs one state copy and one (normally empty) launch.
+            if (!h->dRedo) {
+                CU(cudaMalloc(&h->dRedo, (size_t)h->nStreams * sizeof(int)));
+                CU(cudaMalloc(&h->dSnap, (size_t)h->nStreams * P.stateWords * sizeof(int)));
+            }
+            CU(cudaMemsetAsync(h->dRedo + first, 0, (size_t)n * sizeof(int), stream));
+            CU(cudaMemcpyAsync(h->dSnap + (size_t)first * P.stateWords, st, (size_t)n * P.stateWords * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+            A.redo = h->dRedo + first;
+        }
         if (v3) e = launchChain3(pl->L.chain, pl->geom3, A, stream);
         else e = launchChain2(pl->L.chain, pl->geom2, A, stream);
+        if (flt && e == cudaSuccess) {
+            GenericArgs R{};
+            R.in = in; R.out = out; R.state = st; R.bigPool = pl->dBig;
+            R.nStreams = n; R.nFrames = nFrames;
+            R.inStreamStride = inSS; R.outStreamStride = outSS;
+            R.inFrameStride = inFS; R.inChStride = inCS; R.outFrameStride = outFS; R.outChStride = outCS;
+            R.coreSel = -1; R.period = 0;                    // the chain kernels run the canonical order (chainOrder above)
+            R.redo = h->dRedo + first; R.snapshot = h->dSnap + (size_t)first * P.stateWords;
+            e = launchGeneric(G, R, stream);
+            h->launches++;
+        }
         h->lastChainVariant = v3 ? 3 : 2;
         h->lastKernel = AVDSP_B200_KERNEL_CHAIN;
     } else {

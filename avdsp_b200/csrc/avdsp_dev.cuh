@@ -141,6 +141,22 @@ __device__ __forceinline__ double nanX86d(double r, double a, double b) {
     if ((ub & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return __longlong_as_double((long long)(ub | 0x0008000000000000ull));
     return __longlong_as_double((long long)0xFFF8000000000000ull);
 }
+// ---- exactness guard of the chain kernels' float class ------------------------------------------------------------------
+// mul.rz.ftz.f32 IS dspMulFloatFloat except where the reference's integer code leaves IEEE: it flushes on the exponent sum
+// BEFORE normalisation (a product in [2^-126, 2^-125) becomes 0) and it knows no infinities (an overflowing product wraps).
+// A biquad product is (state value or input) x coefficient.  With every non-zero coefficient in [2^-60, 2^60] (checked on the
+// host, chainFloatCoefsInRange) a product can only reach the flush zone when an operand is a non-zero value below 2^-64,
+// and it can only overflow into a non-finite accumulator, which stays non-finite.  So the cascades keep the minimum of a
+// guard word over every value they load or produce (2 integer instructions per value) and look at their final accumulators:
+// a stream that saw a tiny or non-finite value is flagged and re-executed from its state snapshot by the interpreter, whose
+// multiply is the integer restatement (api.cu).  Everything else is the reference's arithmetic bit for bit.
+constexpr unsigned kFltGuardTiny = 2u * 0x1F800000u - 1u;          // guard word of 2^-64
+__device__ __forceinline__ unsigned fltGuard(unsigned mn, float v) {           // 2*|bits| - 1: zero -> 0xFFFFFFFF, tiny -> small
+    const unsigned b = __float_as_uint(v);
+    return min(mn, b + b - 1u);
+}
+__device__ __forceinline__ bool fltNonFinite(float v) { return (__float_as_uint(v) & 0x7F800000u) == 0x7F800000u; }
+
 // dspMulFloatDouble (:377-410): exact float x float product as a double (zero/denormal inputs -> +0)
 __device__ __forceinline__ double mulFD(float a, float b) {
     const unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);

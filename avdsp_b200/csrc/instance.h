@@ -32,6 +32,9 @@ struct avdsp_b200 {
     unsigned char* dFirWs = nullptr; size_t firWsBytes = 0;     // ... and the packed-sample workspace
     unsigned* dJump = nullptr; int jumpL = -1;      // PRNG jump matrix for segments of jumpL draws
     int* dTpdf = nullptr; size_t tpdfWords = 0;     // scratch dither values of a launch
+    // float class of the chain kernels: per-stream "re-execute me exactly" flags and the state snapshot the interpreter's second
+    // pass starts from (avdsp_dev.cuh fltGuard; launchRun).  Indexed by the instance's stream number: disjoint runs do not collide.
+    int* dRedo = nullptr; int* dSnap = nullptr;
     int period = 0, kernelSel = AVDSP_B200_KERNEL_AUTO, lastKernel = 0;
     long long launches = 0;
     cudaStream_t stream = nullptr;          // for the synchronous calls

@@ -174,7 +174,7 @@ struct Lane2F {
     float b0[K], b1[K], b2[K], a1[K], a2[K];
 };
 template <int K>
-__device__ __forceinline__ void laneStepF(Lane2F<K>& L, float xin) {
+__device__ __forceinline__ void laneStepF(Lane2F<K>& L, float xin, unsigned& mn) {
     float in[K];
     in[0] = xin;
 #pragma unroll
@@ -187,6 +187,7 @@ __device__ __forceinline__ void laneStepF(Lane2F<K>& L, float xin) {
         acc = __fadd_rn(acc, mulFF_fast(L.x2[j], L.b2[j]));
         acc = __fadd_rn(acc, mulFF_fast(L.y1[j], L.a1[j]));
         acc = __fadd_rn(acc, mulFF_fast(L.y2[j], L.a2[j]));
+        mn = fltGuard(mn, acc);
         L.acc[j] = acc;
         L.x2[j] = L.x1[j]; L.x1[j] = in[j];
         L.y2[j] = L.y1[j]; L.y1[j] = acc;
@@ -214,7 +215,7 @@ __device__ __forceinline__ void unpackLane(const Lane2FP& Q, Lane2F<2>& L) {
     L.acc[0] = loF2(Q.acc); L.acc[1] = hiF2(Q.acc); L.x1[0] = loF2(Q.x1); L.x1[1] = hiF2(Q.x1); L.x2[0] = loF2(Q.x2); L.x2[1] = hiF2(Q.x2);
     L.y1[0] = loF2(Q.y1); L.y1[1] = hiF2(Q.y1); L.y2[0] = loF2(Q.y2); L.y2[1] = hiF2(Q.y2);
 }
-__device__ __forceinline__ void laneStepFP(Lane2FP& Q, float xin) {
+__device__ __forceinline__ void laneStepFP(Lane2FP& Q, float xin, unsigned& mn) {
     const unsigned long long in = packF2(xin, loF2(Q.y1));           // section 1 works on section 0's previous output
     unsigned long long acc = Q.acc;
     acc = macF2(acc, in, Q.b0);
@@ -222,13 +223,14 @@ __device__ __forceinline__ void laneStepFP(Lane2FP& Q, float xin) {
     acc = macF2(acc, Q.x2, Q.b2);
     acc = macF2(acc, Q.y1, Q.a1);
     acc = macF2(acc, Q.y2, Q.a2);
+    mn = fltGuard(fltGuard(mn, loF2(acc)), hiF2(acc));
     Q.acc = acc;
     Q.x2 = Q.x1; Q.x1 = in;
     Q.y2 = Q.y1; Q.y1 = acc;
 }
 
 template <int K>
-__device__ __forceinline__ void laneStepPredF(Lane2F<K>& L, float xin, int t, int g0, int T) {
+__device__ __forceinline__ void laneStepPredF(Lane2F<K>& L, float xin, int t, int g0, int T, unsigned& mn) {
     float in[K];
     in[0] = xin;
 #pragma unroll
@@ -242,6 +244,7 @@ __device__ __forceinline__ void laneStepPredF(Lane2F<K>& L, float xin, int t, in
             acc = __fadd_rn(acc, mulFF_fast(L.x2[j], L.b2[j]));
             acc = __fadd_rn(acc, mulFF_fast(L.y1[j], L.a1[j]));
             acc = __fadd_rn(acc, mulFF_fast(L.y2[j], L.a2[j]));
+            mn = fltGuard(mn, acc);
             L.acc[j] = acc;
             L.x2[j] = L.x1[j]; L.x1[j] = in[j];
             L.y2[j] = L.y1[j]; L.y1[j] = acc;
@@ -345,6 +348,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         int* x_s = reinterpret_cast<int*>(smem_raw + G.xOff);
         int* post_s = reinterpret_cast<int*>(smem_raw + G.postOff);
         Lane2F<K> L;
+        unsigned mn = 0xFFFFFFFFu;                       // exactness guard (avdsp_dev.cuh): smallest guard word of every value seen
         const ChainLane e = A.lanes[tid];
         const bool live = e.slot >= 0 && e.slot / C < nsHere;
         const bool head = (e.flags & 1) != 0, tail = (e.flags & 2) != 0;
@@ -368,6 +372,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 const int* q = stLane + P.pool[d.secStateOff + sec];        // [acc, -, x1, x2, y1, y2] (dsp_biquadSTD.h:84-119)
                 L.acc[k] = __int_as_float(q[0]);
                 L.x1[k] = __int_as_float(q[2]); L.x2[k] = __int_as_float(q[3]); L.y1[k] = __int_as_float(q[4]); L.y2[k] = __int_as_float(q[5]);
+                mn = fltGuard(fltGuard(fltGuard(fltGuard(fltGuard(mn, L.acc[k]), L.x1[k]), L.x2[k]), L.y1[k]), L.y2[k]);
             }
         }
         const int* xrow = x_s + (size_t)((slot / C) * nSrc + max(d.srcId, 0)) * XP;
@@ -387,8 +392,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         for (int jj = 0; jj < UNR; jj++) {
                             const int j = j0 + jj;
                             float x = __shfl_up_sync(0xffffffffu, hiF2(Q.y1), 1);
-                            if (head) x = __int_as_float(xs[j]);
-                            laneStepFP(Q, x);
+                            if (head) { x = __int_as_float(xs[j]); mn = fltGuard(mn, x); }
+                            laneStepFP(Q, x, mn);
                             if (tail) ps[j] = __float_as_int(hiF2(Q.acc));
                         }
                     }
@@ -400,8 +405,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                     for (int jj = 0; jj < UNR; jj++) {
                         const int j = j0 + jj;
                         float x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
-                        if (head) x = __int_as_float(xs[j]);
-                        laneStepF<K>(L, x);
+                        if (head) { x = __int_as_float(xs[j]); mn = fltGuard(mn, x); }
+                        laneStepF<K>(L, x, mn);
                         if (tail) ps[j] = __float_as_int(L.acc[K - 1]);     // the sink saturates / converts (satF is idempotent)
                     }
                 }
@@ -410,8 +415,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
 #pragma unroll 1
                 for (int j = 0; j < F; j++) {
                     float x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
-                    if (head) x = __int_as_float(xs[j]);
-                    laneStepPredF<K>(L, x, t0 + j, g0, T);
+                    if (head) { x = __int_as_float(xs[j]); if ((unsigned)(t0 + j - g0) < (unsigned)T) mn = fltGuard(mn, x); }
+                    laneStepPredF<K>(L, x, t0 + j, g0, T, mn);
                     if (tail && (unsigned)(t0 + j - g0 - (K - 1)) < (unsigned)T) ps[j] = __float_as_int(L.acc[K - 1]);
                 }
             }
@@ -424,6 +429,10 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 q[0] = __float_as_int(L.acc[k]);
                 q[2] = __float_as_int(L.x1[k]); q[3] = __float_as_int(L.x2[k]); q[4] = __float_as_int(L.y1[k]); q[5] = __float_as_int(L.y2[k]);
             }
+            bool redo = mn < kFltGuardTiny;
+#pragma unroll
+            for (int k = 0; k < K; k++) redo = redo || fltNonFinite(L.acc[k]);
+            if (redo && A.redo) A.redo[s0 + slot / C] = 1;
         }
         return;
     }
@@ -893,6 +902,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                             int wv = lds32(postA + G.outRowOff[ch] + ((f4 + (unsigned)G.outPos4[ch]) & RM4));
                             if (dc.delayFirst)      // out of line: rare program shape, keeps the common store loop compact
                                 wv = delayFirstFinish(wv, dc.satKind, dc.satGainBits, lds32(tpdfA + ((unsigned)(f & (4 * F - 1)) << 2)), P.h.tpdfShift);
+                            else wv = postToS31<CLS>(wv);      // float class: the ring holds the float (storePasses converts in the fast path)
                             v = wv & (dc.srcKind == SRC_RAW ? -1 : storeMask);
                         }
                         val[q] = v;
@@ -998,7 +1008,22 @@ static int packLanes2(const ChainPlan& p, int NS, int K, ChainLane* out, int* gm
     return threads;
 }
 
+// float class: the exactness guard of the cascades (avdsp_dev.cuh, fltGuard) bounds products through their operands, which needs
+// every non-zero biquad coefficient within [2^-60, 2^60] (2^-64 x 2^-60 > 2^-125: above the flush zone; denormal coefficients are out)
+bool chainFloatCoefsInRange(const ChainPlan& plan) {
+    for (int c = 0; c < plan.h.nChains; c++) {
+        const ChainDesc& d = plan.chains[c];
+        for (int k = 0; k < 5 * d.nsec; k++) {
+            const uint32_t u = (uint32_t)plan.pool[d.coefOff + k] & 0x7FFFFFFFu;
+            const int ex = (int)(u >> 23);
+            if (u != 0 && (ex < 127 - 60 || ex > 127 + 60)) return false;
+        }
+    }
+    return true;
+}
+
 bool chain2Supports(const ChainPlan& plan) {
+    if (plan.h.aluClass == ALU_F32 && !chainFloatCoefsInRange(plan)) return false;
     // the helper warps address everything through the flattened tables (plan.h: kFastTab entries each)
     return (plan.h.aluClass == ALU_INT64 || plan.h.aluClass == ALU_F32) && plan.h.sampleInt && (plan.h.aluClass == ALU_INT64 || (plan.h.nRaw == 0 && plan.h.nMemCopy == 0)) && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nOut <= kFastTab &&
            plan.h.nProc <= kFastTab && plan.h.nSrc <= kFastTab;

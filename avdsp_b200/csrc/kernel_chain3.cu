@@ -373,7 +373,7 @@ struct CascF {
 __device__ __forceinline__ float maccF3(float acc, float a, float b) { return __fadd_rn(acc, mulFF_fast(a, b)); }
 
 template <int NSEC>
-__device__ __forceinline__ float cascStepF(CascF<NSEC>& L, float xin) {
+__device__ __forceinline__ float cascStepF(CascF<NSEC>& L, float xin, unsigned& mn) {
     float acc[NSEC];
 #pragma unroll
     for (int k = 0; k < NSEC; k++) acc[k] = maccF3(L.acc[k], k ? L.y1[k - 1] : xin, L.b0[k]);
@@ -386,14 +386,14 @@ __device__ __forceinline__ float cascStepF(CascF<NSEC>& L, float xin) {
 #pragma unroll
     for (int k = 0; k < NSEC; k++) acc[k] = maccF3(acc[k], L.y2[k], L.a2[k]);
 #pragma unroll
-    for (int k = 0; k < NSEC; k++) { L.acc[k] = acc[k]; L.y3[k] = L.y2[k]; L.y2[k] = L.y1[k]; L.y1[k] = acc[k]; }
+    for (int k = 0; k < NSEC; k++) { mn = fltGuard(mn, acc[k]); L.acc[k] = acc[k]; L.y3[k] = L.y2[k]; L.y2[k] = L.y1[k]; L.y1[k] = acc[k]; }
     L.X2 = L.X1; L.X1 = xin;
     return acc[NSEC - 1];
 }
 // any step of the launch: section k commits only when its frame t-k lies in [0,T); the reference's own x1/x2 words stand in for
 // outputs older than the launch on its first two frames
 template <int NSEC>
-__device__ __forceinline__ float cascStepExactF(CascF<NSEC>& L, float xin, int t, int T) {
+__device__ __forceinline__ float cascStepExactF(CascF<NSEC>& L, float xin, int t, int T, unsigned& mn) {
     float in[NSEC], x1[NSEC], x2[NSEC];
 #pragma unroll
     for (int k = 0; k < NSEC; k++) {
@@ -412,6 +412,7 @@ __device__ __forceinline__ float cascStepExactF(CascF<NSEC>& L, float xin, int t
             acc = maccF3(acc, x2[k], L.b2[k]);
             acc = maccF3(acc, L.y1[k], L.a1[k]);
             acc = maccF3(acc, L.y2[k], L.a2[k]);
+            mn = fltGuard(mn, acc);
             L.acc[k] = acc;
             L.y3[k] = L.y2[k]; L.y2[k] = L.y1[k]; L.y1[k] = acc;
             if (k == NSEC - 1) last = acc;
@@ -438,7 +439,7 @@ __device__ __forceinline__ unsigned long long macF3x2(unsigned long long acc, un
 template <int NP>
 struct CascP { unsigned long long acc[NP], y1[NP], y2[NP], y3[NP], X1, X2, b0[NP], b1[NP], b2[NP], a1[NP], a2[NP]; };
 template <int NP>
-__device__ __forceinline__ float cascStepP(CascP<NP>& Q, float xin) {
+__device__ __forceinline__ float cascStepP(CascP<NP>& Q, float xin, unsigned& mn) {
     unsigned long long acc[NP];
     const unsigned long long in0 = packF3(xin, loF3(Q.y1[NP - 1]));     // section NP works on what section NP-1 produced one step ago
 #pragma unroll
@@ -452,7 +453,10 @@ __device__ __forceinline__ float cascStepP(CascP<NP>& Q, float xin) {
 #pragma unroll
     for (int j = 0; j < NP; j++) acc[j] = macF3x2(acc[j], Q.y2[j], Q.a2[j]);
 #pragma unroll
-    for (int j = 0; j < NP; j++) { Q.acc[j] = acc[j]; Q.y3[j] = Q.y2[j]; Q.y2[j] = Q.y1[j]; Q.y1[j] = acc[j]; }
+    for (int j = 0; j < NP; j++) {
+        mn = fltGuard(fltGuard(mn, loF3(acc[j])), hiF3(acc[j]));
+        Q.acc[j] = acc[j]; Q.y3[j] = Q.y2[j]; Q.y2[j] = Q.y1[j]; Q.y1[j] = acc[j];
+    }
     Q.X2 = Q.X1; Q.X1 = in0;
     return hiF3(acc[NP - 1]);
 }
@@ -489,6 +493,7 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
     int* st = A.state + (size_t)(s0 + sl) * W;
 
     CascF<NSEC> L;
+    unsigned mn = 0xFFFFFFFFu;            // exactness guard (avdsp_dev.cuh fltGuard): smallest guard word of every value loaded or produced
     L.X1 = L.X2 = 0.0f;
 #pragma unroll
     for (int k = 0; k < NSEC; k++) {
@@ -500,6 +505,7 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
         L.acc[k] = __int_as_float(q[0]);
         L.rx1[k] = __int_as_float(q[2]); L.rx2[k] = __int_as_float(q[3]); L.y1[k] = __int_as_float(q[4]); L.y2[k] = __int_as_float(q[5]);
         if (k == 0) { L.X1 = L.rx1[0]; L.X2 = L.rx2[0]; }
+        mn = fltGuard(fltGuard(fltGuard(fltGuard(fltGuard(mn, L.acc[k]), L.rx1[k]), L.rx2[k]), L.y1[k]), L.y2[k]);
     }
     // the post ring is the delay line (ring of s.31 values behind the saturation), exactly as in the fixed-point form
     const int n = fin ? d.delayN : 0;
@@ -576,7 +582,9 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
             auto step = [&](int jj) {
                 const int smp = lds3(rj); rj += rstep;
                 float acc;
-                if constexpr (PACKED) acc = cascStepP<NP>(Q, sourceFast(smp)); else acc = cascStepF<NSEC>(L, sourceFast(smp));
+                const float xs_ = sourceFast(smp);
+                if (!FROMPREV) mn = fltGuard(mn, xs_);
+                if constexpr (PACKED) acc = cascStepP<NP>(Q, xs_, mn); else acc = cascStepF<NSEC>(L, xs_, mn);
                 const int v = emitLazy(acc, fj + jj);
                 if (live) sts3(pj + 4u * jj, v);
             };
@@ -606,7 +614,9 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
                 if (tl >= T + LAG) break;
                 if (tl < 0) continue;
                 const int smp = tl < T ? lds3(ra + (unsigned)j * rstep) : 0;
-                const float acc = cascStepExactF<NSEC>(L, G.floatFast ? sourceFast(smp) : sourceExact(smp), tl, T);
+                const float xs_ = G.floatFast ? sourceFast(smp) : sourceExact(smp);
+                if (!FROMPREV && tl < T) mn = fltGuard(mn, xs_);
+                const float acc = cascStepExactF<NSEC>(L, xs_, tl, T, mn);
                 const int f = tl - LAG;
                 if (f >= 0) {
                     const int v = emit(acc, f);
@@ -632,6 +642,12 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
             else if (T >= 2) { q[2] = __float_as_int(L.y1[k - 1]); q[3] = __float_as_int(L.y2[k - 1]); }
             else if (T == 1) { q[2] = __float_as_int(L.y1[k - 1]); q[3] = __float_as_int(L.rx1[k]); }
             q[4] = __float_as_int(L.y1[k]); q[5] = __float_as_int(L.y2[k]);
+        }
+        {
+            bool redo = mn < kFltGuardTiny;
+#pragma unroll
+            for (int k = 0; k < NSEC; k++) redo = redo || fltNonFinite(L.acc[k]);
+            if (redo && A.redo) A.redo[s0 + sl] = 1;
         }
         if (n > 0 && T > 0) {
             int* ring = st + d.delayOff + 1;
@@ -883,6 +899,7 @@ static int envInt3(const char* name, int dflt) { const char* v = getenv(name); r
 bool chain3Supports(const ChainPlan& plan) {
     const ChainHeader& h = plan.h;
     if ((h.aluClass != ALU_INT64 && h.aluClass != ALU_F32) || !h.sampleInt) return false;      // DSP_FORMAT 2 and 3
+    if (h.aluClass == ALU_F32 && !chainFloatCoefsInRange(plan)) return false;
     if (h.nChains <= 0 || h.nChains > kChain3MaxChains || h.nIn <= 0) return false;
     if (h.nOut <= 0 || h.nOut > 32 || (h.nOut & (h.nOut - 1)) != 0) return false;
     if (h.nRaw || h.nDelayFirst || h.nMemCopy) return false;

@@ -498,12 +498,15 @@ k_generic(const __grid_constant__ GenericPlan P, const GenericArgs A) {
     const int ios = blockDim.x;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.nStreams) return;
+    if (A.redo && !A.redo[s]) return;                   // second pass behind a float chain kernel: flagged streams only
     int* io = io_s + threadIdx.x;
     int* gst = A.state + (size_t)s * P.h.stateWords;
     // longer launches work on a shared-memory copy of the state blocks ([word][lane]); each lane moves its own block
     const bool staged = A.stageState != 0;
     const SPi st = staged ? SPi{io_s + kIoSlots * ios + threadIdx.x, ios} : SPi{gst, 1};
-    if (staged) for (int w = 0; w < P.h.stateWords; w++) st[w] = gst[w];
+    const int* src = A.redo ? A.snapshot + (size_t)s * P.h.stateWords : gst;
+    if (staged) for (int w = 0; w < P.h.stateWords; w++) st[w] = src[w];
+    else if (A.redo) for (int w = 0; w < P.h.stateWords; w++) gst[w] = src[w];
     const SPi aux = st + P.h.auxOff;
     StreamRegs R;
     R.g.s0 = aux[AUX_S0]; R.g.s1 = aux[AUX_S1]; R.g.s2 = aux[AUX_S2]; R.g.s3 = aux[AUX_S3];

@@ -21,6 +21,10 @@ struct GenericArgs {
     int coreSel;                // -1: all cores; k: only core k (0-based)  -- dspRuntime_<fmt> compat path
     int period;                 // 0: canonical order; >0: ALSA plugin order with this period
     int stageState;             // filled by launchGeneric: the CTA works on a shared-memory copy of its streams' state blocks
+    // second pass behind a float-class chain kernel (api.cu): only the streams whose flag word is set run, from the state
+    // block the snapshot holds (what the stream's state was before the chain kernel touched it)
+    const int* redo;            // [nStreams] or nullptr
+    const int* snapshot;        // [nStreams][stateWords]
     unsigned coreInMask[kMaxCores], coreOutMask[kMaxCores];
 };
 cudaError_t launchGeneric(const GenericPlan& plan, const GenericArgs& args, cudaStream_t stream);
@@ -66,7 +70,9 @@ struct Chain2Args {
     int nStreams, nFrames;
     long long inStreamStride, outStreamStride;
     int inFrameStride, inChStride, outFrameStride, outChStride;
+    int* redo;                  // float class: [nStreams] flag words, set to 1 for a stream the interpreter has to re-execute (avdsp_dev.cuh, fltGuard)
 };
+bool chainFloatCoefsInRange(const ChainPlan& plan);     // float class: every non-zero biquad coefficient within [2^-60, 2^60]
 bool chain2Supports(const ChainPlan& plan);
 bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2Geom* geom, ChainLane* lanesOut /*[1024]*/);
 cudaError_t launchChain2(const ChainPlan& plan, const Chain2Geom& geom, const Chain2Args& args, cudaStream_t stream);
