@@ -181,7 +181,8 @@ def test_random_xy_programs(oracle_lib, seed):
     hits = 0
     for k in range(6):
         w = random_program(rng, fs)
-        S, T = 5, 210
+        S, T = (5, 210) if k < 3 else (int(rng.choice([1, 33, 70])), int(rng.choice([1, 2, 31, 333, 1000])))
+        cut = 77 if k < 3 else int(rng.integers(0, T + 1))
         seeds = np.arange(S, dtype=np.int32) + seed
         try:
             ex = Executor(w, fs, 2, S, seeds=seeds, dither=24)
@@ -189,12 +190,10 @@ def test_random_xy_programs(oracle_lib, seed):
             continue                                      # (a generated program the decoder refuses: not this test's subject)
         x = synth.pcm("full" if k & 1 else "noise", S, T, ex.n_in, fs) if ex.n_in else np.zeros((S, T, 0), np.int32)
         ys, sts = oracle_lib.run_streams(w, 2, fs, x, seeds=seeds, dither=24)
-        ya = ex.process(x[:, :77])
-        yb = ex.process(x[:, 77:])
+        y = np.concatenate([ex.process(x[:, a_:b_]) for a_, b_ in ((0, cut), (cut, T)) if b_ > a_], axis=1)
         kern = ex.last_kernel
         hits += kern == "dag"
-        y = np.concatenate([ya, yb], axis=1)
-        assert np.array_equal(y, ys), f"seed {seed}/{k} [{kern}]: {np.count_nonzero(y != ys)} samples differ\n" + "\n".join(wire.disassemble(w))
+        assert np.array_equal(y, ys), f"seed {seed}/{k} [{kern}] S={S} T={T} cut={cut}: {np.count_nonzero(y != ys)} samples differ\n" + "\n".join(wire.disassemble(w))
         for s in (0, S - 1):
             data, aux, code = sts[s]
             st = ex.get_state(s)
