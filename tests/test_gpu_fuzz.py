@@ -269,5 +269,43 @@ def test_random_misc_programs(oracle_lib, seed, fmt):
         assert nan_aware_equal(y2, ys, fmt >= 5), f"fmt {fmt} seed {seed}/{k} [AUTO: {ex2.last_kernel}]: {np.count_nonzero(y2 != ys)} samples differ\n" + "\n".join(wire.disassemble(w))
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_programs_in_plugin_order(oracle_lib, seed):
+    """The ALSA plugin's loop nest (core-major inside a period, linux/avdsp_plugin.c:95-142).  The decoder keeps a fused kernel
+    only where it can prove that both orders give the same result (decoder.cpp analyseOrder); a wrong proof shows here: all three
+    generators, random periods, two calls, against the oracle's restatement of the plugin loop."""
+    from test_gpu_fuzz_chain import random_chain_program
+    rng = np.random.default_rng(9000 + seed)
+    fs = 48000
+    fused = 0
+    for k in range(6):
+        w = (random_program, random_misc_program, random_chain_program)[k % 3](rng, fs, 2)
+        S, T = 3, int(rng.choice([100, 300]))
+        period = int(rng.choice([1, 16, 64, 128, 1000]))
+        cut = int(rng.integers(1, T))
+        seeds = np.arange(S, dtype=np.int32) + seed
+        ex = Executor(w, fs, 2, S, seeds=seeds, dither=24)
+        ex.set_order(period)
+        x = synth.pcm("full" if k & 1 else "noise", S, T, max(ex.n_in, 1), fs)[:, :, : ex.n_in]
+        y = np.concatenate([ex.process(x[:, :cut]), ex.process(x[:, cut:])], axis=1)
+        fused += ex.last_kernel != "generic"
+        nin = (max(ex.in_idx) - 8 + 1) if len(ex.in_idx) else 1
+        nout = max(ex.out_idx) + 1
+        for s_ in range(S):
+            o = oracle_lib.Oracle(w, 2, fs, seed=int(seeds[s_]), dither=24)
+            xin = np.zeros((T, nin), np.int32)
+            for q, slot in enumerate(ex.in_idx):
+                xin[:, slot - 8] = x[s_, :, q]
+            yo = np.concatenate([o.process_plugin_order(xin[:cut], period, nin, nout), o.process_plugin_order(xin[cut:], period, nin, nout)])
+            what = f"seed {seed}/{k} [{ex.last_kernel}] period {period} T={T} cut={cut}\n" + "\n".join(wire.disassemble(w)) + "\n" + ex.trace[-400:]
+            assert np.array_equal(y[s_], yo[:, ex.out_idx]), f"stream {s_}: {np.count_nonzero(y[s_] != yo[:, ex.out_idx])} samples differ: " + what
+            assert np.array_equal(ex.get_state(s_)[: ex.data_size], o.data), f"stream {s_}: data area differs: " + what
+    test_random_programs_in_plugin_order.fused = getattr(test_random_programs_in_plugin_order, "fused", 0) + fused
+
+
+def test_plugin_order_fuzz_keeps_fused_kernels_somewhere():
+    assert getattr(test_random_programs_in_plugin_order, "fused", 0) >= 10, getattr(test_random_programs_in_plugin_order, "fused", 0)
+
+
 def test_fuzz_reaches_the_dag_kernel():
     assert getattr(test_random_xy_programs, "hits", 0) >= 20, "the random programs hardly ever map to k_dag: the generator drifted"
