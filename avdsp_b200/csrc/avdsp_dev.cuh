@@ -103,7 +103,18 @@ __device__ __forceinline__ long long tpdfScaledI(int v, int shift) {       // ds
 // ---------------------------------------------------------------- IEEE helpers -----------------
 // dspMulFloatFloat (dsp_ieee754.h:336-375): 24x24 mantissa product, TRUNCATED, inputs/outputs
 // flushed to +0 when the (pre-normalisation) exponent underflows.  Exact integer restatement.
+static __device__ __forceinline__ float mulFFslow(float a, float b);
+// The truncated 24x24 product with the exponent sum IS the IEEE round-toward-zero product whenever the result is a normal
+// number that stayed clear of both ends: an exponent field of the hardware result in [2, 253] means the reference's
+// pre-normalisation exponent was >= 1 and nothing overflowed (infinite / NaN operands give 255, zero / denormal ones 0, and
+// an overflowing product is CLAMPED to the largest finite number by round-toward-zero: field 254).
+// Everything else takes the integer restatement.
 __device__ __forceinline__ float mulFF(float a, float b) {
+    float r; asm("mul.rz.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    if (__builtin_expect(((__float_as_uint(r) >> 23) & 255u) - 2u < 252u, 1)) return r;
+    return mulFFslow(a, b);
+}
+static __device__ __forceinline__ float mulFFslow(float a, float b) {
     const unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
     const int ea = (ua >> 23) & 255, eb = (ub >> 23) & 255;
     if (ea == 0 || eb == 0) return 0.0f;
@@ -129,13 +140,15 @@ __device__ __forceinline__ double f2dX86(float f) {
     const unsigned long long u = __float_as_uint(f);
     return __longlong_as_double((long long)(((u & 0x80000000ull) << 32) | 0x7FF8000000000000ull | ((u & 0x003FFFFFull) << 29)));
 }
+// (tests on the high word: a binary64 compare costs an FP64-pipe instruction, as much as the add it guards)
+__device__ __forceinline__ bool d64Special(double d) { return ((unsigned)__double2hiint(d) & 0x7FF00000u) == 0x7FF00000u; }   // inf or NaN
 __device__ __forceinline__ float d2fX86(double d) {
-    if (__builtin_expect(d == d, 1)) return (float)d;
+    if (__builtin_expect(!d64Special(d) || d == d, 1)) return (float)d;
     const unsigned long long u = (unsigned long long)__double_as_longlong(d);
     return __uint_as_float((unsigned)((u >> 32) & 0x80000000u) | 0x7FC00000u | (unsigned)((u >> 29) & 0x003FFFFFu));
 }
 __device__ __forceinline__ double nanX86d(double r, double a, double b) {
-    if (__builtin_expect(r == r, 1)) return r;
+    if (__builtin_expect(!d64Special(r) || r == r, 1)) return r;
     const unsigned long long ua = (unsigned long long)__double_as_longlong(a), ub = (unsigned long long)__double_as_longlong(b);
     if ((ua & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return __longlong_as_double((long long)(ua | 0x0008000000000000ull));
     if ((ub & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return __longlong_as_double((long long)(ub | 0x0008000000000000ull));
@@ -143,19 +156,28 @@ __device__ __forceinline__ double nanX86d(double r, double a, double b) {
 }
 // ---- exactness guard of the chain kernels' float class ------------------------------------------------------------------
 // mul.rz.ftz.f32 IS dspMulFloatFloat except where the reference's integer code leaves IEEE: it flushes on the exponent sum
-// BEFORE normalisation (a product in [2^-126, 2^-125) becomes 0) and it knows no infinities (an overflowing product wraps).
-// A biquad product is (state value or input) x coefficient.  With every non-zero coefficient in [2^-60, 2^60] (checked on the
-// host, chainFloatCoefsInRange) a product can only reach the flush zone when an operand is a non-zero value below 2^-64,
-// and it can only overflow into a non-finite accumulator, which stays non-finite.  So the cascades keep the minimum of a
-// guard word over every value they load or produce (2 integer instructions per value) and look at their final accumulators:
-// a stream that saw a tiny or non-finite value is flagged and re-executed from its state snapshot by the interpreter, whose
-// multiply is the integer restatement (api.cu).  Everything else is the reference's arithmetic bit for bit.
+// BEFORE normalisation (a product in [2^-126, 2^-125) becomes 0) and it knows no overflow (the exponent wraps, where
+// round-toward-zero clamps to the largest finite number).  A biquad product is (state value or input) x coefficient, and the
+// host admits a program only when every non-zero coefficient lies in [2^-60, 2^6] (chainFloatCoefsInRange).  Then
+//  * a product can reach the flush zone only when an operand is a non-zero value below 2^-64: the cascades keep the minimum
+//    of the guard word 2*|bits| - 1 (zero maps to the top) over EVERY value they load or produce;
+//  * a product can overflow only when an operand is 2^122 or larger, and a step multiplies the largest value by less than
+//    2^8.4 (five products of at most 2^6): it is enough to see every sixth step that all values are below 2^64 (the five
+//    steps in between stay below 2^106, their products below 2^112) -- the maximum of 2*|bits| on every sixth step (the
+//    unroll group); the check also catches infinities and NaNs that came in through the state or the samples.
+// Two integer instructions per value (+ one on every sixth step), on the ALU pipe.  A stream that fails either test is
+// flagged and re-executed from its state snapshot by the interpreter, whose multiply is the integer restatement (api.cu);
+// every value is tested before it can do harm as an operand, so an unflagged stream is the reference's arithmetic bit for bit.
 constexpr unsigned kFltGuardTiny = 2u * 0x1F800000u - 1u;          // guard word of 2^-64
-__device__ __forceinline__ unsigned fltGuard(unsigned mn, float v) {           // 2*|bits| - 1: zero -> 0xFFFFFFFF, tiny -> small
+constexpr unsigned kFltGuardHuge = 2u * 0x5F800000u;               // 2*|bits| of 2^64
+struct FltGuard { unsigned mn = 0xFFFFFFFFu, mx = 0u; };
+template <bool HUGE = true>
+__device__ __forceinline__ void fltGuard(FltGuard& g, float v) {
     const unsigned b = __float_as_uint(v);
-    return min(mn, b + b - 1u);
+    g.mn = min(g.mn, b + b - 1u);                                  // zero -> 0xFFFFFFFF, tiny -> small
+    if (HUGE) g.mx = max(g.mx, b + b);
 }
-__device__ __forceinline__ bool fltNonFinite(float v) { return (__float_as_uint(v) & 0x7F800000u) == 0x7F800000u; }
+__device__ __forceinline__ bool fltGuardFired(const FltGuard& g) { return g.mn < kFltGuardTiny || g.mx >= kFltGuardHuge; }
 
 // dspMulFloatDouble (:377-410): exact float x float product as a double (zero/denormal inputs -> +0)
 __device__ __forceinline__ double mulFD(float a, float b) {

@@ -228,7 +228,7 @@ void buildChainPlan(Lowered* L) {
     c.h.dataSize = g.h.dataSize; c.h.stateWords = g.h.stateWords; c.h.auxOff = g.h.auxOff;
     c.h.storeDither = g.h.defaultDither;
     for (int k = 0; k < kIoSlots; k++) c.h.chainOfOut[k] = -1;
-    if (!g.h.sampleInt) throw ChainFail{"float-sample formats 5/6 run on the generic executor"};
+    if (!g.h.sampleInt && g.h.aluClass != ALU_F32) throw ChainFail{"DSP_FORMAT 6 (float samples, double ALU) runs on the generic executor"};
 
     int inChOfSlot[kIoSlots], outChOfSlot[kIoSlots];
     for (int k = 0; k < kIoSlots; k++) inChOfSlot[k] = outChOfSlot[k] = -1;

@@ -173,8 +173,8 @@ struct Lane2F {
     float acc[K], x1[K], x2[K], y1[K], y2[K];
     float b0[K], b1[K], b2[K], a1[K], a2[K];
 };
-template <int K>
-__device__ __forceinline__ void laneStepF(Lane2F<K>& L, float xin, unsigned& mn) {
+template <int K, bool HUGE = true>
+__device__ __forceinline__ void laneStepF(Lane2F<K>& L, float xin, FltGuard& mn) {
     float in[K];
     in[0] = xin;
 #pragma unroll
@@ -187,7 +187,7 @@ __device__ __forceinline__ void laneStepF(Lane2F<K>& L, float xin, unsigned& mn)
         acc = __fadd_rn(acc, mulFF_fast(L.x2[j], L.b2[j]));
         acc = __fadd_rn(acc, mulFF_fast(L.y1[j], L.a1[j]));
         acc = __fadd_rn(acc, mulFF_fast(L.y2[j], L.a2[j]));
-        mn = fltGuard(mn, acc);
+        fltGuard<HUGE>(mn, acc);
         L.acc[j] = acc;
         L.x2[j] = L.x1[j]; L.x1[j] = in[j];
         L.y2[j] = L.y1[j]; L.y1[j] = acc;
@@ -215,7 +215,8 @@ __device__ __forceinline__ void unpackLane(const Lane2FP& Q, Lane2F<2>& L) {
     L.acc[0] = loF2(Q.acc); L.acc[1] = hiF2(Q.acc); L.x1[0] = loF2(Q.x1); L.x1[1] = hiF2(Q.x1); L.x2[0] = loF2(Q.x2); L.x2[1] = hiF2(Q.x2);
     L.y1[0] = loF2(Q.y1); L.y1[1] = hiF2(Q.y1); L.y2[0] = loF2(Q.y2); L.y2[1] = hiF2(Q.y2);
 }
-__device__ __forceinline__ void laneStepFP(Lane2FP& Q, float xin, unsigned& mn) {
+template <bool HUGE>
+__device__ __forceinline__ void laneStepFP(Lane2FP& Q, float xin, FltGuard& mn) {
     const unsigned long long in = packF2(xin, loF2(Q.y1));           // section 1 works on section 0's previous output
     unsigned long long acc = Q.acc;
     acc = macF2(acc, in, Q.b0);
@@ -223,14 +224,14 @@ __device__ __forceinline__ void laneStepFP(Lane2FP& Q, float xin, unsigned& mn) 
     acc = macF2(acc, Q.x2, Q.b2);
     acc = macF2(acc, Q.y1, Q.a1);
     acc = macF2(acc, Q.y2, Q.a2);
-    mn = fltGuard(fltGuard(mn, loF2(acc)), hiF2(acc));
+    fltGuard<HUGE>(mn, loF2(acc)); fltGuard<HUGE>(mn, hiF2(acc));
     Q.acc = acc;
     Q.x2 = Q.x1; Q.x1 = in;
     Q.y2 = Q.y1; Q.y1 = acc;
 }
 
 template <int K>
-__device__ __forceinline__ void laneStepPredF(Lane2F<K>& L, float xin, int t, int g0, int T, unsigned& mn) {
+__device__ __forceinline__ void laneStepPredF(Lane2F<K>& L, float xin, int t, int g0, int T, FltGuard& mn) {
     float in[K];
     in[0] = xin;
 #pragma unroll
@@ -244,25 +245,29 @@ __device__ __forceinline__ void laneStepPredF(Lane2F<K>& L, float xin, int t, in
             acc = __fadd_rn(acc, mulFF_fast(L.x2[j], L.b2[j]));
             acc = __fadd_rn(acc, mulFF_fast(L.y1[j], L.a1[j]));
             acc = __fadd_rn(acc, mulFF_fast(L.y2[j], L.a2[j]));
-            mn = fltGuard(mn, acc);
+            fltGuard(mn, acc);
             L.acc[j] = acc;
             L.x2[j] = L.x1[j]; L.x1[j] = in[j];
             L.y2[j] = L.y1[j]; L.y1[j] = acc;
         }
     }
 }
-// float-class source from GLOBAL memory (sample formats 3/4: int32 samples): dsp_runtime.c:565-607, 871-897
+// float-class source from GLOBAL memory: dsp_runtime.c:565-607, 871-897.  DSP_FORMAT 3: int32 samples (dspIntToFloatScaled, LOAD_GAIN
+// through dspMulFloatFloat); DSP_FORMAT 5: the sample IS the float and LOAD_GAIN is a plain C multiply
+__device__ __forceinline__ float sampleF(int smp, bool sampleInt) { return sampleInt ? i2fScaled(smp, 31) : __int_as_float(smp); }
 __device__ __forceinline__ float chainSourceF(const ChainPlan& P, const ChainDesc& d, const int* __restrict__ in, int chStride) {
+    const bool si = P.h.sampleInt != 0;
     if (d.srcKind == SRC_LOAD_MUX) {
         float X = 0.0f;
         for (int k = 0; k < d.srcCh; k++) {
             const int ch = P.pool[d.srcArg + 2 * k], gain = P.pool[d.srcArg + 2 * k + 1];
-            X = __fadd_rn(X, mulFF(i2fScaled(ch >= 0 ? in[(size_t)ch * chStride] : 0, 31), __int_as_float(gain)));
+            X = __fadd_rn(X, mulFF(sampleF(ch >= 0 ? in[(size_t)ch * chStride] : 0, si), __int_as_float(gain)));
         }
         return X;
     }
-    const float t = i2fScaled(d.srcCh >= 0 ? in[(size_t)d.srcCh * chStride] : 0, 31);
-    return (d.srcKind == SRC_LOAD_GAIN) ? mulFF(t, __int_as_float(d.srcArg)) : t;
+    const float t = sampleF(d.srcCh >= 0 ? in[(size_t)d.srcCh * chStride] : 0, si);
+    if (d.srcKind != SRC_LOAD_GAIN) return t;
+    return si ? mulFF(t, __int_as_float(d.srcArg)) : __fmul_rn(t, __int_as_float(d.srcArg));
 }
 // float-class post-processing of one accumulator: [GAIN] -> SAT0DB[_GAIN][_TPDF] (dsp_runtime.c:464-534, 636-640)
 __device__ __forceinline__ float finishF(float X, int flags, int gainBits, int satGainBits, int tv, int dither) {
@@ -306,25 +311,31 @@ __device__ __noinline__ int delayFirstFinish(int wv, int satKind, int satGainBit
 
 // post-ring word -> s.31 sample: fixed point stores it as such; the float class stores the (possibly not yet saturated)
 // float and converts here (dspSaturateFloat0db + dsps31Float0DB, runtime/dsp_ieee754.h:60-83,170-184)
-template <int CLS> __device__ __forceinline__ int postToS31(int v) {
-    if (CLS == ALU_F32) return f2s31SatFast(v);
+template <int CLS, bool FSMP = false> __device__ __forceinline__ int postToS31(int v) {
+    if (CLS == ALU_F32) return FSMP ? __float_as_int(satF(__int_as_float(v))) : f2s31SatFast(v);      // DSP_FORMAT 5 stores the float itself
     return v;
 }
 // Phase B of the sink for interleaved output with NOUT (power of two) channels: 32/NOUT frames per pass.
-template <int F, int NOUT, int CLS>
-__device__ __forceinline__ void storePasses(int* __restrict__ out, unsigned rowA, unsigned p4, unsigned RM4, int mask,
-                                            bool clean, int fw0, int fs, int T) {
+template <int F, int NOUT, int CLS, bool FSMP>
+__device__ __forceinline__ void storePassesT(int* __restrict__ out, unsigned rowA, unsigned p4, unsigned RM4, int mask,
+                                             bool clean, int fw0, int fs, int T) {
     constexpr int FPP = 32 / NOUT, NPASS = F / FPP;
     if (clean) {
 #pragma unroll
-        for (int p = 0; p < NPASS; p++) out[p * 32] = postToS31<CLS>(lds32(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
+        for (int p = 0; p < NPASS; p++) out[p * 32] = postToS31<CLS, FSMP>(lds32(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
     } else {
 #pragma unroll 1
         for (int p = 0; p < NPASS; p++) {
             const int ff = fw0 + p * FPP + fs;
-            if (ff >= 0 && ff < T) out[p * 32] = postToS31<CLS>(lds32(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
+            if (ff >= 0 && ff < T) out[p * 32] = postToS31<CLS, FSMP>(lds32(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
         }
     }
+}
+template <int F, int NOUT, int CLS>
+__device__ __forceinline__ void storePasses(const bool fsmp, int* __restrict__ out, unsigned rowA, unsigned p4, unsigned RM4, int mask,
+                                            bool clean, int fw0, int fs, int T) {
+    if (CLS == ALU_F32 && fsmp) storePassesT<F, NOUT, CLS, true>(out, rowA, p4, RM4, mask, clean, fw0, fs, T);
+    else storePassesT<F, NOUT, CLS, false>(out, rowA, p4, RM4, mask, clean, fw0, fs, T);
 }
 
 template <int K, int F, int CLS>
@@ -348,7 +359,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         int* x_s = reinterpret_cast<int*>(smem_raw + G.xOff);
         int* post_s = reinterpret_cast<int*>(smem_raw + G.postOff);
         Lane2F<K> L;
-        unsigned mn = 0xFFFFFFFFu;                       // exactness guard (avdsp_dev.cuh): smallest guard word of every value seen
+        FltGuard mn;                       // exactness guard (avdsp_dev.cuh): smallest guard word of every value seen
         const ChainLane e = A.lanes[tid];
         const bool live = e.slot >= 0 && e.slot / C < nsHere;
         const bool head = (e.flags & 1) != 0, tail = (e.flags & 2) != 0;
@@ -372,7 +383,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 const int* q = stLane + P.pool[d.secStateOff + sec];        // [acc, -, x1, x2, y1, y2] (dsp_biquadSTD.h:84-119)
                 L.acc[k] = __int_as_float(q[0]);
                 L.x1[k] = __int_as_float(q[2]); L.x2[k] = __int_as_float(q[3]); L.y1[k] = __int_as_float(q[4]); L.y2[k] = __int_as_float(q[5]);
-                mn = fltGuard(fltGuard(fltGuard(fltGuard(fltGuard(mn, L.acc[k]), L.x1[k]), L.x2[k]), L.y1[k]), L.y2[k]);
+                fltGuard(mn, L.acc[k]); fltGuard(mn, L.x1[k]); fltGuard(mn, L.x2[k]); fltGuard(mn, L.y1[k]); fltGuard(mn, L.y2[k]);
             }
         }
         const int* xrow = x_s + (size_t)((slot / C) * nSrc + max(d.srcId, 0)) * XP;
@@ -392,8 +403,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         for (int jj = 0; jj < UNR; jj++) {
                             const int j = j0 + jj;
                             float x = __shfl_up_sync(0xffffffffu, hiF2(Q.y1), 1);
-                            if (head) { x = __int_as_float(xs[j]); mn = fltGuard(mn, x); }
-                            laneStepFP(Q, x, mn);
+                            if (head) { x = __int_as_float(xs[j]); fltGuard(mn, x); }
+                            if (jj % 6 == 0) laneStepFP<true>(Q, x, mn); else laneStepFP<false>(Q, x, mn);
                             if (tail) ps[j] = __float_as_int(hiF2(Q.acc));
                         }
                     }
@@ -405,8 +416,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                     for (int jj = 0; jj < UNR; jj++) {
                         const int j = j0 + jj;
                         float x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
-                        if (head) { x = __int_as_float(xs[j]); mn = fltGuard(mn, x); }
-                        laneStepF<K>(L, x, mn);
+                        if (head) { x = __int_as_float(xs[j]); fltGuard(mn, x); }
+                        if (jj % 6 == 0) laneStepF<K, true>(L, x, mn); else laneStepF<K, false>(L, x, mn);
                         if (tail) ps[j] = __float_as_int(L.acc[K - 1]);     // the sink saturates / converts (satF is idempotent)
                     }
                 }
@@ -415,7 +426,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
 #pragma unroll 1
                 for (int j = 0; j < F; j++) {
                     float x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
-                    if (head) { x = __int_as_float(xs[j]); if ((unsigned)(t0 + j - g0) < (unsigned)T) mn = fltGuard(mn, x); }
+                    if (head) { x = __int_as_float(xs[j]); if ((unsigned)(t0 + j - g0) < (unsigned)T) fltGuard(mn, x); }
                     laneStepPredF<K>(L, x, t0 + j, g0, T, mn);
                     if (tail && (unsigned)(t0 + j - g0 - (K - 1)) < (unsigned)T) ps[j] = __float_as_int(L.acc[K - 1]);
                 }
@@ -429,10 +440,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 q[0] = __float_as_int(L.acc[k]);
                 q[2] = __float_as_int(L.x1[k]); q[3] = __float_as_int(L.x2[k]); q[4] = __float_as_int(L.y1[k]); q[5] = __float_as_int(L.y2[k]);
             }
-            bool redo = mn < kFltGuardTiny;
-#pragma unroll
-            for (int k = 0; k < K; k++) redo = redo || fltNonFinite(L.acc[k]);
-            if (redo && A.redo) A.redo[s0 + slot / C] = 1;
+            if (fltGuardFired(mn) && A.redo) A.redo[s0 + slot / C] = 1;
         }
         return;
     }
@@ -543,7 +551,8 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
 
     // =============================================================================== helper warps
     const int ht = tid - G.secThreads, hw = ht >> 5, nHW = G.helpThreads >> 5;
-    const int storeMask = ditherMask(P.h.storeDither);
+    const bool fsmp = CLS == ALU_F32 && !P.h.sampleInt;       // DSP_FORMAT 5: float samples in, floats out, no STORE mask
+    const int storeMask = fsmp ? -1 : ditherMask(P.h.storeDither);
     const bool hasCalc = P.h.hasTpdfCalc != 0;
     const unsigned sb = smemAddr(smem_raw);
     int* post_s = reinterpret_cast<int*>(smem_raw + G.postOff);
@@ -634,7 +643,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         }
     };
 
-    bool simpleSrc = true;                                  // every source is LOAD_GAIN of a fed input
+    bool simpleSrc = !fsmp;                                 // every source is LOAD_GAIN of a fed input (int32 samples)
     for (int k = 0; k < nSrc && k < kFastTab; k++) simpleSrc = simpleSrc && P.h.sKind[k] == SRC_LOAD_GAIN && P.h.sCh[k] >= 0;
     // ---- source stage of tile `it`: frames [it*F, it*F+F) -> x ring (one value per distinct source), dither values
     auto sourceTile = [&](int it) {
@@ -777,11 +786,11 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 int* out = A.out + (size_t)(s0 + sl) * A.outStreamStride + (size_t)fw0 * A.outFrameStride + lane;
                 const unsigned rowA = postA + bRow;
                 switch (nOut) {
-                case 1:  storePasses<F, 1, CLS>(out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
-                case 2:  storePasses<F, 2, CLS>(out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
-                case 4:  storePasses<F, 4, CLS>(out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
-                case 8:  storePasses<F, 8, CLS>(out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
-                default: storePasses<F, 16, CLS>(out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
+                case 1:  storePasses<F, 1, CLS>(fsmp, out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
+                case 2:  storePasses<F, 2, CLS>(fsmp, out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
+                case 4:  storePasses<F, 4, CLS>(fsmp, out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
+                case 8:  storePasses<F, 8, CLS>(fsmp, out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
+                default: storePasses<F, 16, CLS>(fsmp, out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
                 }
                 __syncwarp(wmask);
             }
@@ -880,11 +889,11 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 const unsigned p4 = (unsigned)(fw0 << 2) + bPos4;           // 4*(post-ring step of this lane's element in pass 0)
                 const bool clean = fw0 >= 0 && fw0 + F <= T;
                 switch (nOut) {
-                case 1:  storePasses<F, 1, CLS>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
-                case 2:  storePasses<F, 2, CLS>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
-                case 4:  storePasses<F, 4, CLS>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
-                case 8:  storePasses<F, 8, CLS>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
-                default: storePasses<F, 16, CLS>(out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                case 1:  storePasses<F, 1, CLS>(fsmp, out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                case 2:  storePasses<F, 2, CLS>(fsmp, out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                case 4:  storePasses<F, 4, CLS>(fsmp, out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                case 8:  storePasses<F, 8, CLS>(fsmp, out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
+                default: storePasses<F, 16, CLS>(fsmp, out, rowA, p4, RM4, bMask, clean, fw0, bFs, T); break;
                 }
             } else if (f >= 0 && f < T) {
                 // any layout: lane = frame, 16-byte stores when the layout allows
@@ -902,7 +911,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                             int wv = lds32(postA + G.outRowOff[ch] + ((f4 + (unsigned)G.outPos4[ch]) & RM4));
                             if (dc.delayFirst)      // out of line: rare program shape, keeps the common store loop compact
                                 wv = delayFirstFinish(wv, dc.satKind, dc.satGainBits, lds32(tpdfA + ((unsigned)(f & (4 * F - 1)) << 2)), P.h.tpdfShift);
-                            else wv = postToS31<CLS>(wv);      // float class: the ring holds the float (storePasses converts in the fast path)
+                            else wv = fsmp ? postToS31<CLS, true>(wv) : postToS31<CLS, false>(wv);      // float class: the ring holds the float (storePasses converts in the fast path)
                             v = wv & (dc.srcKind == SRC_RAW ? -1 : storeMask);
                         }
                         val[q] = v;
@@ -1009,14 +1018,14 @@ static int packLanes2(const ChainPlan& p, int NS, int K, ChainLane* out, int* gm
 }
 
 // float class: the exactness guard of the cascades (avdsp_dev.cuh, fltGuard) bounds products through their operands, which needs
-// every non-zero biquad coefficient within [2^-60, 2^60] (2^-64 x 2^-60 > 2^-125: above the flush zone; denormal coefficients are out)
+// every non-zero biquad coefficient within [2^-60, 2^6] (avdsp_dev.cuh, fltGuard; denormal coefficients are out)
 bool chainFloatCoefsInRange(const ChainPlan& plan) {
     for (int c = 0; c < plan.h.nChains; c++) {
         const ChainDesc& d = plan.chains[c];
         for (int k = 0; k < 5 * d.nsec; k++) {
             const uint32_t u = (uint32_t)plan.pool[d.coefOff + k] & 0x7FFFFFFFu;
             const int ex = (int)(u >> 23);
-            if (u != 0 && (ex < 127 - 60 || ex > 127 + 60)) return false;
+            if (u != 0 && (ex < 127 - 60 || ex > 127 + 6)) return false;
         }
     }
     return true;
@@ -1025,7 +1034,7 @@ bool chainFloatCoefsInRange(const ChainPlan& plan) {
 bool chain2Supports(const ChainPlan& plan) {
     if (plan.h.aluClass == ALU_F32 && !chainFloatCoefsInRange(plan)) return false;
     // the helper warps address everything through the flattened tables (plan.h: kFastTab entries each)
-    return (plan.h.aluClass == ALU_INT64 || plan.h.aluClass == ALU_F32) && plan.h.sampleInt && (plan.h.aluClass == ALU_INT64 || (plan.h.nRaw == 0 && plan.h.nMemCopy == 0)) && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nOut <= kFastTab &&
+    return (plan.h.aluClass == ALU_INT64 || plan.h.aluClass == ALU_F32) && (plan.h.sampleInt || plan.h.aluClass == ALU_F32) && (plan.h.aluClass == ALU_INT64 || (plan.h.nRaw == 0 && plan.h.nMemCopy == 0)) && plan.h.nChains > 0 && plan.h.nOut > 0 && plan.h.nOut <= kFastTab &&
            plan.h.nProc <= kFastTab && plan.h.nSrc <= kFastTab;
 }
 

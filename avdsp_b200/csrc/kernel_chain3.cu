@@ -372,8 +372,8 @@ struct CascF {
 };
 __device__ __forceinline__ float maccF3(float acc, float a, float b) { return __fadd_rn(acc, mulFF_fast(a, b)); }
 
-template <int NSEC>
-__device__ __forceinline__ float cascStepF(CascF<NSEC>& L, float xin, unsigned& mn) {
+template <int NSEC, bool HUGE = true>
+__device__ __forceinline__ float cascStepF(CascF<NSEC>& L, float xin, FltGuard& mn) {
     float acc[NSEC];
 #pragma unroll
     for (int k = 0; k < NSEC; k++) acc[k] = maccF3(L.acc[k], k ? L.y1[k - 1] : xin, L.b0[k]);
@@ -386,14 +386,14 @@ __device__ __forceinline__ float cascStepF(CascF<NSEC>& L, float xin, unsigned& 
 #pragma unroll
     for (int k = 0; k < NSEC; k++) acc[k] = maccF3(acc[k], L.y2[k], L.a2[k]);
 #pragma unroll
-    for (int k = 0; k < NSEC; k++) { mn = fltGuard(mn, acc[k]); L.acc[k] = acc[k]; L.y3[k] = L.y2[k]; L.y2[k] = L.y1[k]; L.y1[k] = acc[k]; }
+    for (int k = 0; k < NSEC; k++) { fltGuard<HUGE>(mn, acc[k]); L.acc[k] = acc[k]; L.y3[k] = L.y2[k]; L.y2[k] = L.y1[k]; L.y1[k] = acc[k]; }
     L.X2 = L.X1; L.X1 = xin;
     return acc[NSEC - 1];
 }
 // any step of the launch: section k commits only when its frame t-k lies in [0,T); the reference's own x1/x2 words stand in for
 // outputs older than the launch on its first two frames
 template <int NSEC>
-__device__ __forceinline__ float cascStepExactF(CascF<NSEC>& L, float xin, int t, int T, unsigned& mn) {
+__device__ __forceinline__ float cascStepExactF(CascF<NSEC>& L, float xin, int t, int T, FltGuard& mn) {
     float in[NSEC], x1[NSEC], x2[NSEC];
 #pragma unroll
     for (int k = 0; k < NSEC; k++) {
@@ -412,7 +412,7 @@ __device__ __forceinline__ float cascStepExactF(CascF<NSEC>& L, float xin, int t
             acc = maccF3(acc, x2[k], L.b2[k]);
             acc = maccF3(acc, L.y1[k], L.a1[k]);
             acc = maccF3(acc, L.y2[k], L.a2[k]);
-            mn = fltGuard(mn, acc);
+            fltGuard(mn, acc);
             L.acc[k] = acc;
             L.y3[k] = L.y2[k]; L.y2[k] = L.y1[k]; L.y1[k] = acc;
             if (k == NSEC - 1) last = acc;
@@ -438,8 +438,8 @@ __device__ __forceinline__ unsigned long long macF3x2(unsigned long long acc, un
 }
 template <int NP>
 struct CascP { unsigned long long acc[NP], y1[NP], y2[NP], y3[NP], X1, X2, b0[NP], b1[NP], b2[NP], a1[NP], a2[NP]; };
-template <int NP>
-__device__ __forceinline__ float cascStepP(CascP<NP>& Q, float xin, unsigned& mn) {
+template <int NP, bool HUGE = true>
+__device__ __forceinline__ float cascStepP(CascP<NP>& Q, float xin, FltGuard& mn) {
     unsigned long long acc[NP];
     const unsigned long long in0 = packF3(xin, loF3(Q.y1[NP - 1]));     // section NP works on what section NP-1 produced one step ago
 #pragma unroll
@@ -454,7 +454,7 @@ __device__ __forceinline__ float cascStepP(CascP<NP>& Q, float xin, unsigned& mn
     for (int j = 0; j < NP; j++) acc[j] = macF3x2(acc[j], Q.y2[j], Q.a2[j]);
 #pragma unroll
     for (int j = 0; j < NP; j++) {
-        mn = fltGuard(fltGuard(mn, loF3(acc[j])), hiF3(acc[j]));
+        fltGuard<HUGE>(mn, loF3(acc[j])); fltGuard<HUGE>(mn, hiF3(acc[j]));
         Q.acc[j] = acc[j]; Q.y3[j] = Q.y2[j]; Q.y2[j] = Q.y1[j]; Q.y1[j] = acc[j];
     }
     Q.X2 = Q.X1; Q.X1 = in0;
@@ -462,8 +462,9 @@ __device__ __forceinline__ float cascStepP(CascP<NP>& Q, float xin, unsigned& mn
 }
 
 // FINM 0: the part hands its float on to the next part; 1: final part, SAT0DB; 2: final part, SAT0DB_TPDF
-// FROMPREV: the part reads the previous part's row (floats) instead of the PCM tile
-template <int NSEC, int FINM, bool FROMPREV>
+// SRC 0: the part reads int32 samples from the PCM tile (DSP_FORMAT 3); 1: the previous part's row (floats); 2: float samples
+// from the PCM tile (DSP_FORMAT 5: the sample is the float, LOAD_GAIN a plain C multiply)
+template <int NSEC, int FINM, int SRC>
 __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Args& A, const Chain3Geom& G, unsigned char* smem, int w, int lane) {
     constexpr int LAG = NSEC - 1;
     constexpr bool fin = FINM != 0;
@@ -486,14 +487,16 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
     const unsigned rawRow = sb + G.rawOff + (unsigned)(sl * G.rawPitchBytes) + (unsigned)d.srcCh * 4u;
     const unsigned fb = (unsigned)P.h.nIn * 4u;
     const unsigned mbar = sb + G.mbarOff;
+    constexpr bool FROMPREV = SRC == 1;
     constexpr bool fromPrev = FROMPREV;
+    constexpr bool fsmp = SRC == 2;
     const bool hasSrcGain = !fromPrev && d.srcKind == SRC_LOAD_GAIN;
     const float gain = hasSrcGain ? __int_as_float(d.srcArg) : 1.0f;     // mul.rz by 1.0 is exact: LOAD and LOAD_GAIN share the fast form
     const int dither = P.h.storeDither;
     int* st = A.state + (size_t)(s0 + sl) * W;
 
     CascF<NSEC> L;
-    unsigned mn = 0xFFFFFFFFu;            // exactness guard (avdsp_dev.cuh fltGuard): smallest guard word of every value loaded or produced
+    FltGuard mn;            // exactness guard (avdsp_dev.cuh fltGuard): smallest guard word of every value loaded or produced
     L.X1 = L.X2 = 0.0f;
 #pragma unroll
     for (int k = 0; k < NSEC; k++) {
@@ -505,7 +508,7 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
         L.acc[k] = __int_as_float(q[0]);
         L.rx1[k] = __int_as_float(q[2]); L.rx2[k] = __int_as_float(q[3]); L.y1[k] = __int_as_float(q[4]); L.y2[k] = __int_as_float(q[5]);
         if (k == 0) { L.X1 = L.rx1[0]; L.X2 = L.rx2[0]; }
-        mn = fltGuard(fltGuard(fltGuard(fltGuard(fltGuard(mn, L.acc[k]), L.rx1[k]), L.rx2[k]), L.y1[k]), L.y2[k]);
+        fltGuard(mn, L.acc[k]); fltGuard(mn, L.rx1[k]); fltGuard(mn, L.rx2[k]); fltGuard(mn, L.y1[k]); fltGuard(mn, L.y2[k]);
     }
     // the post ring is the delay line (ring of s.31 values behind the saturation), exactly as in the fixed-point form
     const int n = fin ? d.delayN : 0;
@@ -526,11 +529,13 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
     // no branches -- the previous part's float and the converted sample are both formed, one is selected
     auto sourceFast = [&](int smp) -> float {
         if (fromPrev) return __int_as_float(smp);
+        if (fsmp) return __fmul_rn(__int_as_float(smp), gain);     // gain 1.0 for a plain LOAD: exact
         const float x = mulFF_fast(i2f31Fast(smp), gain);
         return smp == 0 ? 0.0f : x;                                // the reference's product of a zero is +0, never -0
     };
     auto sourceExact = [&](int smp) -> float {
         if (fromPrev) return __int_as_float(smp);
+        if (fsmp) return __fmul_rn(__int_as_float(smp), gain);
         float x = i2fScaled(smp, 31);
         if (hasSrcGain) { x = mulFF(x, gain); if (smp == 0) x = 0.0f; }
         return x;
@@ -583,8 +588,10 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
                 const int smp = lds3(rj); rj += rstep;
                 float acc;
                 const float xs_ = sourceFast(smp);
-                if (!FROMPREV) mn = fltGuard(mn, xs_);
-                if constexpr (PACKED) acc = cascStepP<NP>(Q, xs_, mn); else acc = cascStepF<NSEC>(L, xs_, mn);
+                if (!FROMPREV) fltGuard(mn, xs_);
+                // (the huge side of the guard on every sixth step: avdsp_dev.cuh; jj is a constant after unrolling)
+                if constexpr (PACKED) acc = (jj % 6 == 0) ? cascStepP<NP, true>(Q, xs_, mn) : cascStepP<NP, false>(Q, xs_, mn);
+                else acc = (jj % 6 == 0) ? cascStepF<NSEC, true>(L, xs_, mn) : cascStepF<NSEC, false>(L, xs_, mn);
                 const int v = emitLazy(acc, fj + jj);
                 if (live) sts3(pj + 4u * jj, v);
             };
@@ -615,7 +622,7 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
                 if (tl < 0) continue;
                 const int smp = tl < T ? lds3(ra + (unsigned)j * rstep) : 0;
                 const float xs_ = G.floatFast ? sourceFast(smp) : sourceExact(smp);
-                if (!FROMPREV && tl < T) mn = fltGuard(mn, xs_);
+                if (!FROMPREV && tl < T) fltGuard(mn, xs_);
                 const float acc = cascStepExactF<NSEC>(L, xs_, tl, T, mn);
                 const int f = tl - LAG;
                 if (f >= 0) {
@@ -643,12 +650,7 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
             else if (T == 1) { q[2] = __float_as_int(L.y1[k - 1]); q[3] = __float_as_int(L.rx1[k]); }
             q[4] = __float_as_int(L.y1[k]); q[5] = __float_as_int(L.y2[k]);
         }
-        {
-            bool redo = mn < kFltGuardTiny;
-#pragma unroll
-            for (int k = 0; k < NSEC; k++) redo = redo || fltNonFinite(L.acc[k]);
-            if (redo && A.redo) A.redo[s0 + sl] = 1;
-        }
+        if (fltGuardFired(mn) && A.redo) A.redo[s0 + sl] = 1;
         if (n > 0 && T > 0) {
             int* ring = st + d.delayOff + 1;
             for (int k = 0; k < n; k++) {
@@ -662,13 +664,17 @@ __device__ __forceinline__ void cascadeWarpF(const ChainPlan& P, const Chain2Arg
 template <int NSEC>
 __device__ __forceinline__ void cascadeWarpFin(const ChainPlan& P, const Chain2Args& A, const Chain3Geom& G, unsigned char* smem, int w, int lane) {
     const int finm = !G.warpFinal[w] ? 0 : (P.chains[G.warpChain[w]].satKind & 1) ? 2 : 1;
-    switch (finm * 2 + (G.warpSrc[w] >= 0 ? 1 : 0)) {
-    case 0:  cascadeWarpF<NSEC, 0, false>(P, A, G, smem, w, lane); break;
-    case 1:  cascadeWarpF<NSEC, 0, true>(P, A, G, smem, w, lane); break;
-    case 2:  cascadeWarpF<NSEC, 1, false>(P, A, G, smem, w, lane); break;
-    case 3:  cascadeWarpF<NSEC, 1, true>(P, A, G, smem, w, lane); break;
-    case 4:  cascadeWarpF<NSEC, 2, false>(P, A, G, smem, w, lane); break;
-    default: cascadeWarpF<NSEC, 2, true>(P, A, G, smem, w, lane); break;
+    const int src = G.warpSrc[w] >= 0 ? 1 : (P.h.sampleInt ? 0 : 2);
+    switch (finm * 3 + src) {
+    case 0:  cascadeWarpF<NSEC, 0, 0>(P, A, G, smem, w, lane); break;
+    case 1:  cascadeWarpF<NSEC, 0, 1>(P, A, G, smem, w, lane); break;
+    case 2:  cascadeWarpF<NSEC, 0, 2>(P, A, G, smem, w, lane); break;
+    case 3:  cascadeWarpF<NSEC, 1, 0>(P, A, G, smem, w, lane); break;
+    case 4:  cascadeWarpF<NSEC, 1, 1>(P, A, G, smem, w, lane); break;
+    case 5:  cascadeWarpF<NSEC, 1, 2>(P, A, G, smem, w, lane); break;
+    case 6:  cascadeWarpF<NSEC, 2, 0>(P, A, G, smem, w, lane); break;
+    case 7:  cascadeWarpF<NSEC, 2, 1>(P, A, G, smem, w, lane); break;
+    default: cascadeWarpF<NSEC, 2, 2>(P, A, G, smem, w, lane); break;
     }
 }
 
@@ -686,31 +692,34 @@ __device__ __forceinline__ void cascadeWarpMode(const ChainPlan& P, const Chain2
 // store pass of one stream's window, interleaved output with NOUT (power of two) channels: 32/NOUT frames per pass, one
 // 128-byte run per pass; per-lane constants (row, lag - delay, mask) in registers
 // post-ring word -> s.31 sample: the fixed-point form parks it as such, the float form parks the saturated float
-template <bool FLT> __device__ __forceinline__ int post3(int v) { if (FLT) return f2s31SatFast(v); return v; }
+template <bool FLT, bool FSMP> __device__ __forceinline__ int post3(int v) {
+    if (FLT) return FSMP ? __float_as_int(satF(__int_as_float(v))) : f2s31SatFast(v);       // DSP_FORMAT 5 stores the float itself
+    return v;
+}
 
-template <int NOUT, bool FLT>
+template <int NOUT, bool FLT, bool FSMP>
 __device__ __forceinline__ void storeTile3(int* __restrict__ out, unsigned rowA, unsigned p4, unsigned RM4, int mask, bool clean,
                                            int f0, int fs, int T) {
     constexpr int FPP = 32 / NOUT, NPASS = F3 / FPP;
     if (clean) {
 #pragma unroll
-        for (int p = 0; p < NPASS; p++) out[p * 32] = post3<FLT>(lds3(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
+        for (int p = 0; p < NPASS; p++) out[p * 32] = post3<FLT, FSMP>(lds3(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
     } else {
 #pragma unroll 1
         for (int p = 0; p < NPASS; p++) {
             const int f = f0 + p * FPP + fs;
-            if (f >= 0 && f < T) out[p * 32] = post3<FLT>(lds3(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
+            if (f >= 0 && f < T) out[p * 32] = post3<FLT, FSMP>(lds3(rowA + ((p4 + (unsigned)(p * FPP * 4)) & RM4))) & mask;
         }
     }
 }
 
 // all streams of one store warp for one window: the channel-count dispatch sits outside the stream loop, the loop itself is
 // pointer bumps + the passes
-template <int NOUT, bool FLT>
+template <int NOUT, bool FLT, bool FSMP>
 __device__ __forceinline__ void storeStreams3(int* __restrict__ out, size_t outStep, unsigned rowA, unsigned rowStep, int cnt, unsigned p4,
                                               unsigned RM4, int mask, bool clean, int f0, int fs, int T) {
 #pragma unroll 1
-    for (int s = 0; s < cnt; s++, out += outStep, rowA += rowStep) storeTile3<NOUT, FLT>(out, rowA, p4, RM4, mask, clean, f0, fs, T);
+    for (int s = 0; s < cnt; s++, out += outStep, rowA += rowStep) storeTile3<NOUT, FLT, FSMP>(out, rowA, p4, RM4, mask, clean, f0, fs, T);
 }
 
 } // namespace
@@ -848,7 +857,8 @@ k_chain3(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
     // ---- store warps: post ring at (frame + lag - delay) -> STORE mask -> global
     const int sw = hw - 1, nSW = G.nStore;
     const int nOut = P.h.nOut;
-    const int storeMask = ditherMask(P.h.storeDither);
+    const bool fsmp = FLT && !P.h.sampleInt;                 // DSP_FORMAT 5: floats out, no STORE mask
+    const int storeMask = fsmp ? -1 : ditherMask(P.h.storeDither);
     const bool laneOut = A.outChStride == 1 && A.outFrameStride == nOut;      // interleaved: lane = (frame inside a pass, channel)
     const int bCh = lane % nOut, bFs = lane / nOut;
     const int bChain = P.h.chainOfOut[bCh];
@@ -867,13 +877,24 @@ k_chain3(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
             int* out = A.out + (size_t)(s0 + sw) * A.outStreamStride + (long long)f0 * A.outFrameStride + lane;
             const size_t outStep = (size_t)nSW * (size_t)A.outStreamStride;
             const unsigned rowA = sb + bRow + (unsigned)(sw * G.postPitch) * 4u, rowStep = (unsigned)(nSW * G.postPitch) * 4u;
-            switch (nOut) {
-            case 1:  storeStreams3<1, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
-            case 2:  storeStreams3<2, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
-            case 4:  storeStreams3<4, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
-            case 8:  storeStreams3<8, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
-            case 16: storeStreams3<16, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
-            default: storeStreams3<32, FLT>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+            if (FLT && fsmp) {
+                switch (nOut) {
+                case 1:  storeStreams3<1, FLT, true>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                case 2:  storeStreams3<2, FLT, true>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                case 4:  storeStreams3<4, FLT, true>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                case 8:  storeStreams3<8, FLT, true>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                case 16: storeStreams3<16, FLT, true>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                default: storeStreams3<32, FLT, true>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                }
+            } else {
+                switch (nOut) {
+                case 1:  storeStreams3<1, FLT, false>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                case 2:  storeStreams3<2, FLT, false>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                case 4:  storeStreams3<4, FLT, false>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                case 8:  storeStreams3<8, FLT, false>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                case 16: storeStreams3<16, FLT, false>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                default: storeStreams3<32, FLT, false>(out, outStep, rowA, rowStep, cnt, p4, RM4, bMask, clean, f0, bFs, T); break;
+                }
             }
         } else {
             // any other layout (planar): lane = frame, channels in a loop; consecutive lanes store consecutive frames
@@ -885,7 +906,7 @@ k_chain3(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         int v = 0;
                         if (oc >= 0) {
                             const int off = G.chainLag[oc] - P.chains[oc].delayN;
-                            v = post3<FLT>(lds3(sb + (unsigned)G.warpRowOff[G.chainRow[oc]] + (unsigned)(sl * G.postPitch) * 4u + ((unsigned)((f + off) << 2) & RM4))) & storeMask;
+                            { const int wv_ = lds3(sb + (unsigned)G.warpRowOff[G.chainRow[oc]] + (unsigned)(sl * G.postPitch) * 4u + ((unsigned)((f + off) << 2) & RM4)); v = (fsmp ? post3<FLT, true>(wv_) : post3<FLT, false>(wv_)) & storeMask; }
                         }
                         A.out[(size_t)(s0 + sl) * A.outStreamStride + (size_t)f * A.outFrameStride + (size_t)ch * A.outChStride] = v;
                     }
@@ -898,7 +919,7 @@ static int envInt3(const char* name, int dflt) { const char* v = getenv(name); r
 
 bool chain3Supports(const ChainPlan& plan) {
     const ChainHeader& h = plan.h;
-    if ((h.aluClass != ALU_INT64 && h.aluClass != ALU_F32) || !h.sampleInt) return false;      // DSP_FORMAT 2 and 3
+    if (h.aluClass != ALU_INT64 && h.aluClass != ALU_F32) return false;                        // DSP_FORMAT 2, 3 and 5
     if (h.aluClass == ALU_F32 && !chainFloatCoefsInRange(plan)) return false;
     if (h.nChains <= 0 || h.nChains > kChain3MaxChains || h.nIn <= 0) return false;
     if (h.nOut <= 0 || h.nOut > 32 || (h.nOut & (h.nOut - 1)) != 0) return false;

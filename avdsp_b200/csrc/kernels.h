@@ -72,7 +72,7 @@ struct Chain2Args {
     int inFrameStride, inChStride, outFrameStride, outChStride;
     int* redo;                  // float class: [nStreams] flag words, set to 1 for a stream the interpreter has to re-execute (avdsp_dev.cuh, fltGuard)
 };
-bool chainFloatCoefsInRange(const ChainPlan& plan);     // float class: every non-zero biquad coefficient within [2^-60, 2^60]
+bool chainFloatCoefsInRange(const ChainPlan& plan);     // float class: every non-zero biquad coefficient within [2^-60, 2^6]
 bool chain2Supports(const ChainPlan& plan);
 bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2Geom* geom, ChainLane* lanesOut /*[1024]*/);
 cudaError_t launchChain2(const ChainPlan& plan, const Chain2Geom& geom, const Chain2Args& args, cudaStream_t stream);

@@ -1,6 +1,6 @@
 """Randomised CHAIN-shaped programs (source -> biquad cascade -> finish -> delay -> stores, several per core) at random batch
 shapes through every chain kernel that accepts them -- k_chain2, k_chain3 (forced, several streams per CTA), AUTO -- against the
-oracle, bit for bit in outputs and every state word, fixed point and float format 3 alike.  The point is the geometry: part cuts of odd cascade lengths, lags
+oracle, bit for bit in outputs and every state word: fixed point, float format 3 and float format 5 (float samples).  The point is the geometry: part cuts of odd cascade lengths, lags
 longer than a call, calls shorter than a tile, partial CTAs, delay rings longer and shorter than the row ring."""
 import numpy as np
 import pytest
@@ -64,7 +64,7 @@ def random_chain_program(rng, fs=48000, fmt=2):
     return a.end()
 
 
-@pytest.mark.parametrize("fmt", [2, 3])
+@pytest.mark.parametrize("fmt", [2, 3, 5])
 @pytest.mark.parametrize("seed", range(16))
 def test_random_chain_programs(oracle_lib, monkeypatch, seed, fmt):
     rng = np.random.default_rng(5000 + seed)
@@ -76,7 +76,7 @@ def test_random_chain_programs(oracle_lib, monkeypatch, seed, fmt):
         T = int(rng.choice([1, 2, 31, 97, 333, 1700]))
         cut = sorted(set(int(v) for v in rng.integers(0, T + 1, size=2)))
         seeds = np.arange(S, dtype=np.int32) * 3 + seed
-        x = synth.pcm(str(rng.choice(["full", "noise", "impulse"])), S, T, 2, fs)
+        x = (synth.pcm_float if fmt >= 5 else synth.pcm)(str(rng.choice(["full", "noise", "impulse"])), S, T, 2, fs)
         monkeypatch.setenv("AVDSP_B200_NS3", str(int(rng.choice([0, 5, 32]))))
         monkeypatch.setenv("AVDSP_B200_PART3", str(int(rng.choice([4, 4, 8, 2]))))
         ys = sts = None
@@ -108,4 +108,4 @@ def test_random_chain_programs(oracle_lib, monkeypatch, seed, fmt):
 
 def test_chain_fuzz_reaches_both_chain_kernels():
     ran = getattr(test_random_chain_programs, "ran", {})
-    assert ran.get("chain2", 0) >= 40 and ran.get("chain3", 0) >= 15, ran
+    assert ran.get("chain2", 0) >= 60 and ran.get("chain3", 0) >= 20, ran
