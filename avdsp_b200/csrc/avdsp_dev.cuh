@@ -142,17 +142,21 @@ __device__ __forceinline__ double f2dX86(float f) {
 }
 // (tests on the high word: a binary64 compare costs an FP64-pipe instruction, as much as the add it guards)
 __device__ __forceinline__ bool d64Special(double d) { return ((unsigned)__double2hiint(d) & 0x7FF00000u) == 0x7FF00000u; }   // inf or NaN
+__device__ __forceinline__ bool d64NaN(double d) {
+    const unsigned hi = (unsigned)__double2hiint(d);
+    return (hi & 0x7FF00000u) == 0x7FF00000u && (((hi & 0x000FFFFFu) | (unsigned)__double2loint(d)) != 0u);
+}
 __device__ __forceinline__ float d2fX86(double d) {
-    if (__builtin_expect(!d64Special(d) || d == d, 1)) return (float)d;
+    if (__builtin_expect(!d64NaN(d), 1)) return (float)d;
     const unsigned long long u = (unsigned long long)__double_as_longlong(d);
     return __uint_as_float((unsigned)((u >> 32) & 0x80000000u) | 0x7FC00000u | (unsigned)((u >> 29) & 0x003FFFFFu));
 }
 __device__ __forceinline__ double nanX86d(double r, double a, double b) {
-    if (__builtin_expect(!d64Special(r) || r == r, 1)) return r;
-    const unsigned long long ua = (unsigned long long)__double_as_longlong(a), ub = (unsigned long long)__double_as_longlong(b);
-    if ((ua & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return __longlong_as_double((long long)(ua | 0x0008000000000000ull));
-    if ((ub & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return __longlong_as_double((long long)(ub | 0x0008000000000000ull));
-    return __longlong_as_double((long long)0xFFF8000000000000ull);
+    if (__builtin_expect(!d64NaN(r), 1)) return r;
+    // (integer tests on the words: the compiler turns a 64-bit mask of the bit pattern into an FP64-pipe |x|)
+    if (d64NaN(a)) return __hiloint2double(__double2hiint(a) | 0x00080000, __double2loint(a));
+    if (d64NaN(b)) return __hiloint2double(__double2hiint(b) | 0x00080000, __double2loint(b));
+    return __hiloint2double((int)0xFFF80000, 0);
 }
 // ---- exactness guard of the chain kernels' float class ------------------------------------------------------------------
 // mul.rz.ftz.f32 IS dspMulFloatFloat except where the reference's integer code leaves IEEE: it flushes on the exponent sum
