@@ -262,6 +262,8 @@ static void freeAll(avdsp_b200* h) {
     if (h->dTpdf) cudaFree(h->dTpdf);
     if (h->dRedo) cudaFree(h->dRedo);
     if (h->dSnap) cudaFree(h->dSnap);
+    if (h->dRedoList) cudaFree(h->dRedoList);
+    if (h->dRedoCount) cudaFree(h->dRedoCount);
     if (h->dFirTaps) cudaFree(h->dFirTaps);
     if (h->dFirWs) cudaFree(h->dFirWs);
     if (h->pcmRaw) cudaFree(h->pcmRaw);
@@ -538,28 +540,33 @@ static int launchRun(avdsp_b200* h, avdsp_b200* pl, const int* in, int* out, int
         const bool flt = pl->L.chain.h.aluClass == ALU_F32;
         if (flt) {
             // the float class is the reference's arithmetic except next to the underflow threshold and beyond the binary32 range
-            // (avdsp_dev.cuh, fltGuard): snapshot the state, let the cascades flag the streams that came near either, and have the
-            // interpreter re-execute exactly those from the snapshot.  Costs one state copy and one (normally empty) launch.
+            // (avdsp_dev.cuh, fltGuard): snapshot the state, let the cascades flag the streams that came near either, then list
+            // the flagged streams, put their state back and run them again through k_chain2's exact form (hardware product +
+            // integer fallback, the host's NaN rules).  Costs one state copy and two small launches when nothing is flagged.
             if (!h->dRedo) {
                 CU(cudaMalloc(&h->dRedo, (size_t)h->nStreams * sizeof(int)));
+                CU(cudaMalloc(&h->dRedoList, (size_t)h->nStreams * sizeof(int)));
+                CU(cudaMalloc(&h->dRedoCount, (size_t)h->nStreams * sizeof(int)));       // one counter per run start (disjoint runs)
                 CU(cudaMalloc(&h->dSnap, (size_t)h->nStreams * P.stateWords * sizeof(int)));
             }
             CU(cudaMemsetAsync(h->dRedo + first, 0, (size_t)n * sizeof(int), stream));
+            CU(cudaMemsetAsync(h->dRedoCount + first, 0, sizeof(int), stream));
             CU(cudaMemcpyAsync(h->dSnap + (size_t)first * P.stateWords, st, (size_t)n * P.stateWords * sizeof(int), cudaMemcpyDeviceToDevice, stream));
             A.redo = h->dRedo + first;
         }
         if (v3) e = launchChain3(pl->L.chain, pl->geom3, A, stream);
         else e = launchChain2(pl->L.chain, pl->geom2, A, stream);
         if (flt && e == cudaSuccess) {
-            GenericArgs R{};
-            R.in = in; R.out = out; R.state = st; R.bigPool = pl->dBig;
-            R.nStreams = n; R.nFrames = nFrames;
-            R.inStreamStride = inSS; R.outStreamStride = outSS;
-            R.inFrameStride = inFS; R.inChStride = inCS; R.outFrameStride = outFS; R.outChStride = outCS;
-            R.coreSel = -1; R.period = 0;                    // the chain kernels run the canonical order (chainOrder above)
-            R.redo = h->dRedo + first; R.snapshot = h->dSnap + (size_t)first * P.stateWords;
-            e = launchGeneric(G, R, stream);
-            h->launches++;
+            e = launchRedoCompact(h->dRedo + first, n, h->dRedoList + first, h->dRedoCount + first, st, h->dSnap + (size_t)first * P.stateWords, P.stateWords, stream);
+            if (e == cudaSuccess) {
+                Chain2Args X = A;
+                X.lanes = pl->dLanes2; X.redo = nullptr;
+                X.map = h->dRedoList + first; X.countPtr = h->dRedoCount + first; X.exact = 1;
+                Chain2Geom gx = pl->geom2;
+                gx.floatFast = 0;                                // sources through the restatement as well
+                e = launchChain2(pl->L.chain, gx, X, stream);
+            }
+            h->launches += 2;
         }
         h->lastChainVariant = v3 ? 3 : 2;
         h->lastKernel = AVDSP_B200_KERNEL_CHAIN;

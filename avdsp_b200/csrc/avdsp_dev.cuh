@@ -131,6 +131,15 @@ static __device__ __forceinline__ float mulFFslow(float a, float b) {
 __device__ __forceinline__ float mulFF_fast(float a, float b) {
     float r; asm("mul.rz.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
 }
+// binary32 arithmetic result with the x86 host's NaN rules: an invalid operation gives the negative "real indefinite", a NaN
+// operand comes back quieted, the first operand first (the device returns the positive canonical NaN for both)
+__device__ __forceinline__ float nanX86(float r, float a, float b) {
+    if (__builtin_expect(r == r, 1)) return r;
+    const unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
+    if ((ua & 0x7FFFFFFFu) > 0x7F800000u) return __uint_as_float(ua | 0x00400000u);
+    if ((ub & 0x7FFFFFFFu) > 0x7F800000u) return __uint_as_float(ub | 0x00400000u);
+    return __uint_as_float(0xFFC00000u);
+}
 // binary32 <-> binary64 conversions and binary64 arithmetic with the x86 host's NaN rules (cvtss2sd / cvtsd2ss keep the sign and the
 // top payload bits and set the quiet bit; addsd & co. return the first NaN operand, quieted, and the negative "real indefinite"
 // for an invalid operation).  The device's converters return canonical NaNs; a cascade that has blown up to NaN then leaves

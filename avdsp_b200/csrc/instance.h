@@ -34,7 +34,7 @@ struct avdsp_b200 {
     int* dTpdf = nullptr; size_t tpdfWords = 0;     // scratch dither values of a launch
     // float class of the chain kernels: per-stream "re-execute me exactly" flags and the state snapshot the interpreter's second
     // pass starts from (avdsp_dev.cuh fltGuard; launchRun).  Indexed by the instance's stream number: disjoint runs do not collide.
-    int* dRedo = nullptr; int* dSnap = nullptr;
+    int* dRedo = nullptr; int* dSnap = nullptr; int* dRedoList = nullptr; int* dRedoCount = nullptr;   // + the compacted list of a run (by instance stream number)
     int period = 0, kernelSel = AVDSP_B200_KERNEL_AUTO, lastKernel = 0;
     long long launches = 0;
     cudaStream_t stream = nullptr;          // for the synchronous calls

@@ -230,7 +230,12 @@ __device__ __forceinline__ void laneStepFP(Lane2FP& Q, float xin, FltGuard& mn) 
     Q.y2 = Q.y1; Q.y1 = acc;
 }
 
-template <int K>
+// EXACT (second pass over flagged streams): dspMulFloatFloat as hardware product + integer fallback, the host's NaN rules on the sums
+template <bool EXACT> __device__ __forceinline__ float maccF2(float acc, float a, float b) {
+    if (EXACT) return nanX86(__fadd_rn(acc, mulFF(a, b)), acc, mulFF(a, b));
+    return __fadd_rn(acc, mulFF_fast(a, b));
+}
+template <int K, bool EXACT = false>
 __device__ __forceinline__ void laneStepPredF(Lane2F<K>& L, float xin, int t, int g0, int T, FltGuard& mn) {
     float in[K];
     in[0] = xin;
@@ -240,12 +245,12 @@ __device__ __forceinline__ void laneStepPredF(Lane2F<K>& L, float xin, int t, in
     for (int j = 0; j < K; j++) {
         if ((unsigned)(t - g0 - j) < (unsigned)T) {
             float acc = L.acc[j];
-            acc = __fadd_rn(acc, mulFF_fast(in[j], L.b0[j]));
-            acc = __fadd_rn(acc, mulFF_fast(L.x1[j], L.b1[j]));
-            acc = __fadd_rn(acc, mulFF_fast(L.x2[j], L.b2[j]));
-            acc = __fadd_rn(acc, mulFF_fast(L.y1[j], L.a1[j]));
-            acc = __fadd_rn(acc, mulFF_fast(L.y2[j], L.a2[j]));
-            fltGuard(mn, acc);
+            acc = maccF2<EXACT>(acc, in[j], L.b0[j]);
+            acc = maccF2<EXACT>(acc, L.x1[j], L.b1[j]);
+            acc = maccF2<EXACT>(acc, L.x2[j], L.b2[j]);
+            acc = maccF2<EXACT>(acc, L.y1[j], L.a1[j]);
+            acc = maccF2<EXACT>(acc, L.y2[j], L.a2[j]);
+            if (!EXACT) fltGuard(mn, acc);
             L.acc[j] = acc;
             L.x2[j] = L.x1[j]; L.x1[j] = in[j];
             L.y2[j] = L.y1[j]; L.y1[j] = acc;
@@ -261,19 +266,20 @@ __device__ __forceinline__ float chainSourceF(const ChainPlan& P, const ChainDes
         float X = 0.0f;
         for (int k = 0; k < d.srcCh; k++) {
             const int ch = P.pool[d.srcArg + 2 * k], gain = P.pool[d.srcArg + 2 * k + 1];
-            X = __fadd_rn(X, mulFF(sampleF(ch >= 0 ? in[(size_t)ch * chStride] : 0, si), __int_as_float(gain)));
+            { const float p_ = mulFF(sampleF(ch >= 0 ? in[(size_t)ch * chStride] : 0, si), __int_as_float(gain)); X = nanX86(__fadd_rn(X, p_), X, p_); }
         }
         return X;
     }
     const float t = sampleF(d.srcCh >= 0 ? in[(size_t)d.srcCh * chStride] : 0, si);
     if (d.srcKind != SRC_LOAD_GAIN) return t;
-    return si ? mulFF(t, __int_as_float(d.srcArg)) : __fmul_rn(t, __int_as_float(d.srcArg));
+    const float g = __int_as_float(d.srcArg);
+    return si ? mulFF(t, g) : nanX86(__fmul_rn(t, g), t, g);
 }
 // float-class post-processing of one accumulator: [GAIN] -> SAT0DB[_GAIN][_TPDF] (dsp_runtime.c:464-534, 636-640)
 __device__ __forceinline__ float finishF(float X, int flags, int gainBits, int satGainBits, int tv, int dither) {
-    if (flags & PF_GAIN) X = __fmul_rn(X, __int_as_float(gainBits));
+    if (flags & PF_GAIN) { const float g = __int_as_float(gainBits); X = nanX86(__fmul_rn(X, g), X, g); }       // a C multiply: the host's NaN rules
     if (flags & PF_SAT_GAIN) X = mulFF(X, __int_as_float(satGainBits));
-    if (flags & PF_SAT_TPDF) X = __fadd_rn(X, i2fScaled(tv, 31 + dither - 1));
+    if (flags & PF_SAT_TPDF) { const float d_ = i2fScaled(tv, 31 + dither - 1); X = nanX86(__fadd_rn(X, d_), X, d_); }
     return satF(X);
 }
 
@@ -347,7 +353,11 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
     // helper warps take the LOW warp ids when G.helpersFirst (scheduler arbitration experiment)
     const int tid = G.helpersFirst ? (threadIdx.x < G.helpThreads ? threadIdx.x + G.secThreads : threadIdx.x - G.helpThreads) : threadIdx.x;
     const int lane = tid & 31;
-    const int s0 = blockIdx.x * NS, nsHere = min(NS, A.nStreams - s0);
+    const int nStreamsRun = A.countPtr ? *A.countPtr : A.nStreams;      // exact second pass: as many streams as the pass before listed
+    const int s0 = blockIdx.x * NS, nsHere = min(NS, nStreamsRun - s0);
+    if (nsHere <= 0) return;
+    const int* const smap = A.map;
+    auto SX = [&](int local) -> int { return smap ? smap[s0 + local] : s0 + local; };      // position in the call's stream range
     const int nAll = G.secThreads + G.helpThreads;
     const int gmax = G.gmax;
     const int nTiles = (T + gmax + F - 1) / F;
@@ -373,7 +383,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         }
         const ChainDesc& d = P.chains[slot % C];
         if (live) {
-            stLane = A.state + (size_t)(s0 + slot / C) * W;
+            stLane = A.state + (size_t)SX(slot / C) * W;
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const int sec = g0 + k;
@@ -393,7 +403,15 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
             const int* xs = xrow + (i & 1) * F;
             const int t0 = i * F;
             int* ps = prow + (t0 & RM);
-            if (t0 >= gmax && t0 + F <= T) {
+            if (A.exact) {
+#pragma unroll 1
+                for (int j = 0; j < F; j++) {
+                    float x = __shfl_up_sync(0xffffffffu, L.y1[K - 1], 1);
+                    if (head) x = __int_as_float(xs[j]);
+                    laneStepPredF<K, true>(L, x, t0 + j, g0, T, mn);
+                    if (tail && (unsigned)(t0 + j - g0 - (K - 1)) < (unsigned)T) ps[j] = __float_as_int(L.acc[K - 1]);
+                }
+            } else if (t0 >= gmax && t0 + F <= T) {
                 if constexpr (K == 2) {
                     Lane2FP Q;
                     packLane(L, Q);
@@ -440,7 +458,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 q[0] = __float_as_int(L.acc[k]);
                 q[2] = __float_as_int(L.x1[k]); q[3] = __float_as_int(L.x2[k]); q[4] = __float_as_int(L.y1[k]); q[5] = __float_as_int(L.y2[k]);
             }
-            if (fltGuardFired(mn) && A.redo) A.redo[s0 + slot / C] = 1;
+            if (!A.exact && fltGuardFired(mn) && A.redo) A.redo[SX(slot / C)] = 1;
         }
         return;
     }
@@ -463,7 +481,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         }
         const ChainDesc& d = P.chains[slot % C];
         if (live) {
-            stLane = A.state + (size_t)(s0 + slot / C) * W;
+            stLane = A.state + (size_t)SX(slot / C) * W;
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const int sec = g0 + k;
@@ -564,7 +582,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
     Prng g = {0, 0, 0, 0}; int tpdfValue = 0, tpdfRandom = 0, dith = 0; bool drew = false;
     int* auxp = nullptr;
     if (hw == 0 && lane < nsHere) {
-        auxp = A.state + (size_t)(s0 + lane) * W + P.h.auxOff;
+        auxp = A.state + (size_t)SX(lane) * W + P.h.auxOff;
         g.s0 = auxp[AUX_S0]; g.s1 = auxp[AUX_S1]; g.s2 = auxp[AUX_S2]; g.s3 = auxp[AUX_S3];
         tpdfValue = auxp[AUX_TPDF_VALUE]; tpdfRandom = auxp[AUX_TPDF_RANDOM]; dith = auxp[AUX_DITHER];
     }
@@ -585,7 +603,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
     bool anyStale = false;
     if (!prngOnly)
         for (int sl = ow; sl < nsHere; sl += nOwn) {
-            int* st = A.state + (size_t)(s0 + sl) * W;
+            int* st = A.state + (size_t)SX(sl) * W;
             for (int c = 0; c < C; c++) {
                 const ChainDesc& d = P.chains[c];
                 const int n = d.delayN;
@@ -636,7 +654,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         if (lane == 0) mbarExpectTx(bar, (unsigned)(cnt * rowBytes));
         for (int j = lane; j < cnt; j += 32) {
             const int sl = ow + j * nOwn;
-            const int* src = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(it * F) * A.inFrameStride;
+            const int* src = A.in + (size_t)SX(sl) * A.inStreamStride + (size_t)(it * F) * A.inFrameStride;
             const unsigned dst = sb + G.rawOff + sl * G.rawStreamBytes + (it & 1) * rowBytes;
             if (interleavedIn) tmaLoad1D(dst, src, (unsigned)rowBytes, bar);
             else for (int ch = 0; ch < nIn; ch++) tmaLoad1D(dst + ch * F * 4, src + (size_t)ch * A.inChStride, (unsigned)(F * 4), bar);
@@ -690,7 +708,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
             unsigned xa = sb + G.xOff + ow * G.xStreamBytes + ((it & 1) * F + lane) * 4;
             unsigned ra = sb + G.rawOff + ow * G.rawStreamBytes + (it & 1) * rowBytes + lane * rawFB;
             for (int sl = ow; sl < nsHere; sl += nOwn, xa += nOwn * G.xStreamBytes, ra += nOwn * G.rawStreamBytes) {
-                const int* in = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(f0 + lane) * A.inFrameStride;
+                const int* in = A.in + (size_t)SX(sl) * A.inStreamStride + (size_t)(f0 + lane) * A.inFrameStride;
                 if (simpleSrc && staged) {
                     // common case, branch-free: LOAD_GAIN sources read from the TMA-staged tile
 #pragma unroll
@@ -783,7 +801,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                     }
                     __syncwarp(wmask);
                 }
-                int* out = A.out + (size_t)(s0 + sl) * A.outStreamStride + (size_t)fw0 * A.outFrameStride + lane;
+                int* out = A.out + (size_t)SX(sl) * A.outStreamStride + (size_t)fw0 * A.outFrameStride + lane;
                 const unsigned rowA = postA + bRow;
                 switch (nOut) {
                 case 1:  storePasses<F, 1, CLS>(fsmp, out, rowA, p4, RM4, bMask, true, fw0, bFs, T); break;
@@ -811,14 +829,14 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                     float X;
                     if (d.nsec > 0) X = __int_as_float(lds32(pa));
                     else {
-                        X = chainSourceF(P, d, A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)fk * A.inFrameStride, A.inChStride);
-                        if (d.srcKind == SRC_LOAD_MUX && fk == T - 1) A.state[(size_t)(s0 + sl) * W + d.muxStateOff] = __float_as_int(X);
+                        X = chainSourceF(P, d, A.in + (size_t)SX(sl) * A.inStreamStride + (size_t)fk * A.inFrameStride, A.inChStride);
+                        if (d.srcKind == SRC_LOAD_MUX && fk == T - 1) A.state[(size_t)SX(sl) * W + d.muxStateOff] = __float_as_int(X);
                     }
                     const int flags = (d.hasGain ? PF_GAIN : 0) | ((d.satKind & 1) ? PF_SAT_TPDF : 0) | (d.satKind >= SAT_GAIN ? PF_SAT_GAIN : 0);
                     const int tv = (flags & PF_SAT_TPDF) ? lds32(tpdfA + ((unsigned)(fk & (4 * F - 1)) << 2)) : 0;
                     const int v = __float_as_int(finishF(X, flags, d.gainBits, d.satGainBits, tv, P.h.storeDither));
                     if (anyStale && fk == 0 && d.delayN > 0 && stale_s[sl * C + c] >= 0)
-                        A.state[(size_t)(s0 + sl) * W + d.delayOff + 1 + stale_s[sl * C + c]] = v;
+                        A.state[(size_t)SX(sl) * W + d.delayOff + 1 + stale_s[sl * C + c]] = v;
                     else sts32(pa, v);
                 }
             } else if (simpleA && iw * F >= gmax && (iw + 1) * F <= T) {
@@ -843,9 +861,9 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         if (flags & PF_SECTIONS) X = lds64(accA + G.pAccOff[k]);
                         else {
                             const ChainDesc& d = P.chains[P.h.pChain[k]];
-                            X = chainSource(P, d, A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)fk * A.inFrameStride, A.inChStride);
+                            X = chainSource(P, d, A.in + (size_t)SX(sl) * A.inStreamStride + (size_t)fk * A.inFrameStride, A.inChStride);
                             if (d.srcKind == SRC_LOAD_MUX && fk == T - 1) {
-                                int* st = A.state + (size_t)(s0 + sl) * W;
+                                int* st = A.state + (size_t)SX(sl) * W;
                                 st[d.muxStateOff] = lo32(X); st[d.muxStateOff + 1] = hi32(X);
                             }
                         }
@@ -858,7 +876,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         // LOAD_STORE: the sample itself; delay-first paths: the accumulator's low word (what the ring stores)
                         const int v = (flags & (PF_RAW | PF_DELAY_FIRST)) ? lo32(X) : sat64_031_s32(X);
                         if (anyStale && fk == 0 && P.h.pDelayN[k] > 0 && stale_s[sl * C + P.h.pChain[k]] >= 0)
-                            A.state[(size_t)(s0 + sl) * W + P.chains[P.h.pChain[k]].delayOff + 1 + stale_s[sl * C + P.h.pChain[k]]] = v;
+                            A.state[(size_t)SX(sl) * W + P.chains[P.h.pChain[k]].delayOff + 1 + stale_s[sl * C + P.h.pChain[k]]] = v;
                         else sts32(postA + G.pPostOff[k] + tpos4, v);
                     }
                 }
@@ -872,7 +890,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                         // (a post-processed chain's post(0) was sent to ring[idx0] by stage A above)
                         int* pr = post_s + (size_t)(sl * C + c) * G.postPitch + ((d.nsec - 1) & RM);
                         if (d.accRow < 0 && !(CLS == ALU_F32 && isProc(c)))
-                            A.state[(size_t)(s0 + sl) * W + d.delayOff + 1 + stale_s[sl * C + c]] = CLS == ALU_F32 ? __float_as_int(satF(__int_as_float(*pr))) : *pr;
+                            A.state[(size_t)SX(sl) * W + d.delayOff + 1 + stale_s[sl * C + c]] = CLS == ALU_F32 ? __float_as_int(satF(__int_as_float(*pr))) : *pr;
                         *pr = sfix_s[sl * C + c];
                     }
                 }
@@ -884,7 +902,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 // pass store one contiguous 128-byte run.  Per-lane constants (row, lag-delay) sit in registers and the
                 // pass geometry is a template constant: a pass is add / and / add / LDS / and / STG with immediate offsets.
                 const int fw0 = iw * F - gmax;
-                int* out = A.out + (size_t)(s0 + sl) * A.outStreamStride + (size_t)fw0 * A.outFrameStride + lane;
+                int* out = A.out + (size_t)SX(sl) * A.outStreamStride + (size_t)fw0 * A.outFrameStride + lane;
                 const unsigned rowA = postA + bRow;
                 const unsigned p4 = (unsigned)(fw0 << 2) + bPos4;           // 4*(post-ring step of this lane's element in pass 0)
                 const bool clean = fw0 >= 0 && fw0 + F <= T;
@@ -897,7 +915,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
                 }
             } else if (f >= 0 && f < T) {
                 // any layout: lane = frame, 16-byte stores when the layout allows
-                int* out = A.out + (size_t)(s0 + sl) * A.outStreamStride + (size_t)f * A.outFrameStride;
+                int* out = A.out + (size_t)SX(sl) * A.outStreamStride + (size_t)f * A.outFrameStride;
 #pragma unroll
                 for (int ch0 = 0; ch0 < kFastTab; ch0 += 4) {
                     if (ch0 >= P.h.nOut) break;
@@ -941,7 +959,7 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
         auxp[AUX_S0] = g.s0; auxp[AUX_S1] = g.s1; auxp[AUX_S2] = g.s2; auxp[AUX_S3] = g.s3;
         auxp[AUX_TPDF_VALUE] = tpdfValue; auxp[AUX_TPDF_RANDOM] = tpdfRandom; auxp[AUX_DITHER] = dith;
         if (drew) {   // TPDF_CALC leaves its last value (as an ALU word) in the data area (dsp_runtime.c:541-543)
-            int* q = A.state + (size_t)(s0 + lane) * W + P.h.tpdfDataOff;
+            int* q = A.state + (size_t)SX(lane) * W + P.h.tpdfDataOff;
             if (CLS == ALU_F32) q[0] = __float_as_int(i2fScaled(tpdfValue, 31));
             else { q[0] = tpdfValue; q[1] = tpdfValue >> 31; }
         }
@@ -949,12 +967,12 @@ k_chain2(const __grid_constant__ ChainPlan P, const Chain2Args A, const __grid_c
     if (prngOnly || T <= 0) return;
     __syncwarp();
     for (int sl = ow; sl < nsHere; sl += nOwn) {
-        int* st = A.state + (size_t)(s0 + sl) * W;
+        int* st = A.state + (size_t)SX(sl) * W;
         for (int c = 0; c < C; c++) {
             const ChainDesc& d = P.chains[c];
             // last LOAD_MUX value of chains with sections stays in the data area (dsp_runtime.c:893-896)
             if (d.srcKind == SRC_LOAD_MUX && d.nsec > 0 && lane == 0) {
-                const int* fr = A.in + (size_t)(s0 + sl) * A.inStreamStride + (size_t)(T - 1) * A.inFrameStride;
+                const int* fr = A.in + (size_t)SX(sl) * A.inStreamStride + (size_t)(T - 1) * A.inFrameStride;
                 if (CLS == ALU_F32) st[d.muxStateOff] = __float_as_int(chainSourceF(P, d, fr, A.inChStride));
                 else { const long long X = chainSource(P, d, fr, A.inChStride); st[d.muxStateOff] = (int)X; st[d.muxStateOff + 1] = (int)(X >> 32); }
             }
@@ -1134,6 +1152,22 @@ __global__ void k_chain2_memfix(const __grid_constant__ ChainPlan P, int* __rest
     if (s >= nStreams) return;
     int* st = state + (size_t)s * P.h.stateWords;
     for (int k = 0; k < P.h.nMemCopy; k++) { st[P.h.memCopyDst[k]] = st[P.h.memCopySrc[k]]; st[P.h.memCopyDst[k] + 1] = st[P.h.memCopySrc[k] + 1]; }
+}
+
+// flagged streams of a range -> list (any order: the streams are independent), their state blocks back to the snapshot
+__global__ void __launch_bounds__(256) k_redo_compact(const int* __restrict__ flags, int nStreams, int* __restrict__ list, int* __restrict__ count,
+                                                      int* __restrict__ state, const int* __restrict__ snapshot, int W) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nStreams || !flags[warp]) return;
+    int pos = 0;
+    if (lane == 0) pos = atomicAdd(count, 1);
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (lane == 0) list[pos] = warp;
+    for (int w = lane; w < W; w += 32) state[(size_t)warp * W + w] = snapshot[(size_t)warp * W + w];
+}
+cudaError_t launchRedoCompact(const int* flags, int nStreams, int* list, int* count, int* state, const int* snapshot, int stateWords, cudaStream_t stream) {
+    k_redo_compact<<<(nStreams * 32 + 255) / 256, 256, 0, stream>>>(flags, nStreams, list, count, state, snapshot, stateWords);
+    return cudaGetLastError();
 }
 
 cudaError_t launchChain2(const ChainPlan& plan, const Chain2Geom& geom, const Chain2Args& args, cudaStream_t stream) {

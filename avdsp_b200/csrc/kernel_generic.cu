@@ -60,13 +60,6 @@ template <int CLS> __device__ __forceinline__ auto par(int bits) {
 // DSP_DITHER in the float formats turns its zero-initialised error word into -inf on the very first frame (dspShiftFloat on
 // 0.0, dsp_ieee754.h:297-314), the next frames compute inf - inf, and the saturation (an exponent test on the raw bits,
 // :170-184) sends a negative NaN to -1.0 and a positive one to +1.0.
-__device__ __forceinline__ float nanX86(float r, float a, float b) {
-    if (__builtin_expect(r == r, 1)) return r;
-    const unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
-    if ((ua & 0x7FFFFFFFu) > 0x7F800000u) return __uint_as_float(ua | 0x00400000u);
-    if ((ub & 0x7FFFFFFFu) > 0x7F800000u) return __uint_as_float(ub | 0x00400000u);
-    return __uint_as_float(0xFFC00000u);
-}
 __device__ __forceinline__ long long aAdd(long long a, long long b) { return (long long)((unsigned long long)a + (unsigned long long)b); }
 __device__ __forceinline__ long long aSub(long long a, long long b) { return (long long)((unsigned long long)a - (unsigned long long)b); }
 __device__ __forceinline__ long long aMul(long long a, long long b) { return (long long)((unsigned long long)a * (unsigned long long)b); }

@@ -70,8 +70,16 @@ struct Chain2Args {
     int nStreams, nFrames;
     long long inStreamStride, outStreamStride;
     int inFrameStride, inChStride, outFrameStride, outChStride;
-    int* redo;                  // float class: [nStreams] flag words, set to 1 for a stream the interpreter has to re-execute (avdsp_dev.cuh, fltGuard)
+    int* redo;                  // float class: [nStreams] flag words, set to 1 for a stream that has to be re-executed exactly (avdsp_dev.cuh, fltGuard)
+    // exact second pass of the float class (k_chain2 only): the launch works on the streams listed in `map` (positions in the
+    // call's stream range), as many as *countPtr says (device memory: the list is built by the pass before), with
+    // dspMulFloatFloat as hardware product + integer fallback and the host's NaN rules on the adds
+    const int* map;
+    const int* countPtr;
+    int exact;
 };
+// after a float-class chain kernel: list the flagged streams of the range and put their state blocks back to the snapshot
+cudaError_t launchRedoCompact(const int* flags, int nStreams, int* list, int* count, int* state, const int* snapshot, int stateWords, cudaStream_t stream);
 bool chainFloatCoefsInRange(const ChainPlan& plan);     // float class: every non-zero biquad coefficient within [2^-60, 2^6]
 bool chain2Supports(const ChainPlan& plan);
 bool planChain2Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain2Geom* geom, ChainLane* lanesOut /*[1024]*/);
