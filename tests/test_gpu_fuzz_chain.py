@@ -13,7 +13,7 @@ from test_gpu_chain3 import _float_state_close
 pytestmark = pytest.mark.gpu
 
 
-def random_chain_program(rng, fs=48000, fmt=2):
+def random_chain_program(rng, fs=48000, fmt=2, unstable=False):
     a = wire.Asm(fmt=fmt, fmin=fs, fmax=fs)
     outs = list(range(8))
     rng.shuffle(outs)
@@ -29,7 +29,7 @@ def random_chain_program(rng, fs=48000, fmt=2):
             if not outs:
                 break
             nsec = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 16]))
-            sec = a.biquad_sections([[wire.rbj_peak(fs, float(rng.uniform(60, 15000)), float(rng.uniform(0.5, 4)), float(rng.uniform(0.5, 1.8)))]
+            sec = a.biquad_sections([[wire.rbj_peak(fs, float(rng.uniform(60, 15000)), float(rng.uniform(-4, 4) if unstable else rng.uniform(0.5, 4)), float(rng.uniform(0.5, 1.8)))]
                                      for _ in range(nsec)])
             dl = a.delay_param(3000, int(rng.integers(0, 2900)), fs) if rng.random() < 0.5 else None
             mux = a.mux_table([(8, float(rng.uniform(-0.6, 0.6))), (9, float(rng.uniform(-0.6, 0.6)))])
@@ -71,7 +71,9 @@ def test_random_chain_programs(oracle_lib, monkeypatch, seed, fmt):
     fs = 48000
     ran = {"chain2": 0, "chain3": 0}
     for k in range(4):
-        w = random_chain_program(rng, fs, fmt)
+        # seeds 12..15: some sections get a negative Q and blow up -- wrapping / saturation replay in fixed point, infinities and NaNs in
+        # the float formats (the exact second pass of the float class: dspMulFloatFloat's integer form, the host's NaN rules)
+        w = random_chain_program(rng, fs, fmt, unstable=seed >= 12)
         S = int(rng.choice([1, 3, 7, 33, 70]))
         T = int(rng.choice([1, 2, 31, 97, 333, 1700]))
         cut = sorted(set(int(v) for v in rng.integers(0, T + 1, size=2)))
@@ -102,7 +104,8 @@ def test_random_chain_programs(oracle_lib, monkeypatch, seed, fmt):
                 if fmt == 2 or ex.last_kernel == "generic":
                     assert np.array_equal(got, exp), f"state of stream {s_} differs at {np.nonzero(got != exp)[0][:8]}: " + what
                 else:
-                    assert _float_state_close(got, exp), f"float state of stream {s_}: " + what
+                    from test_gpu_fuzz import nan_aware_equal      # two NaNs are equal whatever their payload (see there)
+                    assert nan_aware_equal(got, exp), f"float state of stream {s_} differs at {np.nonzero(got != exp)[0][:8]}: " + what
     test_random_chain_programs.ran = {n: getattr(test_random_chain_programs, "ran", {}).get(n, 0) + v for n, v in ran.items()}
 
 
