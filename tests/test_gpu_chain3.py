@@ -1,6 +1,6 @@
-"""k_chain3 (kernel_chain3.cu: one whole biquad cascade per lane, lane = stream) against the CPU oracle through the
-C ABI.  Fixed point only, bar = BIT-EXACT: outputs and every state word (biquad accumulators and histories, delay
-rings + indices, PRNG / TPDF words).  The kernel is forced with KERNEL_CHAIN_V3 and given several streams per CTA
+"""k_chain3 (kernel_chain3.cu: a biquad cascade, or a part of one, per lane, lane = stream) against the CPU oracle through the
+C ABI.  Fixed point and the float class (DSP_FORMAT 3 / 5), bar = BIT-EXACT: outputs and every state word (biquad accumulators
+and histories, delay rings + indices, PRNG / TPDF words).  The kernel is forced with KERNEL_CHAIN_V3 and given several streams per CTA
 through AVDSP_B200_NS3 (AUTO picks it by itself only at batch width, which test_gpu_parity's 4096-stream tests cover).
 """
 import numpy as np
