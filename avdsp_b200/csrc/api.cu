@@ -549,9 +549,8 @@ static int launchRun(avdsp_b200* h, avdsp_b200* pl, const int* in, int* out, int
                 CU(cudaMalloc(&h->dRedoCount, (size_t)h->nStreams * sizeof(int)));       // one counter per run start (disjoint runs)
                 CU(cudaMalloc(&h->dSnap, (size_t)h->nStreams * P.stateWords * sizeof(int)));
             }
-            CU(cudaMemsetAsync(h->dRedo + first, 0, (size_t)n * sizeof(int), stream));
-            CU(cudaMemsetAsync(h->dRedoCount + first, 0, sizeof(int), stream));
-            CU(cudaMemcpyAsync(h->dSnap + (size_t)first * P.stateWords, st, (size_t)n * P.stateWords * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+            e = launchRedoPrepare(st, h->dSnap + (size_t)first * P.stateWords, (size_t)n * P.stateWords, h->dRedo + first, n, h->dRedoCount + first, stream);
+            if (e != cudaSuccess) return cudaErr(e, "kernel launch");
             A.redo = h->dRedo + first;
         }
         if (v3) e = launchChain3(pl->L.chain, pl->geom3, A, stream);
@@ -566,7 +565,7 @@ static int launchRun(avdsp_b200* h, avdsp_b200* pl, const int* in, int* out, int
                 gx.floatFast = 0;                                // sources through the restatement as well
                 e = launchChain2(pl->L.chain, gx, X, stream);
             }
-            h->launches += 2;
+            h->launches += 3;
         }
         h->lastChainVariant = v3 ? 3 : 2;
         h->lastKernel = AVDSP_B200_KERNEL_CHAIN;

@@ -1154,6 +1154,18 @@ __global__ void k_chain2_memfix(const __grid_constant__ ChainPlan P, int* __rest
     for (int k = 0; k < P.h.nMemCopy; k++) { st[P.h.memCopyDst[k]] = st[P.h.memCopySrc[k]]; st[P.h.memCopyDst[k] + 1] = st[P.h.memCopySrc[k] + 1]; }
 }
 
+__global__ void __launch_bounds__(256) k_redo_prepare(const int* __restrict__ state, int* __restrict__ snapshot, size_t words,
+                                                      int* __restrict__ flags, int nStreams, int* __restrict__ count) {
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = i0; i < words; i += step) snapshot[i] = state[i];
+    for (size_t i = i0; i < (size_t)nStreams; i += step) flags[i] = 0;
+    if (i0 == 0) *count = 0;
+}
+cudaError_t launchRedoPrepare(const int* state, int* snapshot, size_t words, int* flags, int nStreams, int* count, cudaStream_t stream) {
+    const int blocks = (int)std::min<size_t>((words + 255) / 256, 148 * 8);
+    k_redo_prepare<<<std::max(blocks, 1), 256, 0, stream>>>(state, snapshot, words, flags, nStreams, count);
+    return cudaGetLastError();
+}
 // flagged streams of a range -> list (any order: the streams are independent), their state blocks back to the snapshot
 __global__ void __launch_bounds__(256) k_redo_compact(const int* __restrict__ flags, int nStreams, int* __restrict__ list, int* __restrict__ count,
                                                       int* __restrict__ state, const int* __restrict__ snapshot, int W) {

@@ -78,6 +78,8 @@ struct Chain2Args {
     const int* countPtr;
     int exact;
 };
+// before a float-class chain kernel, one launch: state blocks of the range -> snapshot, flags and list counter cleared
+cudaError_t launchRedoPrepare(const int* state, int* snapshot, size_t words, int* flags, int nStreams, int* count, cudaStream_t stream);
 // after a float-class chain kernel: list the flagged streams of the range and put their state blocks back to the snapshot
 cudaError_t launchRedoCompact(const int* flags, int nStreams, int* list, int* count, int* state, const int* snapshot, int stateWords, cudaStream_t stream);
 bool chainFloatCoefsInRange(const ChainPlan& plan);     // float class: every non-zero biquad coefficient within [2^-60, 2^6]
