@@ -184,7 +184,10 @@ static void planGeometries(avdsp_b200* h, std::vector<ChainLane>* lanes2) {
         h->trace += line;
     } else if (!L.dagOk && !h->chain2Usable && !h->mixUsable && !h->firUsable) h->trace += "DAG kernel not used: " + L.dagWhyNot + "\n";
     if (!h->chain2Usable && !h->mixUsable) {
-        snprintf(line, sizeof line, "chain kernels not used: %s\n", L.chainOk ? "geometry does not fit" : L.chainWhyNot.c_str());
+        const bool coefRange = L.chainOk && L.chain.h.aluClass == ALU_F32 && !chainFloatCoefsInRange(L.chain);
+        snprintf(line, sizeof line, "chain kernels not used: %s\n",
+                 coefRange ? "a biquad coefficient lies outside [2^-60, 2^7): the float class could not bound its products (exactness guard), the interpreter runs this program"
+                           : L.chainOk ? "geometry does not fit" : L.chainWhyNot.c_str());
         h->trace += line;
     }
 }

@@ -171,12 +171,12 @@ __device__ __forceinline__ double nanX86d(double r, double a, double b) {
 // mul.rz.ftz.f32 IS dspMulFloatFloat except where the reference's integer code leaves IEEE: it flushes on the exponent sum
 // BEFORE normalisation (a product in [2^-126, 2^-125) becomes 0) and it knows no overflow (the exponent wraps, where
 // round-toward-zero clamps to the largest finite number).  A biquad product is (state value or input) x coefficient, and the
-// host admits a program only when every non-zero coefficient lies in [2^-60, 2^6] (chainFloatCoefsInRange).  Then
+// host admits a program only when every non-zero coefficient lies in [2^-60, 2^7) (chainFloatCoefsInRange).  Then
 //  * a product can reach the flush zone only when an operand is a non-zero value below 2^-64: the cascades keep the minimum
 //    of the guard word 2*|bits| - 1 (zero maps to the top) over EVERY value they load or produce;
-//  * a product can overflow only when an operand is 2^122 or larger, and a step multiplies the largest value by less than
-//    2^8.4 (five products of at most 2^6): it is enough to see every sixth step that all values are below 2^64 (the five
-//    steps in between stay below 2^106, their products below 2^112) -- the maximum of 2*|bits| on every sixth step (the
+//  * a product can overflow only when an operand is 2^121 or larger, and a step multiplies the largest value by less than
+//    2^9.4 (five products of less than 2^7): it is enough to see every sixth step that all values are below 2^64 (the five
+//    steps in between stay below 2^111, their products below 2^118) -- the maximum of 2*|bits| on every sixth step (the
 //    unroll group); the check also catches infinities and NaNs that came in through the state or the samples.
 // Two integer instructions per value (+ one on every sixth step), on the ALU pipe.  A stream that fails either test is
 // flagged and re-executed from its state snapshot by the interpreter, whose multiply is the integer restatement (api.cu);

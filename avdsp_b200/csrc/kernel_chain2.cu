@@ -1036,7 +1036,7 @@ static int packLanes2(const ChainPlan& p, int NS, int K, ChainLane* out, int* gm
 }
 
 // float class: the exactness guard of the cascades (avdsp_dev.cuh, fltGuard) bounds products through their operands, which needs
-// every non-zero biquad coefficient within [2^-60, 2^6] (avdsp_dev.cuh, fltGuard; denormal coefficients are out)
+// every non-zero biquad coefficient within [2^-60, 2^7) (avdsp_dev.cuh, fltGuard; denormal coefficients are out)
 bool chainFloatCoefsInRange(const ChainPlan& plan) {
     for (int c = 0; c < plan.h.nChains; c++) {
         const ChainDesc& d = plan.chains[c];

@@ -132,3 +132,29 @@ def test_dump_file_symbol_table_resolves_to_program_words():
         assert (int(w[i]) >> 16) & 0xFFFF == wire.OP["BIQUADS"], name      # the section header the BIQUADS opcode points to
     i = params.word_index(w, t["DELAY_HIGH_LOW_1"])
     assert int(w[i]) & 0xFFFF == 294 and int(w[i]) >> 16 == 71             # microseconds | max samples << 16 (encoder :1111-1118)
+
+
+def test_float_class_needs_coefficients_it_can_bound():
+    """The float class of the chain kernels guards its hardware multiplies through their operands, which needs every non-zero
+    biquad coefficient within [2^-60, 2^7) (avdsp_dev.cuh, fltGuard); anything else stays on the interpreter, and says so."""
+    from oracle import wire
+    fs = 48000
+
+    def prog(b0):
+        a = wire.Asm(fmt=3, fmin=fs, fmax=fs)
+        a.core(); a.param()
+        e = a.biquad_sections([[(b0, 0.1, 0.05, 0.3, -0.2)], [wire.rbj_peak(fs, 1000.0, 1.0, 1.5)]])
+        a.load_gain(8, 0.5); a.biquads(e); a.sat0db(); a.store(0)
+        return a.end()
+
+    ok = avdsp_b200.describe(prog(1.5), fs, 3, 4096)
+    assert "chain kernel v2 geometry" in ok and "chain kernels not used" not in ok
+    for b0 in (200.0, 1e-20):
+        t = avdsp_b200.describe(prog(b0), fs, 3, 4096)
+        assert "chain kernel v2 geometry" not in t and "outside [2^-60, 2^7)" in t, t
+    # the same coefficients in fixed point are no concern
+    a = wire.Asm(fmt=2, fmin=fs, fmax=fs)
+    a.core(); a.param()
+    e = a.biquad_sections([[(7.5, 0.1, 0.05, 0.3, -0.2)]])
+    a.load_gain(8, 0.5); a.biquads(e); a.sat0db(); a.store(0)
+    assert "chain kernel v2 geometry" in avdsp_b200.describe(a.end(), fs, 2, 4096)
