@@ -29,9 +29,9 @@ def highpass(fs, f, q=0.7071):
     return ((1 + c) / 2 / a0, -(1 + c) / a0, (1 + c) / 2 / a0, 2 * c / a0, -(1 - al) / a0)
 
 
-def crossover_program(fx, us, gain, fs=48000):
+def crossover_program(fx, us, gain, fs=48000, fmt=2):
     """2-way LR4 crossover at fx Hz, the tweeter delayed by `us` microseconds, woofer gain `gain`; always the same opcodes"""
-    a = wire.Asm(fmt=2, fmin=fs, fmax=fs)
+    a = wire.Asm(fmt=fmt, fmin=fs, fmax=fs)
     a.core()
     a.tpdf_calc(24)
     a.param()
@@ -61,15 +61,16 @@ def apply_diff(ex, first, n, base, prog):
         ex.set_param(first, n, int(r[0]), prog[r[0]: r[-1] + 1])
 
 
+@pytest.mark.parametrize("fmt", [2, 3])
 @pytest.mark.parametrize("kernel", [KERNEL_AUTO, KERNEL_GENERIC])
-def test_64_streams_64_crossovers(oracle_lib, kernel):
+def test_64_streams_64_crossovers(oracle_lib, kernel, fmt):
     fs, S, T = 48000, 64, 600
-    progs = [crossover_program(200.0 * 1.06 ** s, 100 + 25 * s, 0.5 + 0.005 * s, fs) for s in range(S)]
+    progs = [crossover_program(200.0 * 1.06 ** s, 100 + 25 * s, 0.5 + 0.005 * s, fs, fmt) for s in range(S)]
     assert all(p.shape == progs[0].shape for p in progs)
     ops = [(i, op) for i, op, _ in wire.walk(progs[0].view(np.uint32))]
     assert all([(i, op) for i, op, _ in wire.walk(p.view(np.uint32))] == ops for p in progs)      # same structure
     seeds = np.arange(S, dtype=np.int32)
-    ex = Executor(progs[0], fs, 2, S, seeds=seeds, dither=24)
+    ex = Executor(progs[0], fs, fmt, S, seeds=seeds, dither=24)
     ex.set_kernel(kernel)
     x = synth.pcm("full", S, T, ex.n_in, fs)
     ya = ex.process(x[:, :200])                      # everybody on stream 0's crossover first
@@ -79,7 +80,7 @@ def test_64_streams_64_crossovers(oracle_lib, kernel):
     yb = ex.process(x[:, 200:])                      # state carries over, parameters differ from here on
     y = np.concatenate([ya, yb], axis=1)
     for s in range(S):
-        o = oracle_lib.Oracle(progs[0], 2, fs, seed=s, dither=24)
+        o = oracle_lib.Oracle(progs[0], fmt, fs, seed=s, dither=24)
         ref_a = o.process(x[s, :200])
         # the oracle instance of stream s gets its own PARAM words at the same moment (the reference re-reads the program every frame)
         o.code[:] = np.where(np.arange(len(o.code)) < len(progs[s]), progs[s][: len(o.code)], o.code)
