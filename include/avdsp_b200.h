@@ -11,8 +11,10 @@
  *      calls once per period for all frames -- and for any number of independent streams.
  *
  * All numerics are the reference's: DSP_FORMAT 2 (int64 accumulator) is bit-exact; formats 3..6
- * reproduce the reference's hand-rolled IEEE helpers (runtime/dsp_ieee754.h) bit for bit in the
- * generic executor and within the tolerance stated in DESIGN.md in the fused kernels.
+ * reproduce the reference's hand-rolled IEEE helpers (runtime/dsp_ieee754.h) bit for bit, in the
+ * generic executor and in the fused kernels (formats 3 and 5: hardware multiplies behind a per-stream
+ * exactness guard, flagged streams re-executed exactly inside the same call).  The one path with a
+ * stated tolerance is the opt-in 3xTF32 tensor-core FIR (AVDSP_B200_KERNEL_FIR_TC on a float program).
  *
  * There is no CPU fallback: every compute entry point returns AVDSP_B200_ERR_CUDA when no CUDA
  * device is usable.
