@@ -165,3 +165,38 @@ def test_oracle_matches_compiled_reference_on_random_misc_programs(oracle_lib, f
             assert r.rc == o.rc > 0
             assert nan_aware_equal(r.process(x), o.process(x), fmt >= 5), (fmt, seed, k)
             assert nan_aware_equal(r.data, o.data, fmt != 2), (fmt, seed, k)
+
+
+@pytest.mark.parametrize("family,fmt", [("chain", 2), ("chain", 3), ("chain", 5), ("mix", 2), ("mix", 3), ("fir", 3)])
+def test_oracle_matches_compiled_reference_on_random_kernel_shaped_programs(oracle_lib, family, fmt):
+    """The generators of tests/test_gpu_fuzz_chain.py / test_gpu_fuzz_mix.py (the programs the fused kernels are fuzzed with): the
+    restatement against the compiled reference.  Unstable cascades only in fixed point (wrapping accumulators are defined); in the
+    float formats a cascade that has blown up adds NaNs to NaNs, and which operand's sign and payload an x86 addss keeps is the
+    reference COMPILER's choice of operand order -- visible as +-full scale after the saturation -- so there is no behaviour to pin
+    there (the oracle and the GPU take the accumulator as first operand).  Fixed-point FIR is left out as well: the reference's
+    own kernel is broken there, SURVEY App. C #4-5, and the oracle defines the intended convolution."""
+    from oracle import refdriver, wire
+    if not refdriver.available(fmt):
+        pytest.skip("oracle/_ref not built here (it needs /root/reference)")
+    import importlib
+    from test_gpu_fuzz import nan_aware_equal
+    chain = importlib.import_module("test_gpu_fuzz_chain")
+    mix = importlib.import_module("test_gpu_fuzz_mix")
+    gen = synth.pcm_float if fmt >= 5 else synth.pcm
+    for seed in range(10):
+        rng = np.random.default_rng(13000 + seed)
+        for k in range(4):
+            if family == "chain":
+                w = chain.random_chain_program(rng, 48000, fmt, unstable=seed >= 7 and fmt == 2)
+            elif family == "mix":
+                w = mix.random_mix_program(rng, 48000, fmt)
+            else:
+                w = mix.random_fir_program(rng, 48000, fmt)
+            ins, _ = wire.io_maps(w)
+            T = 1500 if family == "fir" else 400
+            x = gen(("full", "noise", "impulse")[k % 3], 1, T, max(len(ins), 1), 48000)[0][:, : len(ins)]
+            r = refdriver.RefProgram(w, fmt, 48000, seed=seed, dither=24)
+            o = oracle_lib.Oracle(w, fmt, 48000, seed=seed, dither=24)
+            assert r.rc == o.rc > 0
+            assert nan_aware_equal(r.process(x), o.process(x), fmt >= 5), (family, fmt, seed, k)
+            assert nan_aware_equal(r.data, o.data, fmt != 2), (family, fmt, seed, k)
