@@ -984,7 +984,8 @@ bool planChain3Geometry(const ChainPlan& plan, int nStreams, int numSMs, Chain3G
         g.nCascade = nParts;
         g.gmax = gmax;
         g.maxSec = maxSec;
-        g.nStore = std::max(1, std::min(envInt3("AVDSP_B200_SW3", 3), maxThreads / 32 - nParts - 1));
+        // (float class: the store warps also saturate and convert, measured best with four on C3-float: 5.27 ms against 5.40 with three)
+        g.nStore = std::max(1, std::min(envInt3("AVDSP_B200_SW3", plan.h.aluClass == ALU_F32 ? 4 : 3), maxThreads / 32 - nParts - 1));
         g.threads = (nParts + 1 + g.nStore) * 32;
         if (g.threads > maxThreads) continue;
         // the cascades write steps of tile i+1 while the store warps still read window i back to (its first frame - longest delay)
